@@ -1,0 +1,194 @@
+/*
+ * darwin_gpu.h -- C-ABI of the B200-native GACT alignment-extension library
+ * (libdarwin_gact.so).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * This is the boundary a maintainer of yatisht/darwin binds instead of the
+ * software "Processor" (the reference's FPGA/DLL seam):
+ *
+ *   reference seam (software/Processor.h:50-63)        replacement entry point
+ *   -------------------------------------------        -----------------------
+ *   InitializeProcessor_ptr           (:50)            darwin_gpu_create / _destroy
+ *   InitializeScoringParameters_ptr   (:51)            darwin_gpu_set_scoring
+ *   InitializeReferenceMemory_ptr     (:52)            darwin_gpu_upload
+ *   InitializeReadMemory_ptr          (:53)            darwin_gpu_upload
+ *   BatchAlignmentSIMD_ptr            (:55)            darwin_gpu_tiles
+ *   extender_body::operator()  (software/extender.cpp:9, graph.h:219-229)
+ *                                                      darwin_gpu_extend
+ *
+ * All functions return DARWIN_OK (0) or a negative DarwinStatus; they never
+ * fall back to a CPU implementation -- without a usable CUDA device they fail
+ * with DARWIN_ERR_NO_DEVICE.  A handle is single-threaded; use one handle per
+ * host thread / GPU (the reference's `token`, main.cpp:615-624).
+ */
+#ifndef DARWIN_GPU_H
+#define DARWIN_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum DarwinStatus {
+    DARWIN_OK              =  0,
+    DARWIN_ERR_NO_DEVICE   = -1,  /* no CUDA device / driver */
+    DARWIN_ERR_INVALID     = -2,  /* bad argument (== Darwin::Status::InvalidData, Darwin.bond:36-40) */
+    DARWIN_ERR_CUDA        = -3,  /* a CUDA call failed; see darwin_gpu_last_error */
+    DARWIN_ERR_CAPACITY    = -4,  /* caller-provided output buffer too small */
+    DARWIN_ERR_NOT_READY   = -5   /* scoring / arena not initialised */
+} DarwinStatus;
+
+/* align_fields bits (software/graph.h:22-26, Darwin.bond:97) */
+#define DARWIN_REVERSE_REF      (1u << 4)
+#define DARWIN_COMPLEMENT_REF   (1u << 3)
+#define DARWIN_REVERSE_QUERY    (1u << 2)
+#define DARWIN_COMPLEMENT_QUERY (1u << 1)
+#define DARWIN_START_END        (1u << 0)
+
+/* traceback op codes inside TB words / op strings (software/Processor.h:14:
+ * enum states {Z,I,D,M,...}; the long-gap states are stored `% 4`,
+ * Processor.cpp:570, so only I, D, M ever appear). */
+#define DARWIN_OP_I 1u   /* consumes query only  ('-' in the reference string) */
+#define DARWIN_OP_D 2u   /* consumes reference only ('-' in the query string)  */
+#define DARWIN_OP_M 3u   /* consumes both */
+
+/* Largest tile edge the reference ever requests (extender.cpp:70-75). */
+#define DARWIN_MAX_TILE 1984
+
+/* Scoring, in Darwin.bond:45-65 field order (AlignmentScoringParams). */
+typedef struct DarwinScoring {
+    int32_t sub_AA, sub_AC, sub_AG, sub_AT;
+    int32_t sub_CC, sub_CG, sub_CT;
+    int32_t sub_GG, sub_GT;
+    int32_t sub_TT;
+    int32_t sub_N;
+    int32_t gap_open, gap_extend;
+    int32_t long_gap_open, long_gap_extend;
+} DarwinScoring;
+
+/* One tile request == AlignmentInputFieldsDRAM (Darwin.bond:95-112). */
+typedef struct DarwinTileReq {
+    uint64_t ref_bases_start_addr;    /* arena offset of the first reference base of the tile */
+    uint64_t query_bases_start_addr;  /* arena offset of the first query base of the tile */
+    uint32_t score_threshold;         /* carried, unused (as in the reference) */
+    uint16_t index;
+    uint16_t ref_size;
+    uint16_t query_size;
+    uint16_t max_tb_steps;
+    uint8_t  align_fields;
+    uint8_t  reserved[3];
+} DarwinTileReq;
+
+/* One tile result == AlignmentResult (Darwin.bond:114-129) without the vector;
+ * the TB_pointers words go to tb_words[i * tb_words_per_req ...]. */
+typedef struct DarwinTileRes {
+    int32_t  score;
+    uint16_t ref_offset;
+    uint16_t query_offset;
+    uint16_t ref_max_pos;
+    uint16_t query_max_pos;
+    uint16_t total_TB_pointers;
+    uint8_t  index;                   /* uint8 in the reference too (BatchSize) */
+    uint8_t  status;                  /* 0 = OK */
+} DarwinTileRes;
+
+/* One anchor == ExtendLocations (software/graph.h:83-91) plus what
+ * makeForwardAlignment / makeBackwardAlignment look up (extender.cpp:1067-1159). */
+typedef struct DarwinAnchor {
+    uint64_t read_addr;        /* arena offset of the FORWARD read (query_start_addr, both strands) */
+    uint32_t reference_pos;    /* absolute arena offset (ExtendLocations::reference_pos) */
+    uint32_t query_pos;        /* strand-local read offset (ExtendLocations::query_pos) */
+    uint32_t chr_start;        /* Index::chr_coord[chr_id] */
+    uint32_t ref_len;          /* Index::chr_len[chr_id] -- the PADDED length (main.cpp:453) */
+    uint32_t read_len;
+    int32_t  read_num;
+    int32_t  chr_id;
+    int32_t  score;            /* first-tile score, carried through */
+    uint32_t left_hits_off;    /* left_hit_offsets  = hit_pool[left_hits_off  .. +left_hits_n)  ascending  */
+    uint32_t left_hits_n;
+    uint32_t right_hits_off;   /* right_hit_offsets = hit_pool[right_hits_off .. +right_hits_n) descending */
+    uint32_t right_hits_n;
+    uint8_t  strand;           /* 0 = '+', 1 = '-' */
+    uint8_t  reserved[7];
+} DarwinAnchor;
+
+/* DarwinAlnRes.flags */
+#define DARWIN_ALN_EMITTED       (1u << 0)  /* the reference would push this ExtendAlignments */
+#define DARWIN_ALN_OPS_OVERFLOW  (1u << 1)  /* op string did not fit ops_cap; coordinates still valid */
+#define DARWIN_ALN_EXACT_RERUN   (1u << 2)  /* >=1 tile was recomputed with the exact (lazy-F faithful) rule */
+#define DARWIN_ALN_LONG_INS_PATH (1u << 3)  /* a traceback entered the long-insertion state (reference UB bits) */
+
+/* One extended alignment == the fields of ExtendAlignments (graph.h:97-121)
+ * that survive to the printer; gapped strings are rebuilt from the op string. */
+typedef struct DarwinAlnRes {
+    uint64_t ops_offset;        /* first op of this alignment inside ops_pool (1 byte per op, left-to-right) */
+    uint64_t cells;             /* sum of ref_size*query_size over the tile requests issued */
+    uint32_t n_ops;
+    uint32_t reference_start_offset;
+    uint32_t reference_end_offset;
+    uint32_t query_start_offset;
+    uint32_t query_end_offset;
+    uint32_t n_left_ops;        /* ops [0, n_left_ops) came from the left extension */
+    uint32_t n_tiles;           /* tile requests issued (num_active_tiles share, extender.cpp:233) */
+    uint32_t n_large_tiles;     /* 1984x960 / 960x1984 requests (num_large_tiles, extender.cpp:77) */
+    int32_t  score;             /* AlignmentScore (extender.cpp:1161-1200) of the final strings */
+    uint32_t flags;
+} DarwinAlnRes;
+
+typedef struct DarwinExtendParams {
+    int32_t tile_size;      /* params.cfg [GACT_extend] tile_size    */
+    int32_t tile_overlap;   /* params.cfg [GACT_extend] tile_overlap */
+    int32_t do_overlap;     /* argv[3] of the reference (0 = reference-guided, 1 = de novo overlap) */
+    int32_t reserved;
+} DarwinExtendParams;
+
+typedef struct DarwinGpuStats {
+    uint64_t kernel_launches;   /* kernels of this library launched since create */
+    uint64_t tiles_fast;        /* tiles finished by the packed fast path */
+    uint64_t tiles_exact;       /* tiles (re)computed by the exact path */
+    uint64_t cells;             /* DP cells requested (algorithmic) */
+    float    last_kernel_ms;    /* CUDA-event time of the last tiles/extend kernel(s) */
+    float    reserved;
+} DarwinGpuStats;
+
+typedef struct DarwinGpu DarwinGpu;   /* opaque */
+
+/* replaces InitializeProcessor (Processor.h:50): one handle per device/host thread.
+ * arena_bytes = size of the byte-addressed sequence arena this handle mirrors
+ * (the reference's g_DRAM, DRAM.cpp:8); the device keeps it 4-bit packed. */
+int darwin_gpu_create(DarwinGpu** h, int device, uint64_t arena_bytes);
+int darwin_gpu_destroy(DarwinGpu* h);
+
+/* replaces g_InitializeScoringParameters (Processor.cpp:48-80). */
+int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s);
+
+/* replaces g_InitializeReferenceMemory / g_InitializeReadMemory (Processor.cpp:82-85,
+ * sender.cpp:4-97): copy n ASCII bases to arena offset arena_addr (any alignment). */
+int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint64_t n);
+
+/* replaces g_BatchAlignmentSIMD (Processor.cpp:718-762): n independent tiles.
+ * tb_words may be NULL when do_traceback == 0. */
+int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, int n,
+                     DarwinTileRes* res, uint64_t* tb_words, int tb_words_per_req);
+
+/* replaces extender_body::operator() (extender.cpp:9-1065) for n anchors of any
+ * number of reads.  ops_pool receives the op strings; per-anchor capacity is
+ * derived from read_len, overflow is flagged per alignment. */
+int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p,
+                      const DarwinAnchor* anchors, int n,
+                      const uint64_t* hit_pool, uint64_t n_hits,
+                      DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes);
+
+/* device-resident variants used by bench.py's `value` leg: same work, inputs and
+ * outputs stay in HBM (pointers are device pointers of this handle's device). */
+int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, int n,
+                            void* d_res, void* d_tb_words, int tb_words_per_req);
+
+int darwin_gpu_stats(DarwinGpu* h, DarwinGpuStats* out);
+const char* darwin_gpu_last_error(DarwinGpu* h);
+const char* darwin_gpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DARWIN_GPU_H */

@@ -1,0 +1,187 @@
+"""TEST INFRASTRUCTURE ONLY -- loaders for the parity oracles.
+
+* ``port()``            -> oracle/libgact_oracle.so, our CPU restatement (oracle/gact_oracle.c)
+* ``reference(flavour)``-> oracle/_ref/libdarwin_ref{,_patched}.so, the reference's own translation
+                          units compiled unmodified (recipe: oracle/Makefile, driver: oracle/ref_driver.cpp)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import this
+package; the product (darwin_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from darwin_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_cache = {}
+
+
+def build(target="all"):
+    """(Re)build the oracle libraries; the `ref` target is a no-op when /root/reference is absent."""
+    subprocess.run(["make", "-C", _HERE, target], check=True, stdout=subprocess.DEVNULL)
+
+
+def _load(path):
+    if path not in _cache:
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle`)")
+        _cache[path] = C.CDLL(path)
+    return _cache[path]
+
+
+class Port:
+    """oracle/gact_oracle.c through ctypes."""
+    STRIPED, STREAM, CLEAN = 0, 1, 2
+
+    def __init__(self, scoring):
+        self.lib = _load(os.path.join(_HERE, "libgact_oracle.so"))
+        self.sc = (C.c_int * 64)()          # GactScoring (25+4+11 ints) with slack
+        self.lib.gact_scoring_init(self.sc, C.byref(scoring))
+        self.lib.gact_alignment_score.restype = C.c_int
+
+    def tiles(self, dram, req, do_traceback=1, rule=1, tb_words_per_req=None):
+        n = len(req)
+        res = np.zeros(n, abi.TILE_RES)
+        if tb_words_per_req is None:
+            tb_words_per_req = int(req["max_tb_steps"].max()) // 16 + 2 if n else 1
+        tb = np.zeros((n, tb_words_per_req), np.uint64)
+        flags = np.zeros(n, np.uint32)
+        rc = self.lib.gact_tiles(self.sc, abi.ptr(dram), int(do_traceback), int(rule), abi.ptr(req), n,
+                                 abi.ptr(res), abi.ptr(tb), tb_words_per_req, abi.ptr(flags))
+        if rc:
+            raise RuntimeError("gact_tiles rc=%d" % rc)
+        return res, tb, flags
+
+    def extend(self, dram, params, anchors, hit_pool, rule=1, ops_cap=None):
+        n = len(anchors)
+        res = np.zeros(n, abi.ALN_RES)
+        if ops_cap is None:
+            ops_cap = int(anchors["read_len"].astype(np.int64).sum()) * 3 + 65536
+        ops = np.zeros(ops_cap, np.uint8)
+        hp = hit_pool if len(hit_pool) else np.zeros(1, np.uint64)
+        rc = self.lib.gact_extend(self.sc, abi.ptr(dram), C.byref(params), int(rule), abi.ptr(anchors), n,
+                                  abi.ptr(hp), abi.ptr(res), abi.ptr(ops), C.c_uint64(ops_cap))
+        if rc:
+            raise RuntimeError("gact_extend rc=%d" % rc)
+        return res, ops
+
+
+class Reference:
+    """The compiled reference (oracle/_ref) through oracle/ref_driver.cpp."""
+
+    def __init__(self, flavour="patched"):
+        name = "libdarwin_ref_patched.so" if flavour == "patched" else "libdarwin_ref.so"
+        self.lib = _load(os.path.join(_HERE, "_ref", name))
+        L = self.lib
+        L.dref_flavour.restype = C.c_char_p
+        L.dref_arena.restype = C.c_void_p
+        L.dref_arena_reference_size.restype = C.c_uint64
+        L.dref_arena_position.restype = C.c_uint64
+        L.dref_add_chr.restype = C.c_uint64
+        L.dref_anchor_hits_total.restype = C.c_uint64
+        L.dref_tiles_mt.restype = C.c_double
+        L.dref_extend_mt.restype = C.c_double
+        self.flavour = L.dref_flavour().decode()
+
+    # -- configuration ---------------------------------------------------------------------
+    def load_cfg(self, path, do_overlap=0):
+        if self.lib.dref_load_cfg(path.encode(), int(do_overlap)):
+            raise RuntimeError("cannot read " + path)
+
+    def set_scoring(self, scoring):
+        self.lib.dref_set_scoring(C.byref(scoring))
+
+    def set_extend(self, tile_size, tile_overlap, batch_size=2, do_overlap=0):
+        self.lib.dref_set_extend(tile_size, tile_overlap, batch_size, do_overlap)
+
+    def set_dsoft_defaults(self):
+        """software/params.cfg:18-35"""
+        self.lib.dref_set_dsoft(14, 3, 64, 26, 1000, 40, 1000, 4, 128, 60, 64, 1000, C.c_float(0.05))
+
+    # -- arena ------------------------------------------------------------------------------
+    def reset_arena(self):
+        if self.lib.dref_reset_arena():
+            raise MemoryError("reference arena")
+
+    def add_chr(self, name, seq, index=True):
+        return self.lib.dref_add_chr(name.encode(), seq, C.c_uint64(len(seq)), int(index))
+
+    def build_index(self):
+        if self.lib.dref_build_index():
+            raise RuntimeError("no minimizers collected")
+
+    def add_read(self, name, seq):
+        addr = C.c_uint64(0)
+        num = self.lib.dref_add_read(name.encode(), seq, C.c_uint64(len(seq)), C.byref(addr))
+        return num, addr.value
+
+    def arena(self, nbytes=None):
+        """numpy view (uint8) of the first nbytes of the reference's byte arena."""
+        if nbytes is None:
+            nbytes = self.lib.dref_arena_position()
+        buf = (C.c_uint8 * nbytes).from_address(self.lib.dref_arena())
+        return np.frombuffer(buf, np.uint8)
+
+    # -- tiles ------------------------------------------------------------------------------
+    def tiles(self, dram, req, do_traceback=1, tb_words_per_req=None, threads=0):
+        n = len(req)
+        res = np.zeros(n, abi.TILE_RES)
+        if tb_words_per_req is None:
+            tb_words_per_req = int(req["max_tb_steps"].max()) // 16 + 2 if n else 1
+        tb = np.zeros((n, tb_words_per_req), np.uint64)
+        d = abi.ptr(dram) if dram is not None else None
+        if threads:
+            secs = self.lib.dref_tiles_mt(d, int(do_traceback), abi.ptr(req), n, abi.ptr(res), abi.ptr(tb),
+                                          tb_words_per_req, int(threads))
+            return res, tb, secs
+        rc = self.lib.dref_tiles(d, int(do_traceback), abi.ptr(req), n, abi.ptr(res), abi.ptr(tb), tb_words_per_req)
+        if rc:
+            raise RuntimeError("dref_tiles rc=%d" % rc)
+        return res, tb
+
+    # -- anchors / extension --------------------------------------------------------------------
+    def seed_filter(self, first, count):
+        n = self.lib.dref_seed_filter(int(first), int(count))
+        if n < 0:
+            raise RuntimeError("index not built")
+        nh = self.lib.dref_anchor_hits_total()
+        anchors = np.zeros(max(n, 1), abi.ANCHOR)
+        hits = np.zeros(max(nh, 1), np.uint64)
+        got = self.lib.dref_get_anchors(abi.ptr(anchors), n, abi.ptr(hits), C.c_uint64(nh), C.c_uint64(0))
+        assert got == n
+        return anchors[:n], hits[:nh]
+
+    def extend(self, anchors, hit_pool, ops_cap=None):
+        n = len(anchors)
+        res = np.zeros(n, abi.ALN_RES)
+        if ops_cap is None:
+            ops_cap = int(anchors["read_len"].astype(np.int64).sum()) * 3 + 65536
+        ops = np.zeros(ops_cap, np.uint8)
+        hp = hit_pool if len(hit_pool) else np.zeros(1, np.uint64)
+        rc = self.lib.dref_extend(abi.ptr(anchors), n, abi.ptr(hp), abi.ptr(res), abi.ptr(ops), C.c_uint64(ops_cap))
+        if rc:
+            raise RuntimeError("dref_extend rc=%d" % rc)
+        return res, ops
+
+    def extend_mt(self, anchors, hit_pool, threads):
+        cells = C.c_uint64(0)
+        alns = C.c_uint64(0)
+        hp = hit_pool if len(hit_pool) else np.zeros(1, np.uint64)
+        secs = self.lib.dref_extend_mt(abi.ptr(anchors), len(anchors), abi.ptr(hp), int(threads),
+                                       C.byref(cells), C.byref(alns))
+        return secs, cells.value, alns.value
+
+
+def port(scoring):
+    return Port(scoring)
+
+
+def reference(flavour="patched"):
+    return Reference(flavour)
+
+
+def have_reference():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libdarwin_ref_patched.so"))

@@ -1,0 +1,447 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product.
+//
+// C-callable driver around the UNMODIFIED reference translation units of
+// yatisht/darwin (compiled where they lie under /root/reference/software by
+// oracle/Makefile, against the shim headers in oracle/ref_shim).  It replaces
+// the reference's main.cpp (which needs kseq.h and a real TBB flow graph):
+// the arena/index/read bookkeeping below follows main.cpp:294-296, :418-466,
+// :508, :631-698 step by step, then the reference's own stage functors are
+// called directly (seeder_body, filter_body, extender_body).
+//
+// Built into oracle/_ref/libdarwin_ref{,_patched}.so.  Only tests/, smoke() and
+// bench.py's cpu_baseline / --impl reference leg may load it.
+#include "../include/darwin_gpu.h"
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include <atomic>
+#include <mutex>
+#include <chrono>
+
+#include "graph.h"        // reference: software/graph.h (pulls Processor.h, seed_pos_table.h, Index.h, DRAM.h)
+#include "ConfigFile.h"   // reference: software/ConfigFile.h
+
+// defined (external linkage) in the reference's Processor.cpp:718 but not declared in Processor.h
+void BatchAlignmentSIMD(size_t token, char* dram, Darwin::BatchAlignmentInputFieldsDRAM& request,
+                        Darwin::BatchAlignmentResultDRAM& result);
+
+// ---- globals main.cpp would have defined (main.cpp:45, :55) -------------------
+Configuration cfg;
+SeedPosTable* sa = nullptr;
+
+using namespace Darwin;
+
+static std::vector<Read> g_reads;                 // every read added so far
+static tbb::concurrent_vector<mini_list>* g_minimizers = nullptr;
+static uint32_t* g_seed_hist = nullptr;
+static size_t g_hist_size = 0;
+static filter_data g_last_filter;                 // output of the last dref_seed_filter
+static std::atomic<uint64_t> g_cells(0);          // ref_size*query_size over non-dummy requests
+static std::atomic<uint64_t> g_tiles(0);
+static int g_count_cells = 0;
+
+// Counting wrapper installed into the reference's own seam (Processor.h:61).
+static void CountingBatchAlignmentSIMD(size_t token, char* dram, BatchAlignmentInputFieldsDRAM& request,
+                                       BatchAlignmentResultDRAM& result) {
+    if (g_count_cells) {
+        uint64_t c = 0, t = 0;
+        for (auto& r : request.requests) {
+            // idle-slot filler of the extender: 8x8 at address 0 with no flags (extender.cpp:209-220)
+            bool dummy = (r.ref_size == 8 && r.query_size == 8 && r.ref_bases_start_addr == 0 &&
+                          r.query_bases_start_addr == 0 && r.align_fields == 0);
+            if (!dummy) { c += (uint64_t)r.ref_size * r.query_size; t++; }
+        }
+        g_cells += c; g_tiles += t;
+    }
+    BatchAlignmentSIMD(token, dram, request, result);
+}
+
+static void to_params(const DarwinScoring* s, AlignmentScoringParams& p) {
+    p.sub_AA = s->sub_AA; p.sub_AC = s->sub_AC; p.sub_AG = s->sub_AG; p.sub_AT = s->sub_AT;
+    p.sub_CC = s->sub_CC; p.sub_CG = s->sub_CG; p.sub_CT = s->sub_CT;
+    p.sub_GG = s->sub_GG; p.sub_GT = s->sub_GT; p.sub_TT = s->sub_TT; p.sub_N = s->sub_N;
+    p.gap_open = s->gap_open; p.gap_extend = s->gap_extend;
+    p.long_gap_open = s->long_gap_open; p.long_gap_extend = s->long_gap_extend;
+}
+
+// main.cpp:59-121 equivalent (reverse complement, case preserved, 'N'-padded to WORD_SIZE)
+static char* rev_comp(const char* seq, size_t n) {
+    size_t padded = n + ((n % WORD_SIZE) ? WORD_SIZE - (n % WORD_SIZE) : 0);
+    char* rc = (char*)scalable_aligned_malloc(padded ? padded : WORD_SIZE, 64);
+    size_t r = 0;
+    for (size_t i = n; i-- > 0;) {
+        char c = seq[i], o;
+        switch (c) {
+            case 'a': o = 't'; break; case 'A': o = 'T'; break;
+            case 'c': o = 'g'; break; case 'C': o = 'G'; break;
+            case 'g': o = 'c'; break; case 'G': o = 'C'; break;
+            case 't': o = 'a'; break; case 'T': o = 'A'; break;
+            case 'n': o = 'n'; break; default: o = 'N'; break;
+        }
+        rc[r++] = o;
+    }
+    for (; r < padded; r++) rc[r] = 'N';
+    return rc;
+}
+
+extern "C" {
+
+const char* dref_flavour(void) {
+#ifdef DREF_PATCHED
+    return "patched";   // Processor.cpp:384 also initialises vF_La / vF_La_ext
+#else
+    return "as-is";
+#endif
+}
+
+// main.cpp:178-230 (+ :262-288): read params.cfg, push scoring into the Processor.
+int dref_load_cfg(const char* path, int do_overlap) {
+    try {
+        ConfigFile f(path);
+        const char* S = "GACT_scoring";
+        const char* names[11] = {"sub_AA","sub_AC","sub_AG","sub_AT","sub_CC","sub_CG","sub_CT","sub_GG","sub_GT","sub_TT","sub_N"};
+        for (int i = 0; i < 11; i++) cfg.gact_sub_mat[i] = f.Value(S, names[i]);
+        cfg.gap_open = f.Value(S, "gap_open"); cfg.gap_extend = f.Value(S, "gap_extend");
+        cfg.long_gap_open = f.Value(S, "long_gap_open"); cfg.long_gap_extend = f.Value(S, "long_gap_extend");
+        const char* D = "DSOFT_params";
+        cfg.seed_size = f.Value(D, "seed_size"); cfg.minimizer_window = f.Value(D, "minimizer_window");
+        cfg.bin_size = f.Value(D, "bin_size"); cfg.dsoft_threshold = f.Value(D, "threshold");
+        cfg.num_seeds = f.Value(D, "num_seeds"); cfg.seed_occurence_multiple = f.Value(D, "seed_occurence_multiple");
+        cfg.max_candidates = f.Value(D, "max_candidates"); cfg.max_stride = f.Value(D, "max_stride");
+        cfg.do_overlap = do_overlap;
+        const char* F = "GACT_first_tile";
+        cfg.first_tile_size = f.Value(F, "first_tile_size");
+        cfg.first_tile_score_threshold = f.Value(F, "first_tile_score_threshold");
+        cfg.first_tile_batch_size = f.Value(F, "first_tile_batch_size");
+        cfg.min_overlap = f.Value(F, "min_overlap");
+        cfg.slope_threshold = (float)f.Value(F, "slope_threshold");
+        const char* E = "GACT_extend";
+        cfg.tile_size = f.Value(E, "tile_size"); cfg.tile_overlap = f.Value(E, "tile_overlap");
+        cfg.batch_size = f.Value(E, "batch_size");
+        cfg.num_threads = f.Value("Multithreading", "num_threads");
+    } catch (...) { return -1; }
+    AlignmentScoringParams p; AlignmentScoringParamsResponse resp;
+    p.sub_AA = cfg.gact_sub_mat[0]; p.sub_AC = cfg.gact_sub_mat[1]; p.sub_AG = cfg.gact_sub_mat[2]; p.sub_AT = cfg.gact_sub_mat[3];
+    p.sub_CC = cfg.gact_sub_mat[4]; p.sub_CG = cfg.gact_sub_mat[5]; p.sub_CT = cfg.gact_sub_mat[6];
+    p.sub_GG = cfg.gact_sub_mat[7]; p.sub_GT = cfg.gact_sub_mat[8]; p.sub_TT = cfg.gact_sub_mat[9];
+    p.sub_N = cfg.gact_sub_mat[10];
+    p.gap_open = cfg.gap_open; p.gap_extend = cfg.gap_extend;
+    p.long_gap_open = cfg.long_gap_open; p.long_gap_extend = cfg.long_gap_extend;
+    g_InitializeScoringParameters(0, p, resp);
+    g_BatchAlignmentSIMD = CountingBatchAlignmentSIMD;
+    return 0;
+}
+
+// Set scoring both in the Processor statics and in cfg (AlignmentScore reads cfg).
+int dref_set_scoring(const DarwinScoring* s) {
+    AlignmentScoringParams p; AlignmentScoringParamsResponse resp;
+    to_params(s, p);
+    g_InitializeScoringParameters(0, p, resp);
+    const int32_t* v = (const int32_t*)s;
+    for (int i = 0; i < 11; i++) cfg.gact_sub_mat[i] = v[i];
+    cfg.gap_open = s->gap_open; cfg.gap_extend = s->gap_extend;
+    cfg.long_gap_open = s->long_gap_open; cfg.long_gap_extend = s->long_gap_extend;
+    g_BatchAlignmentSIMD = CountingBatchAlignmentSIMD;
+    return 0;
+}
+
+int dref_set_extend(int tile_size, int tile_overlap, int batch_size, int do_overlap) {
+    cfg.tile_size = tile_size; cfg.tile_overlap = tile_overlap; cfg.batch_size = batch_size;
+    cfg.do_overlap = do_overlap;
+    return 0;
+}
+
+// DSOFT / first-tile parameters for callers that do not load a params.cfg.
+int dref_set_dsoft(int seed_size, int minimizer_window, int bin_size, int threshold, int num_seeds,
+                   int seed_occurence_multiple, int max_candidates, int max_stride,
+                   int first_tile_size, int first_tile_score_threshold, int first_tile_batch_size,
+                   int min_overlap, float slope_threshold) {
+    cfg.seed_size = seed_size; cfg.minimizer_window = minimizer_window; cfg.bin_size = bin_size;
+    cfg.dsoft_threshold = threshold; cfg.num_seeds = num_seeds;
+    cfg.seed_occurence_multiple = seed_occurence_multiple; cfg.max_candidates = max_candidates;
+    cfg.max_stride = max_stride; cfg.first_tile_size = first_tile_size;
+    cfg.first_tile_score_threshold = first_tile_score_threshold;
+    cfg.first_tile_batch_size = first_tile_batch_size; cfg.min_overlap = min_overlap;
+    cfg.slope_threshold = slope_threshold;
+    return 0;
+}
+
+// main.cpp:294-296: one arena per process (4 GiB of lazily committed virtual memory).
+int dref_reset_arena(void) {
+    if (!g_DRAM) g_DRAM = new DRAM;
+    if (!g_DRAM->buffer) return -1;
+    g_DRAM->referenceSize = 0;
+    g_DRAM->bufferPosition = 0;
+    Index::chr_id.clear(); Index::chr_coord.clear(); Index::chr_len.clear(); Index::chr_len_unpadded.clear();
+    Index::init();
+    for (auto& r : g_reads) scalable_aligned_free((void*)r.rc_seq.data());
+    g_reads.clear();
+    if (g_minimizers) { delete g_minimizers; g_minimizers = nullptr; }
+    if (g_seed_hist) { scalable_free(g_seed_hist); g_seed_hist = nullptr; }
+    if (sa) { delete sa; sa = nullptr; }
+    return 0;
+}
+
+char* dref_arena(void) { return g_DRAM ? g_DRAM->buffer : nullptr; }
+uint64_t dref_arena_reference_size(void) { return g_DRAM ? g_DRAM->referenceSize : 0; }
+uint64_t dref_arena_position(void) { return g_DRAM ? g_DRAM->bufferPosition : 0; }
+
+// main.cpp:418-466 (reference reader) + :323-341 (minimizer node) for one sequence.
+// Returns the arena offset of the sequence, or 0 when the reference would stop reading (len <= 64).
+uint64_t dref_add_chr(const char* name, const char* seq, uint64_t len, int collect_minimizers) {
+    const size_t readBufferLimit = 1 << 6;                       // main.cpp:299
+    if (len <= readBufferLimit) return 0;
+    size_t seq_len = len, seq_len_unpadded = len;
+    uint64_t at = g_DRAM->referenceSize;
+    memcpy(g_DRAM->buffer + at, seq, seq_len);
+    size_t extra = seq_len % WORD_SIZE;
+    if (extra != 0) { extra = WORD_SIZE - extra; memset(g_DRAM->buffer + at + seq_len, 'N', extra); seq_len += extra; }
+    g_DRAM->referenceSize += seq_len;
+    Index::chr_id.push_back(std::string(name));
+    Index::chr_len.push_back(seq_len);
+    Index::chr_len_unpadded.push_back(seq_len_unpadded);
+    Index::chr_coord.push_back(g_DRAM->referenceSize);
+    g_DRAM->bufferPosition = g_DRAM->referenceSize;              // main.cpp:483
+    if (collect_minimizers) {
+        int kmer_size = cfg.seed_size;
+        if (!g_minimizers) {
+            g_minimizers = new tbb::concurrent_vector<mini_list>();
+            g_hist_size = 1ull << (kmer_size << 1);
+            g_seed_hist = (uint32_t*)scalable_calloc(g_hist_size, sizeof(uint32_t));
+        }
+        auto miniList = g_minimizers->grow_by(1);
+        miniList->reserve(seq_len_unpadded);
+        uint32_t seq_start = (uint32_t)at;
+        iterate_minimizers(g_DRAM->buffer + at, (uint32_t)seq_len_unpadded, kmer_size, cfg.minimizer_window,
+            [&](uint64_t p, uint32_t m) {
+                g_seed_hist[m]++;
+                miniList->push_back(((uint64_t)m << 32) + p + seq_start);
+            });
+    }
+    return at;
+}
+
+// main.cpp:508
+int dref_build_index(void) {
+    if (!g_minimizers) return -1;
+    sa = new SeedPosTable((uint32_t)g_DRAM->referenceSize, cfg.seed_size, cfg.minimizer_window, cfg.max_stride,
+                          cfg.seed_occurence_multiple, cfg.bin_size, *g_minimizers, g_seed_hist, g_hist_size);
+    return 0;
+}
+
+// main.cpp:631-698 for one read.  Returns the read number (index into the driver's read list) or -1 if skipped.
+int dref_add_read(const char* name, const char* seq, uint64_t len, uint64_t* arena_addr) {
+    const size_t readBufferLimit = 1 << 6;
+    size_t extra = g_DRAM->bufferPosition % WORD_SIZE;
+    if (extra != 0) g_DRAM->bufferPosition += WORD_SIZE - extra;
+    size_t seq_len = len;
+    if (seq_len <= readBufferLimit) return -1;
+    if (g_DRAM->bufferPosition + WORD_SIZE + seq_len > g_DRAM->size) g_DRAM->bufferPosition = g_DRAM->referenceSize;
+    memcpy(g_DRAM->buffer + g_DRAM->bufferPosition, seq, seq_len);
+    Read read;
+    read.description = std::string(name);
+    read.seq = bond::blob(g_DRAM->buffer + g_DRAM->bufferPosition, seq_len);
+    read.rc_seq = bond::blob(rev_comp(read.seq.data(), seq_len), seq_len);
+    if (arena_addr) *arena_addr = g_DRAM->bufferPosition;
+    extra = seq_len % WORD_SIZE;
+    if (extra != 0) { extra = WORD_SIZE - extra; memset(g_DRAM->buffer + g_DRAM->bufferPosition + seq_len, 'N', extra); seq_len += extra; }
+    g_DRAM->bufferPosition += seq_len;
+    g_reads.push_back(read);
+    return (int)g_reads.size() - 1;
+}
+
+// ---- tile level: the reference's BatchAlignmentSIMD on an arbitrary byte buffer -------------
+int dref_tiles(const char* dram, int do_traceback, const DarwinTileReq* req, int n,
+               DarwinTileRes* res, uint64_t* tb_words, int tb_words_per_req) {
+    if (!dram) dram = g_DRAM->buffer;
+    BatchAlignmentInputFieldsDRAM in; BatchAlignmentResultDRAM out;
+    in.do_traceback = (uint8_t)do_traceback;
+    in.requests.resize(1);
+    for (int i = 0; i < n; i++) {
+        AlignmentInputFieldsDRAM& r = in.requests[0];
+        r.align_fields = req[i].align_fields; r.index = req[i].index;
+        r.ref_bases_start_addr = req[i].ref_bases_start_addr; r.query_bases_start_addr = req[i].query_bases_start_addr;
+        r.ref_size = req[i].ref_size; r.query_size = req[i].query_size;
+        r.max_tb_steps = req[i].max_tb_steps; r.score_threshold = req[i].score_threshold;
+        BatchAlignmentSIMD(0, (char*)dram, in, out);
+        const AlignmentResult& a = out.results[0];
+        res[i].score = (int32_t)a.score; res[i].ref_offset = a.ref_offset; res[i].query_offset = a.query_offset;
+        res[i].ref_max_pos = a.ref_max_pos; res[i].query_max_pos = a.query_max_pos;
+        res[i].total_TB_pointers = a.total_TB_pointers; res[i].index = a.index; res[i].status = 0;
+        if (tb_words && do_traceback) {
+            if ((int)a.TB_pointers.size() > tb_words_per_req) return DARWIN_ERR_CAPACITY;
+            for (size_t w = 0; w < a.TB_pointers.size(); w++) tb_words[(size_t)i * tb_words_per_req + w] = a.TB_pointers[w];
+        }
+    }
+    return 0;
+}
+
+// Multi-threaded timing leg for the tile-only workload: std::thread x nthreads,
+// one stream of BatchAlignmentSIMD calls per thread.  Returns wall seconds.
+double dref_tiles_mt(const char* dram, int do_traceback, const DarwinTileReq* req, int n,
+                     DarwinTileRes* res, uint64_t* tb_words, int tb_words_per_req, int nthreads) {
+    if (nthreads < 1) nthreads = 1;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) {
+        th.emplace_back([=]() {
+            int lo = (int)((int64_t)n * t / nthreads), hi = (int)((int64_t)n * (t + 1) / nthreads);
+            if (hi > lo)
+                dref_tiles(dram, do_traceback, req + lo, hi - lo, res + lo,
+                           tb_words ? tb_words + (size_t)lo * tb_words_per_req : nullptr, tb_words_per_req);
+        });
+    }
+    for (auto& x : th) x.join();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// ---- anchors: seeder_body + filter_body on reads [first, first+count) ------------------------
+// Results are kept in the driver and fetched with dref_get_anchors.
+int dref_seed_filter(int first, int count) {
+    if (!sa) return -1;
+    reader_output reads(g_reads.begin() + first, g_reads.begin() + first + count);
+    seeder_input sin(reads, 0);
+    filter_input fin = seeder_body()(sin);
+    extender_input ein = filter_body()(fin);
+    g_last_filter = std::get<1>(std::get<0>(ein));
+    // read_num inside the locations is relative to the batch: make it absolute
+    for (auto& l : g_last_filter.fwLocations) l.read_num += first;
+    for (auto& l : g_last_filter.rcLocations) l.read_num += first;
+    return (int)(g_last_filter.fwLocations.size() + g_last_filter.rcLocations.size());
+}
+
+uint64_t dref_anchor_hits_total(void) {
+    uint64_t n = 0;
+    for (auto& l : g_last_filter.fwLocations) n += l.left_hit_offsets.size() + l.right_hit_offsets.size();
+    for (auto& l : g_last_filter.rcLocations) n += l.left_hit_offsets.size() + l.right_hit_offsets.size();
+    return n;
+}
+
+// Serialise the last filter output: forward-strand anchors first, then reverse (extender order).
+int dref_get_anchors(DarwinAnchor* out, int cap, uint64_t* hit_pool, uint64_t hit_cap, uint64_t hit_base) {
+    int n = 0; uint64_t h = 0;
+    for (int strand = 0; strand < 2; strand++) {
+        auto& v = strand ? g_last_filter.rcLocations : g_last_filter.fwLocations;
+        for (auto& l : v) {
+            if (n >= cap) return DARWIN_ERR_CAPACITY;
+            if (h + l.left_hit_offsets.size() + l.right_hit_offsets.size() > hit_cap) return DARWIN_ERR_CAPACITY;
+            DarwinAnchor& a = out[n++];
+            memset(&a, 0, sizeof(a));
+            const Read& rd = g_reads[l.read_num];
+            a.read_addr = (uint64_t)(rd.seq.data() - g_DRAM->buffer);
+            a.reference_pos = l.reference_pos; a.query_pos = l.query_pos;
+            a.chr_start = Index::chr_coord[l.chr_id]; a.ref_len = Index::chr_len[l.chr_id];
+            a.read_len = (uint32_t)rd.seq.size(); a.read_num = l.read_num; a.chr_id = l.chr_id; a.score = l.score;
+            a.left_hits_off = (uint32_t)(hit_base + h); a.left_hits_n = (uint32_t)l.left_hit_offsets.size();
+            for (auto x : l.left_hit_offsets) hit_pool[h++] = x;
+            a.right_hits_off = (uint32_t)(hit_base + h); a.right_hits_n = (uint32_t)l.right_hit_offsets.size();
+            for (auto x : l.right_hit_offsets) hit_pool[h++] = x;
+            a.strand = (uint8_t)strand;
+        }
+    }
+    return n;
+}
+
+static ExtendLocations to_location(const DarwinAnchor& a, const uint64_t* hit_pool, int read_num) {
+    ExtendLocations l;
+    l.read_num = read_num; l.chr_id = a.chr_id; l.score = a.score;
+    l.reference_pos = a.reference_pos; l.query_pos = a.query_pos;
+    l.left_hit_offsets.assign(hit_pool + a.left_hits_off, hit_pool + a.left_hits_off + a.left_hits_n);
+    l.right_hit_offsets.assign(hit_pool + a.right_hits_off, hit_pool + a.right_hits_off + a.right_hits_n);
+    return l;
+}
+
+static void fill_result(const ExtendAlignments& e, DarwinAlnRes& r, uint8_t* ops_pool, uint64_t& used, uint64_t cap) {
+    r.flags |= DARWIN_ALN_EMITTED;
+    r.reference_start_offset = e.reference_start_offset; r.reference_end_offset = e.reference_end_offset;
+    r.query_start_offset = e.query_start_offset; r.query_end_offset = e.query_end_offset;
+    r.score = e.score;
+    size_t n = e.aligned_reference_str.size();
+    r.n_ops = (uint32_t)n; r.ops_offset = used;
+    if (used + n > cap) { r.flags |= DARWIN_ALN_OPS_OVERFLOW; return; }
+    for (size_t k = 0; k < n; k++) {
+        char rc = e.aligned_reference_str[k], qc = e.aligned_query_str[k];
+        ops_pool[used + k] = (rc == '-') ? DARWIN_OP_I : (qc == '-') ? DARWIN_OP_D : DARWIN_OP_M;
+    }
+    used += n;
+}
+
+// ---- anchor level: extender_body, ONE anchor per call so results map 1:1 onto anchors --------
+// (cfg.batch_size lock-step batching does not change any anchor's result, only the output order;
+//  SURVEY Appendix B.)  The anchor's read must have been added with dref_add_read (read_num).
+int dref_extend(const DarwinAnchor* anchors, int n, const uint64_t* hit_pool,
+                DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes) {
+    uint64_t used = 0;
+    g_count_cells = 1;
+    for (int i = 0; i < n; i++) {
+        const DarwinAnchor& a = anchors[i];
+        DarwinAlnRes& r = res[i];
+        memset(&r, 0, sizeof(r));
+        if (a.read_num < 0 || a.read_num >= (int)g_reads.size()) return DARWIN_ERR_INVALID;
+        reader_output reads(1, g_reads[a.read_num]);
+        filter_data fd;
+        (a.strand ? fd.rcLocations : fd.fwLocations).push_back(to_location(a, hit_pool, 0));
+        extender_input in(extender_payload(reads, fd), 0);
+        extender_node::output_ports_type ports;
+        int large0 = extender_body::num_large_tiles;
+        g_cells = 0; g_tiles = 0;
+        extender_body()(in, ports);
+        r.n_tiles = (uint32_t)g_tiles; r.cells = g_cells;
+        r.n_large_tiles = (uint32_t)(extender_body::num_large_tiles - large0);
+        auto& outv = std::get<1>(std::get<0>(std::get<0>(ports).items[0])).extend_alignments;
+        if (!outv.empty()) fill_result(outv[0], r, ops_pool, used, ops_pool_bytes);
+    }
+    g_count_cells = 0;
+    return 0;
+}
+
+// Timing leg: the reference's own call pattern (all anchors of one read per extender_body call,
+// cfg.batch_size slots in lock-step), std::thread x nthreads over reads.  anchors must be grouped by
+// read_num (as dref_get_anchors emits per dref_seed_filter call).  Returns wall seconds; *cells gets
+// the algorithmic cell count, *n_alignments the number of emitted alignments.
+double dref_extend_mt(const DarwinAnchor* anchors, int n, const uint64_t* hit_pool, int nthreads,
+                      uint64_t* cells, uint64_t* n_alignments) {
+    struct Group { int read_num; std::vector<int> idx; };
+    std::vector<Group> groups;
+    for (int i = 0; i < n; i++) {
+        if (groups.empty() || groups.back().read_num != anchors[i].read_num) groups.push_back({anchors[i].read_num, {}});
+        groups.back().idx.push_back(i);
+    }
+    std::atomic<size_t> next(0); std::atomic<uint64_t> alns(0);
+    g_cells = 0; g_tiles = 0; g_count_cells = 1;
+    if (nthreads < 1) nthreads = 1;
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) {
+        th.emplace_back([&, t]() {
+            for (;;) {
+                size_t g = next++;
+                if (g >= groups.size()) break;
+                reader_output reads(1, g_reads[groups[g].read_num]);
+                filter_data fd;
+                for (int i : groups[g].idx)
+                    (anchors[i].strand ? fd.rcLocations : fd.fwLocations).push_back(to_location(anchors[i], hit_pool, 0));
+                extender_input in(extender_payload(reads, fd), (size_t)t);
+                extender_node::output_ports_type ports;
+                extender_body()(in, ports);
+                alns += std::get<1>(std::get<0>(std::get<0>(ports).items[0])).extend_alignments.size();
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    g_count_cells = 0;
+    if (cells) *cells = g_cells;
+    if (n_alignments) *n_alignments = alns;
+    return s;
+}
+
+int dref_num_reads(void) { return (int)g_reads.size(); }
+int dref_num_chr(void) { return (int)Index::chr_id.size(); }
+int dref_hw_threads(void) { return (int)std::thread::hardware_concurrency(); }
+
+} // extern "C"

@@ -1,0 +1,3 @@
+// TEST INFRASTRUCTURE ONLY (oracle build shim)
+#pragma once
+#include "blocked_range.h"
