@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- GACT throughput on B200 (BASELINE.json: "GACT GCUPS ... vs reference TBB+AVX CPU").
+
+Workload (config.workload = "gact_tiles_T320_O128"): BASELINE.json configs[1] / SURVEY 8(d).2 -- independent
+320x320 tiles on random sequences with 15 % mutations (5/5/5 sub/ins/del), half left-extension
+(start_end) and half right-extension (reverse_ref|reverse_query|start_end) requests, corner traceback,
+max_tb_steps 640.  One "step" = one pass of the hot path over the whole batch (default 1M tiles per GPU).
+
+  value : GCUPS with the packed arena, requests and outputs resident in HBM (CUDA events on the library's stream)
+  e2e   : GCUPS through the public call `Processor.BatchAlignmentSIMD` with HOST buffers: ASCII upload of the
+          batch's sequences + request H2D + result/TB-word D2H inside the timed region
+  roofline: integer-pipe cell-update roofline of SURVEY 8(d): achieved = cells/s * 32 int-ops, peak = measured
+          packed-int16 ALU issue rate of this GPU (darwin_gpu_int_peak microbenchmark, run live)
+  cpu_baseline: the reference's own BatchAlignmentSIMD (oracle/_ref, compiled from the unmodified sources) on a
+          bounded sample of the same tiles, all host cores
+
+`--impl reference` times that CPU path alone (rank 0 only).  Multi-GPU: launched under torchrun, one rank per GPU,
+each rank owns an independent shard of tiles (weak scaling), no data-path collective; the barrier and the max over
+ranks go through torch.distributed (NCCL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TILE, OVERLAP = 320, 128
+OPS_PER_CELL = 32          # algorithmic integer ops per DP cell
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons of one GPU during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+
+    def run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def make_workload(n_tiles, seed):
+    from darwin_b200 import synth
+    chunks, reqs, base = [], [], 0
+    step = 100000
+    for c0 in range(0, n_tiles, step):
+        n = min(step, n_tiles - c0)
+        arena, req = synth.tile_batch_fast(seed * 1000 + c0 // step, n, TILE)
+        arena = arena[:n * 2 * TILE]
+        req["ref_bases_start_addr"] += base
+        req["query_bases_start_addr"] += base
+        base += len(arena)
+        chunks.append(arena)
+        reqs.append(req)
+    arena = np.concatenate(chunks + [np.full(128, ord("N"), np.uint8)])
+    return arena, np.concatenate(reqs)
+
+
+def cpu_reference_leg(arena, req, seconds_target, threads=None):
+    """The reference's own BatchAlignmentSIMD (oracle/_ref) on a bounded sample, all host cores."""
+    import oracle
+    from darwin_b200 import abi
+    kind = "reference" if oracle.have_reference() else "port"
+    cores = threads or os.cpu_count() or 1
+    cells_per_tile = TILE * TILE
+    if kind == "reference":
+        ref = oracle.reference("as-is")
+        ref.set_scoring(abi.Scoring.from_values())
+        # ~0.2 GCUPS/core: size the sample for `seconds_target`
+        n = int(min(len(req), max(cores * 8, seconds_target * cores * 0.2e9 / cells_per_tile)))
+        sample = np.ascontiguousarray(req[:n])
+        _, _, secs = ref.tiles(arena, sample, 1, tb_words_per_req=44, threads=cores)
+    else:
+        port = oracle.port(abi.Scoring.from_values())
+        cores = 1
+        n = int(min(len(req), max(8, seconds_target * 0.02e9 / cells_per_tile)))
+        sample = np.ascontiguousarray(req[:n])
+        t0 = time.time()
+        port.tiles(arena, sample, 1, oracle.Port.STREAM, tb_words_per_req=44)
+        secs = time.time() - t0
+    gcups = n * cells_per_tile / secs / 1e9
+    return {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind,
+            "sample": "%d of the workload's %dx%d tiles, %.1f s wall, %s" % (
+                n, TILE, TILE, secs, "oracle/_ref BatchAlignmentSIMD (AVX2), std::thread x cores" if kind == "reference"
+                else "oracle/gact_oracle.c scalar port"),
+            "tiles_per_s": n / secs}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    arena, req = make_workload(min(args.tiles, 200000), 1)
+    per_step = max(4.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    cb = None
+    for s in range(args.warmup + args.steps):
+        cb = cpu_reference_leg(arena, req, per_step)
+        if s >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    line = {"impl": "reference", "metric": "gact_gcups", "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int16", "data": "synthetic",
+            "config": {"workload": "gact_tiles_T%d_O%d" % (TILE, OVERLAP), "tile_size": TILE, "tile_overlap": OVERLAP,
+                       "error_rate": 0.15, "note": "bounded sample of the same tile batch per step"},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "reads_per_s_equiv": cb["tiles_per_s"] * (TILE - OVERLAP) / 2.0 / 10000.0}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tiles", type=int, default=1000000, help="tiles per GPU per step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import darwin_b200
+    from darwin_b200 import abi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for the GACT path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    warm = max(3, args.warmup)
+    arena, req = make_workload(args.tiles, 1 + rank)          # each rank owns an independent shard (weak scaling)
+    n = len(req)
+    cells = float(n) * TILE * TILE
+    tbw = 2 * TILE // 16 + 2
+    sc = abi.Scoring.from_values()
+    proc = darwin_b200.Processor(len(arena), local)
+    proc.InitializeScoringParameters(sc)
+    proc.InitializeReferenceMemory(0, arena)
+
+    # ---- device-resident leg (value) -------------------------------------------------------------------
+    dev = torch.device("cuda", local)
+    d_req = torch.from_numpy(req.view(np.uint8).reshape(n, -1)).to(dev)
+    d_res = torch.zeros((n, abi.TILE_RES.itemsize), dtype=torch.uint8, device=dev)
+    d_tb = torch.zeros((n, tbw), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    launches0 = proc.stats().kernel_launches
+    for _ in range(warm):
+        proc.BatchAlignmentSIMD_device(d_req.data_ptr(), n, d_res.data_ptr(), d_tb.data_ptr(), tbw)
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    launches_t0 = proc.stats().kernel_launches
+    kernel_ms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        proc.BatchAlignmentSIMD_device(d_req.data_ptr(), n, d_res.data_ptr(), d_tb.data_ptr(), tbw)
+        kernel_ms.append(proc.stats().last_kernel_ms)          # CUDA events on the library's own stream
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = proc.stats().kernel_launches - launches_t0
+    dev_ms = float(np.sum(kernel_ms))
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    value = world * cells * args.steps / (dev_ms_max * 1e-3) / 1e9
+
+    # ---- end-to-end leg: host buffers through the public call ----------------------------------------------
+    e2e_steps = max(1, min(args.steps, 3))
+    h2d = len(arena) + req.nbytes
+    d2h = n * abi.TILE_RES.itemsize + n * tbw * 8
+    proc.InitializeReferenceMemory(0, arena)
+    proc.BatchAlignmentSIMD(req[:1024], 1, tbw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        proc.InitializeReferenceMemory(0, arena)               # H2D of the step's sequences (ASCII) + device packing
+        res, tb = proc.BatchAlignmentSIMD(req, 1, tbw)         # H2D requests, kernel, D2H results + TB words
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * cells * e2e_steps / (float(t[0]) * 1e-3) / 1e9
+    sampler.stop_flag = True
+    sampler.join(timeout=3)
+
+    # checksum of the last step (guards against "fast because wrong"): every tile must have produced a path
+    assert int((res["total_TB_pointers"] > 0).sum()) > 0.99 * n, "tiles without traceback"
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        int_peak = None
+        try:
+            int_peak = proc.int_peak_gops()
+        except Exception:
+            pass
+        per_gpu_gcups = value / world
+        roof = {"bound": "int_alu", "achieved": per_gpu_gcups * OPS_PER_CELL, "peak": int_peak,
+                "unit": "Gint-op/s", "frac": (per_gpu_gcups * OPS_PER_CELL / int_peak) if int_peak else None,
+                "traffic": None,
+                "note": "SURVEY 8(d) integer-pipe roofline: 32 algorithmic int-ops per cell; peak = measured packed "
+                        "s16x2 DPX/ALU issue rate (2 cells per lane-op) of this GPU; HBM is not the bound "
+                        "(%.3f B/cell algorithmic)" % ((2 * TILE / 2 + 32 + 16 + tbw * 8) / (TILE * TILE)),
+                "hbm_frac_of_measured": (n * (2 * TILE / 2 + 32 + 16 + tbw * 8) / (np.mean(kernel_ms) * 1e-3) / 1e9) /
+                peaks.get("hbm_gbs", 6650.0)}
+        line = {"metric": "gact_gcups", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": warm,
+                "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "int16", "data": "synthetic",
+                "config": {"workload": "gact_tiles_T%d_O%d" % (TILE, OVERLAP), "tiles_per_gpu": n, "tile_size": TILE,
+                           "tile_overlap": OVERLAP, "error_rate": 0.15, "cells_per_step": cells * world,
+                           "l2": "inputs+outputs per step (%d MB) exceed the 126 MB L2" % ((len(arena) // 2 + req.nbytes + d2h) >> 20)},
+                "tiles_per_s": world * n * args.steps / (dev_ms_max * 1e-3),
+                "reads_per_s_equiv": world * n * args.steps / (dev_ms_max * 1e-3) * (TILE - OVERLAP) / 2.0 / 10000.0,
+                "wall_ms_per_step": wall_ms_max / args.steps,
+                "clocks": sampler.summary(),
+                "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps},
+                "gpu_launches": int(launches), "roofline": roof}
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_reference_leg(arena, req, args.cpu_seconds)
+        print(json.dumps(line))
+    proc.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,616 @@
+// libdarwin_gact.so -- kernels + C-ABI (include/darwin_gpu.h) of the B200-native GACT path.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// (see __graft_entry__.build()).  There is no CPU fallback anywhere in this file: without a CUDA
+// device every entry point fails with DARWIN_ERR_NO_DEVICE.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "gact_common.cuh"
+#include "gact_exact.cuh"
+#include "gact_extend.cuh"
+
+using namespace gact;
+
+// =====================================================================================================
+// Kernels
+// =====================================================================================================
+
+// ASCII -> 4-bit arena codes (Nt2Int, Processor.cpp:21-46: ACGT either case -> 0..3, everything else -> N).
+// One thread per output byte (two bases); bytes only half covered by [addr, addr+n) are read-modify-written.
+__global__ void pack_arena_kernel(uint8_t* __restrict__ arena, const char* __restrict__ ascii, uint64_t addr, uint64_t n) {
+    const uint64_t first = addr >> 1, last = (addr + n - 1) >> 1;
+    const uint64_t b = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > last) return;
+    uint32_t out = arena[b];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint64_t a = 2 * b + h;
+        if (a >= addr && a < addr + n) {
+            const char c = ascii[a - addr];
+            uint32_t code;
+            switch (c) {
+                case 'a': case 'A': code = 0; break;
+                case 'c': case 'C': code = 1; break;
+                case 'g': case 'G': code = 2; break;
+                case 't': case 'T': code = 3; break;
+                default: code = 4; break;
+            }
+            out = (out & ~(0xFu << (4 * h))) | (code << (4 * h));
+        }
+    }
+    arena[b] = (uint8_t)out;
+}
+
+struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568-582
+    uint64_t* words; int cap; int n; uint64_t cur; int overflow;
+    __device__ __forceinline__ void operator()(uint32_t d) {
+        const int k = n & 31;
+        if (k == 0) cur = d; else cur |= (uint64_t)d << (2 * k);
+        n++;
+        if ((n & 31) == 0) { if ((n >> 5) <= cap) words[(n >> 5) - 1] = cur; else overflow = 1; }
+    }
+    __device__ __forceinline__ void finish() {
+        if (n & 31) { if ((n >> 5) < cap) words[n >> 5] = cur; else overflow = 1; }
+    }
+};
+
+struct KernelScoring { DevScoring sc; };
+
+__device__ __forceinline__ void load_scoring(const DevScoring& sc, int* ssub) {
+    if (threadIdx.x < 25) ssub[threadIdx.x] = sc.sub[threadIdx.x];
+    __syncthreads();
+}
+
+// BatchAlignmentSIMD (Processor.cpp:718-762) for n independent tiles: persistent warps pull tiles from a
+// global counter.
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+tiles_exact_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
+                   const DarwinTileReq* __restrict__ req, int n, int do_traceback,
+                   DarwinTileRes* __restrict__ res, uint64_t* __restrict__ tb_words, int tb_words_per_req,
+                   uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base, unsigned int* counter) {
+    __shared__ int ssub[32];
+    __shared__ ExactSmem smem[kWarpsPerCta];
+    load_scoring(ks.sc, ssub);
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int gw = blockIdx.x * kWarpsPerCta + warp;
+    ExactSmem* sm = &smem[warp];
+    WarpScratch ws{trace_base + (size_t)gw * trace_stride, bound_base + (size_t)gw * kMaxTile};
+    const int go = ks.sc.go, ge = ks.sc.ge, lgo = ks.sc.lgo, lge = ks.sc.lge;
+
+    for (;;) {
+        unsigned int idx = 0;
+        if (lane == 0) idx = atomicAdd(counter, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= (unsigned)n) break;
+        const DarwinTileReq rq = req[idx];
+        TileJob t{rq.ref_bases_start_addr, rq.query_bases_start_addr, (int)rq.ref_size, (int)rq.query_size,
+                  rq.align_fields, (int)rq.max_tb_steps};
+        TileOut out{};
+        const bool se = t.flags & DARWIN_START_END;
+        if (t.Q > 0 && t.R > 0 && t.Q <= kMaxTile && t.R <= kMaxTile) {       // Processor.cpp:177-182
+            stage_sequences(arena, t, sm->ref, sm->qry);
+            if (do_traceback) {
+                if (se) exact_forward<true, true>(ssub, go, ge, lgo, lge, t, sm, ws, out);
+                else    exact_forward<false, true>(ssub, go, ge, lgo, lge, t, sm, ws, out);
+                __syncwarp();
+                if (lane == 0) {
+                    TbWordSink sink{tb_words + (size_t)idx * tb_words_per_req, tb_words_per_req, 0, 0, 0};
+                    const int i = se ? t.Q - 1 : out.query_max_pos, j = se ? t.R - 1 : out.ref_max_pos;
+                    exact_traceback(ws.trace, t.Q, t.R, i, j, t.max_tb, out, sink);
+                    sink.finish();
+                    if (sink.overflow) out.tflags |= 0x80;
+                }
+            } else {
+                if (se) exact_forward<true, false>(ssub, go, ge, lgo, lge, t, sm, ws, out);
+                else    exact_forward<false, false>(ssub, go, ge, lgo, lge, t, sm, ws, out);
+            }
+        }
+        if (lane == 0) {
+            DarwinTileRes r;
+            r.score = out.score; r.ref_offset = (uint16_t)out.ref_offset; r.query_offset = (uint16_t)out.query_offset;
+            r.ref_max_pos = (uint16_t)out.ref_max_pos; r.query_max_pos = (uint16_t)out.query_max_pos;
+            r.total_TB_pointers = (uint16_t)out.total; r.index = (uint8_t)rq.index;
+            r.status = (t.Q > kMaxTile || t.R > kMaxTile) ? 1 : ((out.tflags & 0x80) ? 2 : 0);
+            res[idx] = r;
+        }
+        __syncwarp();
+    }
+}
+
+// extender_body::operator() (extender.cpp:9-1065): persistent warps pull ANCHORS and walk their tiles.
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+extend_exact_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ ExtendArgs ea,
+                    uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base) {
+    __shared__ int ssub[32];
+    __shared__ ExactSmem smem[kWarpsPerCta];
+    load_scoring(ks.sc, ssub);
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int gw = blockIdx.x * kWarpsPerCta + warp;
+    ExactSmem* sm = &smem[warp];
+    WarpScratch ws{trace_base + (size_t)gw * trace_stride, bound_base + (size_t)gw * kMaxTile};
+    const int go = ks.sc.go, ge = ks.sc.ge, lgo = ks.sc.lgo, lge = ks.sc.lge;
+    const int T = ea.T, O = ea.O;
+
+    for (;;) {
+        unsigned int idx = 0;
+        if (lane == 0) idx = atomicAdd(ea.counter, 1u);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= (unsigned)ea.n) break;
+        const DarwinAnchor an = ea.anchors[idx];
+        AnchorState a;
+        a.cr = an.reference_pos - an.chr_start; a.cq = an.query_pos;           // extender.cpp:1083-1088
+        a.rso = a.reo = a.cr; a.qso = a.qeo = a.cq;
+        a.rsa = an.chr_start; a.RL = an.ref_len; a.QL = an.read_len; a.read_addr = an.read_addr;
+        a.large = 0; a.ldone = 0; a.rdone = 0; a.emit = 0; a.rc = an.strand;
+        a.nl = an.left_hits_n; a.nr = an.right_hits_n;
+        a.lh = ea.hit_pool + an.left_hits_off; a.rh = ea.hit_pool + an.right_hits_off;
+        a.nleft = a.nright = a.n_tiles = a.n_large = a.flags = 0; a.cells = 0;
+        uint8_t* const slot = ea.ops + ea.slot_base[idx];
+        const uint32_t lcap = ea.slot_left[idx], rcap = ea.slot_size[idx] - lcap;
+        uint32_t overflow = 0;
+
+        while (!(a.ldone && a.rdone)) {
+            const int left = !a.ldone;
+            if (a.large && (left ? a.nl : a.nr) <= 0) { a.flags |= 0x80000000u; break; }   // cannot happen (SURVEY B); guards .back()
+            TileJob t; int rt, qt;
+            next_tile(a, T, t, rt, qt);
+            t.max_tb = 2 * T;                                                    // extender.cpp:127
+            if (a.large) a.n_large++;
+            a.n_tiles++; a.cells += (uint64_t)t.R * (uint64_t)t.Q;
+            TileOut out{};
+            int len = 0;
+            if (t.Q > 0 && t.R > 0) {
+                stage_sequences(ea.arena, t, sm->ref, sm->qry);
+                exact_forward<true, true>(ssub, go, ge, lgo, lge, t, sm, ws, out);
+                __syncwarp();
+            }
+            // consumption (lane 0), then broadcast of the updated offsets
+            int crt = T, cqt = T;
+            if (a.large && ea.do_overlap == 0) { crt = rt; cqt = qt; }           // extender.cpp:261 / :408
+            uint32_t pk[8] = {a.cr, a.cq, a.rso, a.qso, a.nleft, a.nright, 0u, 0u};
+            if (lane == 0 && t.Q > 0 && t.R > 0) {
+                ConsumeSink sink;
+                sink.cr = a.cr; sink.cq = a.cq; sink.rso = a.rso; sink.qso = a.qso; sink.RL = a.RL; sink.QL = a.QL;
+                sink.left = left; sink.S = min(crt, cqt) - O; sink.steps = 0; sink.pos_in_word = 0; sink.skipping = 0;
+                sink.lptr = slot + lcap - a.nleft; sink.rptr = slot + lcap + a.nright;
+                sink.lroom = lcap; sink.rroom = rcap; sink.nl = a.nleft; sink.nr = a.nright; sink.overflow = 0;
+                exact_traceback(ws.trace, t.Q, t.R, t.Q - 1, t.R - 1, t.max_tb, out, sink);
+                pk[0] = sink.cr; pk[1] = sink.cq; pk[2] = sink.rso; pk[3] = sink.qso; pk[4] = sink.nl; pk[5] = sink.nr;
+                pk[6] = (uint32_t)out.total; pk[7] = out.tflags | (sink.overflow << 8);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) pk[k] = __shfl_sync(0xffffffffu, pk[k], 0);
+            a.cr = pk[0]; a.cq = pk[1]; a.rso = pk[2]; a.qso = pk[3]; a.nleft = pk[4]; a.nright = pk[5];
+            len = (int)pk[6];
+            if (pk[7] & 1) a.flags |= DARWIN_ALN_LONG_INS_PATH;
+            if (pk[7] & 0x100) overflow = 1;
+            after_tile(a, len);
+        }
+        if (lane == 0) {
+            DarwinAlnRes r;
+            r.ops_offset = ea.slot_base[idx] + lcap - min(a.nleft, lcap);
+            r.cells = a.cells;
+            r.n_ops = a.emit ? a.nleft + a.nright : 0;
+            r.reference_start_offset = a.rso; r.reference_end_offset = a.reo;
+            r.query_start_offset = a.qso; r.query_end_offset = a.qeo;
+            r.n_left_ops = a.emit ? a.nleft : 0;
+            r.n_tiles = a.n_tiles; r.n_large_tiles = a.n_large; r.score = 0;
+            r.flags = (a.flags & ~0x80000000u) | (a.emit ? DARWIN_ALN_EMITTED : 0) | (overflow ? DARWIN_ALN_OPS_OVERFLOW : 0);
+            ea.res[idx] = r;
+        }
+        __syncwarp();
+    }
+}
+
+// AlignmentScore (extender.cpp:1161-1200) + compaction of the op slots into a dense pool.
+// One thread per alignment: walks its ops left to right exactly as the reference walks the strings.
+__global__ void score_compact_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
+                                     const DarwinAnchor* __restrict__ anchors, DarwinAlnRes* __restrict__ res, int n,
+                                     const uint8_t* __restrict__ slots, const uint64_t* __restrict__ dense_off,
+                                     uint8_t* __restrict__ dense) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    DarwinAlnRes r = res[k];
+    const uint64_t dst = dense_off[k];
+    if (!(r.flags & DARWIN_ALN_EMITTED) || (r.flags & DARWIN_ALN_OPS_OVERFLOW)) { r.ops_offset = dst; if (r.flags & DARWIN_ALN_OPS_OVERFLOW) r.n_ops = 0; res[k] = r; return; }
+    const DarwinAnchor an = anchors[k];
+    const DevScoring& sc = ks.sc;
+    // string position p corresponds to: left part ops[0..n_left) end at the anchor, right part starts at anchor+1
+    // left-to-right walk: the first left op consumed LAST, so start offsets are derived from the op counts.
+    uint32_t nl = r.n_left_ops;
+    uint32_t ref_cons = 0, qry_cons = 0;
+    for (uint32_t p = 0; p < nl; p++) { const uint8_t d = slots[r.ops_offset + p]; ref_cons += (d != DARWIN_OP_I); qry_cons += (d != DARWIN_OP_D); }
+    const uint32_t ar = an.reference_pos - an.chr_start, aq = an.query_pos;
+    // The reference clamps at offset 0 (extender.cpp:289-300); a left walk never consumes more than ar+1 / aq+1 bases.
+    int64_t cr = (int64_t)ar + 1 - ref_cons, cq = (int64_t)aq + 1 - qry_cons;
+    int score = 0, open = 0, sgp = 0, lgp = 0;
+    const int mat_offset[4] = {0, 1, 3, 6};
+    for (uint32_t p = 0; p < r.n_ops; p++) {
+        const uint8_t d = slots[r.ops_offset + p];
+        dense[dst + p] = d;
+        if (d != DARWIN_OP_M) {
+            sgp += open ? sc.ge : sc.go; lgp += open ? sc.lge : sc.lgo; open = 1;
+            if (d == DARWIN_OP_D) cr++; else cq++;
+        } else {
+            const int64_t rclamp = cr < 0 ? 0 : cr, qclamp = cq < 0 ? 0 : cq;
+            uint32_t rn = arena_code(arena, an.chr_start + (uint64_t)rclamp);
+            uint32_t qn;
+            if (!an.strand) qn = arena_code(arena, an.read_addr + (uint64_t)qclamp);
+            else if ((uint64_t)qclamp >= an.read_len) qn = 4;
+            else { qn = arena_code(arena, an.read_addr + (an.read_len - 1 - (uint64_t)qclamp)); if (qn < 4) qn = 3 - qn; }
+            if (rn <= 3 && qn <= 3) {
+                const int idx = (rn > qn) ? qn * 4 + rn - mat_offset[qn] : rn * 4 + qn - mat_offset[rn];
+                score += sc.tri[idx];
+            } else score += sc.tri[10];
+            score += (lgp < sgp) ? sgp : lgp;
+            open = 0; sgp = 0; lgp = 0;
+            cr++; cq++;
+        }
+    }
+    r.score = score; r.ops_offset = dst;
+    res[k] = r;
+}
+
+// Integer-pipe microbenchmark: 8 independent accumulators per thread, 16 ops per loop trip, no memory traffic.
+template <int KIND>
+__global__ void int_peak_kernel(uint32_t* out, const uint32_t* in, int iters) {
+    uint32_t a[8];
+    const uint32_t b = in[0] + threadIdx.x, c = in[1] ^ threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 8; k++) a[k] = in[2 + k] + threadIdx.x * (k + 1);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 2; rep++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (KIND == 0) a[k] = __vmaxs2(a[k], b + rep);
+                else if (KIND == 1) a[k] = __viaddmax_s16x2(a[k], b, c + rep);
+                else if (KIND == 2) a[k] = __vimax3_s16x2(a[k], b, c + rep);
+                else a[k] = (rep ? (a[k] + b + c) : ((a[k] & b) ^ c));
+            }
+        }
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) r ^= a[k];
+    if (r == 0x12345678u) out[0] = r;          // keeps the chain alive without a store in the common case
+}
+
+// =====================================================================================================
+// Host side: handle + C-ABI
+// =====================================================================================================
+struct DarwinGpu {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint8_t* d_arena = nullptr; uint64_t arena_bytes = 0;
+    char* h_stage = nullptr; char* d_stage = nullptr; size_t stage_bytes = 0;
+    KernelScoring ks{}; bool have_scoring = false;
+    int sm_count = 0, ctas = 0;
+    uint8_t* d_trace = nullptr; size_t trace_stride = 0; ChainRec* d_bound = nullptr;
+    unsigned int* d_counter = nullptr;
+    // growable device buffers
+    void* d_buf[8] = {nullptr}; size_t d_cap[8] = {0};
+    void* h_buf[4] = {nullptr}; size_t h_cap[4] = {0};
+    DarwinGpuStats stats{};
+    std::string err;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DARWIN_ERR_CUDA; } } while (0)
+
+static int grow_dev(DarwinGpu* h, int slot, size_t bytes) {
+    if (bytes <= h->d_cap[slot]) return DARWIN_OK;
+    if (h->d_buf[slot]) cudaFree(h->d_buf[slot]);
+    h->d_buf[slot] = nullptr; h->d_cap[slot] = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&h->d_buf[slot], want));
+    h->d_cap[slot] = want;
+    return DARWIN_OK;
+}
+static int grow_host(DarwinGpu* h, int slot, size_t bytes) {
+    if (bytes <= h->h_cap[slot]) return DARWIN_OK;
+    if (h->h_buf[slot]) cudaFreeHost(h->h_buf[slot]);
+    h->h_buf[slot] = nullptr; h->h_cap[slot] = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMallocHost(&h->h_buf[slot], want));
+    h->h_cap[slot] = want;
+    return DARWIN_OK;
+}
+
+// per-warp exact-path scratch sized for the largest tile of the call
+static int ensure_scratch(DarwinGpu* h, size_t need) {
+    need = (need + 255) & ~(size_t)255;
+    const size_t warps = (size_t)h->ctas * kWarpsPerCta;
+    if (!h->d_bound) CK(cudaMalloc(&h->d_bound, warps * kMaxTile * sizeof(ChainRec)));
+    if (need <= h->trace_stride && h->d_trace) return DARWIN_OK;
+    if (h->d_trace) cudaFree(h->d_trace);
+    h->d_trace = nullptr; h->trace_stride = 0;
+    CK(cudaMalloc(&h->d_trace, need * warps));
+    h->trace_stride = need;
+    return DARWIN_OK;
+}
+
+extern "C" {
+
+const char* darwin_gpu_version(void) { return "darwin-gact-b200 0.1 (sm_100a)"; }
+
+int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) {
+    if (!out) return DARWIN_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return DARWIN_ERR_NO_DEVICE;
+    DarwinGpu* h = new DarwinGpu();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+    h->arena_bytes = arena_bytes;
+    const size_t packed = (arena_bytes + 1) / 2 + 16;
+    CK(cudaMalloc(&h->d_arena, packed));
+    CK(cudaMemsetAsync(h->d_arena, 0x44, packed, h->stream));                  // all 'N' (Index.cpp:12 pads with 'N')
+    h->stage_bytes = 32u << 20;
+    CK(cudaMallocHost(&h->h_stage, h->stage_bytes));
+    CK(cudaMalloc(&h->d_stage, h->stage_bytes));
+    CK(cudaMalloc(&h->d_counter, sizeof(unsigned int) * 4));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiles_exact_kernel, kWarpsPerCta * 32, 0));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    h->ctas = h->sm_count * per_sm;                                            // persistent grid: multiple of the SM count
+    CK(cudaStreamSynchronize(h->stream));
+    return DARWIN_OK;
+}
+
+int darwin_gpu_destroy(DarwinGpu* h) {
+    if (!h) return DARWIN_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < 8; i++) if (h->d_buf[i]) cudaFree(h->d_buf[i]);
+    for (int i = 0; i < 4; i++) if (h->h_buf[i]) cudaFreeHost(h->h_buf[i]);
+    if (h->d_trace) cudaFree(h->d_trace);
+    if (h->d_bound) cudaFree(h->d_bound);
+    if (h->d_counter) cudaFree(h->d_counter);
+    if (h->d_stage) cudaFree(h->d_stage);
+    if (h->h_stage) cudaFreeHost(h->h_stage);
+    if (h->d_arena) cudaFree(h->d_arena);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return DARWIN_OK;
+}
+
+const char* darwin_gpu_last_error(DarwinGpu* h) { return h ? h->err.c_str() : "null handle"; }
+
+int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s) {
+    if (!h || !s) return DARWIN_ERR_INVALID;
+    // closed-form preconditions of the exact rule (oracle/gact_oracle.c header): opening a gap is never
+    // cheaper than extending one, and penalties are non-positive.  Scores must stay inside int16 like the
+    // reference's vectors (Processor.cpp:202-205).
+    if (s->gap_open > s->gap_extend || s->gap_extend > 0 || s->long_gap_open > s->long_gap_extend || s->long_gap_extend > 0) {
+        h->err = "scoring: need gap_open <= gap_extend <= 0 and long_gap_open <= long_gap_extend <= 0";
+        return DARWIN_ERR_INVALID;
+    }
+    const int32_t* v = reinterpret_cast<const int32_t*>(s);
+    for (int i = 0; i < 15; i++) if (v[i] > 127 || v[i] < -127) { h->err = "scoring: |value| must be <= 127"; return DARWIN_ERR_INVALID; }
+    DevScoring& d = h->ks.sc;
+    const int AA = s->sub_AA, AC = s->sub_AC, AG = s->sub_AG, AT = s->sub_AT, CC = s->sub_CC, CG = s->sub_CG,
+              CT = s->sub_CT, GG = s->sub_GG, GT = s->sub_GT, TT = s->sub_TT, N = s->sub_N;
+    const int m[25] = {AA, AC, AG, AT, N, AC, CC, CG, CT, N, AG, CG, GG, GT, N, AT, CT, GT, TT, N, N, N, N, N, N};   // Processor.cpp:50-74
+    memcpy(d.sub, m, sizeof(m));
+    d.go = s->gap_open; d.ge = s->gap_extend; d.lgo = s->long_gap_open; d.lge = s->long_gap_extend;
+    const int t[11] = {AA, AC, AG, AT, CC, CG, CT, GG, GT, TT, N};
+    memcpy(d.tri, t, sizeof(t));
+    d.uniform = (AA == CC && AA == GG && AA == TT && AC == AG && AC == AT && AC == CG && AC == CT && AC == GT);
+    d.match = AA; d.mismatch = AC; d.subn = N;
+    h->have_scoring = true;
+    return DARWIN_OK;
+}
+
+int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint64_t n) {
+    if (!h || (!ascii && n)) return DARWIN_ERR_INVALID;
+    if (arena_addr + n > h->arena_bytes) { h->err = "upload beyond arena"; return DARWIN_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    uint64_t done = 0;
+    while (done < n) {
+        const uint64_t chunk = std::min<uint64_t>(n - done, h->stage_bytes);
+        memcpy(h->h_stage, ascii + done, chunk);
+        CK(cudaMemcpyAsync(h->d_stage, h->h_stage, chunk, cudaMemcpyHostToDevice, h->stream));
+        const uint64_t a = arena_addr + done;
+        const uint64_t nbytes = ((a + chunk - 1) >> 1) - (a >> 1) + 1;
+        pack_arena_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(h->d_arena, h->d_stage, a, chunk);
+        h->stats.kernel_launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->stream));      // the pinned staging buffer is reused by the next chunk
+        done += chunk;
+    }
+    return DARWIN_OK;
+}
+
+static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_req, int n,
+                        DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR) {
+    int rc = ensure_scratch(h, exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)));
+    if (rc) return rc;
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    tiles_exact_kernel<<<h->ctas, kWarpsPerCta * 32, 0, h->stream>>>(h->d_arena, h->ks, d_req, n, do_traceback, d_res,
+                                                                    d_tb, tb_words_per_req, h->d_trace, h->trace_stride,
+                                                                    h->d_bound, h->d_counter);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->stats.kernel_launches++;
+    h->stats.tiles_exact += n;
+    return DARWIN_OK;
+}
+
+int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, int n,
+                     DarwinTileRes* res, uint64_t* tb_words, int tb_words_per_req) {
+    if (!h || n < 0 || (n && (!req || !res))) return DARWIN_ERR_INVALID;
+    if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
+    if (do_traceback && (!tb_words || tb_words_per_req <= 0)) return DARWIN_ERR_INVALID;
+    if (n == 0) return DARWIN_OK;
+    CK(cudaSetDevice(h->device));
+    int maxQ = 0, maxR = 0; uint64_t cells = 0;
+    for (int i = 0; i < n; i++) {
+        maxQ = std::max<int>(maxQ, req[i].query_size); maxR = std::max<int>(maxR, req[i].ref_size);
+        cells += (uint64_t)req[i].query_size * req[i].ref_size;
+        if (req[i].query_size > kMaxTile || req[i].ref_size > kMaxTile) { h->err = "tile larger than 1984"; return DARWIN_ERR_INVALID; }
+        const uint64_t re = req[i].ref_bases_start_addr + req[i].ref_size, qe = req[i].query_bases_start_addr + req[i].query_size;
+        if (re > h->arena_bytes || qe > h->arena_bytes) { h->err = "tile outside arena"; return DARWIN_ERR_INVALID; }
+    }
+    const size_t req_b = (size_t)n * sizeof(DarwinTileReq), res_b = (size_t)n * sizeof(DarwinTileRes);
+    const size_t tb_b = do_traceback ? (size_t)n * tb_words_per_req * sizeof(uint64_t) : 0;
+    int rc;
+    if ((rc = grow_dev(h, 0, req_b)) || (rc = grow_dev(h, 1, res_b)) || (rc = grow_dev(h, 2, tb_b + 8))) return rc;
+    CK(cudaMemcpyAsync(h->d_buf[0], req, req_b, cudaMemcpyHostToDevice, h->stream));
+    rc = launch_tiles(h, do_traceback, (const DarwinTileReq*)h->d_buf[0], n, (DarwinTileRes*)h->d_buf[1],
+                      (uint64_t*)h->d_buf[2], tb_words_per_req, maxQ, maxR);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
+    if (do_traceback) CK(cudaMemcpyAsync(tb_words, h->d_buf[2], tb_b, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
+    h->stats.cells += cells;
+    for (int i = 0; i < n; i++) if (res[i].status == 2) { h->err = "tb_words_per_req too small"; return DARWIN_ERR_CAPACITY; }
+    return DARWIN_OK;
+}
+
+int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, int n,
+                            void* d_res, void* d_tb_words, int tb_words_per_req) {
+    if (!h || n <= 0 || !d_req || !d_res) return DARWIN_ERR_INVALID;
+    if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
+    CK(cudaSetDevice(h->device));
+    int rc = launch_tiles(h, do_traceback, (const DarwinTileReq*)d_req, n, (DarwinTileRes*)d_res,
+                          (uint64_t*)d_tb_words, tb_words_per_req, 512, 512);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
+    return DARWIN_OK;
+}
+
+int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n,
+                      const uint64_t* hit_pool, uint64_t n_hits,
+                      DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes) {
+    if (!h || !p || n < 0 || (n && (!anchors || !res))) return DARWIN_ERR_INVALID;
+    if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
+    if (p->tile_size < 16 || p->tile_size > 1024 || p->tile_overlap < 0 || p->tile_overlap >= p->tile_size) {
+        h->err = "tile_size must be in [16,1024] and 0 <= tile_overlap < tile_size"; return DARWIN_ERR_INVALID;
+    }
+    if (n == 0) return DARWIN_OK;
+    CK(cudaSetDevice(h->device));
+    // op slots: left part holds the (reversed) left extension, right part the right extension
+    std::vector<uint64_t> base(n); std::vector<uint32_t> lcap(n), size(n);
+    uint64_t total = 0;
+    const uint32_t slack = 2u * (uint32_t)p->tile_size + 128u;
+    for (int i = 0; i < n; i++) {
+        const DarwinAnchor& a = anchors[i];
+        if (a.query_pos >= a.read_len || a.reference_pos < a.chr_start || a.reference_pos - a.chr_start >= a.ref_len ||
+            a.read_addr + a.read_len > h->arena_bytes || (uint64_t)a.chr_start + a.ref_len > h->arena_bytes ||
+            (uint64_t)a.left_hits_off + a.left_hits_n > n_hits || (uint64_t)a.right_hits_off + a.right_hits_n > n_hits) {
+            h->err = "anchor " + std::to_string(i) + " is inconsistent"; return DARWIN_ERR_INVALID;
+        }
+        lcap[i] = 2u * (a.query_pos + 1) + slack;
+        size[i] = lcap[i] + 2u * (a.read_len - a.query_pos) + slack;
+        base[i] = total; total += size[i];
+    }
+    int rc;
+    const size_t an_b = (size_t)n * sizeof(DarwinAnchor), res_b = (size_t)n * sizeof(DarwinAlnRes);
+    const size_t hit_b = (size_t)std::max<uint64_t>(n_hits, 1) * 8;
+    if ((rc = grow_dev(h, 0, an_b)) || (rc = grow_dev(h, 1, res_b)) || (rc = grow_dev(h, 2, hit_b)) ||
+        (rc = grow_dev(h, 3, total + 16)) || (rc = grow_dev(h, 4, (size_t)n * 8)) || (rc = grow_dev(h, 5, (size_t)n * 4)) ||
+        (rc = grow_dev(h, 6, (size_t)n * 4)) || (rc = grow_dev(h, 7, (size_t)n * 8))) return rc;
+    CK(cudaMemcpyAsync(h->d_buf[0], anchors, an_b, cudaMemcpyHostToDevice, h->stream));
+    if (n_hits) CK(cudaMemcpyAsync(h->d_buf[2], hit_pool, n_hits * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_buf[4], base.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_buf[5], lcap.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_buf[6], size.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(1984, 960), exact_trace_bytes(960, 1984)),
+                                         exact_trace_bytes(p->tile_size, p->tile_size))))) return rc;
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));
+    ExtendArgs ea;
+    ea.arena = h->d_arena; ea.anchors = (const DarwinAnchor*)h->d_buf[0]; ea.hit_pool = (const uint64_t*)h->d_buf[2];
+    ea.res = (DarwinAlnRes*)h->d_buf[1]; ea.ops = (uint8_t*)h->d_buf[3];
+    ea.slot_base = (const uint64_t*)h->d_buf[4]; ea.slot_left = (const uint32_t*)h->d_buf[5]; ea.slot_size = (const uint32_t*)h->d_buf[6];
+    ea.n = n; ea.T = p->tile_size; ea.O = p->tile_overlap; ea.do_overlap = p->do_overlap; ea.counter = h->d_counter;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    extend_exact_kernel<<<h->ctas, kWarpsPerCta * 32, 0, h->stream>>>(h->ks, ea, h->d_trace, h->trace_stride, h->d_bound);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->stats.kernel_launches++;
+    // first D2H: op counts -> dense offsets (host prefix sum), then score + compaction on the device
+    CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
+    std::vector<uint64_t> dense(n);
+    uint64_t used = 0; int overflow = 0;
+    for (int i = 0; i < n; i++) {
+        dense[i] = used;
+        if (res[i].flags & DARWIN_ALN_OPS_OVERFLOW) overflow = 1;
+        else if (res[i].flags & DARWIN_ALN_EMITTED) used += res[i].n_ops;
+        h->stats.cells += res[i].cells; h->stats.tiles_exact += res[i].n_tiles;
+    }
+    if (used > ops_pool_bytes) { h->err = "ops_pool too small: need " + std::to_string(used); return DARWIN_ERR_CAPACITY; }
+    CK(cudaMemcpyAsync(h->d_buf[7], dense.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+    uint8_t* d_dense = nullptr;
+    CK(cudaMallocAsync(&d_dense, used + 16, h->stream));
+    score_compact_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_arena, h->ks, (const DarwinAnchor*)h->d_buf[0],
+                                                                (DarwinAlnRes*)h->d_buf[1], n, (const uint8_t*)h->d_buf[3],
+                                                                (const uint64_t*)h->d_buf[7], d_dense);
+    CK(cudaGetLastError());
+    h->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
+    if (used && ops_pool) CK(cudaMemcpyAsync(ops_pool, d_dense, used, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaFreeAsync(d_dense, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    (void)overflow;
+    return DARWIN_OK;
+}
+
+int darwin_gpu_int_peak(DarwinGpu* h, double out[4]) {
+    if (!h || !out) return DARWIN_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    uint32_t host_in[16];
+    for (int i = 0; i < 16; i++) host_in[i] = 0x00030001u * (i + 3);
+    uint32_t* d = nullptr;
+    CK(cudaMalloc(&d, 64 * sizeof(uint32_t)));
+    CK(cudaMemcpy(d, host_in, sizeof(host_in), cudaMemcpyHostToDevice));
+    const int iters = 4096, blocks = h->sm_count * 8, threads = 256;
+    for (int kind = 0; kind < 4; kind++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            CK(cudaEventRecord(h->ev0, h->stream));
+            switch (kind) {
+                case 0: int_peak_kernel<0><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                case 1: int_peak_kernel<1><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                case 2: int_peak_kernel<2><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                default: int_peak_kernel<3><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+            }
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(h->ev1, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            if (rep > 0 && ms < best) best = ms;
+            h->stats.kernel_launches++;
+        }
+        out[kind] = (double)blocks * threads * iters * 16.0 / (best * 1e-3) / 1e9;
+    }
+    cudaFree(d);
+    return DARWIN_OK;
+}
+
+int darwin_gpu_stats(DarwinGpu* h, DarwinGpuStats* out) {
+    if (!h || !out) return DARWIN_ERR_INVALID;
+    *out = h->stats;
+    return DARWIN_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,129 @@
+// GACT anchor state machine on the device: one persistent warp owns one anchor and walks its tiles
+// in-kernel (left extension, then right extension, large-tile fallback, chained-hit popping).
+//
+// Follows extender_body::operator() of the reference (software/extender.cpp:45-530 forward strand,
+// :557-1051 reverse strand) and makeForward/BackwardAlignment (:1067-1159); CPU twin:
+// oracle/gact_oracle.c extend_one().  The traceback of each tile feeds the consumption rule
+// directly (including the word-granular `break` quirk, extender.cpp:327-329), so no TB words and no
+// per-tile round trip to the host exist on this path.
+#pragma once
+#include "gact_common.cuh"
+
+namespace gact {
+
+struct ExtendArgs {
+    const uint8_t*  arena;
+    const DarwinAnchor* anchors;
+    const uint64_t* hit_pool;
+    DarwinAlnRes*   res;
+    uint8_t*        ops;          // device op slots
+    const uint64_t* slot_base;    // per anchor: first byte of its slot
+    const uint32_t* slot_left;    // per anchor: capacity of the left part (right part = slot_size - left)
+    const uint32_t* slot_size;
+    int n;
+    int T, O, do_overlap;
+    unsigned int* counter;        // work queue head
+};
+
+// Anchor registers shared by the whole warp (all lanes hold identical copies).
+struct AnchorState {
+    uint32_t cr, cq, rso, reo, qso, qeo;
+    uint32_t RL, QL;
+    uint64_t rsa, read_addr;
+    int large, ldone, rdone, emit, rc;
+    int64_t nl, nr;
+    const uint64_t* lh; const uint64_t* rh;
+    uint32_t nleft, nright, n_tiles, n_large, flags;
+    uint64_t cells;
+};
+
+// Consumption of one tile's ops by lane 0 (extender.cpp:280-331 / :427-466 and the rc twins).
+struct ConsumeSink {
+    uint32_t cr, cq, rso, qso;      // running offsets
+    uint32_t RL, QL;
+    int left, S, steps, pos_in_word, skipping;
+    uint8_t* lptr;                  // next left op goes to *--lptr
+    uint8_t* rptr;                  // next right op goes to *rptr++
+    uint32_t lroom, rroom, nl, nr, overflow;
+
+    __device__ __forceinline__ void operator()(uint32_t d) {
+        // ops arrive in traceback order; a new 32-op word clears the `break`
+        if (pos_in_word == 32) { pos_in_word = 0; skipping = 0; }
+        pos_in_word++;
+        if (skipping) return;
+        if (left) {
+            if (nl < lroom) *--lptr = (uint8_t)d; else overflow = 1;
+            nl++;
+            if (d != DARWIN_OP_I) { if (cr > 0) cr--; else rso = 0; }
+            if (d != DARWIN_OP_D) { if (cq > 0) cq--; else qso = 0; }
+        } else {
+            if (nr < rroom) *rptr++ = (uint8_t)d; else overflow = 1;
+            nr++;
+            if (d != DARWIN_OP_I) { if (cr < RL) cr++; }
+            if (d != DARWIN_OP_D) { if (cq < QL) cq++; }
+        }
+        steps++;
+        if (steps >= S && d == DARWIN_OP_M) skipping = 1;          // leaves only the 32-op loop
+    }
+};
+
+// Build the next tile request of an anchor (extender.cpp:58-207 / :573-722).  Returns rt/qt through refs.
+__device__ __forceinline__ void next_tile(const AnchorState& a, int T, TileJob& t, int& rt, int& qt) {
+    const bool left = !a.ldone;
+    rt = T; qt = T;
+    if (a.large) {
+        const uint64_t ho = left ? a.lh[a.nl - 1] : a.rh[a.nr - 1];
+        const uint64_t h1 = a.rsa + a.cr, o1 = a.cq, h2 = ho >> 32, o2 = (ho << 32) >> 32;
+        const bool wide = left ? ((h1 - h2) > (o1 - o2)) : ((h2 - h1) > (o2 - o1));   // uint64 arithmetic, as the reference
+        rt = wide ? 1984 : 960; qt = wide ? 960 : 1984;
+    }
+    if (left) {
+        t.R = (int)min((uint64_t)a.cr + 1, (uint64_t)rt);
+        t.Q = (int)min((uint64_t)a.cq + 1, (uint64_t)qt);
+        t.ra = a.rsa + (a.cr >= (uint32_t)rt ? a.cr - rt + 1 : 0);
+        const uint32_t qoff = (a.cq >= (uint32_t)qt ? a.cq - qt + 1 : 0);
+        t.qa = a.rc ? a.read_addr + a.QL - t.Q - qoff : a.read_addr + qoff;
+        t.flags = a.rc ? (DARWIN_REVERSE_QUERY | DARWIN_COMPLEMENT_QUERY | DARWIN_START_END) : DARWIN_START_END;
+    } else {
+        t.R = (int)min(a.RL - a.cr, (uint32_t)rt);
+        t.Q = (int)min(a.QL - a.cq, (uint32_t)qt);
+        t.ra = a.rsa + a.cr;
+        t.qa = a.rc ? a.read_addr + a.QL - t.Q - a.cq : a.read_addr + a.cq;
+        t.flags = a.rc ? (DARWIN_REVERSE_REF | DARWIN_COMPLEMENT_QUERY | DARWIN_START_END)
+                       : (DARWIN_REVERSE_REF | DARWIN_REVERSE_QUERY | DARWIN_START_END);
+    }
+}
+
+// State transition after a tile has been consumed (extender.cpp:336-394 / :472-524 and rc twins).
+__device__ __forceinline__ void after_tile(AnchorState& a, int len) {
+    if (!a.ldone) {
+        while (a.nl > 0) {
+            const uint64_t ho = a.lh[a.nl - 1], hit = ho >> 32, off = (ho << 32) >> 32;
+            if (hit < a.rsa + a.cr && off < a.cq) break;
+            a.nl--;
+        }
+        const bool stall = a.rc ? (len == 0 || a.rso == 0 || a.qso == 0)
+                                : (len == 0 || a.nl == 0 || a.rso == 0 || a.qso == 0);
+        if (stall) {
+            if (a.large || a.nl == 0 || a.rso == 0 || a.qso == 0) {
+                a.ldone = 1;
+                if (a.rso > 0) a.rso = a.cr + 1;
+                if (a.qso > 0) a.qso = a.cq + 1;
+                if ((a.cr + 1 < a.RL) && (a.cq + 1 < a.QL) && !a.rdone) { a.cr = a.reo + 1; a.cq = a.qeo + 1; }
+                else { a.rdone = 1; if (a.rc) a.emit = 1; }
+            } else a.large = 1;
+        } else a.large = 0;
+    } else {
+        while (a.nr > 0) {
+            const uint64_t ho = a.rh[a.nr - 1], hit = ho >> 32, off = (ho << 32) >> 32;
+            if (hit > a.rsa + a.cr && off > a.cq) break;
+            a.nr--;
+        }
+        if (len == 0 || a.cr == a.RL || a.cq == a.QL) {
+            if (a.large || a.nr == 0 || a.cr == a.RL || a.cq == a.QL) { a.reo = a.cr - 1; a.qeo = a.cq - 1; a.emit = 1; a.rdone = 1; }
+            else a.large = 1;
+        } else a.large = 0;
+    }
+}
+
+} // namespace gact

@@ -1,0 +1,163 @@
+"""Python binding of libdarwin_gact.so (the C-ABI in include/darwin_gpu.h).
+
+The names mirror the reference's Processor seam (software/Processor.h:50-63) and its extender stage
+(software/graph.h:219-229): `Processor.InitializeScoringParameters`, `.InitializeReferenceMemory`,
+`.InitializeReadMemory`, `.BatchAlignmentSIMD` and `.extender_body`.  There is no CPU fallback: if the
+CUDA library is missing or no device is usable, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdarwin_gact.so")
+_lib = None
+
+
+class DarwinGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("darwin_gpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load_library():
+    """Load the in-tree CUDA library; raises if it has not been built (python __graft_entry__.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise FileNotFoundError(_LIB_PATH + " is missing: run `python __graft_entry__.py` (nvcc, sm_100a). "
+                                    "There is no CPU fallback for the GACT path.")
+        L = C.CDLL(_LIB_PATH)
+        L.darwin_gpu_version.restype = C.c_char_p
+        L.darwin_gpu_last_error.restype = C.c_char_p
+        L.darwin_gpu_last_error.argtypes = [C.c_void_p]
+        L.darwin_gpu_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint64]
+        L.darwin_gpu_destroy.argtypes = [C.c_void_p]
+        L.darwin_gpu_set_scoring.argtypes = [C.c_void_p, C.POINTER(abi.Scoring)]
+        L.darwin_gpu_upload.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.darwin_gpu_tiles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.darwin_gpu_tiles_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.darwin_gpu_extend.argtypes = [C.c_void_p, C.POINTER(abi.ExtendParams), C.c_void_p, C.c_int, C.c_void_p,
+                                        C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.darwin_gpu_stats.argtypes = [C.c_void_p, C.POINTER(abi.GpuStats)]
+        L.darwin_gpu_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+EXPORTS = ("darwin_gpu_create", "darwin_gpu_destroy", "darwin_gpu_set_scoring", "darwin_gpu_upload",
+           "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_stats", "darwin_gpu_int_peak",
+           "darwin_gpu_last_error", "darwin_gpu_version")
+
+
+class Processor:
+    """One GPU-backed Processor (== one `token` of the reference, main.cpp:615-624)."""
+
+    def __init__(self, arena_bytes, device=0):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        rc = self.lib.darwin_gpu_create(C.byref(self.h), int(device), C.c_uint64(int(arena_bytes)))
+        if rc:
+            msg = self.lib.darwin_gpu_last_error(self.h).decode() if self.h else "no usable CUDA device"
+            raise DarwinGpuError(rc, msg)
+        self.arena_bytes = int(arena_bytes)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.darwin_gpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise DarwinGpuError(rc, self.lib.darwin_gpu_last_error(self.h).decode())
+
+    # g_InitializeScoringParameters (Processor.cpp:48-80)
+    def InitializeScoringParameters(self, scoring):
+        self._check(self.lib.darwin_gpu_set_scoring(self.h, C.byref(scoring)))
+
+    # g_InitializeReferenceMemory / g_InitializeReadMemory (Processor.cpp:82-85, sender.cpp:4-97)
+    def InitializeReferenceMemory(self, arena_addr, ascii_bytes):
+        a = np.ascontiguousarray(np.frombuffer(ascii_bytes, np.uint8) if not isinstance(ascii_bytes, np.ndarray) else ascii_bytes)
+        self._check(self.lib.darwin_gpu_upload(self.h, C.c_uint64(int(arena_addr)), abi.ptr(a), C.c_uint64(a.size)))
+
+    InitializeReadMemory = InitializeReferenceMemory
+
+    # g_BatchAlignmentSIMD (Processor.cpp:718-762)
+    def BatchAlignmentSIMD(self, requests, do_traceback=1, tb_words_per_req=None):
+        req = np.ascontiguousarray(requests, dtype=abi.TILE_REQ)
+        n = len(req)
+        res = np.zeros(n, abi.TILE_RES)
+        if tb_words_per_req is None:
+            tb_words_per_req = (int(req["max_tb_steps"].max()) // 16 + 2) if n else 1
+        tb = np.zeros((n, tb_words_per_req), np.uint64) if do_traceback else None
+        self._check(self.lib.darwin_gpu_tiles(self.h, int(do_traceback), abi.ptr(req), n, abi.ptr(res),
+                                              abi.ptr(tb) if tb is not None else None, int(tb_words_per_req)))
+        return res, tb
+
+    def BatchAlignmentSIMD_device(self, d_req, n, d_res, d_tb, tb_words_per_req, do_traceback=1):
+        """Device-resident variant (bench `value` leg): raw device pointers (ints)."""
+        self._check(self.lib.darwin_gpu_tiles_device(self.h, int(do_traceback), C.c_void_p(d_req), int(n),
+                                                     C.c_void_p(d_res), C.c_void_p(d_tb), int(tb_words_per_req)))
+
+    # extender_body::operator() (extender.cpp:9-1065) for a batch of anchors
+    def extender_body(self, anchors, hit_pool, tile_size=384, tile_overlap=64, do_overlap=0, ops_cap=None):
+        an = np.ascontiguousarray(anchors, dtype=abi.ANCHOR)
+        hp = np.ascontiguousarray(hit_pool, dtype=np.uint64)
+        n = len(an)
+        res = np.zeros(n, abi.ALN_RES)
+        if ops_cap is None:
+            ops_cap = int(an["read_len"].astype(np.int64).sum()) * 3 + 65536
+        ops = np.zeros(ops_cap, np.uint8)
+        prm = abi.ExtendParams(int(tile_size), int(tile_overlap), int(do_overlap), 0)
+        self._check(self.lib.darwin_gpu_extend(self.h, C.byref(prm), abi.ptr(an), n,
+                                               abi.ptr(hp) if len(hp) else None, C.c_uint64(len(hp)),
+                                               abi.ptr(res), abi.ptr(ops), C.c_uint64(ops_cap)))
+        return res, ops
+
+    def int_peak(self):
+        """Measured issue rates (G lane-ops/s) of VIMNMX.S16x2, VIADDMNMX.S16x2, VIMNMX3.S16x2, IADD3/LOP3."""
+        out = (C.c_double * 4)()
+        self._check(self.lib.darwin_gpu_int_peak(self.h, out))
+        return list(out)
+
+    def int_peak_gops(self):
+        """P_int of SURVEY 8(d) in G int16-element-ops/s: best packed lane-op rate x 2 cells per lane-op."""
+        return 2.0 * max(self.int_peak())
+
+    def stats(self):
+        s = abi.GpuStats()
+        self._check(self.lib.darwin_gpu_stats(self.h, C.byref(s)))
+        return s
+
+
+def read_params_cfg(path):
+    """params.cfg semantics of the reference (software/ConfigFile.cpp, main.cpp:183-230):
+    `[section]` headers, `key = value`, `//`-style comments ignored.  Returns {section: {key: value}}."""
+    out, sec = {}, None
+    for raw in open(path):
+        line = raw.split("//")[0].split("#")[0].strip()
+        if not line:
+            continue
+        if line.startswith("[") and line.endswith("]"):
+            sec = line[1:-1].strip()
+            out.setdefault(sec, {})
+        elif "=" in line and sec is not None:
+            k, v = line.split("=", 1)
+            out[sec][k.strip()] = v.strip()
+    return out
+
+
+def scoring_from_cfg(cfg):
+    s = cfg["GACT_scoring"]
+    return abi.Scoring(*[int(float(s[k])) for k in (
+        "sub_AA", "sub_AC", "sub_AG", "sub_AT", "sub_CC", "sub_CG", "sub_CT", "sub_GG", "sub_GT", "sub_TT",
+        "sub_N", "gap_open", "gap_extend", "long_gap_open", "long_gap_extend")])

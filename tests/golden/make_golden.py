@@ -1,0 +1,177 @@
+"""Regenerates the golden fixtures under tests/golden/ from the COMPILED REFERENCE (oracle/_ref, built by
+oracle/Makefile from the unmodified sources under /root/reference).  Run here (CPU container):
+
+    python tests/golden/make_golden.py
+
+Fixtures (all seeded; inputs are synthetic, expected outputs come from the reference itself):
+  tiles_v1.npz   tile requests of many shapes/flags/scoring schemes + BatchAlignmentSIMD results (patched flavour;
+                 `asis_same` marks tiles where the as-is flavour gave the identical answer)
+  extend_v1.npz  synthetic 150 kbp reference + 10 reads, anchors from the reference's own D-SOFT + filter,
+                 extender_body results for T/O = 384/64 and 320/128 (+ do_overlap=1)
+  rtl_kat.npz    the RTL testbench's 10 known-answer pairs (RTL/GACT/test_data/{ref,query}_320.txt) and
+                 their "Total score" lines (test_align.txt) -- score-level vectors only
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+from darwin_b200 import abi, synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+SCHEMES = {   # (match, mismatch, N; go, ge; lgo, lge) -- SURVEY Appendix D
+    "stock": (2, -6, -1, -4, -2, -25, -1),
+    "tie": (1, -1, 0, -1, -1, -1, -1),
+    "s2": (1, -1, 0, -2, -1, -4, 0),
+    "s3": (2, -3, -1, -3, -2, -8, -1),
+}
+FLAGSETS = [1, 1 | 4 | 16, 1 | 4 | 2, 1 | 16 | 2, 0, 4 | 2, 1 | 8, 1 | 8 | 16 | 4 | 2]
+
+
+def make_tiles(seed, n, sizes, big=0):
+    rng = np.random.default_rng(seed)
+    arena = [np.full(128, ord("N"), np.uint8)]
+    pos = 128
+    req = np.zeros(n + big, abi.TILE_REQ)
+    for k in range(n + big):
+        if k >= n:
+            R, Qc = (1984, 960) if k % 2 else (960, 1984)
+        else:
+            R = int(rng.choice(sizes)) if rng.random() < 0.3 else int(rng.integers(1, max(sizes) + 1))
+            Qc = None
+        r = synth.random_seq(rng, R)
+        q = synth.mutate(rng, r, 0.05 + 0.1 * rng.random(), 0.02 + 0.05 * rng.random(), 0.02 + 0.05 * rng.random(),
+                         0.003 if k % 3 == 0 else 0.0, (2, 40) if k % 2 else None)
+        if Qc is not None:
+            q = np.concatenate([q, synth.random_seq(rng, max(0, Qc - len(q)))])[:Qc]
+        elif rng.random() < 0.5:
+            q = q[:max(1, min(len(q), int(rng.integers(1, max(sizes) + 1))))]
+        if len(q) == 0:
+            q = synth.random_seq(rng, 1)
+        if rng.random() < 0.1:
+            q = np.char.lower(q.view("S1")).view(np.uint8)           # Nt2Int accepts either case
+        req[k]["ref_bases_start_addr"] = pos
+        arena.append(r)
+        pos += len(r)
+        req[k]["query_bases_start_addr"] = pos
+        arena.append(q)
+        pos += len(q)
+        req[k]["ref_size"] = len(r)
+        req[k]["query_size"] = len(q)
+        req[k]["max_tb_steps"] = 768 if k >= n else int(rng.choice([2 * max(len(r), len(q)), 64, 768]))
+        req[k]["align_fields"] = 1 if k >= n else int(rng.choice(FLAGSETS))
+        req[k]["index"] = k % 250
+    arena.append(np.full(128, ord("N"), np.uint8))
+    return np.concatenate(arena), req
+
+
+def gen_tiles():
+    out = {}
+    for si, (name, vals) in enumerate(SCHEMES.items()):
+        sc = abi.Scoring.from_values(*vals)
+        arena, req = make_tiles(100 + si, 120, [64, 128, 320, 400], big=2 if name == "stock" else 0)
+        res = {}
+        for fl in ("patched", "as-is"):
+            ref = oracle.reference(fl)
+            ref.set_scoring(sc)
+            res[fl] = ref.tiles(arena, req, 1, tb_words_per_req=260)
+        rp, tp = res["patched"]
+        ra, ta = res["as-is"]
+        same = np.array([(rp[k] == ra[k]) and np.array_equal(tp[k], ta[k]) for k in range(len(req))])
+        # score-only pass (do_traceback = 0), as the first-tile filter calls it (filter.cpp:40,:77)
+        ref = oracle.reference("patched")
+        ref.set_scoring(sc)
+        r0, _ = ref.tiles(arena, req, 0, tb_words_per_req=1)
+        used = int(((rp["total_TB_pointers"].astype(int) + 31) // 32).max())
+        out[name + "_scoring"] = np.array(vals, np.int32)
+        out[name + "_arena"] = arena
+        out[name + "_req"] = req
+        out[name + "_res"] = rp
+        out[name + "_tb"] = tp[:, :used + 1].copy()
+        out[name + "_res_notb"] = r0
+        out[name + "_asis_same"] = same
+        print("tiles", name, len(req), "as-is identical:", int(same.sum()))
+    np.savez_compressed(os.path.join(OUT, "tiles_v1.npz"), **out)
+
+
+def gen_extend():
+    rng = np.random.default_rng(7)
+    genome = synth.random_seq(rng, 150000)
+    reads = []
+    for k in range(10):
+        L = int(rng.integers(5000, 8000))
+        p = int(rng.integers(0, len(genome) - L))
+        src = genome[p:p + L]
+        if k % 4 == 1:      # structural insertion in the read: stalls a normal tile, chained hits remain -> large tile
+            src = np.concatenate([src[:L // 2], synth.random_seq(rng, 450), src[L // 2:]])
+        elif k % 4 == 2:    # structural deletion
+            src = np.concatenate([src[:L // 3], src[L // 3 + 600:]])
+        r = synth.mutate(rng, src, 0.05, 0.05, 0.05, indel_run=(3, 60) if k % 2 else None)
+        if k % 3 == 0:
+            r = synth.revcomp(r)
+        reads.append(np.ascontiguousarray(r))
+    out = {}
+    for (T, O, ovl) in ((384, 64, 0), (320, 128, 0), (256, 64, 1)):
+        res = {}
+        for fl in ("patched", "as-is"):
+            ref = oracle.reference(fl)
+            ref.set_scoring(abi.Scoring.from_values(*SCHEMES["stock"]))
+            ref.set_dsoft_defaults()
+            ref.set_extend(T, O, 2, ovl)
+            ref.reset_arena()
+            ref.add_chr("chrS", genome.tobytes(), True)
+            ref.build_index()
+            for k, r in enumerate(reads):
+                ref.add_read("r%d" % k, r.tobytes())
+            A, H, hb = [], [], 0
+            for k in range(len(reads)):
+                a, h = ref.seed_filter(k, 1)
+                a = a.copy()
+                a["left_hits_off"] += hb
+                a["right_hits_off"] += hb
+                hb += len(h)
+                A.append(a)
+                H.append(h)
+            anchors, hits = np.concatenate(A), np.concatenate(H)
+            r_, ops = ref.extend(anchors, hits)
+            used = int((r_["ops_offset"] + r_["n_ops"]).max())
+            res[fl] = (anchors, hits, r_, ops[:used].copy(), ref.arena().copy())
+        (anchors, hits, rp, opsp, arena) = res["patched"]
+        (_, _, ra, opsa, _) = res["as-is"]
+        same = np.array([rp[k] == ra[k] and np.array_equal(opsp[rp[k]["ops_offset"]:rp[k]["ops_offset"] + rp[k]["n_ops"]],
+                                                          opsa[ra[k]["ops_offset"]:ra[k]["ops_offset"] + ra[k]["n_ops"]])
+                         for k in range(len(anchors))])
+        tag = "T%d_O%d_ovl%d" % (T, O, ovl)
+        out[tag + "_anchors"] = anchors
+        out[tag + "_hits"] = hits
+        out[tag + "_res"] = rp
+        out[tag + "_ops"] = opsp
+        out[tag + "_asis_same"] = same
+        out["arena"] = arena
+        print("extend", tag, "anchors", len(anchors), "emitted", int((rp["flags"] & 1).sum()), "tiles", int(rp["n_tiles"].sum()),
+              "large", int(rp["n_large_tiles"].sum()), "as-is identical", int(same.sum()))
+    out["scoring"] = np.array(SCHEMES["stock"], np.int32)
+    np.savez_compressed(os.path.join(OUT, "extend_v1.npz"), **out)
+
+
+def gen_rtl():
+    d = os.path.join(REF, "RTL", "GACT", "test_data")
+    refs = open(os.path.join(d, "ref_320.txt")).read().split()
+    qrys = open(os.path.join(d, "query_320.txt")).read().split()
+    scores = [int(l.split(":")[1]) for l in open(os.path.join(d, "test_align.txt")) if l.startswith("Total score")]
+    assert len(refs) == len(qrys) == len(scores) == 10
+    np.savez_compressed(os.path.join(OUT, "rtl_kat.npz"), refs=np.array(refs), queries=np.array(qrys),
+                        scores=np.array(scores, np.int32))
+    print("rtl", scores)
+
+
+if __name__ == "__main__":
+    oracle.build()
+    gen_tiles()
+    gen_extend()
+    gen_rtl()

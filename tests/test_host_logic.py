@@ -1,0 +1,100 @@
+"""CPU: host-side logic -- synthetic input generators, the consumption rule helper, params.cfg parsing."""
+import os
+
+import numpy as np
+
+import oracle
+from darwin_b200 import abi, synth, gact
+
+
+def synthetic_anchor_set(seed, n_reads, read_len, ref_len=60000):
+    """Arena laid out like the reference's (Index.cpp:10-17, main.cpp:430-456, :645-686): 128 'N', one padded
+    chromosome, then 128-aligned 'N'-padded reads.  One anchor per read at its true position, with chained
+    hits every ~60 bases along the true diagonal (ascending left list, descending right list)."""
+    rng = np.random.default_rng(seed)
+    genome = synth.random_seq(rng, ref_len)
+    pad = (-ref_len) % 128
+    parts = [np.full(128, ord("N"), np.uint8), genome, np.full(pad, ord("N"), np.uint8)]
+    chr_start, chr_len = 128, ref_len + pad
+    pos = 128 + chr_len
+    anchors = np.zeros(n_reads, abi.ANCHOR)
+    hits = []
+    for k in range(n_reads):
+        L = read_len + int(rng.integers(0, 200))
+        if k % 6 == 0:
+            g0 = 0                                   # read hanging over the left end
+        elif k % 6 == 1:
+            g0 = ref_len - L + 40                    # over the right end (into the 'N' padding)
+        else:
+            g0 = int(rng.integers(0, ref_len - L))
+        src = genome[g0:min(ref_len, g0 + L)]
+        read = synth.mutate(rng, src, 0.05, 0.05, 0.05, indel_run=(2, 50) if k % 2 else None)
+        strand = k % 2
+        fwd = synth.revcomp(read) if strand else read     # what is stored in the arena is the forward read
+        rl = len(fwd)
+        rpad = (-rl) % 128
+        parts += [fwd, np.full(rpad, ord("N"), np.uint8)]
+        # anchor in the middle of the read; reference position estimated along the diagonal
+        qa = rl // 2
+        ra = min(ref_len - 1, g0 + int(qa * len(src) / max(rl, 1)))
+        a = anchors[k]
+        a["read_addr"], a["read_len"], a["read_num"] = pos, rl, k
+        a["reference_pos"], a["query_pos"] = chr_start + ra, qa
+        a["chr_start"], a["ref_len"], a["chr_id"], a["score"], a["strand"] = chr_start, chr_len, 0, 100, strand
+        lh = [((chr_start + ra - d) << 32) | (qa - d) for d in range(0, min(ra, qa), 61)][::-1]
+        rh = [((chr_start + ra + d) << 32) | (qa + d) for d in range(0, min(ref_len - ra, rl - qa), 59)][::-1]
+        a["left_hits_off"], a["left_hits_n"] = len(hits), len(lh)
+        hits += lh
+        a["right_hits_off"], a["right_hits_n"] = len(hits), len(rh)
+        hits += rh
+        pos += rl + rpad
+    arena = np.concatenate(parts + [np.full(128, ord("N"), np.uint8)])
+    return arena, anchors, np.array(hits, np.uint64)
+
+
+def test_tile_batch_generators_agree_in_shape():
+    a1, r1 = synth.tile_batch(1, 50, 64)
+    a2, r2 = synth.tile_batch_fast(1, 50, 64)
+    assert a1.shape == a2.shape and np.array_equal(r1, r2)
+    assert set(np.unique(a2[:50 * 128])) <= set(b"ACGT")
+    # the mutated query still aligns: oracle score of a tile is far above random
+    port = oracle.port(abi.Scoring.from_values())
+    res, _, _ = port.tiles(a2, r2, 1, oracle.Port.STREAM)
+    assert np.median(res["score"]) > 20
+
+
+def test_consumed_ops_quirk():
+    """extender.cpp:327-329: after S steps an M only ends the current 32-op word."""
+    ops = [3] * 40 + [1, 1, 3] + [3] * 30
+    words = np.zeros(3, np.uint64)
+    for k, d in enumerate(ops):
+        words[k // 32] |= np.uint64(d << (2 * (k % 32)))
+    got = synth.consumed_ops(words, len(ops), 36)
+    # word 0 fully (32 ops), word 1: ops 32..35 -> steps 36 at k=35 (M) -> break; word 2 starts again: first op M -> break
+    assert got == ops[:36] + [ops[64]]
+
+
+def test_params_cfg_semantics(tmp_path):
+    p = tmp_path / "params.cfg"
+    p.write_text("[GACT_scoring]\nsub_AA = 2\nsub_AC = -6\nsub_AG = -6\nsub_AT = -6\nsub_CC = 2\nsub_CG = -6\nsub_CT = -6\n"
+                 "sub_GG = 2\nsub_GT = -6\nsub_TT = 2\nsub_N = -1\ngap_open = -4\ngap_extend = -2\nlong_gap_open = -25\n"
+                 "long_gap_extend = -1\n\n[GACT_extend]\ntile_size = 384\ntile_overlap = 64\nbatch_size = 2\n//x = 1\n")
+    cfg = gact.read_params_cfg(str(p))
+    assert cfg["GACT_extend"] == {"tile_size": "384", "tile_overlap": "64", "batch_size": "2"}
+    assert gact.scoring_from_cfg(cfg).as_tuple() == abi.Scoring.from_values().as_tuple()
+    ref_cfg = "/root/reference/software/params.cfg"
+    if os.path.exists(ref_cfg):
+        assert gact.scoring_from_cfg(gact.read_params_cfg(ref_cfg)).as_tuple() == abi.Scoring.from_values().as_tuple()
+
+
+def test_synthetic_anchor_set_runs_through_oracle():
+    arena, anchors, hits = synthetic_anchor_set(3, 6, 1500, ref_len=20000)
+    port = oracle.port(abi.Scoring.from_values())
+    res, ops = port.extend(arena, abi.ExtendParams(384, 64, 0, 0), anchors, hits, oracle.Port.STREAM)
+    assert (res["flags"] & 1).sum() >= 4
+    em = res[(res["flags"] & 1) == 1]
+    assert (em["n_ops"] > 1000).all()
+    # clean + rerun scheme gives identical answers
+    res2, ops2 = port.extend(arena, abi.ExtendParams(384, 64, 0, 0), anchors, hits, oracle.Port.CLEAN)
+    from conftest import alignments_equal, ALN_FIELDS_OURS
+    assert alignments_equal(res, ops, res2, ops2, ALN_FIELDS_OURS) == []

@@ -1,0 +1,56 @@
+"""CPU: fresh random inputs through the compiled reference (oracle/_ref) and the restatement.  Skipped only
+when oracle/_ref has not been built (no /root/reference and no prebuilt library)."""
+import numpy as np
+import pytest
+
+import oracle
+from darwin_b200 import abi, synth
+from conftest import tiles_equal
+
+pytestmark = pytest.mark.skipif(not oracle.have_reference(), reason="oracle/_ref not built")
+
+
+def _random_tiles(seed, n, maxsize):
+    rng = np.random.default_rng(seed)
+    arena, req, pos = [np.full(64, ord("N"), np.uint8)], np.zeros(n, abi.TILE_REQ), 64
+    for k in range(n):
+        R = int(rng.integers(1, maxsize + 1))
+        r = synth.random_seq(rng, R)
+        q = synth.mutate(rng, r, 0.1 * rng.random(), 0.08 * rng.random(), 0.08 * rng.random(), 0.002, (1, 30))
+        if len(q) == 0:
+            q = synth.random_seq(rng, 3)
+        for name, s in (("ref", r), ("query", q)):
+            req[k][name + "_bases_start_addr"], req[k][name + "_size"] = pos, len(s)
+            arena.append(s)
+            pos += len(s)
+        req[k]["max_tb_steps"] = int(rng.choice([2 * maxsize, 48]))
+        req[k]["align_fields"] = int(rng.choice([1, 21, 7, 19, 0, 6]))
+        req[k]["index"] = k % 256
+    return np.concatenate(arena + [np.full(64, ord("N"), np.uint8)]), req
+
+
+@pytest.mark.parametrize("vals", [(2, -6, -1, -4, -2, -25, -1), (1, -1, 0, -1, -1, -1, -1), (2, -3, -1, -3, -2, -8, -1),
+                                  (5, -4, -1, -10, -1, -1000, -1)])
+def test_random_tiles_port_equals_reference(vals):
+    sc = abi.Scoring.from_values(*vals)
+    ref = oracle.reference("patched")
+    ref.set_scoring(sc)
+    port = oracle.port(sc)
+    arena, req = _random_tiles(hash(vals) & 0xFFFF, 150, 260)
+    rres, rtb = ref.tiles(arena, req, 1, tb_words_per_req=80)
+    for rule in (oracle.Port.STRIPED, oracle.Port.STREAM):
+        pres, ptb, _ = port.tiles(arena, req, 1, rule, tb_words_per_req=80)
+        assert tiles_equal(rres, rtb, pres, ptb) == []
+
+
+def test_general_matrix_port_equals_reference():
+    """Non-uniform substitution matrix (transitions cheaper than transversions)."""
+    m = dict(AA=3, AC=-5, AG=-2, AT=-5, CC=3, CG=-5, CT=-2, GG=3, GT=-5, TT=4)
+    sc = abi.Scoring.from_values(matrix=m, sub_n=-1, go=-5, ge=-2, lgo=-20, lge=-1)
+    ref = oracle.reference("patched")
+    ref.set_scoring(sc)
+    port = oracle.port(sc)
+    arena, req = _random_tiles(5, 120, 200)
+    rres, rtb = ref.tiles(arena, req, 1, tb_words_per_req=80)
+    pres, ptb, _ = port.tiles(arena, req, 1, oracle.Port.STREAM, tb_words_per_req=80)
+    assert tiles_equal(rres, rtb, pres, ptb) == []
