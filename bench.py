@@ -239,15 +239,17 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        int_peak = None
+        int_peak, int_detail = None, None
         try:
-            int_peak = proc.int_peak_gops()
+            int_detail = proc.int_peak()
+            int_peak = 2.0 * max(int_detail)
         except Exception:
             pass
         per_gpu_gcups = value / world
         roof = {"bound": "int_alu", "achieved": per_gpu_gcups * OPS_PER_CELL, "peak": int_peak,
                 "unit": "Gint-op/s", "frac": (per_gpu_gcups * OPS_PER_CELL / int_peak) if int_peak else None,
                 "traffic": None,
+                "peak_detail_glaneops": dict(zip(["vimnmx_s16x2", "viaddmnmx_s16x2", "vimnmx3_s16x2", "iadd3_lop3"], int_detail)) if int_detail else None,
                 "note": "SURVEY 8(d) integer-pipe roofline: 32 algorithmic int-ops per cell; peak = measured packed "
                         "s16x2 DPX/ALU issue rate (2 cells per lane-op) of this GPU; HBM is not the bound "
                         "(%.3f B/cell algorithmic)" % ((2 * TILE / 2 + 32 + 16 + tbw * 8) / (TILE * TILE)),

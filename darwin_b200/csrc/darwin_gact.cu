@@ -189,6 +189,10 @@ extend_exact_kernel(const __grid_constant__ KernelScoring ks, const __grid_const
             len = (int)pk[6];
             if (pk[7] & 1) a.flags |= DARWIN_ALN_LONG_INS_PATH;
             if (pk[7] & 0x100) overflow = 1;
+            if (ea.dbg && lane == 0 && a.n_tiles <= 128) {
+                uint32_t* d = ea.dbg + ((size_t)idx * 128 + (a.n_tiles - 1)) * 8;
+                d[0] = t.R; d[1] = t.Q; d[2] = len; d[3] = a.cr; d[4] = a.cq; d[5] = a.rso; d[6] = a.qso; d[7] = a.large | (left << 1);
+            }
             after_tile(a, len);
         }
         if (lane == 0) {
@@ -540,6 +544,8 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     ea.arena = h->d_arena; ea.anchors = (const DarwinAnchor*)h->d_buf[0]; ea.hit_pool = (const uint64_t*)h->d_buf[2];
     ea.res = (DarwinAlnRes*)h->d_buf[1]; ea.ops = (uint8_t*)h->d_buf[3];
     ea.slot_base = (const uint64_t*)h->d_buf[4]; ea.slot_left = (const uint32_t*)h->d_buf[5]; ea.slot_size = (const uint32_t*)h->d_buf[6];
+    ea.dbg = nullptr;
+    if (getenv("DARWIN_GPU_DEBUG")) { CK(cudaMalloc(&ea.dbg, (size_t)n * 128 * 8 * 4)); CK(cudaMemset(ea.dbg, 0, (size_t)n * 128 * 8 * 4)); }
     ea.n = n; ea.T = p->tile_size; ea.O = p->tile_overlap; ea.do_overlap = p->do_overlap; ea.counter = h->d_counter;
     CK(cudaEventRecord(h->ev0, h->stream));
     extend_exact_kernel<<<h->ctas, kWarpsPerCta * 32, 0, h->stream>>>(h->ks, ea, h->d_trace, h->trace_stride, h->d_bound);
@@ -572,6 +578,12 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     CK(cudaFreeAsync(d_dense, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     (void)overflow;
+    if (ea.dbg) {
+        std::vector<uint32_t> hd((size_t)n * 128 * 8);
+        CK(cudaMemcpy(hd.data(), ea.dbg, hd.size() * 4, cudaMemcpyDeviceToHost));
+        FILE* f = fopen(getenv("DARWIN_GPU_DEBUG"), "wb"); if (f) { fwrite(hd.data(), 4, hd.size(), f); fclose(f); }
+        cudaFree(ea.dbg);
+    }
     return DARWIN_OK;
 }
 

@@ -72,22 +72,22 @@ __device__ void exact_forward(const int* __restrict__ ssub, int go, int ge, int 
         ChainRec o;                                         // my state below my last row, column of the previous step
         o.hbot = 0; o.F = go; o.FL = lgo; o.f0 = go; o.fl0 = lgo; o.fc = kNegInf; o.flc = kNegInf; o.misc = 3 << 16;
         int diag_prev = 0;                                  // H(i0-1, j-1)
+        int4 pre0 = make_int4(0, 0, 0, 0), pre1 = make_int4(0, 0, 0, 0);   // prefetched boundary record
         uint8_t* tr = ws.trace + (size_t)strip * steps * (32 * KX) + lane * KX;
 
         for (int s = 0; s < steps; s++) {
             if (strip > 0 && (s & 31) == 0) {
-                // cp.async the boundary records of the NEXT 32 columns (32 B per lane) one window ahead
-                for (int wdw = (s == 0 ? 0 : (s >> 5) + 1); wdw <= (s >> 5) + 1; wdw++) {
-                    const int jj = wdw * 32 + lane;
-                    if (jj < R) {
-                        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm->rec[wdw & 1][lane]);
-                        const ChainRec* src = ws.bound + jj;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + 16), "l"((const char*)src + 16));
-                    }
-                    asm volatile("cp.async.commit_group;\n" ::);
-                }
-                asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+                // Boundary records of the previous strip, 32 columns per window.  Each lane keeps the record of
+                // column 32*(w+1)+lane in registers one window ahead (ld.global.cg issued a window early, so its
+                // latency hides behind 32 steps) and publishes it to shared memory when the window starts.
+                // (cp.async.cg is NOT used here: on sm_100a it returned stale lines for addresses this SM had
+                // re-written with st.global.cg since the previous tile -- measured, see DESIGN.md.)
+                const int w = s >> 5;
+                if (s == 0) { const int jj = lane; if (jj < R) { const int4* src = reinterpret_cast<const int4*>(ws.bound + jj); pre0 = __ldcg(src); pre1 = __ldcg(src + 1); } }
+                int4* dst = reinterpret_cast<int4*>(&sm->rec[w & 1][lane]);
+                dst[0] = pre0; dst[1] = pre1;
+                const int jn = (w + 1) * 32 + lane;
+                if (jn < R) { const int4* src = reinterpret_cast<const int4*>(ws.bound + jn); pre0 = __ldcg(src); pre1 = __ldcg(src + 1); }
                 __syncwarp();
             }
             ChainRec in;

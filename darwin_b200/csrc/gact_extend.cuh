@@ -23,6 +23,7 @@ struct ExtendArgs {
     int n;
     int T, O, do_overlap;
     unsigned int* counter;        // work queue head
+    uint32_t* dbg;                // optional: per anchor 128 tiles x 8 words (R, Q, len, cr, cq, rso, qso, large)
 };
 
 // Anchor registers shared by the whole warp (all lanes hold identical copies).

@@ -449,6 +449,11 @@ int gact_build_strings(const char* dram, const DarwinAnchor* a, const DarwinAlnR
  * Anchor state machine: extender_body::operator() for ONE anchor (extender.cpp:45-530 forward
  * strand, :557-1051 reverse strand) + makeForward/BackwardAlignment (:1067-1159).
  * ------------------------------------------------------------------------------------------ */
+/* optional log of every tile request the state machine issues (debugging / tile-level parity of the extender) */
+static DarwinTileReq* g_tile_log = 0; static int g_tile_log_cap = 0, g_tile_log_n = 0;
+void gact_set_tile_log(DarwinTileReq* buf, int cap) { g_tile_log = buf; g_tile_log_cap = cap; g_tile_log_n = 0; }
+int gact_tile_log_count(void) { return g_tile_log_n; }
+
 typedef struct OpBuf { uint8_t* left; uint64_t nleft, capleft; uint8_t* right; uint64_t nright, capright; } OpBuf;
 
 static void push_op(uint8_t** buf, uint64_t* n, uint64_t* cap, uint8_t d) {
@@ -501,6 +506,7 @@ static int extend_one(const GactScoring* sc, const char* dram, const DarwinExten
         }
         rq.max_tb_steps = (uint16_t)(2 * T);                      /* :127 */
         DarwinTileRes tr; uint32_t tfl = 0;
+        if (g_tile_log) { if (g_tile_log_n < g_tile_log_cap) g_tile_log[g_tile_log_n] = rq; g_tile_log_n++; }
         int trc = gact_tile(sc, dram, &rq, 1, rule, &tr, NULL, 0, tops, maxops, &tfl);
         if (!trc && rule == GACT_RULE_CLEAN && (tfl & GACT_TILE_LFLAG)) {
             /* two-tier scheme of the product: a flagged clean tile is recomputed with the exact rule */
@@ -533,6 +539,10 @@ static int extend_one(const GactScoring* sc, const char* dram, const DarwinExten
                 steps++;
                 if (steps >= S && d == DARWIN_OP_M) break;
             }
+        }
+        if (g_tile_log && g_tile_log_n <= g_tile_log_cap) {      /* debugging: state after consumption */
+            DarwinTileReq* L = &g_tile_log[g_tile_log_n - 1];
+            L->score_threshold = (uint32_t)len; L->ref_bases_start_addr = cr; L->query_bases_start_addr = cq;
         }
         if (left) {
             while (nl > 0) {                                      /* :336-351 */

@@ -54,6 +54,10 @@ int gact_extend(const GactScoring* sc, const char* dram, const DarwinExtendParam
                 const DarwinAnchor* anchors, int n, const uint64_t* hit_pool,
                 DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes);
 
+/* debugging aid: log every tile request gact_extend issues (cap entries kept, count keeps running) */
+void gact_set_tile_log(DarwinTileReq* buf, int cap);
+int  gact_tile_log_count(void);
+
 /* AlignmentScore (extender.cpp:1161-1200) evaluated on an op string + the sequences it was cut from. */
 int gact_alignment_score(const GactScoring* sc, const char* ref_str, const char* query_str, uint64_t n);
 

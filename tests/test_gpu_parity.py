@@ -96,7 +96,7 @@ def test_upload_chunks_and_odd_addresses(gpu):
         p2.InitializeReadMemory(a, arena[a:b])
     r1, t1 = p1.BatchAlignmentSIMD(req, 1)
     r2, t2 = p2.BatchAlignmentSIMD(req, 1)
-    assert np.array_equal(r1, r2) and np.array_equal(t1, t2)
+    assert tiles_equal(r1, t1, r2, t2) == []      # TB words beyond total_TB_pointers are unspecified
     p1.close()
     p2.close()
 
