@@ -190,7 +190,7 @@ def main():
 
     launches0 = proc.stats().kernel_launches
     for _ in range(warm):
-        proc.BatchAlignmentSIMD_device(d_req.data_ptr(), n, d_res.data_ptr(), d_tb.data_ptr(), tbw)
+        proc.BatchAlignmentSIMD_device(d_req.data_ptr(), n, d_res.data_ptr(), d_tb.data_ptr(), tbw, TILE, TILE)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -198,7 +198,7 @@ def main():
     kernel_ms = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        proc.BatchAlignmentSIMD_device(d_req.data_ptr(), n, d_res.data_ptr(), d_tb.data_ptr(), tbw)
+        proc.BatchAlignmentSIMD_device(d_req.data_ptr(), n, d_res.data_ptr(), d_tb.data_ptr(), tbw, TILE, TILE)
         kernel_ms.append(proc.stats().last_kernel_ms)          # CUDA events on the library's own stream
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3

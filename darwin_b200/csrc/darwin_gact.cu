@@ -12,6 +12,7 @@
 
 #include "gact_common.cuh"
 #include "gact_exact.cuh"
+#include "gact_fast.cuh"
 #include "gact_extend.cuh"
 
 using namespace gact;
@@ -59,28 +60,117 @@ struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568
     }
 };
 
-struct KernelScoring { DevScoring sc; };
+struct KernelScoring { DevScoring sc; FastConst fc; };
 
 __device__ __forceinline__ void load_scoring(const DevScoring& sc, int* ssub) {
     if (threadIdx.x < 25) ssub[threadIdx.x] = sc.sub[threadIdx.x];
     __syncthreads();
 }
 
+// Kernel geometry: K = rows per virtual lane of the packed fast path (gact_fast.cuh); K = 0 -> exact path only.
+template <int K> struct KernelGeom {
+    static constexpr int kWarps = (K == 0) ? kWarpsPerCta : 1;
+    static constexpr size_t kFast = (K == 0) ? 0 : FastGeom<(K == 0 ? 4 : K)>::kSmemBytes;
+    static constexpr size_t kPerWarp = ((kFast > sizeof(ExactSmem) ? kFast : sizeof(ExactSmem)) + 15) & ~(size_t)15;
+    static constexpr size_t kSmem = kPerWarp * kWarps;
+};
+
+struct WarpCtx {
+    const uint8_t* arena;
+    const int* ssub;
+    unsigned char* wsmem;         // this warp's dynamic shared memory (fast view and ExactSmem alias each other)
+    WarpScratch ws;
+    uint32_t n_fast, n_exact, n_rerun;
+};
+
+// One tile for one warp: packed fast path when the tile qualifies, exact path otherwise or when the fast
+// traceback asks for it.  `out` offsets/total and the sink are meaningful in lane 0 only.
+template <int K, class Sink>
+__device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob& t, bool do_traceback,
+                             TileOut& out, Sink& sink) {
+    const int lane = lane_id();
+    out = TileOut{};
+    if (t.Q <= 0 || t.R <= 0) return;                                       // Processor.cpp:177-182
+    const bool se = t.flags & DARWIN_START_END;
+    if (K > 0) {
+        constexpr int KK = (K == 0 ? 4 : K);
+        const FastConst& fc = ks.fc;
+        const bool fast = fc.eligible && do_traceback && se && t.Q <= 64 * KK && t.R <= 64 * KK &&
+                          fc.match * min(t.Q, t.R) <= fc.max_score;
+        if (fast) {
+            FastSmemView<KK> v(cx.wsmem);
+            const bool has_n = stage_sequences(cx.arena, t, v.sref, v.sqry);
+            if (!has_n) {
+                const int score = fast_forward<KK>(fc, v, t.Q, t.R);
+                int rc = FAST_OK;
+                if (lane == 0) {
+                    Sink trial = sink;
+                    TileOut o2{};
+                    rc = fast_traceback<KK>(v, t.Q, t.R, t.max_tb, o2, trial);
+                    if (rc == FAST_OK) { sink = trial; out = o2; }
+                }
+                rc = __shfl_sync(0xffffffffu, rc, 0);
+                if (rc == FAST_OK) {
+                    out.score = score; out.ref_max_pos = t.R - 1; out.query_max_pos = t.Q - 1;
+                    cx.n_fast++;
+                    return;
+                }
+                cx.n_rerun++;
+            }
+            __syncwarp();
+        }
+    }
+    ExactSmem* sm = reinterpret_cast<ExactSmem*>(cx.wsmem);
+    stage_sequences(cx.arena, t, sm->ref, sm->qry);
+    const int go = ks.sc.go, ge = ks.sc.ge, lgo = ks.sc.lgo, lge = ks.sc.lge;
+    if (do_traceback) {
+        if (se) exact_forward<true, true>(cx.ssub, go, ge, lgo, lge, t, sm, cx.ws, out);
+        else    exact_forward<false, true>(cx.ssub, go, ge, lgo, lge, t, sm, cx.ws, out);
+        __syncwarp();
+        if (lane == 0) {
+            const int i = se ? t.Q - 1 : out.query_max_pos, j = se ? t.R - 1 : out.ref_max_pos;
+            exact_traceback(cx.ws.trace, t.Q, t.R, i, j, t.max_tb, out, sink);
+        }
+    } else {
+        if (se) exact_forward<true, false>(cx.ssub, go, ge, lgo, lge, t, sm, cx.ws, out);
+        else    exact_forward<false, false>(cx.ssub, go, ge, lgo, lge, t, sm, cx.ws, out);
+    }
+    cx.n_exact++;
+}
+
+template <int K>
+__device__ __forceinline__ WarpCtx make_ctx(const uint8_t* arena, const int* ssub, unsigned char* dyn,
+                                            uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base) {
+    const int warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * KernelGeom<K>::kWarps + warp;
+    WarpCtx cx;
+    cx.arena = arena; cx.ssub = ssub; cx.wsmem = dyn + (size_t)warp * KernelGeom<K>::kPerWarp;
+    cx.ws = WarpScratch{trace_base + (size_t)gw * trace_stride, bound_base + (size_t)gw * kMaxTile};
+    cx.n_fast = cx.n_exact = cx.n_rerun = 0;
+    return cx;
+}
+
+__device__ __forceinline__ void flush_counters(const WarpCtx& cx, unsigned int* counter) {
+    if (lane_id() == 0) {
+        if (cx.n_fast) atomicAdd(counter + 1, cx.n_fast);
+        if (cx.n_exact) atomicAdd(counter + 2, cx.n_exact);
+        if (cx.n_rerun) atomicAdd(counter + 3, cx.n_rerun);
+    }
+}
+
 // BatchAlignmentSIMD (Processor.cpp:718-762) for n independent tiles: persistent warps pull tiles from a
 // global counter.
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-tiles_exact_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
-                   const DarwinTileReq* __restrict__ req, int n, int do_traceback,
-                   DarwinTileRes* __restrict__ res, uint64_t* __restrict__ tb_words, int tb_words_per_req,
-                   uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base, unsigned int* counter) {
+template <int K>
+__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32)
+tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
+             const DarwinTileReq* __restrict__ req, int n, int do_traceback,
+             DarwinTileRes* __restrict__ res, uint64_t* __restrict__ tb_words, int tb_words_per_req,
+             uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base, unsigned int* counter) {
     __shared__ int ssub[32];
-    __shared__ ExactSmem smem[kWarpsPerCta];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     load_scoring(ks.sc, ssub);
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int gw = blockIdx.x * kWarpsPerCta + warp;
-    ExactSmem* sm = &smem[warp];
-    WarpScratch ws{trace_base + (size_t)gw * trace_stride, bound_base + (size_t)gw * kMaxTile};
-    const int go = ks.sc.go, ge = ks.sc.ge, lgo = ks.sc.lgo, lge = ks.sc.lge;
+    const int lane = lane_id();
+    WarpCtx cx = make_ctx<K>(arena, ssub, dyn_smem, trace_base, trace_stride, bound_base);
 
     for (;;) {
         unsigned int idx = 0;
@@ -91,49 +181,33 @@ tiles_exact_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ Ke
         TileJob t{rq.ref_bases_start_addr, rq.query_bases_start_addr, (int)rq.ref_size, (int)rq.query_size,
                   rq.align_fields, (int)rq.max_tb_steps};
         TileOut out{};
-        const bool se = t.flags & DARWIN_START_END;
-        if (t.Q > 0 && t.R > 0 && t.Q <= kMaxTile && t.R <= kMaxTile) {       // Processor.cpp:177-182
-            stage_sequences(arena, t, sm->ref, sm->qry);
-            if (do_traceback) {
-                if (se) exact_forward<true, true>(ssub, go, ge, lgo, lge, t, sm, ws, out);
-                else    exact_forward<false, true>(ssub, go, ge, lgo, lge, t, sm, ws, out);
-                __syncwarp();
-                if (lane == 0) {
-                    TbWordSink sink{tb_words + (size_t)idx * tb_words_per_req, tb_words_per_req, 0, 0, 0};
-                    const int i = se ? t.Q - 1 : out.query_max_pos, j = se ? t.R - 1 : out.ref_max_pos;
-                    exact_traceback(ws.trace, t.Q, t.R, i, j, t.max_tb, out, sink);
-                    sink.finish();
-                    if (sink.overflow) out.tflags |= 0x80;
-                }
-            } else {
-                if (se) exact_forward<true, false>(ssub, go, ge, lgo, lge, t, sm, ws, out);
-                else    exact_forward<false, false>(ssub, go, ge, lgo, lge, t, sm, ws, out);
-            }
-        }
+        const bool too_big = t.Q > kMaxTile || t.R > kMaxTile;
+        TbWordSink sink{tb_words + (size_t)idx * tb_words_per_req, tb_words_per_req, 0, 0, 0};
+        if (!too_big) process_tile<K>(cx, ks, t, do_traceback != 0, out, sink);
         if (lane == 0) {
+            if (do_traceback) sink.finish();
             DarwinTileRes r;
             r.score = out.score; r.ref_offset = (uint16_t)out.ref_offset; r.query_offset = (uint16_t)out.query_offset;
             r.ref_max_pos = (uint16_t)out.ref_max_pos; r.query_max_pos = (uint16_t)out.query_max_pos;
             r.total_TB_pointers = (uint16_t)out.total; r.index = (uint8_t)rq.index;
-            r.status = (t.Q > kMaxTile || t.R > kMaxTile) ? 1 : ((out.tflags & 0x80) ? 2 : 0);
+            r.status = too_big ? 1 : (sink.overflow ? 2 : 0);
             res[idx] = r;
         }
         __syncwarp();
     }
+    flush_counters(cx, counter);
 }
 
 // extender_body::operator() (extender.cpp:9-1065): persistent warps pull ANCHORS and walk their tiles.
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-extend_exact_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ ExtendArgs ea,
-                    uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base) {
+template <int K>
+__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32)
+extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ ExtendArgs ea,
+              uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base) {
     __shared__ int ssub[32];
-    __shared__ ExactSmem smem[kWarpsPerCta];
+    extern __shared__ __align__(16) unsigned char dyn_smem[];
     load_scoring(ks.sc, ssub);
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int gw = blockIdx.x * kWarpsPerCta + warp;
-    ExactSmem* sm = &smem[warp];
-    WarpScratch ws{trace_base + (size_t)gw * trace_stride, bound_base + (size_t)gw * kMaxTile};
-    const int go = ks.sc.go, ge = ks.sc.ge, lgo = ks.sc.lgo, lge = ks.sc.lge;
+    const int lane = lane_id();
+    WarpCtx cx = make_ctx<K>(ea.arena, ssub, dyn_smem, trace_base, trace_stride, bound_base);
     const int T = ea.T, O = ea.O;
 
     for (;;) {
@@ -153,6 +227,7 @@ extend_exact_kernel(const __grid_constant__ KernelScoring ks, const __grid_const
         uint8_t* const slot = ea.ops + ea.slot_base[idx];
         const uint32_t lcap = ea.slot_left[idx], rcap = ea.slot_size[idx] - lcap;
         uint32_t overflow = 0;
+        const uint32_t rerun0 = cx.n_rerun;
 
         while (!(a.ldone && a.rdone)) {
             const int left = !a.ldone;
@@ -162,31 +237,22 @@ extend_exact_kernel(const __grid_constant__ KernelScoring ks, const __grid_const
             t.max_tb = 2 * T;                                                    // extender.cpp:127
             if (a.large) a.n_large++;
             a.n_tiles++; a.cells += (uint64_t)t.R * (uint64_t)t.Q;
-            TileOut out{};
-            int len = 0;
-            if (t.Q > 0 && t.R > 0) {
-                stage_sequences(ea.arena, t, sm->ref, sm->qry);
-                exact_forward<true, true>(ssub, go, ge, lgo, lge, t, sm, ws, out);
-                __syncwarp();
-            }
-            // consumption (lane 0), then broadcast of the updated offsets
             int crt = T, cqt = T;
             if (a.large && ea.do_overlap == 0) { crt = rt; cqt = qt; }           // extender.cpp:261 / :408
-            uint32_t pk[8] = {a.cr, a.cq, a.rso, a.qso, a.nleft, a.nright, 0u, 0u};
-            if (lane == 0 && t.Q > 0 && t.R > 0) {
-                ConsumeSink sink;
-                sink.cr = a.cr; sink.cq = a.cq; sink.rso = a.rso; sink.qso = a.qso; sink.RL = a.RL; sink.QL = a.QL;
-                sink.left = left; sink.S = min(crt, cqt) - O; sink.steps = 0; sink.pos_in_word = 0; sink.skipping = 0;
-                sink.lptr = slot + lcap - a.nleft; sink.rptr = slot + lcap + a.nright;
-                sink.lroom = lcap; sink.rroom = rcap; sink.nl = a.nleft; sink.nr = a.nright; sink.overflow = 0;
-                exact_traceback(ws.trace, t.Q, t.R, t.Q - 1, t.R - 1, t.max_tb, out, sink);
-                pk[0] = sink.cr; pk[1] = sink.cq; pk[2] = sink.rso; pk[3] = sink.qso; pk[4] = sink.nl; pk[5] = sink.nr;
-                pk[6] = (uint32_t)out.total; pk[7] = out.tflags | (sink.overflow << 8);
-            }
+            ConsumeSink sink;
+            sink.cr = a.cr; sink.cq = a.cq; sink.rso = a.rso; sink.qso = a.qso; sink.RL = a.RL; sink.QL = a.QL;
+            sink.left = left; sink.S = min(crt, cqt) - O; sink.steps = 0; sink.pos_in_word = 0; sink.skipping = 0;
+            sink.lptr = slot + lcap - a.nleft; sink.rptr = slot + lcap + a.nright;
+            sink.lroom = lcap; sink.rroom = rcap; sink.nl = a.nleft; sink.nr = a.nright; sink.overflow = 0;
+            TileOut out{};
+            process_tile<K>(cx, ks, t, true, out, sink);
+            // lane 0 consumed the ops while walking the traceback: broadcast the updated offsets
+            uint32_t pk[8] = {sink.cr, sink.cq, sink.rso, sink.qso, sink.nl, sink.nr, (uint32_t)out.total,
+                              out.tflags | (sink.overflow << 8)};
 #pragma unroll
             for (int k = 0; k < 8; k++) pk[k] = __shfl_sync(0xffffffffu, pk[k], 0);
             a.cr = pk[0]; a.cq = pk[1]; a.rso = pk[2]; a.qso = pk[3]; a.nleft = pk[4]; a.nright = pk[5];
-            len = (int)pk[6];
+            const int len = (int)pk[6];
             if (pk[7] & 1) a.flags |= DARWIN_ALN_LONG_INS_PATH;
             if (pk[7] & 0x100) overflow = 1;
             if (ea.dbg && lane == 0 && a.n_tiles <= 128) {
@@ -195,6 +261,7 @@ extend_exact_kernel(const __grid_constant__ KernelScoring ks, const __grid_const
             }
             after_tile(a, len);
         }
+        if (cx.n_rerun != rerun0) a.flags |= DARWIN_ALN_EXACT_RERUN;
         if (lane == 0) {
             DarwinAlnRes r;
             r.ops_offset = ea.slot_base[idx] + lcap - min(a.nleft, lcap);
@@ -209,6 +276,7 @@ extend_exact_kernel(const __grid_constant__ KernelScoring ks, const __grid_const
         }
         __syncwarp();
     }
+    flush_counters(cx, ea.counter);
 }
 
 // AlignmentScore (extender.cpp:1161-1200) + compaction of the op slots into a dense pool.
@@ -295,7 +363,8 @@ struct DarwinGpu {
     uint8_t* d_arena = nullptr; uint64_t arena_bytes = 0;
     char* h_stage = nullptr; char* d_stage = nullptr; size_t stage_bytes = 0;
     KernelScoring ks{}; bool have_scoring = false;
-    int sm_count = 0, ctas = 0;
+    int sm_count = 0, max_warps = 0;
+    int ctas_tiles[4] = {0, 0, 0, 0}, ctas_extend[4] = {0, 0, 0, 0};   // persistent grid per kernel variant (K = 0,4,5,6)
     uint8_t* d_trace = nullptr; size_t trace_stride = 0; ChainRec* d_bound = nullptr;
     unsigned int* d_counter = nullptr;
     // growable device buffers
@@ -329,13 +398,60 @@ static int grow_host(DarwinGpu* h, int slot, size_t bytes) {
 // per-warp exact-path scratch sized for the largest tile of the call
 static int ensure_scratch(DarwinGpu* h, size_t need) {
     need = (need + 255) & ~(size_t)255;
-    const size_t warps = (size_t)h->ctas * kWarpsPerCta;
+    const size_t warps = (size_t)h->max_warps;
     if (!h->d_bound) CK(cudaMalloc(&h->d_bound, warps * kMaxTile * sizeof(ChainRec)));
     if (need <= h->trace_stride && h->d_trace) return DARWIN_OK;
     if (h->d_trace) cudaFree(h->d_trace);
     h->d_trace = nullptr; h->trace_stride = 0;
     CK(cudaMalloc(&h->d_trace, need * warps));
     h->trace_stride = need;
+    return DARWIN_OK;
+}
+
+
+static int variant_index(int K) { return K == 0 ? 0 : K - 3; }                 // K in {0,4,5,6} -> 0..3
+
+// Smallest fast-path geometry that holds a maxdim x maxdim tile (0 = exact path only).
+static int pick_k(const DarwinGpu* h, int maxdim, int do_traceback) {
+    if (!h->ks.fc.eligible || !do_traceback) return 0;
+    if (maxdim <= 256) return 4;
+    if (maxdim <= 320) return 5;
+    if (maxdim <= 384) return 6;
+    return 0;
+}
+
+template <int K>
+static int configure_variant(DarwinGpu* h) {
+    const size_t smem = KernelGeom<K>::kSmem;
+    const int threads = KernelGeom<K>::kWarps * 32;
+    CK(cudaFuncSetAttribute(tiles_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(extend_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    if (smem > 48 * 1024) {
+        CK(cudaFuncSetAttribute(tiles_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(extend_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    int a = 0, b = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, tiles_kernel<K>, threads, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, extend_kernel<K>, threads, smem));
+    const int cap = h->max_warps / h->sm_count / KernelGeom<K>::kWarps;       // scratch bound
+    a = std::max(1, std::min(a, cap)); b = std::max(1, std::min(b, cap));
+    h->ctas_tiles[variant_index(K)] = h->sm_count * a;                        // persistent grids: multiples of the SM count
+    h->ctas_extend[variant_index(K)] = h->sm_count * b;
+    return DARWIN_OK;
+}
+
+static int configure_kernels(DarwinGpu* h) {
+    int rc;
+    if ((rc = configure_variant<0>(h)) || (rc = configure_variant<4>(h)) || (rc = configure_variant<5>(h)) ||
+        (rc = configure_variant<6>(h))) return rc;
+    return DARWIN_OK;
+}
+
+static int read_counters(DarwinGpu* h) {
+    unsigned int c[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(c, h->d_counter, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stats.tiles_fast += c[1]; h->stats.tiles_exact += c[2]; h->stats.tiles_rerun += c[3];
     return DARWIN_OK;
 }
 
@@ -365,11 +481,9 @@ int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) {
     CK(cudaMallocHost(&h->h_stage, h->stage_bytes));
     CK(cudaMalloc(&h->d_stage, h->stage_bytes));
     CK(cudaMalloc(&h->d_counter, sizeof(unsigned int) * 4));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tiles_exact_kernel, kWarpsPerCta * 32, 0));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    h->ctas = h->sm_count * per_sm;                                            // persistent grid: multiple of the SM count
+    h->max_warps = h->sm_count * 16;                                           // scratch is sized for this many resident warps
+    int rc = configure_kernels(h);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return DARWIN_OK;
 }
@@ -416,6 +530,7 @@ int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s) {
     memcpy(d.tri, t, sizeof(t));
     d.uniform = (AA == CC && AA == GG && AA == TT && AC == AG && AC == AT && AC == CG && AC == CT && AC == GT);
     d.match = AA; d.mismatch = AC; d.subn = N;
+    h->ks.fc = make_fast_const(d);
     h->have_scoring = true;
     return DARWIN_OK;
 }
@@ -444,15 +559,22 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
                         DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR) {
     int rc = ensure_scratch(h, exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)));
     if (rc) return rc;
-    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));
+    const int K = pick_k(h, std::max(maxQ, maxR), do_traceback);
+    const int ctas = h->ctas_tiles[variant_index(K)];
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 4, h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
-    tiles_exact_kernel<<<h->ctas, kWarpsPerCta * 32, 0, h->stream>>>(h->d_arena, h->ks, d_req, n, do_traceback, d_res,
-                                                                    d_tb, tb_words_per_req, h->d_trace, h->trace_stride,
-                                                                    h->d_bound, h->d_counter);
+#define LAUNCH_TILES(KK) tiles_kernel<KK><<<ctas, KernelGeom<KK>::kWarps * 32, KernelGeom<KK>::kSmem, h->stream>>>( \
+        h->d_arena, h->ks, d_req, n, do_traceback, d_res, d_tb, tb_words_per_req, h->d_trace, h->trace_stride, h->d_bound, h->d_counter)
+    switch (K) {
+        case 4: LAUNCH_TILES(4); break;
+        case 5: LAUNCH_TILES(5); break;
+        case 6: LAUNCH_TILES(6); break;
+        default: LAUNCH_TILES(0); break;
+    }
+#undef LAUNCH_TILES
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->stats.kernel_launches++;
-    h->stats.tiles_exact += n;
     return DARWIN_OK;
 }
 
@@ -481,7 +603,7 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
     if (rc) return rc;
     CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
     if (do_traceback) CK(cudaMemcpyAsync(tb_words, h->d_buf[2], tb_b, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if ((rc = read_counters(h))) return rc;
     CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
     h->stats.cells += cells;
     for (int i = 0; i < n; i++) if (res[i].status == 2) { h->err = "tb_words_per_req too small"; return DARWIN_ERR_CAPACITY; }
@@ -489,14 +611,15 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
 }
 
 int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, int n,
-                            void* d_res, void* d_tb_words, int tb_words_per_req) {
+                            void* d_res, void* d_tb_words, int tb_words_per_req, int max_ref_size, int max_query_size) {
     if (!h || n <= 0 || !d_req || !d_res) return DARWIN_ERR_INVALID;
+    if (max_ref_size <= 0 || max_query_size <= 0 || max_ref_size > kMaxTile || max_query_size > kMaxTile) return DARWIN_ERR_INVALID;
     if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
     CK(cudaSetDevice(h->device));
     int rc = launch_tiles(h, do_traceback, (const DarwinTileReq*)d_req, n, (DarwinTileRes*)d_res,
-                          (uint64_t*)d_tb_words, tb_words_per_req, 512, 512);
+                          (uint64_t*)d_tb_words, tb_words_per_req, max_query_size, max_ref_size);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(h->stream));
+    if ((rc = read_counters(h))) return rc;
     CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
     return DARWIN_OK;
 }
@@ -539,7 +662,7 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     CK(cudaMemcpyAsync(h->d_buf[6], size.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     if ((rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(1984, 960), exact_trace_bytes(960, 1984)),
                                          exact_trace_bytes(p->tile_size, p->tile_size))))) return rc;
-    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 4, h->stream));
     ExtendArgs ea;
     ea.arena = h->d_arena; ea.anchors = (const DarwinAnchor*)h->d_buf[0]; ea.hit_pool = (const uint64_t*)h->d_buf[2];
     ea.res = (DarwinAlnRes*)h->d_buf[1]; ea.ops = (uint8_t*)h->d_buf[3];
@@ -548,13 +671,23 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     if (getenv("DARWIN_GPU_DEBUG")) { CK(cudaMalloc(&ea.dbg, (size_t)n * 128 * 8 * 4)); CK(cudaMemset(ea.dbg, 0, (size_t)n * 128 * 8 * 4)); }
     ea.n = n; ea.T = p->tile_size; ea.O = p->tile_overlap; ea.do_overlap = p->do_overlap; ea.counter = h->d_counter;
     CK(cudaEventRecord(h->ev0, h->stream));
-    extend_exact_kernel<<<h->ctas, kWarpsPerCta * 32, 0, h->stream>>>(h->ks, ea, h->d_trace, h->trace_stride, h->d_bound);
+    const int K = pick_k(h, p->tile_size, 1);
+    const int ctas = h->ctas_extend[variant_index(K)];
+#define LAUNCH_EXTEND(KK) extend_kernel<KK><<<ctas, KernelGeom<KK>::kWarps * 32, KernelGeom<KK>::kSmem, h->stream>>>( \
+        h->ks, ea, h->d_trace, h->trace_stride, h->d_bound)
+    switch (K) {
+        case 4: LAUNCH_EXTEND(4); break;
+        case 5: LAUNCH_EXTEND(5); break;
+        case 6: LAUNCH_EXTEND(6); break;
+        default: LAUNCH_EXTEND(0); break;
+    }
+#undef LAUNCH_EXTEND
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->stats.kernel_launches++;
     // first D2H: op counts -> dense offsets (host prefix sum), then score + compaction on the device
     CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if ((rc = read_counters(h))) return rc;
     CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
     std::vector<uint64_t> dense(n);
     uint64_t used = 0; int overflow = 0;
@@ -562,7 +695,7 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
         dense[i] = used;
         if (res[i].flags & DARWIN_ALN_OPS_OVERFLOW) overflow = 1;
         else if (res[i].flags & DARWIN_ALN_EMITTED) used += res[i].n_ops;
-        h->stats.cells += res[i].cells; h->stats.tiles_exact += res[i].n_tiles;
+        h->stats.cells += res[i].cells;
     }
     if (used > ops_pool_bytes) { h->err = "ops_pool too small: need " + std::to_string(used); return DARWIN_ERR_CAPACITY; }
     CK(cudaMemcpyAsync(h->d_buf[7], dense.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));

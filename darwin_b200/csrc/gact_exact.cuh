@@ -23,24 +23,29 @@ struct ExactSmem {                       // per warp
 };
 
 // Stage one tile's sequences into shared memory (Processor.cpp:105-106 and :276-277 index rules).
-__device__ __forceinline__ void stage_sequences(const uint8_t* __restrict__ arena, const TileJob& t,
+// Returns (warp-uniform) whether any staged base is N.
+__device__ __forceinline__ bool stage_sequences(const uint8_t* __restrict__ arena, const TileJob& t,
                                                 uint8_t* sref, uint8_t* sqry) {
     const int lane = lane_id();
     const bool rr = t.flags & DARWIN_REVERSE_REF, cr = t.flags & DARWIN_COMPLEMENT_REF;
     const bool rq = t.flags & DARWIN_REVERSE_QUERY, cq = t.flags & DARWIN_COMPLEMENT_QUERY;
+    uint32_t seen = 0;
     for (int k = lane; k < t.R; k += 32) {
         uint64_t a = rr ? t.ra + (uint64_t)(t.R - 1 - k) : t.ra + (uint64_t)k;
         uint32_t c = arena_code(arena, a);
         if (cr && c < 4) c = 3 - c;
+        seen |= c;
         sref[k] = (uint8_t)c;
     }
     for (int k = lane; k < t.Q; k += 32) {
         uint64_t a = rq ? t.qa + (uint64_t)(t.Q - 1 - k) : t.qa + (uint64_t)k;
         uint32_t c = arena_code(arena, a);
         if (cq && c < 4) c = 3 - c;
+        seen |= c;
         sqry[k] = (uint8_t)c;
     }
-    __syncwarp();
+    const bool has_n = __any_sync(0xffffffffu, seen >= 4u);     // also the warp barrier that publishes the staging
+    return has_n;
 }
 
 // Forward pass.  ssub = 25-entry substitution table in shared memory.

@@ -38,7 +38,7 @@ def load_library():
         L.darwin_gpu_set_scoring.argtypes = [C.c_void_p, C.POINTER(abi.Scoring)]
         L.darwin_gpu_upload.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
         L.darwin_gpu_tiles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
-        L.darwin_gpu_tiles_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.darwin_gpu_tiles_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.darwin_gpu_extend.argtypes = [C.c_void_p, C.POINTER(abi.ExtendParams), C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
         L.darwin_gpu_stats.argtypes = [C.c_void_p, C.POINTER(abi.GpuStats)]
@@ -103,10 +103,12 @@ class Processor:
                                               abi.ptr(tb) if tb is not None else None, int(tb_words_per_req)))
         return res, tb
 
-    def BatchAlignmentSIMD_device(self, d_req, n, d_res, d_tb, tb_words_per_req, do_traceback=1):
+    def BatchAlignmentSIMD_device(self, d_req, n, d_res, d_tb, tb_words_per_req, max_ref_size, max_query_size,
+                                  do_traceback=1):
         """Device-resident variant (bench `value` leg): raw device pointers (ints)."""
         self._check(self.lib.darwin_gpu_tiles_device(self.h, int(do_traceback), C.c_void_p(d_req), int(n),
-                                                     C.c_void_p(d_res), C.c_void_p(d_tb), int(tb_words_per_req)))
+                                                     C.c_void_p(d_res), C.c_void_p(d_tb), int(tb_words_per_req),
+                                                     int(max_ref_size), int(max_query_size)))
 
     # extender_body::operator() (extender.cpp:9-1065) for a batch of anchors
     def extender_body(self, anchors, hit_pool, tile_size=384, tile_overlap=64, do_overlap=0, ops_cap=None):

@@ -146,6 +146,7 @@ typedef struct DarwinGpuStats {
     uint64_t kernel_launches;   /* kernels of this library launched since create */
     uint64_t tiles_fast;        /* tiles finished by the packed fast path */
     uint64_t tiles_exact;       /* tiles (re)computed by the exact path */
+    uint64_t tiles_rerun;       /* fast tiles whose traceback asked for the exact path (subset of tiles_exact) */
     uint64_t cells;             /* DP cells requested (algorithmic) */
     float    last_kernel_ms;    /* CUDA-event time of the last tiles/extend kernel(s) */
     float    reserved;
@@ -182,7 +183,8 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p,
 /* device-resident variants used by bench.py's `value` leg: same work, inputs and
  * outputs stay in HBM (pointers are device pointers of this handle's device). */
 int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, int n,
-                            void* d_res, void* d_tb_words, int tb_words_per_req);
+                            void* d_res, void* d_tb_words, int tb_words_per_req,
+                            int max_ref_size, int max_query_size);
 
 int darwin_gpu_stats(DarwinGpu* h, DarwinGpuStats* out);
 
