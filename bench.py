@@ -194,7 +194,8 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    launches_t0 = proc.stats().kernel_launches
+    st0 = proc.stats()
+    launches_t0 = st0.kernel_launches
     kernel_ms = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -202,7 +203,8 @@ def main():
         kernel_ms.append(proc.stats().last_kernel_ms)          # CUDA events on the library's own stream
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
-    launches = proc.stats().kernel_launches - launches_t0
+    st_end = proc.stats()
+    launches = st_end.kernel_launches - launches_t0
     dev_ms = float(np.sum(kernel_ms))
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -242,14 +244,14 @@ def main():
         int_peak, int_detail = None, None
         try:
             int_detail = proc.int_peak()
-            int_peak = 2.0 * max(int_detail)
+            int_peak = 2.0 * max(int_detail[:3])      # packed s16x2 ops only (alu pipe); IADD3/LOP3/IMAD are reported
         except Exception:
             pass
         per_gpu_gcups = value / world
         roof = {"bound": "int_alu", "achieved": per_gpu_gcups * OPS_PER_CELL, "peak": int_peak,
                 "unit": "Gint-op/s", "frac": (per_gpu_gcups * OPS_PER_CELL / int_peak) if int_peak else None,
                 "traffic": None,
-                "peak_detail_glaneops": dict(zip(["vimnmx_s16x2", "viaddmnmx_s16x2", "vimnmx3_s16x2", "iadd3_lop3"], int_detail)) if int_detail else None,
+                "peak_detail_glaneops": dict(zip(["vimnmx_u16x2", "viaddmnmx_u16x2", "vimnmx3_u16x2", "iadd3", "lop3", "imad"], int_detail)) if int_detail else None,
                 "note": "SURVEY 8(d) integer-pipe roofline: 32 algorithmic int-ops per cell; peak = measured packed "
                         "s16x2 DPX/ALU issue rate (2 cells per lane-op) of this GPU; HBM is not the bound "
                         "(%.3f B/cell algorithmic)" % ((2 * TILE / 2 + 32 + 16 + tbw * 8) / (TILE * TILE)),
@@ -267,7 +269,9 @@ def main():
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps},
-                "gpu_launches": int(launches), "roofline": roof}
+                "gpu_launches": int(launches), "roofline": roof,
+                "tiles": {"fast": int(st_end.tiles_fast - st0.tiles_fast), "exact": int(st_end.tiles_exact - st0.tiles_exact),
+                          "rerun": int(st_end.tiles_rerun - st0.tiles_rerun)}}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_leg(arena, req, args.cpu_seconds)
         print(json.dumps(line))

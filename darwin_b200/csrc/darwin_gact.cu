@@ -328,11 +328,12 @@ __global__ void score_compact_kernel(const uint8_t* __restrict__ arena, const __
     res[k] = r;
 }
 
-// Integer-pipe microbenchmark: 8 independent accumulators per thread, 16 ops per loop trip, no memory traffic.
+// Integer-pipe microbenchmark: 8 accumulators per thread, 16 ops per loop trip, no memory traffic.  Every op takes a
+// second loop-variant operand (the neighbouring accumulator), so no chain of max/min can be folded algebraically.
 template <int KIND>
 __global__ void int_peak_kernel(uint32_t* out, const uint32_t* in, int iters) {
     uint32_t a[8];
-    const uint32_t b = in[0] + threadIdx.x, c = in[1] ^ threadIdx.x;
+    const uint32_t c = in[1] ^ threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 8; k++) a[k] = in[2 + k] + threadIdx.x * (k + 1);
     for (int it = 0; it < iters; it++) {
@@ -340,17 +341,20 @@ __global__ void int_peak_kernel(uint32_t* out, const uint32_t* in, int iters) {
         for (int rep = 0; rep < 2; rep++) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                if (KIND == 0) a[k] = __vmaxs2(a[k], b + rep);
-                else if (KIND == 1) a[k] = __viaddmax_s16x2(a[k], b, c + rep);
-                else if (KIND == 2) a[k] = __vimax3_s16x2(a[k], b, c + rep);
-                else a[k] = (rep ? (a[k] + b + c) : ((a[k] & b) ^ c));
+                const uint32_t o = a[(k + 1) & 7];
+                if (KIND == 0) a[k] = rep ? __vmaxu2(a[k], o) : __vminu2(a[k], o);
+                else if (KIND == 1) a[k] = __viaddmax_u16x2(a[k], o, c);
+                else if (KIND == 2) a[k] = __vimax3_u16x2(a[k], o, c);
+                else if (KIND == 3) a[k] = a[k] + o + c;
+                else if (KIND == 4) a[k] = (a[k] & o) ^ c;
+                else a[k] = a[k] * c + o;
             }
         }
     }
     uint32_t r = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) r ^= a[k];
-    if (r == 0x12345678u) out[0] = r;          // keeps the chain alive without a store in the common case
+    if (r == 0x12345678u) out[0] = r;          // keeps the chains alive without a store in the common case
 }
 
 // =====================================================================================================
@@ -720,7 +724,7 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     return DARWIN_OK;
 }
 
-int darwin_gpu_int_peak(DarwinGpu* h, double out[4]) {
+int darwin_gpu_int_peak(DarwinGpu* h, double out[6]) {
     if (!h || !out) return DARWIN_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     uint32_t host_in[16];
@@ -729,7 +733,7 @@ int darwin_gpu_int_peak(DarwinGpu* h, double out[4]) {
     CK(cudaMalloc(&d, 64 * sizeof(uint32_t)));
     CK(cudaMemcpy(d, host_in, sizeof(host_in), cudaMemcpyHostToDevice));
     const int iters = 4096, blocks = h->sm_count * 8, threads = 256;
-    for (int kind = 0; kind < 4; kind++) {
+    for (int kind = 0; kind < 6; kind++) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; rep++) {
             CK(cudaEventRecord(h->ev0, h->stream));
@@ -737,7 +741,9 @@ int darwin_gpu_int_peak(DarwinGpu* h, double out[4]) {
                 case 0: int_peak_kernel<0><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
                 case 1: int_peak_kernel<1><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
                 case 2: int_peak_kernel<2><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
-                default: int_peak_kernel<3><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                case 3: int_peak_kernel<3><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                case 4: int_peak_kernel<4><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                default: int_peak_kernel<5><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
             }
             CK(cudaGetLastError());
             CK(cudaEventRecord(h->ev1, h->stream));

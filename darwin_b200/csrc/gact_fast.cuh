@@ -26,14 +26,18 @@
 
 namespace gact {
 
-constexpr int kBandHalf = 48;                       // +-rows around the corner diagonal kept in shared memory
+constexpr int kBandHalf = 40;                       // +-steps around the corner diagonal kept per virtual lane
 
+// Band layout: virtual lane v keeps the trace words of the 2*kBandHalf+1 steps centred on the step at which it
+// crosses the corner diagonal, contiguously: word(v, s) = band[v * kLp + t],  t = s - (K+1)*v - c2  in [0, kL).
+// For a cell (i, j), i = K*v + r:  t = j - K*v + c1  -- linear in v and j, so the traceback needs no division.
 template <int K> struct FastGeom {
     static constexpr int kRows  = 64 * K;           // max query rows (and reference columns) of a fast tile
     static constexpr int kSteps = kRows + 63;
-    static constexpr int kNB    = 2 * kBandHalf / (K + 1) + 2;      // band slots (virtual lanes) per step
+    static constexpr int kL     = 2 * kBandHalf + 1;
+    static constexpr int kLp    = kL + (((kL - K - 1) & 1) ? 0 : 1);   // lane stride kLp-(K+1) odd -> conflict-free stores
     static constexpr int kPWords = kRows + 128;     // packed reference pairs P[j + 32] = r[j] | r[j-32] << 16
-    static constexpr size_t kBandWords = (size_t)kSteps * kNB;
+    static constexpr size_t kBandWords = (size_t)64 * kLp;
     static constexpr size_t kSmemBytes = (kBandWords + kPWords) * 4 + 2 * kRows;    // + staged byte sequences
 };
 
@@ -50,10 +54,12 @@ struct FastConst {                                  // packed constants derived 
     int32_t  goa, gofa;   // go*32 * 65537, (go*32 + INS tag) * 65537
     int32_t  gea;         // ge*32 * 65537
     int32_t  lgoa, lgea;  // (lgo*32 + L tag) * 65537, lge*32 * 65537
+    uint32_t geh, lgeh;   // ge*32 and lge*32 as two's-complement halves (operand b of VIADDMNMX.U16x2)
     int32_t  bias;        // B
     int32_t  max_score;   // largest corner score representable: 2047 - B
     int32_t  eligible;    // scoring admits the fast path
     int32_t  match;
+    uint32_t one;         // 1, opaque to the compiler: `x * one + c` stays an IMAD (fma pipe) instead of an ALU add
 };
 
 constexpr uint32_t FT_DEL = 0, FT_INS = 1, FT_DIAG = 2, FT_ZERO = 3, FT_L = 4;
@@ -68,7 +74,7 @@ __host__ inline FastConst make_fast_const(const DevScoring& sc) {
     B += 1;
     f.eligible = sc.uniform && m > 0 && mm < 0 && go <= ge && ge < 0 && lgo <= lge && lge <= 0 && B < 512;
     auto pk = [](int v) { return (uint32_t)(v & 0xFFFF) * 0x00010001u; };
-    f.bias = B; f.match = m; f.max_score = 2047 - B - m;
+    f.bias = B; f.match = m; f.max_score = 2047 - B - m; f.one = 1;
     f.zeroc = pk((B << 5) | (FT_ZERO << 2));
     f.hm_init = pk(((B + mm) << 5) | (FT_DIAG << 2));
     f.e_init = pk((B + go) << 5);
@@ -81,6 +87,7 @@ __host__ inline FastConst make_fast_const(const DevScoring& sc) {
     f.goa = (go * 32) * 65537; f.gofa = (go * 32 + (int)(FT_INS << 2)) * 65537;
     f.gea = (ge * 32) * 65537;
     f.lgoa = (lgo * 32 + (int)(FT_L << 2)) * 65537; f.lgea = (lge * 32) * 65537;
+    f.geh = pk(ge * 32); f.lgeh = pk(lge * 32);
     return f;
 }
 
@@ -98,16 +105,15 @@ template <int K> struct FastSmemView {
     }
 };
 
-// Band addressing shared by the forward pass and the traceback: slot of virtual lane v at step s.
+// Band addressing shared by the forward pass and the traceback.
 template <int K> struct BandMap {
-    int off, c;           // qd(s) = (s + off) / (K+1);  slot = v - qd + c
+    int c1;               // t(i,j) = j - K*v + c1
     __device__ BandMap(int Q, int R) {
-        const int vc = (Q - 1) / K;                   // virtual lane of the corner row
-        // u(s) = s - s_c + (K+1) * v_c with s_c = R - 1 + v_c; +(K+1)*512 keeps the dividend positive
-        off = -(R - 1 + vc) + (K + 1) * vc + (K + 1) * 512;
-        c = 512 + FastGeom<K>::kNB / 2;
+        // virtual lane v crosses the corner diagonal (i - j = Q - R) at its middle row K*v + K/2:
+        // step s_c(v) = (K+1)*v + K/2 - (Q - R); window t = s - s_c(v) + kBandHalf
+        c1 = (Q - R) - K / 2 + kBandHalf;
     }
-    __device__ __forceinline__ int slot(int s, int v) const { return v - (s + off) / (K + 1) + c; }
+    __device__ __forceinline__ int t_of(int j, int v) const { return j - K * v + c1; }
 };
 
 // Forward pass of one tile.  Sequences must already be staged (codes 0..3) in v.sref / v.sqry.
@@ -133,12 +139,20 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
     __syncwarp();
     const BandMap<K> bm(Q, R);
     const int vc = (Q - 1) / K, rc = (Q - 1) - vc * K, sc_step = R - 1 + vc;
+    // scoring constants in registers for the whole tile
+    const uint32_t zeroc = fc.zeroc, pkc32 = fc.pkc32, negc32 = (uint32_t)fc.negc32, diaga = (uint32_t)fc.diaga;
+    const uint32_t goa = (uint32_t)fc.goa, gofa = (uint32_t)fc.gofa, lgoa = (uint32_t)fc.lgoa;
+    const uint32_t geh = fc.geh, lgeh = fc.lgeh, one = fc.one;
     uint32_t sendH = fc.hm_init, sendF = fc.f_top, sendFL = fc.fl_top;   // state below my last row (previous step)
     uint32_t diag_in = fc.hm_init;                                       // Hm(row above, previous column)
     uint32_t corner = 0;
     const int src = (lane + 31) & 31;
     const int steps = R + 63;
     uint32_t rq_next = v.P[32 - lane];                                   // step 0: j = -lane (dummy unless lane 0)
+    // band window of my two virtual lanes: t = s - (K+1)*v + c1 (t(i,j) with j = s - v)
+    int t_lo = -(K + 1) * lane + bm.c1;                                  // at s = 0
+    uint32_t* bp = v.band + lane * G::kLp + t_lo;                        // &band[v_lo * kLp + t_lo]; hi: + 32*(kLp - (K+1))
+    constexpr int kHiOff = 32 * (G::kLp - (K + 1));
 
     for (int s = 0; s < steps; s++) {
         // values from the virtual lane above: rotate by one lane; lane 0 shifts lane 31's low half up and
@@ -158,32 +172,33 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
 #pragma unroll
         for (int r = 0; r < K; r++) {
             const uint32_t x  = rq ^ qq[r];
-            const uint32_t t  = __vminu2(x, 0x00010001u);
-            const uint32_t sb = t * (uint32_t)fc.negc32 + fc.pkc32;
-            const uint32_t hd = __viaddmax_u16x2(d, sb, fc.zeroc);
+            const uint32_t t  = __vminu2(x, 0x00010001u);                // 1 = mismatch, per half
+            const uint32_t sb = t * negc32 + pkc32;                      // IMAD: (match-mismatch)*32 or 0
+            const uint32_t hd = __viaddmax_u16x2(d, sb, zeroc);          // max(Hdiag + s, 0)          :298-299
             const uint32_t h1 = __vimax3_u16x2(hd, E[r], F);
-            const uint32_t Hk = __vmaxu2(h1, __vmaxu2(EL[r], FL));
-            const uint32_t code = (Hk & kMaskT) | ((E[r] | F) & kMaskM);
+            const uint32_t Hk = __vimax3_u16x2(h1, EL[r], FL);           // H with the winner's tag      :300-303
+            const uint32_t em = E[r] | F;
+            const uint32_t code = (Hk & kMaskT) | (em & kMaskM);
             const uint32_t Hc = Hk & kMaskClean;
             d = Hm[r];
-            Hm[r] = Hc + (uint32_t)fc.diaga;
-            const uint32_t Ho = Hc + (uint32_t)fc.goa, HoF = Hc + (uint32_t)fc.gofa, HoL = Hc + (uint32_t)fc.lgoa;
-            E[r]  = __vmaxu2((E[r] | 0x00010001u) + (uint32_t)fc.gea, Ho);
-            F     = __vmaxu2((F | 0x00020002u) + (uint32_t)fc.gea, HoF);
-            EL[r] = __vmaxu2(EL[r] + (uint32_t)fc.lgea, HoL);
-            FL    = __vmaxu2(FL + (uint32_t)fc.lgea, HoL);
+            Hm[r] = Hc * one + diaga;                                    // IMADs: the fma pipe idles otherwise
+            const uint32_t Ho = Hc * one + goa, HoF = Hc * one + gofa, HoL = Hc * one + lgoa;
+            E[r]  = __viaddmax_u16x2(E[r] | 0x00010001u, geh, Ho);       // ties extend                  :336-337,:353
+            F     = __viaddmax_u16x2(F | 0x00020002u, geh, HoF);         //                              :363-364,:369
+            EL[r] = __viaddmax_u16x2(EL[r], lgeh, HoL);                  //                              :339-340
+            FL    = __viaddmax_u16x2(FL, lgeh, HoL);                     //                              :365-366
             if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
-            if (r == rc && s == sc_step) corner = Hc;                    // s, rc warp-uniform: taken at one step only
+        }
+        if (s == sc_step) {                                              // warp-uniform, taken once per tile
+#pragma unroll
+            for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - diaga;
         }
         diag_in = inH;
         sendH = Hm[K - 1]; sendF = F; sendFL = FL;
         // band store: one word per (virtual lane, step): rows 0-2 in bits 0-14, rows 3-5 in bits 16-30
-        const int qd = (s + bm.off) / (K + 1);
-        const int slot_lo = lane - qd + bm.c, slot_hi = slot_lo + 32;
-        if ((unsigned)slot_lo < (unsigned)G::kNB && (unsigned)(s - lane) < (unsigned)R)
-            v.band[s * G::kNB + slot_lo] = __byte_perm(acc0, acc1, 0x5410);
-        if ((unsigned)slot_hi < (unsigned)G::kNB && (unsigned)(s - lane - 32) < (unsigned)R)
-            v.band[s * G::kNB + slot_hi] = __byte_perm(acc0, acc1, 0x7632);
+        if ((unsigned)t_lo < (unsigned)G::kL) bp[0] = __byte_perm(acc0, acc1, 0x5410);
+        if ((unsigned)(t_lo - 32 * (K + 1)) < (unsigned)G::kL) bp[kHiOff] = __byte_perm(acc0, acc1, 0x7632);
+        t_lo++; bp++;
     }
     __syncwarp();
     // corner owner: virtual lane vc -> physical lane vc & 31, half vc >> 5
@@ -202,30 +217,35 @@ __device__ int fast_traceback(const FastSmemView<K>& vw, int Q, int R, int max_t
     const BandMap<K> bm(Q, R);
     int i = Q - 1, j = R - 1;
     int v = i / K, r = i - v * K;
+    int t = bm.t_of(j, v);                       // position inside virtual lane v's window
+    const uint32_t* wp = vw.band + v * G::kLp + t;
+    int sh = (r < 3) ? 5 * r : 16 + 5 * (r - 3); // bit position of row r inside the word
     int is = 0, js = 0, total = 0;
     uint32_t where = FT_DIAG;
+    // moving up one row: same word while r > 0; crossing into virtual lane v-1 moves t by +K and the word by -(kLp - K)
     while (i >= 0 && j >= 0) {
         if (is == max_tb || js == max_tb) break;
-        const int s = j + v;
-        const int slot = bm.slot(s, v);
-        if ((unsigned)slot >= (unsigned)G::kNB) return FAST_BAND;
-        const uint32_t w = vw.band[s * G::kNB + slot];
-        const uint32_t code = (w >> (r < 3 ? 5 * r : 16 + 5 * (r - 3))) & 31u;
+        if ((unsigned)t >= (unsigned)G::kL) return FAST_BAND;
+        const uint32_t code = (*wp >> sh) & 31u;
+        bool up = false, left = false;
         if (where == FT_DIAG) {
             const uint32_t T = code >> 2;
-            if (T == FT_DIAG) {
-                sink(DARWIN_OP_M); total++; i--; j--; is++; js++;
-                if (r == 0) { r = K - 1; v--; } else r--;
-            } else if (T == FT_ZERO) break;
+            if (T == FT_DIAG) { sink(DARWIN_OP_M); total++; is++; js++; up = true; left = true; }
+            else if (T == FT_ZERO) break;
             else if (T == FT_L) return FAST_LFLAG;
             else where = T;                                   // FT_DEL / FT_INS
         } else if (where == FT_DEL) {
-            sink(DARWIN_OP_D); total++; j--; js++;
+            sink(DARWIN_OP_D); total++; js++; left = true;
             where = (code & 1u) ? FT_DEL : FT_DIAG;           // bit 0: E was extended
         } else {
-            sink(DARWIN_OP_I); total++; i--; is++;
-            if (r == 0) { r = K - 1; v--; } else r--;
+            sink(DARWIN_OP_I); total++; is++; up = true;
             where = (code & 2u) ? FT_INS : FT_DIAG;           // bit 1: F was extended
+        }
+        if (left) { j--; t--; wp--; }
+        if (up) {
+            i--;
+            if (r == 0) { r = K - 1; sh = (K - 1 < 3) ? 5 * (K - 1) : 16 + 5 * (K - 1 - 3); t += K; wp -= (G::kLp - K); }
+            else { r--; sh = (r == 2) ? 10 : sh - 5; }
         }
     }
     out.query_offset = is; out.ref_offset = js; out.total = total; out.tflags = 0;

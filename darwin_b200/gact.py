@@ -126,14 +126,14 @@ class Processor:
         return res, ops
 
     def int_peak(self):
-        """Measured issue rates (G lane-ops/s) of VIMNMX.S16x2, VIADDMNMX.S16x2, VIMNMX3.S16x2, IADD3/LOP3."""
-        out = (C.c_double * 4)()
+        """Measured issue rates (G lane-ops/s): VIMNMX.U16x2, VIADDMNMX.U16x2, VIMNMX3.U16x2, IADD3, LOP3, IMAD."""
+        out = (C.c_double * 6)()
         self._check(self.lib.darwin_gpu_int_peak(self.h, out))
         return list(out)
 
     def int_peak_gops(self):
-        """P_int of SURVEY 8(d) in G int16-element-ops/s: best packed lane-op rate x 2 cells per lane-op."""
-        return 2.0 * max(self.int_peak())
+        """P_int of SURVEY 8(d) in G int16-element-ops/s: best PACKED (alu-pipe) lane-op rate x 2 cells per lane-op."""
+        return 2.0 * max(self.int_peak()[:3])
 
     def stats(self):
         s = abi.GpuStats()

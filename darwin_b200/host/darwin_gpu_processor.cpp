@@ -1,0 +1,194 @@
+// See darwin_gpu_processor.h.  Host-side only; all arithmetic of the path runs in libdarwin_gact.so.
+#include "darwin_gpu_processor.h"
+
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace darwin_gpu_host {
+
+static std::vector<DarwinGpu*> g_handles;
+static std::string g_error;
+static uint64_t g_arena_bytes = 4ull * 1024ull * 1024ull * 1024ull;       // DRAM.cpp:8
+
+static void fail(DarwinGpu* h, int rc, const char* what) {
+    g_error = std::string(what) + ": " + (h ? darwin_gpu_last_error(h) : "no handle") + " (" + std::to_string(rc) + ")";
+    throw std::runtime_error(g_error);                                   // no silent CPU fallback
+}
+
+const char* last_error() { return g_error.c_str(); }
+
+DarwinGpu* handle_for_token(size_t token) {
+    if (g_handles.empty()) { g_error = "InitializeProcessor was not called"; throw std::runtime_error(g_error); }
+    return g_handles[token % g_handles.size()];
+}
+
+size_t InitializeProcessor(int threads, int gpus, std::string /*chip_ids*/) {
+    (void)threads;
+    if (gpus < 1) gpus = 1;
+    if (g_DRAM) g_arena_bytes = g_DRAM->size;
+    for (int d = 0; d < gpus; d++) {
+        DarwinGpu* h = nullptr;
+        int rc = darwin_gpu_create(&h, d, g_arena_bytes);
+        if (rc != DARWIN_OK) { if (d == 0) fail(h, rc, "darwin_gpu_create"); break; }
+        g_handles.push_back(h);
+    }
+    return g_handles.size();
+}
+
+void ShutdownProcessor() {
+    for (auto h : g_handles) darwin_gpu_destroy(h);
+    g_handles.clear();
+}
+
+void InitializeScoringParameters(size_t /*token*/, Darwin::AlignmentScoringParams& r,
+                                 Darwin::AlignmentScoringParamsResponse& response) {
+    DarwinScoring s{r.sub_AA, r.sub_AC, r.sub_AG, r.sub_AT, r.sub_CC, r.sub_CG, r.sub_CT, r.sub_GG, r.sub_GT, r.sub_TT,
+                    r.sub_N, r.gap_open, r.gap_extend, r.long_gap_open, r.long_gap_extend};
+    response.status = Darwin::Status::OK;
+    for (auto h : g_handles)                                             // scoring is global state in the reference (Processor.cpp:15-19)
+        if (darwin_gpu_set_scoring(h, &s) != DARWIN_OK) response.status = Darwin::Status::InvalidData;
+}
+
+// sender.cpp:26-44: <= 2048 bytes, 8 ASCII bases per u64, little-endian (main.cpp:131-145)
+static void upload(size_t token, Darwin::InitializeDRAMMessage& m, Darwin::InitializeDRAMMessageResponse& response) {
+    response.status = Darwin::Status::OK;
+    if (m.data.size() * 8 < m.num_bytes) { response.status = Darwin::Status::InvalidData; return; }
+    (void)token;
+    for (auto h : g_handles)                                             // every GPU keeps a replica of the arena
+        if (darwin_gpu_upload(h, m.start_addr, reinterpret_cast<const char*>(m.data.data()), m.num_bytes) != DARWIN_OK)
+            response.status = Darwin::Status::InvalidData;
+}
+void InitializeReferenceMemory(size_t token, char*, Darwin::InitializeDRAMMessage& m, Darwin::InitializeDRAMMessageResponse& r) { upload(token, m, r); }
+void InitializeReadMemory(size_t token, char*, Darwin::InitializeDRAMMessage& m, Darwin::InitializeDRAMMessageResponse& r) { upload(token, m, r); }
+
+void BatchAlignmentSIMD(size_t token, char* /*dram*/, Darwin::BatchAlignmentInputFieldsDRAM& request,
+                        Darwin::BatchAlignmentResultDRAM& result) {
+    DarwinGpu* h = handle_for_token(token);
+    const size_t n = request.requests.size();
+    result.results.resize(n);
+    if (n == 0) return;
+    std::vector<DarwinTileReq> req(n);
+    int max_tb = 1;
+    for (size_t i = 0; i < n; i++) {
+        const auto& r = request.requests[i];
+        req[i] = DarwinTileReq{r.ref_bases_start_addr, r.query_bases_start_addr, r.score_threshold, r.index, r.ref_size,
+                               r.query_size, r.max_tb_steps, r.align_fields, {0, 0, 0}};
+        if (r.max_tb_steps > max_tb) max_tb = r.max_tb_steps;
+    }
+    const int words = max_tb / 16 + 2;
+    std::vector<DarwinTileRes> res(n);
+    std::vector<uint64_t> tb(request.do_traceback ? n * words : 1);
+    int rc = darwin_gpu_tiles(h, request.do_traceback, req.data(), (int)n, res.data(), tb.data(), words);
+    if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_tiles");
+    for (size_t i = 0; i < n; i++) {
+        auto& o = result.results[i];
+        o.index = res[i].index; o.score = (uint32_t)res[i].score;
+        o.ref_offset = res[i].ref_offset; o.query_offset = res[i].query_offset;
+        o.ref_max_pos = res[i].ref_max_pos; o.query_max_pos = res[i].query_max_pos;
+        o.total_TB_pointers = res[i].total_TB_pointers;
+        o.TB_pointers.clear();
+        if (request.do_traceback)
+            o.TB_pointers.assign(tb.begin() + i * words, tb.begin() + i * words + (res[i].total_TB_pointers + 31) / 32);
+    }
+}
+
+void InstallProcessorTable() {
+    g_InitializeScoringParameters = InitializeScoringParameters;
+    g_InitializeReferenceMemory = InitializeReferenceMemory;
+    g_InitializeReadMemory = InitializeReadMemory;
+    g_BatchAlignmentSIMD = BatchAlignmentSIMD;
+}
+
+// ExtendLocations (graph.h:83-91) -> DarwinAnchor (what makeForward/BackwardAlignment look up, extender.cpp:1067-1159)
+static void to_anchor(const ExtendLocations& l, const Read& rd, int strand, std::vector<uint64_t>& pool, DarwinAnchor& a) {
+    a = DarwinAnchor{};
+    a.read_addr = (uint64_t)(rd.seq.data() - g_DRAM->buffer);
+    a.reference_pos = l.reference_pos; a.query_pos = l.query_pos;
+    a.chr_start = Index::chr_coord[l.chr_id]; a.ref_len = Index::chr_len[l.chr_id];
+    a.read_len = (uint32_t)rd.seq.size(); a.read_num = l.read_num; a.chr_id = l.chr_id; a.score = l.score;
+    a.left_hits_off = (uint32_t)pool.size(); a.left_hits_n = (uint32_t)l.left_hit_offsets.size();
+    pool.insert(pool.end(), l.left_hit_offsets.begin(), l.left_hit_offsets.end());
+    a.right_hits_off = (uint32_t)pool.size(); a.right_hits_n = (uint32_t)l.right_hit_offsets.size();
+    pool.insert(pool.end(), l.right_hit_offsets.begin(), l.right_hit_offsets.end());
+    a.strand = (uint8_t)strand;
+}
+
+void gpu_extender_body::operator()(extender_input input, extender_node::output_ports_type& op) {
+    auto& payload = get<0>(input);
+    auto& reads = get<0>(payload);
+    auto& data = get<1>(payload);
+    size_t token = get<1>(input);
+    DarwinGpu* h = handle_for_token(token);
+    extend_data output;
+
+    std::vector<DarwinAnchor> anchors;
+    std::vector<uint64_t> pool;
+    for (int strand = 0; strand < 2; strand++)
+        for (const auto& l : (strand ? data.rcLocations : data.fwLocations)) {
+            anchors.emplace_back();
+            to_anchor(l, reads[l.read_num], strand, pool, anchors.back());
+        }
+    const int n = (int)anchors.size();
+    if (n > 0) {
+        // the reads of this batch must be resident: upload them (the software reference reads g_DRAM directly)
+        for (const auto& rd : reads) {
+            const uint64_t at = (uint64_t)(rd.seq.data() - g_DRAM->buffer);
+            int rc = darwin_gpu_upload(h, at, rd.seq.data(), rd.seq.size());
+            if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_upload(read)");
+        }
+        DarwinExtendParams prm{cfg.tile_size, cfg.tile_overlap, cfg.do_overlap, 0};
+        std::vector<DarwinAlnRes> res(n);
+        uint64_t cap = 65536;
+        for (const auto& a : anchors) cap += 3ull * a.read_len;
+        std::vector<uint8_t> ops(cap);
+        int rc = darwin_gpu_extend(h, &prm, anchors.data(), n, pool.data(), pool.size(), res.data(), ops.data(), cap);
+        if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_extend");
+        for (int k = 0; k < n; k++) {
+            const DarwinAlnRes& r = res[k];
+            if (!(r.flags & DARWIN_ALN_EMITTED)) continue;
+            if (r.flags & DARWIN_ALN_OPS_OVERFLOW) fail(h, DARWIN_ERR_CAPACITY, "op string overflow");
+            const DarwinAnchor& a = anchors[k];
+            const Read& rd = reads[a.read_num];
+            const char* qchars = a.strand ? rd.rc_seq.data() : rd.seq.data();        // extender.cpp:243 / :758
+            ExtendAlignments e;
+            e.read_num = a.read_num; e.chr_id = a.chr_id;
+            e.reference_start_offset = r.reference_start_offset; e.reference_end_offset = r.reference_end_offset;
+            e.query_start_offset = r.query_start_offset; e.query_end_offset = r.query_end_offset;
+            e.curr_reference_offset = r.reference_end_offset + 1; e.curr_query_offset = r.query_end_offset + 1;
+            e.reference_start_addr = a.chr_start; e.query_start_addr = (uint32_t)a.read_addr;
+            e.reference_length = a.ref_len; e.query_length = a.read_len;
+            e.left_extension_done = 1; e.right_extension_done = 1;
+            e.used_large_tile = false; e.do_print = true; e.strand = a.strand ? '-' : '+';
+            e.score = r.score; e.chain_score = 0;
+            // gapped strings from the op string (extender.cpp:287-323 / :434-458)
+            e.aligned_reference_str.resize(r.n_ops); e.aligned_query_str.resize(r.n_ops);
+            const uint8_t* o = ops.data() + r.ops_offset;
+            uint32_t cr = a.reference_pos - a.chr_start, cq = a.query_pos;
+            for (int64_t p = (int64_t)r.n_left_ops - 1; p >= 0; p--) {
+                const uint8_t d = o[p];
+                e.aligned_reference_str[p] = (d == DARWIN_OP_I) ? '-' : g_DRAM->buffer[a.chr_start + cr];
+                e.aligned_query_str[p] = (d == DARWIN_OP_D) ? '-' : qchars[cq];
+                if (d != DARWIN_OP_I && cr > 0) cr--;
+                if (d != DARWIN_OP_D && cq > 0) cq--;
+            }
+            cr = a.reference_pos - a.chr_start + 1; cq = a.query_pos + 1;
+            for (uint32_t p = r.n_left_ops; p < r.n_ops; p++) {
+                const uint8_t d = o[p];
+                e.aligned_reference_str[p] = (d == DARWIN_OP_I) ? '-' : g_DRAM->buffer[a.chr_start + cr];
+                e.aligned_query_str[p] = (d == DARWIN_OP_D) ? '-' : qchars[cq];
+                if (d != DARWIN_OP_I && cr < a.ref_len) cr++;
+                if (d != DARWIN_OP_D && cq < a.read_len) cq++;
+            }
+            output.extend_alignments.push_back(e);
+            extender_body::num_extend_tiles += (int)r.n_tiles;
+            extender_body::num_active_tiles += (int)r.n_tiles;
+            extender_body::num_large_tiles += (int)r.n_large_tiles;
+        }
+    }
+    get<1>(op).try_put(token);                                                        // extender.cpp:1062-1063
+    get<0>(op).try_put(printer_input(printer_payload(reads, output), token));
+}
+
+} // namespace darwin_gpu_host

@@ -1,0 +1,43 @@
+// C++ host adapter: the reference's own Processor / extender signatures on top of the C-ABI
+// (include/darwin_gpu.h).  A maintainer of yatisht/darwin adds this file + darwin_gpu_processor.cpp to the
+// build, links libdarwin_gact.so and points the g_* table at these functions.
+//
+// Compiles against the reference's headers (software/graph.h, Processor.h and the Bond-generated
+// Darwin_reflection.h); nothing here is needed by the CUDA library itself.
+#pragma once
+#include "graph.h"               // reference: software/graph.h
+#include "darwin_gpu.h"          // include/darwin_gpu.h
+
+namespace darwin_gpu_host {
+
+// == InitializeProcessor_ptr (software/Processor.h:50): one GPU handle per token (token -> device round-robin).
+// `fpgas` is read as the number of GPUs to use (params.cfg [FPGA] num_fpgas), `chip_ids` is ignored.
+// Returns the number of processors created.  arena_bytes defaults to the reference's 4 GiB arena (DRAM.cpp:8).
+size_t InitializeProcessor(int threads, int gpus, std::string chip_ids);
+void   ShutdownProcessor();
+
+// == the g_* table entries (software/Processor.h:51-55, defaults at Processor.cpp:1063-1069)
+void InitializeScoringParameters(size_t token, Darwin::AlignmentScoringParams& request,
+                                 Darwin::AlignmentScoringParamsResponse& response);
+void InitializeReferenceMemory(size_t token, char* dram, Darwin::InitializeDRAMMessage& request,
+                               Darwin::InitializeDRAMMessageResponse& response);
+void InitializeReadMemory(size_t token, char* dram, Darwin::InitializeDRAMMessage& request,
+                          Darwin::InitializeDRAMMessageResponse& response);
+void BatchAlignmentSIMD(size_t token, char* dram, Darwin::BatchAlignmentInputFieldsDRAM& request,
+                        Darwin::BatchAlignmentResultDRAM& result);
+
+// == extender_body (software/graph.h:219-229, extender.cpp:9-1065): same input/output ports; all anchors of the
+// batch go to the GPU in one darwin_gpu_extend call, ExtendAlignments (gapped strings, offsets, score) are rebuilt
+// from the op strings.  Output order: forward-strand anchors in input order, then reverse-strand (the printer
+// re-sorts by read and score, printer.cpp:18-21).
+struct gpu_extender_body {
+    void operator()(extender_input input, extender_node::output_ports_type& op);
+};
+
+// install the functions above into the reference's table (g_InitializeScoringParameters, ...).
+void InstallProcessorTable();
+
+DarwinGpu* handle_for_token(size_t token);
+const char* last_error();
+
+} // namespace darwin_gpu_host

@@ -188,10 +188,11 @@ int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, i
 
 int darwin_gpu_stats(DarwinGpu* h, DarwinGpuStats* out);
 
-/* Roofline denominator: measured issue rate, in 1e9 32-bit lane-ops per second, of dependent-free
- * packed-int16 integer instructions on this GPU: out[0] VIMNMX.S16x2, out[1] VIADDMNMX.S16x2, out[2] VIMNMX3.S16x2,
- * out[3] IADD3/LOP3 mix.  Each lane-op updates two int16 cells. */
-int darwin_gpu_int_peak(DarwinGpu* h, double out_glaneops[4]);
+/* Roofline denominator: measured issue rate, in 1e9 32-bit lane-ops per second, of packed-int16 /
+ * integer instructions on this GPU (8 independent chains per thread, operands all loop-variant):
+ * out[0] VIMNMX.U16x2 (2-input min/max), out[1] VIADDMNMX.U16x2, out[2] VIMNMX3.U16x2, out[3] IADD3, out[4] LOP3,
+ * out[5] IMAD (fma pipe).  Each packed lane-op updates two int16 cells. */
+int darwin_gpu_int_peak(DarwinGpu* h, double out_glaneops[6]);
 const char* darwin_gpu_last_error(DarwinGpu* h);
 const char* darwin_gpu_version(void);
 
