@@ -365,7 +365,10 @@ struct DarwinGpu {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint8_t* d_arena = nullptr; uint64_t arena_bytes = 0;
-    char* h_stage = nullptr; char* d_stage = nullptr; size_t stage_bytes = 0;
+    char* h_stage[2] = {nullptr, nullptr}; char* d_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0;
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;         // D2H of finished chunks overlaps the next chunk's kernel
+    cudaEvent_t ev_chunk[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     KernelScoring ks{}; bool have_scoring = false;
     int sm_count = 0, max_warps = 0;
     int ctas_tiles[4] = {0, 0, 0, 0}, ctas_extend[4] = {0, 0, 0, 0};   // persistent grid per kernel variant (K = 0,4,5,6)
@@ -482,8 +485,14 @@ int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) {
     CK(cudaMalloc(&h->d_arena, packed));
     CK(cudaMemsetAsync(h->d_arena, 0x44, packed, h->stream));                  // all 'N' (Index.cpp:12 pads with 'N')
     h->stage_bytes = 32u << 20;
-    CK(cudaMallocHost(&h->h_stage, h->stage_bytes));
-    CK(cudaMalloc(&h->d_stage, h->stage_bytes));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; b++) {
+        CK(cudaMallocHost(&h->h_stage[b], h->stage_bytes));
+        CK(cudaMalloc(&h->d_stage[b], h->stage_bytes));
+        CK(cudaEventCreateWithFlags(&h->ev_stage[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_chunk[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
+    }
     CK(cudaMalloc(&h->d_counter, sizeof(unsigned int) * 4));
     h->max_warps = h->sm_count * 16;                                           // scratch is sized for this many resident warps
     int rc = configure_kernels(h);
@@ -501,8 +510,14 @@ int darwin_gpu_destroy(DarwinGpu* h) {
     if (h->d_trace) cudaFree(h->d_trace);
     if (h->d_bound) cudaFree(h->d_bound);
     if (h->d_counter) cudaFree(h->d_counter);
-    if (h->d_stage) cudaFree(h->d_stage);
-    if (h->h_stage) cudaFreeHost(h->h_stage);
+    for (int b = 0; b < 2; b++) {
+        if (h->d_stage[b]) cudaFree(h->d_stage[b]);
+        if (h->h_stage[b]) cudaFreeHost(h->h_stage[b]);
+        if (h->ev_stage[b]) cudaEventDestroy(h->ev_stage[b]);
+        if (h->ev_chunk[b]) cudaEventDestroy(h->ev_chunk[b]);
+        if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
+    }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->d_arena) cudaFree(h->d_arena);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -539,23 +554,36 @@ int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s) {
     return DARWIN_OK;
 }
 
+// true when `p` is page-locked host memory CUDA can DMA from/to directly
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint64_t n) {
     if (!h || (!ascii && n)) return DARWIN_ERR_INVALID;
     if (arena_addr + n > h->arena_bytes) { h->err = "upload beyond arena"; return DARWIN_ERR_INVALID; }
+    if (n == 0) return DARWIN_OK;
     CK(cudaSetDevice(h->device));
+    const bool pinned = is_pinned(ascii);
     uint64_t done = 0;
-    while (done < n) {
+    for (int c = 0; done < n; c++) {
+        const int b = c & 1;
         const uint64_t chunk = std::min<uint64_t>(n - done, h->stage_bytes);
-        memcpy(h->h_stage, ascii + done, chunk);
-        CK(cudaMemcpyAsync(h->d_stage, h->h_stage, chunk, cudaMemcpyHostToDevice, h->stream));
+        const char* src = ascii + done;
+        if (c >= 2) CK(cudaEventSynchronize(h->ev_stage[b]));       // staging buffer b is free again
+        if (!pinned) { memcpy(h->h_stage[b], src, chunk); src = h->h_stage[b]; }   // overlaps the previous chunk's DMA
+        CK(cudaMemcpyAsync(h->d_stage[b], src, chunk, cudaMemcpyHostToDevice, h->stream));
         const uint64_t a = arena_addr + done;
         const uint64_t nbytes = ((a + chunk - 1) >> 1) - (a >> 1) + 1;
-        pack_arena_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(h->d_arena, h->d_stage, a, chunk);
-        h->stats.kernel_launches++;
+        pack_arena_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(h->d_arena, h->d_stage[b], a, chunk);
         CK(cudaGetLastError());
-        CK(cudaStreamSynchronize(h->stream));      // the pinned staging buffer is reused by the next chunk
+        CK(cudaEventRecord(h->ev_stage[b], h->stream));
+        h->stats.kernel_launches++;
         done += chunk;
     }
+    CK(cudaStreamSynchronize(h->stream));                            // synchronous like the reference's memcpy into g_DRAM
     return DARWIN_OK;
 }
 
@@ -565,8 +593,7 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
     if (rc) return rc;
     const int K = pick_k(h, std::max(maxQ, maxR), do_traceback);
     const int ctas = h->ctas_tiles[variant_index(K)];
-    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 4, h->stream));
-    CK(cudaEventRecord(h->ev0, h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));      // queue head; [1..3] accumulate
 #define LAUNCH_TILES(KK) tiles_kernel<KK><<<ctas, KernelGeom<KK>::kWarps * 32, KernelGeom<KK>::kSmem, h->stream>>>( \
         h->d_arena, h->ks, d_req, n, do_traceback, d_res, d_tb, tb_words_per_req, h->d_trace, h->trace_stride, h->d_bound, h->d_counter)
     switch (K) {
@@ -577,7 +604,6 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
     }
 #undef LAUNCH_TILES
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev1, h->stream));
     h->stats.kernel_launches++;
     return DARWIN_OK;
 }
@@ -598,15 +624,46 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
         if (re > h->arena_bytes || qe > h->arena_bytes) { h->err = "tile outside arena"; return DARWIN_ERR_INVALID; }
     }
     const size_t req_b = (size_t)n * sizeof(DarwinTileReq), res_b = (size_t)n * sizeof(DarwinTileRes);
-    const size_t tb_b = do_traceback ? (size_t)n * tb_words_per_req * sizeof(uint64_t) : 0;
+    const size_t tb_row = do_traceback ? (size_t)tb_words_per_req * sizeof(uint64_t) : 0;
     int rc;
-    if ((rc = grow_dev(h, 0, req_b)) || (rc = grow_dev(h, 1, res_b)) || (rc = grow_dev(h, 2, tb_b + 8))) return rc;
+    if ((rc = grow_dev(h, 0, req_b)) || (rc = grow_dev(h, 1, res_b)) || (rc = grow_dev(h, 2, tb_row * n + 8))) return rc;
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 4, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[0], req, req_b, cudaMemcpyHostToDevice, h->stream));
-    rc = launch_tiles(h, do_traceback, (const DarwinTileReq*)h->d_buf[0], n, (DarwinTileRes*)h->d_buf[1],
-                      (uint64_t*)h->d_buf[2], tb_words_per_req, maxQ, maxR);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
-    if (do_traceback) CK(cudaMemcpyAsync(tb_words, h->d_buf[2], tb_b, cudaMemcpyDeviceToHost, h->stream));
+    // Chunked pipeline: kernel(c+1) on the compute stream overlaps the D2H of chunk c on the copy stream.  Page-locked
+    // caller buffers receive the DMA directly; pageable ones go through the two pinned staging buffers.
+    const bool pin_res = is_pinned(res), pin_tb = !do_traceback || is_pinned(tb_words);
+    const size_t per_tile = sizeof(DarwinTileRes) + tb_row;
+    int chunk = (pin_res && pin_tb) ? 131072 : (int)std::max<size_t>(1024, h->stage_bytes / per_tile);
+    chunk = std::min(chunk, n);
+    const int nchunks = (n + chunk - 1) / chunk;
+    CK(cudaEventRecord(h->ev0, h->stream));
+    for (int c = 0; c <= nchunks; c++) {
+        if (c < nchunks) {
+            const int lo = c * chunk, cnt = std::min(chunk, n - lo), b = c & 1;
+            rc = launch_tiles(h, do_traceback, (const DarwinTileReq*)h->d_buf[0] + lo, cnt, (DarwinTileRes*)h->d_buf[1] + lo,
+                              (uint64_t*)h->d_buf[2] + (size_t)lo * tb_words_per_req, tb_words_per_req, maxQ, maxR);
+            if (rc) return rc;
+            CK(cudaEventRecord(h->ev_chunk[b], h->stream));
+        }
+        if (c > 0) {                                                   // drain chunk c-1
+            const int p = c - 1, lo = p * chunk, cnt = std::min(chunk, n - lo), b = p & 1;
+            CK(cudaStreamWaitEvent(h->copy_stream, h->ev_chunk[b], 0));
+            char* st = h->h_stage[b];
+            void* dst_res = pin_res ? (void*)(res + lo) : (void*)st;
+            void* dst_tb = pin_tb ? (void*)(tb_words + (size_t)lo * tb_words_per_req) : (void*)(st + (size_t)cnt * sizeof(DarwinTileRes));
+            CK(cudaMemcpyAsync(dst_res, (DarwinTileRes*)h->d_buf[1] + lo, (size_t)cnt * sizeof(DarwinTileRes), cudaMemcpyDeviceToHost, h->copy_stream));
+            if (do_traceback)
+                CK(cudaMemcpyAsync(dst_tb, (uint64_t*)h->d_buf[2] + (size_t)lo * tb_words_per_req, tb_row * cnt, cudaMemcpyDeviceToHost, h->copy_stream));
+            CK(cudaEventRecord(h->ev_copied[b], h->copy_stream));
+            if (!(pin_res && pin_tb)) {                                // host copy out of the staging buffer (overlaps the running kernel)
+                CK(cudaEventSynchronize(h->ev_copied[b]));
+                if (!pin_res) memcpy(res + lo, st, (size_t)cnt * sizeof(DarwinTileRes));
+                if (do_traceback && !pin_tb) memcpy(tb_words + (size_t)lo * tb_words_per_req, st + (size_t)cnt * sizeof(DarwinTileRes), tb_row * cnt);
+            }
+        }
+    }
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaStreamSynchronize(h->copy_stream));
     if ((rc = read_counters(h))) return rc;
     CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
     h->stats.cells += cells;
@@ -620,9 +677,12 @@ int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, i
     if (max_ref_size <= 0 || max_query_size <= 0 || max_ref_size > kMaxTile || max_query_size > kMaxTile) return DARWIN_ERR_INVALID;
     if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
     CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 4, h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
     int rc = launch_tiles(h, do_traceback, (const DarwinTileReq*)d_req, n, (DarwinTileRes*)d_res,
                           (uint64_t*)d_tb_words, tb_words_per_req, max_query_size, max_ref_size);
     if (rc) return rc;
+    CK(cudaEventRecord(h->ev1, h->stream));
     if ((rc = read_counters(h))) return rc;
     CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
     return DARWIN_OK;

@@ -86,19 +86,27 @@ class Processor:
 
     # g_InitializeReferenceMemory / g_InitializeReadMemory (Processor.cpp:82-85, sender.cpp:4-97)
     def InitializeReferenceMemory(self, arena_addr, ascii_bytes):
-        a = np.ascontiguousarray(np.frombuffer(ascii_bytes, np.uint8) if not isinstance(ascii_bytes, np.ndarray) else ascii_bytes)
+        a = ascii_bytes if isinstance(ascii_bytes, np.ndarray) else np.frombuffer(ascii_bytes, np.uint8)
+        a = np.ascontiguousarray(a)
         self._check(self.lib.darwin_gpu_upload(self.h, C.c_uint64(int(arena_addr)), abi.ptr(a), C.c_uint64(a.size)))
 
     InitializeReadMemory = InitializeReferenceMemory
 
     # g_BatchAlignmentSIMD (Processor.cpp:718-762)
-    def BatchAlignmentSIMD(self, requests, do_traceback=1, tb_words_per_req=None):
-        req = np.ascontiguousarray(requests, dtype=abi.TILE_REQ)
+    def BatchAlignmentSIMD(self, requests, do_traceback=1, tb_words_per_req=None, out=None):
+        """`out=(res, tb)` lets the caller supply (page-locked) result buffers; otherwise they are allocated."""
+        req = requests if (isinstance(requests, np.ndarray) and requests.dtype == abi.TILE_REQ and
+                           requests.flags["C_CONTIGUOUS"]) else np.ascontiguousarray(requests, dtype=abi.TILE_REQ)
         n = len(req)
-        res = np.zeros(n, abi.TILE_RES)
         if tb_words_per_req is None:
             tb_words_per_req = (int(req["max_tb_steps"].max()) // 16 + 2) if n else 1
-        tb = np.zeros((n, tb_words_per_req), np.uint64) if do_traceback else None
+        if out is not None:
+            res, tb = out
+            assert res.dtype == abi.TILE_RES and len(res) >= n
+            assert (not do_traceback) or (tb.dtype == np.uint64 and tb.shape[0] >= n and tb.shape[1] == tb_words_per_req)
+        else:
+            res = np.empty(n, abi.TILE_RES)
+            tb = np.empty((n, tb_words_per_req), np.uint64) if do_traceback else None
         self._check(self.lib.darwin_gpu_tiles(self.h, int(do_traceback), abi.ptr(req), n, abi.ptr(res),
                                               abi.ptr(tb) if tb is not None else None, int(tb_words_per_req)))
         return res, tb
