@@ -445,3 +445,102 @@ int dref_num_chr(void) { return (int)Index::chr_id.size(); }
 int dref_hw_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
 } // extern "C"
+
+// ---- drop-in check: the reference pipeline with the GPU library swapped in through the host adapter ----------
+// (darwin_b200/host/darwin_gpu_processor.cpp).  Built only into libdarwin_ref_gpu.so.
+#ifdef DREF_WITH_GPU
+#include "../darwin_b200/host/darwin_gpu_processor.h"
+#include <algorithm>
+
+// software defaults of the reference (external linkage in Processor.cpp:48,:82; not declared in Processor.h)
+void InitializeScoringParams(size_t token, Darwin::AlignmentScoringParams& request, Darwin::AlignmentScoringParamsResponse& response);
+void InitializeMemory(size_t token, char* dram, Darwin::InitializeDRAMMessage& request, Darwin::InitializeDRAMMessageResponse& response);
+
+static Darwin::AlignmentScoringParams cfg_params() {
+    Darwin::AlignmentScoringParams p;
+    p.sub_AA = cfg.gact_sub_mat[0]; p.sub_AC = cfg.gact_sub_mat[1]; p.sub_AG = cfg.gact_sub_mat[2]; p.sub_AT = cfg.gact_sub_mat[3];
+    p.sub_CC = cfg.gact_sub_mat[4]; p.sub_CG = cfg.gact_sub_mat[5]; p.sub_CT = cfg.gact_sub_mat[6];
+    p.sub_GG = cfg.gact_sub_mat[7]; p.sub_GT = cfg.gact_sub_mat[8]; p.sub_TT = cfg.gact_sub_mat[9]; p.sub_N = cfg.gact_sub_mat[10];
+    p.gap_open = cfg.gap_open; p.gap_extend = cfg.gap_extend; p.long_gap_open = cfg.long_gap_open; p.long_gap_extend = cfg.long_gap_extend;
+    return p;
+}
+
+extern "C" {
+
+// what main() would do once: create the GPU processors, install the g_* table, push the
+// scoring and the arena (reference + reads) through the reference's own upload messages (sender.cpp chunking).
+int dref_gpu_init(int gpus) {
+    try {
+        if (darwin_gpu_host::InitializeProcessor(cfg.num_threads, gpus, "") == 0) return -1;
+        darwin_gpu_host::InstallProcessorTable();
+        Darwin::AlignmentScoringParams p = cfg_params();
+        Darwin::AlignmentScoringParamsResponse resp;
+        g_InitializeScoringParameters(0, p, resp);
+        if (resp.status != Darwin::Status::OK) return -2;
+        // sender.cpp:26-44: 2048-byte, 128-aligned messages, 8 bases per u64
+        const uint64_t total = g_DRAM->bufferPosition;
+        for (uint64_t at = 0; at < total; at += MAX_CHAR_TO_SEND) {
+            uint64_t nb = std::min<uint64_t>(MAX_CHAR_TO_SEND, total - at);
+            if (nb % 8) nb += 8 - nb % 8;
+            Darwin::InitializeDRAMMessage m; Darwin::InitializeDRAMMessageResponse r;
+            m.start_addr = at; m.num_bytes = (uint16_t)nb; m.data.resize(nb / 8);
+            memcpy(m.data.data(), g_DRAM->buffer + at, nb);
+            g_InitializeReferenceMemory(0, g_DRAM->buffer, m, r);
+            if (r.status != Darwin::Status::OK) return -3;
+        }
+    } catch (const std::exception& e) { fprintf(stderr, "dref_gpu_init: %s\n", e.what()); return -4; }
+    return 0;
+}
+
+void dref_gpu_shutdown(void) {
+    darwin_gpu_host::ShutdownProcessor();
+}
+
+// seeder -> filter -> extender for reads [first, first+count); use_gpu selects gpu_extender_body (the filter always
+// goes through g_BatchAlignmentSIMD, i.e. through the GPU once dref_gpu_init has installed the table).
+// Writes one canonical text line per alignment, sorted; returns the number of alignments or <0.
+int dref_pipeline(int first, int count, int use_gpu, char* out, uint64_t cap) {
+    try {
+        reader_output reads(g_reads.begin() + first, g_reads.begin() + first + count);
+        seeder_input sin(reads, 0);
+        filter_input fin = seeder_body()(sin);
+        extender_input ein = filter_body()(fin);
+        extender_node::output_ports_type ports;
+        if (getenv("DREF_DEBUG")) fprintf(stderr, "dref_pipeline: %zu fw + %zu rc anchors\n", std::get<1>(std::get<0>(ein)).fwLocations.size(), std::get<1>(std::get<0>(ein)).rcLocations.size());
+        if (use_gpu) darwin_gpu_host::gpu_extender_body()(ein, ports);
+        else extender_body()(ein, ports);
+        if (getenv("DREF_DEBUG")) fprintf(stderr, "dref_pipeline: extender done\n");
+        auto& al = std::get<1>(std::get<0>(std::get<0>(ports).items[0])).extend_alignments;
+        std::vector<std::string> lines;
+        if (getenv("DREF_DEBUG")) fprintf(stderr, "dref_pipeline: %zu alignments\n", al.size());
+        for (auto& e : al) {
+            if (getenv("DREF_DEBUG")) fprintf(stderr, "  aln read %d chr %d len %zu %zu\n", e.read_num, e.chr_id, e.aligned_reference_str.size(), e.aligned_query_str.size());
+            std::string o = std::to_string(e.read_num) + " " + std::to_string(e.chr_id) + " " + std::string(1, e.strand) + " " +
+                            std::to_string(e.reference_start_offset) + " " + std::to_string(e.reference_end_offset) + " " +
+                            std::to_string(e.query_start_offset) + " " + std::to_string(e.query_end_offset) + " " +
+                            std::to_string(e.score) + " " + e.aligned_reference_str + " " + e.aligned_query_str;
+            lines.push_back(o);
+        }
+        std::sort(lines.begin(), lines.end());
+        if (getenv("DREF_DEBUG")) fprintf(stderr, "dref_pipeline: %zu lines, cap %llu out %p\n", lines.size(), (unsigned long long)cap, (void*)out);
+        uint64_t pos = 0;
+        for (auto& l : lines) {
+            if (pos + l.size() + 2 > cap) return -2;
+            memcpy(out + pos, l.data(), l.size()); pos += l.size(); out[pos++] = '\n';
+        }
+        out[pos] = 0;
+        return (int)lines.size();
+    } catch (const std::exception& e) { fprintf(stderr, "dref_pipeline: %s\n", e.what()); return -1; }
+}
+
+// back to the software Processor (the reference's defaults, Processor.cpp:1063-1069)
+void dref_use_cpu_table(void) {
+    g_InitializeScoringParameters = InitializeScoringParams;
+    g_InitializeReferenceMemory = InitializeMemory; g_InitializeReadMemory = InitializeMemory;
+    g_BatchAlignmentSIMD = BatchAlignmentSIMD;
+    Darwin::AlignmentScoringParams p = cfg_params(); Darwin::AlignmentScoringParamsResponse resp;
+    g_InitializeScoringParameters(0, p, resp);
+}
+
+} // extern "C"
+#endif

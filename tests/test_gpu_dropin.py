@@ -1,0 +1,55 @@
+"""GPU: the reference's own pipeline (its seeder and filter, unmodified) with libdarwin_gact.so swapped in through the
+C++ host adapter (darwin_b200/host/): g_BatchAlignmentSIMD -> darwin_gpu_tiles (first-tile filter),
+extender_body -> gpu_extender_body -> darwin_gpu_extend.  The ExtendAlignments (offsets, strand, AlignmentScore and the
+gapped strings) must equal those of the untouched CPU pipeline."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from darwin_b200 import abi, synth
+
+pytestmark = pytest.mark.gpu
+LIB = os.path.join(os.path.dirname(os.path.abspath(oracle.__file__)), "_ref", "libdarwin_ref_gpu.so")
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libdarwin_ref_gpu.so not built (needs /root/reference at build time)")
+def test_reference_pipeline_with_gpu_processor():
+    ref = oracle.Reference.__new__(oracle.Reference)
+    ref.lib = C.CDLL(LIB)
+    L = ref.lib
+    L.dref_arena.restype = C.c_void_p
+    L.dref_arena_position.restype = C.c_uint64
+    L.dref_add_chr.restype = C.c_uint64
+    ref.set_scoring(abi.Scoring.from_values())
+    ref.set_dsoft_defaults()
+    ref.set_extend(384, 64, 2, 0)
+    L.dref_set_dsoft(14, 3, 64, 26, 1000, 40, 1000, 4, 128, 60, 64, 1000, C.c_float(0.05))
+    ref.reset_arena()
+    rng = np.random.default_rng(42)
+    genome = synth.random_seq(rng, 120000)
+    ref.add_chr("chrS", genome.tobytes(), True)
+    ref.build_index()
+    nreads = 8
+    for k in range(nreads):
+        Lr = int(rng.integers(4000, 6000))
+        p = int(rng.integers(0, len(genome) - Lr))
+        src = genome[p:p + Lr]
+        if k % 4 == 1:
+            src = np.concatenate([src[:Lr // 2], synth.random_seq(rng, 450), src[Lr // 2:]])    # forces large tiles
+        r = synth.mutate(rng, src, 0.05, 0.05, 0.05)
+        if k % 2:
+            r = synth.revcomp(r)
+        ref.add_read("r%d" % k, np.ascontiguousarray(r).tobytes())
+    cap = 64 << 20
+    buf_cpu, buf_gpu = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    n_cpu = L.dref_pipeline(0, nreads, 0, buf_cpu, C.c_uint64(cap))           # software Processor + extender_body
+    assert n_cpu > 0
+    assert L.dref_gpu_init(1) == 0                                            # install the GPU table, upload the arena
+    n_gpu = L.dref_pipeline(0, nreads, 1, buf_gpu, C.c_uint64(cap))           # GPU filter tiles + gpu_extender_body
+    L.dref_use_cpu_table()
+    L.dref_gpu_shutdown()
+    assert n_gpu == n_cpu
+    assert buf_gpu.value == buf_cpu.value
