@@ -47,16 +47,24 @@ __global__ void pack_arena_kernel(uint8_t* __restrict__ arena, const char* __res
     arena[b] = (uint8_t)out;
 }
 
-struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568-582
-    uint64_t* words; int cap; int n; uint64_t cur; int overflow;
+struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568-582 (32 ops per u64; written as 2 x u32)
+    uint32_t* words; int cap32; int n; uint32_t cur; int shift; int overflow;
+    __device__ TbWordSink(uint64_t* w, int cap64) : words(reinterpret_cast<uint32_t*>(w)), cap32(2 * cap64), n(0), cur(0), shift(0), overflow(0) {}
     __device__ __forceinline__ void operator()(uint32_t d) {
-        const int k = n & 31;
-        if (k == 0) cur = d; else cur |= (uint64_t)d << (2 * k);
-        n++;
-        if ((n & 31) == 0) { if ((n >> 5) <= cap) words[(n >> 5) - 1] = cur; else overflow = 1; }
+        cur |= d << shift;
+        shift += 2; n++;
+        if (shift == 32) {
+            const int w = (n >> 4) - 1;
+            if (w < cap32) words[w] = cur; else overflow = 1;
+            cur = 0; shift = 0;
+        }
     }
+    __device__ __forceinline__ int count() const { return n; }
     __device__ __forceinline__ void finish() {
-        if (n & 31) { if ((n >> 5) < cap) words[n >> 5] = cur; else overflow = 1; }
+        if (n == 0) return;
+        int w = n >> 4;                                       // next 32-bit word to write
+        if (shift) { if (w < cap32) words[w] = cur; else overflow = 1; w++; }
+        if (w & 1) { if (w < cap32) words[w] = 0; else overflow = 1; }     // zero the upper half of the last u64
     }
 };
 
@@ -182,7 +190,7 @@ tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelSc
                   rq.align_fields, (int)rq.max_tb_steps};
         TileOut out{};
         const bool too_big = t.Q > kMaxTile || t.R > kMaxTile;
-        TbWordSink sink{tb_words + (size_t)idx * tb_words_per_req, tb_words_per_req, 0, 0, 0};
+        TbWordSink sink(tb_words + (size_t)idx * tb_words_per_req, tb_words_per_req);
         if (!too_big) process_tile<K>(cx, ks, t, do_traceback != 0, out, sink);
         if (lane == 0) {
             if (do_traceback) sink.finish();
@@ -243,7 +251,7 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
             sink.cr = a.cr; sink.cq = a.cq; sink.rso = a.rso; sink.qso = a.qso; sink.RL = a.RL; sink.QL = a.QL;
             sink.left = left; sink.S = min(crt, cqt) - O; sink.steps = 0; sink.pos_in_word = 0; sink.skipping = 0;
             sink.lptr = slot + lcap - a.nleft; sink.rptr = slot + lcap + a.nright;
-            sink.lroom = lcap; sink.rroom = rcap; sink.nl = a.nleft; sink.nr = a.nright; sink.overflow = 0;
+            sink.lroom = lcap; sink.rroom = rcap; sink.nl = a.nleft; sink.nr = a.nright; sink.overflow = 0; sink.emitted = 0;
             TileOut out{};
             process_tile<K>(cx, ks, t, true, out, sink);
             // lane 0 consumed the ops while walking the traceback: broadcast the updated offsets

@@ -46,11 +46,13 @@ struct ConsumeSink {
     uint8_t* lptr;                  // next left op goes to *--lptr
     uint8_t* rptr;                  // next right op goes to *rptr++
     uint32_t lroom, rroom, nl, nr, overflow;
+    int emitted;                    // ops seen (consumed or skipped) == total_TB_pointers of the tile
+    __device__ __forceinline__ int count() const { return emitted; }
 
     __device__ __forceinline__ void operator()(uint32_t d) {
         // ops arrive in traceback order; a new 32-op word clears the `break`
         if (pos_in_word == 32) { pos_in_word = 0; skipping = 0; }
-        pos_in_word++;
+        pos_in_word++; emitted++;
         if (skipping) return;
         if (left) {
             if (nl < lroom) *--lptr = (uint8_t)d; else overflow = 1;

@@ -26,7 +26,7 @@
 
 namespace gact {
 
-constexpr int kBandHalf = 40;                       // +-steps around the corner diagonal kept per virtual lane
+constexpr int kBandHalf = 32;                       // +-steps around the corner diagonal kept per virtual lane
 
 // Band layout: virtual lane v keeps the trace words of the 2*kBandHalf+1 steps centred on the step at which it
 // crosses the corner diagonal, contiguously: word(v, s) = band[v * kLp + t],  t = s - (K+1)*v - c2  in [0, kL).
@@ -59,7 +59,7 @@ struct FastConst {                                  // packed constants derived 
     int32_t  max_score;   // largest corner score representable: 2047 - B
     int32_t  eligible;    // scoring admits the fast path
     int32_t  match;
-    uint32_t one;         // 1, opaque to the compiler: `x * one + c` stays an IMAD (fma pipe) instead of an ALU add
+    uint32_t one[4];      // all 1, opaque to the compiler: `x * one[k] + c` stays an IMAD (fma pipe) instead of an ALU add
 };
 
 constexpr uint32_t FT_DEL = 0, FT_INS = 1, FT_DIAG = 2, FT_ZERO = 3, FT_L = 4;
@@ -74,7 +74,7 @@ __host__ inline FastConst make_fast_const(const DevScoring& sc) {
     B += 1;
     f.eligible = sc.uniform && m > 0 && mm < 0 && go <= ge && ge < 0 && lgo <= lge && lge <= 0 && B < 512;
     auto pk = [](int v) { return (uint32_t)(v & 0xFFFF) * 0x00010001u; };
-    f.bias = B; f.match = m; f.max_score = 2047 - B - m; f.one = 1;
+    f.bias = B; f.match = m; f.max_score = 2047 - B - m; f.one[0] = f.one[1] = f.one[2] = f.one[3] = 1;
     f.zeroc = pk((B << 5) | (FT_ZERO << 2));
     f.hm_init = pk(((B + mm) << 5) | (FT_DIAG << 2));
     f.e_init = pk((B + go) << 5);
@@ -142,7 +142,8 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
     // scoring constants in registers for the whole tile
     const uint32_t zeroc = fc.zeroc, pkc32 = fc.pkc32, negc32 = (uint32_t)fc.negc32, diaga = (uint32_t)fc.diaga;
     const uint32_t goa = (uint32_t)fc.goa, gofa = (uint32_t)fc.gofa, lgoa = (uint32_t)fc.lgoa;
-    const uint32_t geh = fc.geh, lgeh = fc.lgeh, one = fc.one;
+    const uint32_t geh = fc.geh, lgeh = fc.lgeh;
+    const uint32_t one0 = fc.one[0], one1 = fc.one[1], one2 = fc.one[2], one3 = fc.one[3];
     uint32_t sendH = fc.hm_init, sendF = fc.f_top, sendFL = fc.fl_top;   // state below my last row (previous step)
     uint32_t diag_in = fc.hm_init;                                       // Hm(row above, previous column)
     uint32_t corner = 0;
@@ -181,8 +182,8 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
             const uint32_t code = (Hk & kMaskT) | (em & kMaskM);
             const uint32_t Hc = Hk & kMaskClean;
             d = Hm[r];
-            Hm[r] = Hc * one + diaga;                                    // IMADs: the fma pipe idles otherwise
-            const uint32_t Ho = Hc * one + goa, HoF = Hc * one + gofa, HoL = Hc * one + lgoa;
+            Hm[r] = Hc * one0 + diaga;                                   // IMADs: keeps the adds off the ALU pipe
+            const uint32_t Ho = Hc * one1 + goa, HoF = Hc * one2 + gofa, HoL = Hc * one3 + lgoa;
             E[r]  = __viaddmax_u16x2(E[r] | 0x00010001u, geh, Ho);       // ties extend                  :336-337,:353
             F     = __viaddmax_u16x2(F | 0x00020002u, geh, HoF);         //                              :363-364,:369
             EL[r] = __viaddmax_u16x2(EL[r], lgeh, HoL);                  //                              :339-340
@@ -215,40 +216,37 @@ template <int K, class Sink>
 __device__ int fast_traceback(const FastSmemView<K>& vw, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
     using G = FastGeom<K>;
     const BandMap<K> bm(Q, R);
-    int i = Q - 1, j = R - 1;
-    int v = i / K, r = i - v * K;
-    int t = bm.t_of(j, v);                       // position inside virtual lane v's window
+    const int i0 = Q - 1, j0 = R - 1;
+    int v = i0 / K, r = i0 - v * K;
+    int t = bm.t_of(j0, v);                       // position inside virtual lane v's window
     const uint32_t* wp = vw.band + v * G::kLp + t;
-    int sh = (r < 3) ? 5 * r : 16 + 5 * (r - 3); // bit position of row r inside the word
-    int is = 0, js = 0, total = 0;
+    int sh = (r < 3) ? 5 * r : 16 + 5 * (r - 3);  // bit position of row r inside the word
+    // i = i0 - is, j = j0 - js: the loop of Processor.cpp:613-618 runs while is < min(Q, max_tb) and js < min(R, max_tb)
+    const int lim_i = min(Q, max_tb), lim_j = min(R, max_tb);
+    int is = 0, js = 0;
     uint32_t where = FT_DIAG;
-    // moving up one row: same word while r > 0; crossing into virtual lane v-1 moves t by +K and the word by -(kLp - K)
-    while (i >= 0 && j >= 0) {
-        if (is == max_tb || js == max_tb) break;
-        if ((unsigned)t >= (unsigned)G::kL) return FAST_BAND;
+    int rc = FAST_OK;
+    while (is < lim_i && js < lim_j) {
+        if ((unsigned)t >= (unsigned)G::kL) { rc = FAST_BAND; break; }
         const uint32_t code = (*wp >> sh) & 31u;
-        bool up = false, left = false;
-        if (where == FT_DIAG) {
-            const uint32_t T = code >> 2;
-            if (T == FT_DIAG) { sink(DARWIN_OP_M); total++; is++; js++; up = true; left = true; }
-            else if (T == FT_ZERO) break;
-            else if (T == FT_L) return FAST_LFLAG;
-            else where = T;                                   // FT_DEL / FT_INS
-        } else if (where == FT_DEL) {
-            sink(DARWIN_OP_D); total++; js++; left = true;
-            where = (code & 1u) ? FT_DEL : FT_DIAG;           // bit 0: E was extended
-        } else {
-            sink(DARWIN_OP_I); total++; is++; up = true;
-            where = (code & 2u) ? FT_INS : FT_DIAG;           // bit 1: F was extended
-        }
-        if (left) { j--; t--; wp--; }
+        const uint32_t T = code >> 2;
+        // a DIAG-state cell whose pointer is DEL/INS switches state and is re-read by the reference (:628-633):
+        // nothing moves in between, so the gap step is taken right away
+        const uint32_t st = (where == FT_DIAG) ? T : where;
+        if (st >= FT_ZERO) { if (st == FT_L) rc = FAST_LFLAG; break; }          // ZERO: path ends (:640-642)
+        const bool up = (st != FT_DEL), left = (st != FT_INS);
+        sink(st == FT_DIAG ? DARWIN_OP_M : (st == FT_DEL ? DARWIN_OP_D : DARWIN_OP_I));
+        // next state: gaps stay open while their "extended" bit is set (:648-653, :662-667)
+        where = (st == FT_DEL && (code & 1u)) ? FT_DEL : (st == FT_INS && (code & 2u)) ? FT_INS : FT_DIAG;
+        if (left) { js++; t--; wp--; }
         if (up) {
-            i--;
+            is++;
             if (r == 0) { r = K - 1; sh = (K - 1 < 3) ? 5 * (K - 1) : 16 + 5 * (K - 1 - 3); t += K; wp -= (G::kLp - K); }
             else { r--; sh = (r == 2) ? 10 : sh - 5; }
         }
     }
-    out.query_offset = is; out.ref_offset = js; out.total = total; out.tflags = 0;
+    if (rc != FAST_OK) return rc;
+    out.query_offset = is; out.ref_offset = js; out.total = sink.count(); out.tflags = 0;
     return FAST_OK;
 }
 
