@@ -1,0 +1,142 @@
+"""GPU: the packed fast path and its hand-over to the exact path (long-gap ties, band exits, N bases, ragged shapes,
+truncated tracebacks), always bit-exact against the oracle's exact rule; plus size-independent properties on a
+bench-sized batch."""
+import numpy as np
+import pytest
+
+import oracle
+from darwin_b200 import abi, synth
+from conftest import tiles_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _ragged_batch(seed, n, tmax, long_indel=0, n_rate=0.0, small_tb=False):
+    rng = np.random.default_rng(seed)
+    arena, req, pos = [np.full(33, ord("N"), np.uint8)], np.zeros(n, abi.TILE_REQ), 33
+    for k in range(n):
+        R = tmax if k % 3 == 0 else int(rng.integers(1, tmax + 1))
+        r = synth.random_seq(rng, R)
+        q = synth.mutate(rng, r, 0.05, 0.05, 0.05, n_rate, (1, long_indel) if long_indel and k % 2 else None)
+        Q = min(len(q), tmax) if k % 4 else min(len(q), int(rng.integers(1, tmax + 1)))
+        q = q[:max(Q, 1)]
+        req[k]["ref_bases_start_addr"], req[k]["ref_size"] = pos, R
+        arena.append(r)
+        pos += R
+        req[k]["query_bases_start_addr"], req[k]["query_size"] = pos, len(q)
+        arena.append(q)
+        pos += len(q)
+        req[k]["max_tb_steps"] = int(rng.choice([24, 100])) if (small_tb and k % 2) else 2 * tmax
+        req[k]["align_fields"] = int(rng.choice([1, 21, 7, 19]))
+        req[k]["index"] = k % 256
+    return np.concatenate(arena + [np.full(64, ord("N"), np.uint8)]), req
+
+
+def _run(gpu, sc, arena, req):
+    p = gpu(len(arena), sc)
+    p.InitializeReferenceMemory(0, arena)
+    st0 = p.stats()
+    res, tb = p.BatchAlignmentSIMD(req, 1)
+    st1 = p.stats()
+    pres, ptb, _ = oracle.port(sc).tiles(arena, req, 1, oracle.Port.STREAM, tb_words_per_req=tb.shape[1])
+    assert tiles_equal(pres, ptb, res, tb) == []
+    p.close()
+    return (st1.tiles_fast - st0.tiles_fast, st1.tiles_exact - st0.tiles_exact, st1.tiles_rerun - st0.tiles_rerun)
+
+
+@pytest.mark.parametrize("vals", [(2, -6, -1, -4, -2, -25, -1), (1, -1, 0, -1, -1, -1, -1), (1, -1, 0, -2, -1, -4, 0),
+                                  (2, -3, -1, -3, -2, -8, -1), (5, -4, -1, -10, -1, -1000, -1)])
+@pytest.mark.parametrize("tmax", [256, 320, 384])
+def test_fast_path_all_schemes_ragged(gpu, vals, tmax):
+    """K = 4/5/6 geometries; tie-heavy schemes force many exact reruns (long-gap candidates on the path)."""
+    fast, exact, rerun = _run(gpu, abi.Scoring.from_values(*vals), *_ragged_batch(hash(vals) % 1000 + tmax, 600, tmax))
+    assert fast + exact == 600 and fast > 0
+    if vals[5] == -1:                       # tie-saturated scoring: long gaps tie everywhere
+        assert rerun > 0
+
+
+def test_band_exit_falls_back_to_exact(gpu):
+    """Indels longer than the stored band push the path out of shared memory -> exact recomputation."""
+    fast, exact, rerun = _run(gpu, abi.Scoring.from_values(), *_ragged_batch(5, 500, 320, long_indel=90))
+    assert rerun > 0 and fast > 0
+
+
+def test_tiles_with_n_use_exact_path(gpu):
+    fast, exact, rerun = _run(gpu, abi.Scoring.from_values(), *_ragged_batch(6, 400, 320, n_rate=0.004))
+    assert exact > 0 and fast > 0
+
+
+def test_truncated_traceback(gpu):
+    """max_tb_steps smaller than the path (Processor.cpp:616) in both paths."""
+    _run(gpu, abi.Scoring.from_values(), *_ragged_batch(7, 400, 320, small_tb=True))
+
+
+def test_non_uniform_matrix_is_exact_only(gpu):
+    m = dict(AA=3, AC=-5, AG=-2, AT=-5, CC=3, CG=-5, CT=-2, GG=3, GT=-5, TT=4)
+    sc = abi.Scoring.from_values(matrix=m, sub_n=-1, go=-5, ge=-2, lgo=-20, lge=-1)
+    fast, exact, rerun = _run(gpu, sc, *_ragged_batch(8, 300, 256))
+    assert fast == 0 and exact == 300
+
+
+def test_invalid_scoring_is_rejected(gpu):
+    import darwin_b200
+    p = darwin_b200.Processor(1 << 16)
+    with pytest.raises(darwin_b200.DarwinGpuError) as e:
+        p.InitializeScoringParameters(abi.Scoring.from_values(2, -6, -1, -1, -3, -25, -1))    # open cheaper than extend
+    assert e.value.code == abi.ERR_INVALID
+    p.close()
+
+
+def test_bench_sized_batch_properties(gpu):
+    """200k tiles of the bench workload: properties that need no oracle -- every op string is consistent with the
+    reported offsets, ends where the reference's loop must end, and a 2 % sample is bit-exact against the oracle."""
+    sc = abi.Scoring.from_values()
+    n, T = 200000, 320
+    arena, req = synth.tile_batch_fast(99, n, T)
+    p = gpu(len(arena), sc)
+    p.InitializeReferenceMemory(0, arena)
+    res, tb = p.BatchAlignmentSIMD(req, 1)
+    total = res["total_TB_pointers"].astype(np.int64)
+    nw = tb.shape[1]
+    shifts = (2 * np.arange(32, dtype=np.uint64))[None, None, :]
+    cnt = np.zeros((n, 4), np.int64)
+    for lo in range(0, n, 20000):
+        hi = min(n, lo + 20000)
+        ops = ((tb[lo:hi, :, None] >> shifts) & np.uint64(3)).reshape(hi - lo, nw * 32)
+        valid = np.arange(nw * 32)[None, :] < total[lo:hi, None]
+        for d in (1, 2, 3):
+            cnt[lo:hi, d] = ((ops == d) & valid).sum(1)
+        assert not ((ops == 0) & valid).any()                   # only I, D, M are ever emitted (Processor.cpp:570)
+    assert np.array_equal(cnt[:, 3] + cnt[:, 1], res["query_offset"].astype(np.int64))     # M + I = query steps
+    assert np.array_equal(cnt[:, 3] + cnt[:, 2], res["ref_offset"].astype(np.int64))       # M + D = reference steps
+    assert (res["query_offset"] <= T).all() and (res["ref_offset"] <= T).all()
+    assert (res["ref_max_pos"] == T - 1).all() and (res["query_max_pos"] == T - 1).all()   # corner start (Processor.cpp:544-547)
+    assert (res["score"] >= 0).all() and np.median(res["score"]) > 100
+    sample = np.arange(0, n, 50)
+    pres, ptb, _ = oracle.port(sc).tiles(arena, req[sample], 1, oracle.Port.STREAM, tb_words_per_req=nw)
+    assert tiles_equal(pres, ptb, res[sample], tb[sample]) == []
+    p.close()
+
+
+def test_sharded_extend_matches_single(gpu):
+    """darwin_b200.shard with the GPU worker (world = 1 here; the world-2 plumbing is covered under gloo on CPU)."""
+    from darwin_b200 import shard
+    from test_host_logic import synthetic_anchor_set
+    from conftest import alignments_equal, ALN_FIELDS_OURS
+    sc = abi.Scoring.from_values()
+    arena, anchors, hits = synthetic_anchor_set(31, 16, 2500)
+    p = gpu(len(arena), sc)
+    p.InitializeReferenceMemory(0, arena)
+    whole = p.extender_body(anchors, hits, 320, 128, 0)
+    parts_res, parts_ops, base = [], [], 0
+    for rank in range(2):                                       # emulate two ranks on the one GPU, then concatenate
+        a, hp, _ = shard.local_shard(anchors, hits, rank, 2)
+        r, o = p.extender_body(a, hp, 320, 128, 0)
+        used = int((r["ops_offset"] + r["n_ops"]).max())
+        r = r.copy()
+        r["ops_offset"] += base
+        base += used
+        parts_res.append(r)
+        parts_ops.append(o[:used])
+    assert alignments_equal(whole[0], whole[1], np.concatenate(parts_res), np.concatenate(parts_ops), ALN_FIELDS_OURS) == []
+    p.close()
