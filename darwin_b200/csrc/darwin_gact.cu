@@ -546,7 +546,8 @@ int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s) {
         return DARWIN_ERR_INVALID;
     }
     const int32_t* v = reinterpret_cast<const int32_t*>(s);
-    for (int i = 0; i < 15; i++) if (v[i] > 127 || v[i] < -127) { h->err = "scoring: |value| must be <= 127"; return DARWIN_ERR_INVALID; }
+    for (int i = 0; i < 11; i++) if (v[i] > 127 || v[i] < -127) { h->err = "scoring: |substitution score| must be <= 127"; return DARWIN_ERR_INVALID; }
+    for (int i = 11; i < 15; i++) if (v[i] < -8192) { h->err = "scoring: gap penalties must be >= -8192 (int16 headroom, like the reference's vectors)"; return DARWIN_ERR_INVALID; }
     DevScoring& d = h->ks.sc;
     const int AA = s->sub_AA, AC = s->sub_AC, AG = s->sub_AG, AT = s->sub_AT, CC = s->sub_CC, CG = s->sub_CG,
               CT = s->sub_CT, GG = s->sub_GG, GT = s->sub_GT, TT = s->sub_TT, N = s->sub_N;

@@ -50,7 +50,11 @@ def _run(gpu, sc, arena, req):
 def test_fast_path_all_schemes_ragged(gpu, vals, tmax):
     """K = 4/5/6 geometries; tie-heavy schemes force many exact reruns (long-gap candidates on the path)."""
     fast, exact, rerun = _run(gpu, abi.Scoring.from_values(*vals), *_ragged_batch(hash(vals) % 1000 + tmax, 600, tmax))
-    assert fast + exact == 600 and fast > 0
+    assert fast + exact == 600
+    if vals[5] == -1000:                    # bias would not fit 16 bits: exact path only
+        assert fast == 0
+    else:
+        assert fast > 0
     if vals[5] == -1:                       # tie-saturated scoring: long gaps tie everywhere
         assert rerun > 0
 
