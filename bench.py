@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--tiles", type=int, default=1000000, help="tiles per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extend-reads", type=int, default=4000,
+                    help="secondary measurement: reads of 10 kbp through the in-kernel anchor walker (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -242,6 +244,29 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=3)
 
+    # ---- secondary: whole anchors through extender_body (in-kernel tile walking), stock params.cfg T=384/O=64 ----
+    extend_info = None
+    if args.extend_reads > 0 and rank == 0:
+        from darwin_b200 import synth
+        ex_arena, ex_anchors, ex_hits = synth.anchor_batch(7, args.extend_reads, 10000, 4000000)
+        ex = darwin_b200.Processor(len(ex_arena), local)
+        ex.InitializeScoringParameters(sc)
+        ex.InitializeReferenceMemory(0, ex_arena)
+        ex.extender_body(ex_anchors[:64], ex_hits, 384, 64, 0)                     # warm-up
+        t0 = time.perf_counter()
+        ex_res, ex_ops = ex.extender_body(ex_anchors, ex_hits, 384, 64, 0)
+        ex_wall = time.perf_counter() - t0
+        ex_st = ex.stats()
+        ex_cells = float(ex_res["cells"].sum())
+        extend_info = {"workload": "extend_10kbp_T384_O64", "reads": int(args.extend_reads), "anchors": int(len(ex_anchors)),
+                       "aligned": int((ex_res["flags"] & 1).sum()), "tiles": int(ex_res["n_tiles"].sum()),
+                       "cells": ex_cells, "kernel_ms": ex_st.last_kernel_ms,
+                       "gcups_kernel": ex_cells / (ex_st.last_kernel_ms * 1e-3) / 1e9,
+                       "reads_per_s_kernel": args.extend_reads / (ex_st.last_kernel_ms * 1e-3),
+                       "reads_per_s_e2e": args.extend_reads / ex_wall,
+                       "note": "one anchor per read at its true locus, synthetic chained hits; host D-SOFT not included"}
+        ex.close()
+
     # checksum of the last step (guards against "fast because wrong"): every tile must have produced a path
     assert int((res["total_TB_pointers"] > 0).sum()) > 0.99 * n, "tiles without traceback"
 
@@ -282,6 +307,8 @@ def main():
                 "gpu_launches": int(launches), "roofline": roof,
                 "tiles": {"fast": int(st_end.tiles_fast - st0.tiles_fast), "exact": int(st_end.tiles_exact - st0.tiles_exact),
                           "rerun": int(st_end.tiles_rerun - st0.tiles_rerun)}}
+        if extend_info:
+            line["extend"] = extend_info
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_leg(arena, req, args.cpu_seconds)
         print(json.dumps(line))

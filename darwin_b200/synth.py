@@ -46,6 +46,69 @@ def mutate(rng, seq, sub=0.05, ins=0.05, dele=0.05, n_rate=0.0, indel_run=None):
     return res
 
 
+def mutate_fast(rng, seq, sub=0.05, ins=0.05, dele=0.05):
+    """Vectorised mutate(): same error model (per-base substitution / insertion-before / deletion), no Python loop."""
+    n = len(seq)
+    r = rng.random(n)
+    is_del = r < dele
+    is_sub = (r >= dele) & (r < dele + sub)
+    is_ins = rng.random(n) < ins
+    codes = np.searchsorted(_ACGT, seq)
+    codes = np.where(is_sub, (codes + rng.integers(1, 4, n)) % 4, codes)
+    contrib = (~is_del).astype(np.int64) + is_ins.astype(np.int64)
+    end = np.cumsum(contrib)
+    start = end - contrib
+    out = np.empty(int(end[-1]) if n else 0, np.uint8)
+    out[start[is_ins]] = _ACGT[rng.integers(0, 4, int(is_ins.sum()))]
+    keep = ~is_del
+    out[(start + is_ins)[keep]] = _ACGT[codes[keep]]
+    return out
+
+
+def anchor_batch(seed, n_reads, read_len=10000, ref_len=1000000, err=(0.05, 0.05, 0.05), hit_spacing=60):
+    """Synthetic reference-guided extension workload (SURVEY 8(d).3 without the host D-SOFT stage): an arena laid
+    out like the reference's (Index.cpp:10-17, main.cpp:430-456, :645-686: 128 'N', one 'N'-padded chromosome,
+    128-aligned 'N'-padded reads), one anchor per read at its true position (both strands) with chained hits every
+    `hit_spacing` bases along the true diagonal (left list ascending, right list descending, seed_pos_table.cpp:432-490).
+    Returns (arena uint8, anchors, hit_pool)."""
+    rng = np.random.default_rng(seed)
+    genome = random_seq(rng, ref_len)
+    pad = (-ref_len) % 128
+    parts = [np.full(128, ord("N"), np.uint8), genome, np.full(pad, ord("N"), np.uint8)]
+    chr_start, chr_len = 128, ref_len + pad
+    pos = 128 + chr_len
+    anchors = np.zeros(n_reads, abi.ANCHOR)
+    hit_parts, nh = [], 0
+    for k in range(n_reads):
+        L = read_len + int(rng.integers(0, read_len // 50 + 1))
+        g0 = int(rng.integers(0, ref_len - L))
+        src = genome[g0:g0 + L]
+        read = mutate_fast(rng, src, *err)
+        strand = k & 1
+        fwd = revcomp(read) if strand else read            # the arena holds the forward read (main.cpp:662-670)
+        rl = len(fwd)
+        rpad = (-rl) % 128
+        parts += [fwd, np.full(rpad, ord("N"), np.uint8)]
+        qa = rl // 2
+        ra = min(ref_len - 1, g0 + int(qa * len(src) / max(rl, 1)))
+        a = anchors[k]
+        a["read_addr"], a["read_len"], a["read_num"] = pos, rl, k
+        a["reference_pos"], a["query_pos"] = chr_start + ra, qa
+        a["chr_start"], a["ref_len"], a["chr_id"], a["score"], a["strand"] = chr_start, chr_len, 0, 100, strand
+        dl = np.arange(0, min(ra, qa), hit_spacing, dtype=np.uint64)[::-1]
+        dr = np.arange(0, min(ref_len - ra, rl - qa), hit_spacing - 1, dtype=np.uint64)[::-1]
+        lh = ((np.uint64(chr_start + ra) - dl) << np.uint64(32)) | (np.uint64(qa) - dl)
+        rh = ((np.uint64(chr_start + ra) + dr) << np.uint64(32)) | (np.uint64(qa) + dr)
+        a["left_hits_off"], a["left_hits_n"] = nh, len(lh)
+        nh += len(lh)
+        a["right_hits_off"], a["right_hits_n"] = nh, len(rh)
+        nh += len(rh)
+        hit_parts += [lh, rh]
+        pos += rl + rpad
+    arena = np.concatenate(parts + [np.full(128, ord("N"), np.uint8)])
+    return arena, anchors, (np.concatenate(hit_parts) if hit_parts else np.zeros(0, np.uint64))
+
+
 def revcomp(seq):
     """main.cpp:59-121 semantics on uint8 ASCII (case preserved)."""
     lut = np.full(256, ord("N"), np.uint8)
