@@ -79,7 +79,8 @@ __device__ __forceinline__ void load_scoring(const DevScoring& sc, int* ssub) {
 template <int K> struct KernelGeom {
     static constexpr int kWarps = (K == 0) ? kWarpsPerCta : 1;
     static constexpr size_t kFast = (K == 0) ? 0 : FastGeom<(K == 0 ? 4 : K)>::kSmemBytes;
-    static constexpr size_t kPerWarp = ((kFast > sizeof(ExactSmem) ? kFast : sizeof(ExactSmem)) + 15) & ~(size_t)15;
+    static constexpr size_t kNeed = (K == 0) ? sizeof(ExactSmem) : (kFast > MultiSmemView::kBytes ? kFast : MultiSmemView::kBytes);
+    static constexpr size_t kPerWarp = ((kNeed > sizeof(ExactSmem) ? kNeed : sizeof(ExactSmem)) + 15) & ~(size_t)15;
     static constexpr size_t kSmem = kPerWarp * kWarps;
 };
 
@@ -103,18 +104,22 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
     if (K > 0) {
         constexpr int KK = (K == 0 ? 4 : K);
         const FastConst& fc = ks.fc;
-        const bool fast = fc.eligible && do_traceback && se && t.Q <= 64 * KK && t.R <= 64 * KK &&
-                          fc.match * min(t.Q, t.R) <= fc.max_score;
+        const bool fast = fc.eligible && do_traceback && se && fc.match * min(t.Q, t.R) <= fc.max_score;
+        const bool single = t.Q <= 64 * KK && t.R <= 64 * KK;
         if (fast) {
             FastSmemView<KK> v(cx.wsmem);
-            const bool has_n = stage_sequences(cx.arena, t, v.sref, v.sqry);
+            MultiSmemView mv(cx.wsmem);
+            const bool has_n = single ? stage_sequences(cx.arena, t, v.sref, v.sqry)
+                                      : stage_sequences(cx.arena, t, mv.sref, mv.sqry);
             if (!has_n) {
-                const int score = fast_forward<KK>(fc, v, t.Q, t.R);
+                uint32_t* gband = reinterpret_cast<uint32_t*>(cx.ws.trace);
+                const int score = single ? fast_forward<KK>(fc, v, t.Q, t.R) : fast_forward_multi<KK>(fc, mv, gband, t.Q, t.R);
                 int rc = FAST_OK;
                 if (lane == 0) {
                     Sink trial = sink;
                     TileOut o2{};
-                    rc = fast_traceback<KK>(v, t.Q, t.R, t.max_tb, o2, trial);
+                    rc = single ? fast_traceback<KK, false>(v.band, t.Q, t.R, t.max_tb, o2, trial)
+                                : fast_traceback<KK, true>(gband, t.Q, t.R, t.max_tb, o2, trial);
                     if (rc == FAST_OK) { sink = trial; out = o2; }
                 }
                 rc = __shfl_sync(0xffffffffu, rc, 0);
@@ -432,7 +437,8 @@ static int pick_k(const DarwinGpu* h, int maxdim, int do_traceback) {
     if (maxdim <= 256) return 4;
     if (maxdim <= 320) return 5;
     if (maxdim <= 384) return 6;
-    return 0;
+    if (maxdim <= 512) return 4;            // two strips of 256 rows (multi-strip fast path)
+    return 6;                               // strips of 384 rows (large tiles, T up to 1024 where the score range allows)
 }
 
 template <int K>
@@ -598,7 +604,8 @@ int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint
 
 static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_req, int n,
                         DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR) {
-    int rc = ensure_scratch(h, exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)));
+    // per-warp scratch: exact-path trace (1 B/cell) or the multi-strip fast path's band, whichever is larger
+    int rc = ensure_scratch(h, std::max(exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)), multi_band_bytes<4>(std::max(maxQ, 1))));
     if (rc) return rc;
     const int K = pick_k(h, std::max(maxQ, maxR), do_traceback);
     const int ctas = h->ctas_tiles[variant_index(K)];
@@ -734,7 +741,7 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     CK(cudaMemcpyAsync(h->d_buf[5], lcap.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[6], size.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     if ((rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(1984, 960), exact_trace_bytes(960, 1984)),
-                                         exact_trace_bytes(p->tile_size, p->tile_size))))) return rc;
+                                         std::max(exact_trace_bytes(p->tile_size, p->tile_size), multi_band_bytes<4>(kMaxTile)))))) return rc;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 4, h->stream));
     ExtendArgs ea;
     ea.arena = h->d_arena; ea.anchors = (const DarwinAnchor*)h->d_buf[0]; ea.hit_pool = (const uint64_t*)h->d_buf[2];

@@ -116,6 +116,38 @@ template <int K> struct BandMap {
     __device__ __forceinline__ int t_of(int j, int v) const { return j - K * v + c1; }
 };
 
+// Scoring constants of one tile in registers.
+struct FastRegs {
+    uint32_t zeroc, pkc32, negc32, diaga, goa, gofa, lgoa, geh, lgeh, one0, one1, one2, one3;
+    __device__ explicit FastRegs(const FastConst& fc)
+        : zeroc(fc.zeroc), pkc32(fc.pkc32), negc32((uint32_t)fc.negc32), diaga((uint32_t)fc.diaga), goa((uint32_t)fc.goa),
+          gofa((uint32_t)fc.gofa), lgoa((uint32_t)fc.lgoa), geh(fc.geh), lgeh(fc.lgeh),
+          one0(fc.one[0]), one1(fc.one[1]), one2(fc.one[2]), one3(fc.one[3]) {}
+};
+
+// One packed cell pair (two int16 cells): recurrence of Processor.cpp:293-366 on tagged scores.
+// d = Hm of the row above at the previous column (in), Hm of this row at the previous column (out).
+__device__ __forceinline__ uint32_t fast_cell(const FastRegs& k, uint32_t rq, uint32_t qq, uint32_t& d, uint32_t& Hm,
+                                              uint32_t& E, uint32_t& EL, uint32_t& F, uint32_t& FL) {
+    const uint32_t x  = rq ^ qq;
+    const uint32_t t  = __vminu2(x, 0x00010001u);                // 1 = mismatch, per half
+    const uint32_t sb = t * k.negc32 + k.pkc32;                  // IMAD: (match-mismatch)*32 or 0
+    const uint32_t hd = __viaddmax_u16x2(d, sb, k.zeroc);        // max(Hdiag + s, 0)          :298-299
+    const uint32_t h1 = __vimax3_u16x2(hd, E, F);
+    const uint32_t Hk = __vimax3_u16x2(h1, EL, FL);              // H with the winner's tag      :300-303
+    const uint32_t em = E | F;
+    const uint32_t code = (Hk & kMaskT) | (em & kMaskM);
+    const uint32_t Hc = Hk & kMaskClean;
+    d = Hm;
+    Hm = Hc * k.one0 + k.diaga;                                  // IMADs: keeps the adds off the ALU pipe
+    const uint32_t Ho = Hc * k.one1 + k.goa, HoF = Hc * k.one2 + k.gofa, HoL = Hc * k.one3 + k.lgoa;
+    E  = __viaddmax_u16x2(E | 0x00010001u, k.geh, Ho);           // ties extend                  :336-337,:353
+    F  = __viaddmax_u16x2(F | 0x00020002u, k.geh, HoF);          //                              :363-364,:369
+    EL = __viaddmax_u16x2(EL, k.lgeh, HoL);                      //                              :339-340
+    FL = __viaddmax_u16x2(FL, k.lgeh, HoL);                      //                              :365-366
+    return code;
+}
+
 // Forward pass of one tile.  Sequences must already be staged (codes 0..3) in v.sref / v.sqry.
 // Returns the corner score H(Q-1, R-1) in all lanes.
 template <int K>
@@ -139,11 +171,7 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
     __syncwarp();
     const BandMap<K> bm(Q, R);
     const int vc = (Q - 1) / K, rc = (Q - 1) - vc * K, sc_step = R - 1 + vc;
-    // scoring constants in registers for the whole tile
-    const uint32_t zeroc = fc.zeroc, pkc32 = fc.pkc32, negc32 = (uint32_t)fc.negc32, diaga = (uint32_t)fc.diaga;
-    const uint32_t goa = (uint32_t)fc.goa, gofa = (uint32_t)fc.gofa, lgoa = (uint32_t)fc.lgoa;
-    const uint32_t geh = fc.geh, lgeh = fc.lgeh;
-    const uint32_t one0 = fc.one[0], one1 = fc.one[1], one2 = fc.one[2], one3 = fc.one[3];
+    const FastRegs kr(fc);                                               // scoring constants in registers
     uint32_t sendH = fc.hm_init, sendF = fc.f_top, sendFL = fc.fl_top;   // state below my last row (previous step)
     uint32_t diag_in = fc.hm_init;                                       // Hm(row above, previous column)
     uint32_t corner = 0;
@@ -172,27 +200,12 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
         uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
         for (int r = 0; r < K; r++) {
-            const uint32_t x  = rq ^ qq[r];
-            const uint32_t t  = __vminu2(x, 0x00010001u);                // 1 = mismatch, per half
-            const uint32_t sb = t * negc32 + pkc32;                      // IMAD: (match-mismatch)*32 or 0
-            const uint32_t hd = __viaddmax_u16x2(d, sb, zeroc);          // max(Hdiag + s, 0)          :298-299
-            const uint32_t h1 = __vimax3_u16x2(hd, E[r], F);
-            const uint32_t Hk = __vimax3_u16x2(h1, EL[r], FL);           // H with the winner's tag      :300-303
-            const uint32_t em = E[r] | F;
-            const uint32_t code = (Hk & kMaskT) | (em & kMaskM);
-            const uint32_t Hc = Hk & kMaskClean;
-            d = Hm[r];
-            Hm[r] = Hc * one0 + diaga;                                   // IMADs: keeps the adds off the ALU pipe
-            const uint32_t Ho = Hc * one1 + goa, HoF = Hc * one2 + gofa, HoL = Hc * one3 + lgoa;
-            E[r]  = __viaddmax_u16x2(E[r] | 0x00010001u, geh, Ho);       // ties extend                  :336-337,:353
-            F     = __viaddmax_u16x2(F | 0x00020002u, geh, HoF);         //                              :363-364,:369
-            EL[r] = __viaddmax_u16x2(EL[r], lgeh, HoL);                  //                              :339-340
-            FL    = __viaddmax_u16x2(FL, lgeh, HoL);                     //                              :365-366
+            const uint32_t code = fast_cell(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
             if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
         }
         if (s == sc_step) {                                              // warp-uniform, taken once per tile
 #pragma unroll
-            for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - diaga;
+            for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - kr.diaga;
         }
         diag_in = inH;
         sendH = Hm[K - 1]; sendF = F; sendFL = FL;
@@ -208,18 +221,119 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
     return (int)(cw >> 5) - fc.bias;
 }
 
+// ---- multi-strip variant: tiles with more than 64*K rows or columns (T = 512, the 1984x960 / 960x1984 large tiles) ----
+// Strips of 64*K query rows run one after the other; the bottom row of a strip (Hm, F, F_L of virtual lane 63) is kept
+// per reference column in shared memory and becomes the top boundary of the next strip.  The traceback band goes to
+// the warp's global scratch (same per-virtual-lane window layout, virtual lanes numbered across strips).
+struct MultiSmemView {
+    uint8_t*  sref;       // [kSeqSmem]
+    uint8_t*  sqry;       // [kSeqSmem]
+    uint32_t* bHF;        // [kMaxTile]  Hm (low half) | F (high half) below the previous strip, per column
+    uint16_t* bFL;        // [kMaxTile]
+    static constexpr size_t kBytes = 2 * kSeqSmem + kMaxTile * 4 + kMaxTile * 2;
+    __device__ explicit MultiSmemView(unsigned char* base) {
+        sref = base; sqry = base + kSeqSmem;
+        bHF = reinterpret_cast<uint32_t*>(base + 2 * kSeqSmem);
+        bFL = reinterpret_cast<uint16_t*>(base + 2 * kSeqSmem + kMaxTile * 4);
+    }
+};
+
+template <int K> __host__ __device__ inline size_t multi_band_bytes(int Q) {
+    return (size_t)((Q + K - 1) / K + 64) * FastGeom<K>::kLp * 4;
+}
+
+template <int K>
+__device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, uint32_t* gband, int Q, int R) {
+    using G = FastGeom<K>;
+    const int lane = lane_id();
+    const FastRegs kr(fc);
+    const BandMap<K> bm(Q, R);
+    const int nstrips = (Q + 64 * K - 1) / (64 * K);
+    const int vc = (Q - 1) / K, rc = (Q - 1) - vc * K;                   // global virtual lane / row of the corner
+    const int sc_step = R - 1 + (vc & 63);                               // step of the corner inside the last strip
+    const int src = (lane + 31) & 31;
+    const int steps = R + 63;
+    constexpr int kHiOff = 32 * (G::kLp - (K + 1));
+    uint32_t corner = 0;
+
+    for (int strip = 0; strip < nstrips; strip++) {
+        const int row0 = strip * 64 * K;
+        uint32_t qq[K], Hm[K], E[K], EL[K];
+#pragma unroll
+        for (int r = 0; r < K; r++) {
+            const int ilo = row0 + K * lane + r, ihi = row0 + K * (lane + 32) + r;
+            qq[r] = (ilo < Q ? (uint32_t)v.sqry[ilo] : 6u) | ((ihi < Q ? (uint32_t)v.sqry[ihi] : 6u) << 16);
+            Hm[r] = fc.hm_init; E[r] = fc.e_init; EL[r] = fc.el_init;
+        }
+        uint32_t sendH = fc.hm_init, sendF = fc.f_top, sendFL = fc.fl_top;
+        uint32_t diag_in = fc.hm_init;
+        // top boundary of this strip for lane 0's low half, prefetched one step ahead
+        uint32_t topHF = fc.hm_init & 0xFFFFu | (fc.f_top << 16), topFL = fc.fl_top & 0xFFFFu;
+        uint32_t nextHF = topHF, nextFL = topFL;
+        if (strip > 0 && lane == 0) { nextHF = v.bHF[0]; nextFL = v.bFL[0]; }
+        const int vg = strip * 64 + lane;                                // my low-half global virtual lane
+        int t_lo = -lane - K * vg + bm.c1;                               // t(i,j) at s = 0 (j = -lane)
+        uint32_t* bp = gband + (size_t)vg * G::kLp + t_lo;
+        uint32_t rlo = (lane == 0 && R > 0) ? v.sref[0] : 5u, rhi = 5u;  // reference bases of step 0
+
+        for (int s = 0; s < steps; s++) {
+            uint32_t inH = __shfl_sync(0xffffffffu, sendH, src);
+            uint32_t F   = __shfl_sync(0xffffffffu, sendF, src);
+            uint32_t FL  = __shfl_sync(0xffffffffu, sendFL, src);
+            if (lane == 0) {
+                if (strip > 0) { topHF = nextHF; topFL = nextFL; if (s + 1 < R) { nextHF = v.bHF[s + 1]; nextFL = v.bFL[s + 1]; } }
+                inH = __byte_perm(topHF, inH, 0x5410);                   // low half: boundary Hm; high half: lane 31's low
+                F   = __byte_perm(topHF, F, 0x5432);                     // low half: boundary F (upper half of topHF)
+                FL  = __byte_perm(topFL, FL, 0x5410);
+            }
+            const uint32_t rq = rlo | (rhi << 16);
+            {   // prefetch the reference bases of step s+1: columns s+1-lane and s+1-lane-32
+                const int jl = s + 1 - lane, jh = jl - 32;
+                rlo = ((unsigned)jl < (unsigned)R) ? v.sref[jl] : 5u;
+                rhi = ((unsigned)jh < (unsigned)R) ? v.sref[jh] : 5u;
+            }
+            uint32_t d = diag_in;
+            uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+            for (int r = 0; r < K; r++) {
+                const uint32_t code = fast_cell(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
+                if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
+            }
+            if (strip == nstrips - 1 && s == sc_step) {
+#pragma unroll
+                for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - kr.diaga;
+            }
+            diag_in = inH;
+            sendH = Hm[K - 1]; sendF = F; sendFL = FL;
+            if (lane == 31 && strip + 1 < nstrips && (unsigned)(s - 63) < (unsigned)R) {   // bottom row of the strip
+                v.bHF[s - 63] = __byte_perm(sendH, sendF, 0x7632);
+                v.bFL[s - 63] = (uint16_t)(sendFL >> 16);
+            }
+            if ((unsigned)t_lo < (unsigned)G::kL) __stcg(bp, __byte_perm(acc0, acc1, 0x5410));
+            if ((unsigned)(t_lo - 32 * (K + 1)) < (unsigned)G::kL) __stcg(bp + kHiOff, __byte_perm(acc0, acc1, 0x7632));
+            t_lo++; bp++;
+        }
+        __syncwarp();
+    }
+    const int vl = vc & 63;
+    uint32_t cw = __shfl_sync(0xffffffffu, corner, vl & 31);
+    cw = (vl >= 32) ? (cw >> 16) : (cw & 0xFFFFu);
+    return (int)(cw >> 5) - fc.bias;
+}
+
 enum : int { FAST_OK = 0, FAST_LFLAG = 1, FAST_BAND = 2 };
 
-// Traceback over the shared-memory band (Processor.cpp:585-716 with the clean rule), ONE lane.
+// Traceback over the band (Processor.cpp:585-716 with the clean rule), ONE lane.  GLOBAL: the band lives in the
+// warp's global scratch (multi-strip tiles) instead of shared memory.
 // Returns FAST_OK, or the reason the tile must be recomputed by the exact path.
-template <int K, class Sink>
-__device__ int fast_traceback(const FastSmemView<K>& vw, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
+template <int K, bool GLOBAL, class Sink>
+__device__ int fast_traceback(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
     using G = FastGeom<K>;
     const BandMap<K> bm(Q, R);
     const int i0 = Q - 1, j0 = R - 1;
     int v = i0 / K, r = i0 - v * K;
     int t = bm.t_of(j0, v);                       // position inside virtual lane v's window
-    const uint32_t* wp = vw.band + v * G::kLp + t;
+    const uint32_t* wp = band + (size_t)v * G::kLp + t;
     int sh = (r < 3) ? 5 * r : 16 + 5 * (r - 3);  // bit position of row r inside the word
     // i = i0 - is, j = j0 - js: the loop of Processor.cpp:613-618 runs while is < min(Q, max_tb) and js < min(R, max_tb)
     const int lim_i = min(Q, max_tb), lim_j = min(R, max_tb);
@@ -228,7 +342,8 @@ __device__ int fast_traceback(const FastSmemView<K>& vw, int Q, int R, int max_t
     int rc = FAST_OK;
     while (is < lim_i && js < lim_j) {
         if ((unsigned)t >= (unsigned)G::kL) { rc = FAST_BAND; break; }
-        const uint32_t code = (*wp >> sh) & 31u;
+        const uint32_t w = GLOBAL ? __ldcg(wp) : *wp;
+        const uint32_t code = (w >> sh) & 31u;
         const uint32_t T = code >> 2;
         // a DIAG-state cell whose pointer is DEL/INS switches state and is re-read by the reference (:628-633):
         // nothing moves in between, so the gap step is taken right away
