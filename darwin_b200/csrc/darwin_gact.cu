@@ -80,7 +80,10 @@ template <int K> struct KernelGeom {
     static constexpr int kWarps = (K == 0) ? kWarpsPerCta : 1;
     static constexpr size_t kFast = (K == 0) ? 0 : FastGeom<(K == 0 ? 4 : K)>::kSmemBytes;
     static constexpr size_t kNeed = (K == 0) ? sizeof(ExactSmem) : (kFast > MultiSmemView::kBytes ? kFast : MultiSmemView::kBytes);
-    static constexpr size_t kPerWarp = ((kNeed > sizeof(ExactSmem) ? kNeed : sizeof(ExactSmem)) + 15) & ~(size_t)15;
+    static constexpr size_t kTileBytes = ((kNeed > sizeof(ExactSmem) ? kNeed : sizeof(ExactSmem)) + 15) & ~(size_t)15;
+    static constexpr size_t kPerWarp = kTileBytes;                      // tiles kernel
+    static constexpr size_t kPerWarpExtend = kTileBytes + kOpsSmemBytes; // + op buffer of the anchor walker
+    static constexpr size_t kSmemExtend = kPerWarpExtend * kWarps;
     static constexpr size_t kSmem = kPerWarp * kWarps;
 };
 
@@ -152,12 +155,12 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
 }
 
 template <int K>
-__device__ __forceinline__ WarpCtx make_ctx(const uint8_t* arena, const int* ssub, unsigned char* dyn,
+__device__ __forceinline__ WarpCtx make_ctx(const uint8_t* arena, const int* ssub, unsigned char* dyn, size_t per_warp,
                                             uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base) {
     const int warp = threadIdx.x >> 5;
     const int gw = blockIdx.x * KernelGeom<K>::kWarps + warp;
     WarpCtx cx;
-    cx.arena = arena; cx.ssub = ssub; cx.wsmem = dyn + (size_t)warp * KernelGeom<K>::kPerWarp;
+    cx.arena = arena; cx.ssub = ssub; cx.wsmem = dyn + (size_t)warp * per_warp;
     cx.ws = WarpScratch{trace_base + (size_t)gw * trace_stride, bound_base + (size_t)gw * kMaxTile};
     cx.n_fast = cx.n_exact = cx.n_rerun = 0;
     return cx;
@@ -174,7 +177,7 @@ __device__ __forceinline__ void flush_counters(const WarpCtx& cx, unsigned int* 
 // BatchAlignmentSIMD (Processor.cpp:718-762) for n independent tiles: persistent warps pull tiles from a
 // global counter.
 template <int K>
-__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32)
+__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 4 : 11)
 tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
              const DarwinTileReq* __restrict__ req, int n, int do_traceback,
              DarwinTileRes* __restrict__ res, uint64_t* __restrict__ tb_words, int tb_words_per_req,
@@ -183,7 +186,7 @@ tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelSc
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     load_scoring(ks.sc, ssub);
     const int lane = lane_id();
-    WarpCtx cx = make_ctx<K>(arena, ssub, dyn_smem, trace_base, trace_stride, bound_base);
+    WarpCtx cx = make_ctx<K>(arena, ssub, dyn_smem, KernelGeom<K>::kPerWarp, trace_base, trace_stride, bound_base);
 
     for (;;) {
         unsigned int idx = 0;
@@ -213,14 +216,14 @@ tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelSc
 
 // extender_body::operator() (extender.cpp:9-1065): persistent warps pull ANCHORS and walk their tiles.
 template <int K>
-__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32)
+__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 3 : 11)
 extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ ExtendArgs ea,
               uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base) {
     __shared__ int ssub[32];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     load_scoring(ks.sc, ssub);
     const int lane = lane_id();
-    WarpCtx cx = make_ctx<K>(ea.arena, ssub, dyn_smem, trace_base, trace_stride, bound_base);
+    WarpCtx cx = make_ctx<K>(ea.arena, ssub, dyn_smem, KernelGeom<K>::kPerWarpExtend, trace_base, trace_stride, bound_base);
     const int T = ea.T, O = ea.O;
 
     for (;;) {
@@ -252,22 +255,26 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
             a.n_tiles++; a.cells += (uint64_t)t.R * (uint64_t)t.Q;
             int crt = T, cqt = T;
             if (a.large && ea.do_overlap == 0) { crt = rt; cqt = qt; }           // extender.cpp:261 / :408
-            ConsumeSink sink;
-            sink.cr = a.cr; sink.cq = a.cq; sink.rso = a.rso; sink.qso = a.qso; sink.RL = a.RL; sink.QL = a.QL;
-            sink.left = left; sink.S = min(crt, cqt) - O; sink.steps = 0; sink.pos_in_word = 0; sink.skipping = 0;
-            sink.lptr = slot + lcap - a.nleft; sink.rptr = slot + lcap + a.nright;
-            sink.lroom = lcap; sink.rroom = rcap; sink.nl = a.nleft; sink.nr = a.nright; sink.overflow = 0; sink.emitted = 0;
+            // lane 0 walks the traceback and records the ops in shared memory; the warp then consumes them together
+            uint8_t* opbuf = cx.wsmem + KernelGeom<K>::kTileBytes;          // behind the tile's own shared memory
+            SmemOpSink sink{opbuf, 0, kOpsSmemBytes, 0};
             TileOut out{};
             process_tile<K>(cx, ks, t, true, out, sink);
-            // lane 0 consumed the ops while walking the traceback: broadcast the updated offsets
-            uint32_t pk[8] = {sink.cr, sink.cq, sink.rso, sink.qso, sink.nl, sink.nr, (uint32_t)out.total,
-                              out.tflags | (sink.overflow << 8)};
-#pragma unroll
-            for (int k = 0; k < 8; k++) pk[k] = __shfl_sync(0xffffffffu, pk[k], 0);
-            a.cr = pk[0]; a.cq = pk[1]; a.rso = pk[2]; a.qso = pk[3]; a.nleft = pk[4]; a.nright = pk[5];
-            const int len = (int)pk[6];
-            if (pk[7] & 1) a.flags |= DARWIN_ALN_LONG_INS_PATH;
-            if (pk[7] & 0x100) overflow = 1;
+            const int len = __shfl_sync(0xffffffffu, out.total, 0);
+            const uint32_t tfl = __shfl_sync(0xffffffffu, out.tflags | ((uint32_t)sink.overflow << 8), 0);
+            __syncwarp();
+            const ConsumeResult cr_ = consume_ops_warp(opbuf, len, min(crt, cqt) - O, left != 0, slot, lcap, rcap, a.nleft, a.nright, overflow);
+            if (left) {                                                          // extender.cpp:286-324
+                if (cr_.ref_steps > a.cr) { a.cr = 0; a.rso = 0; } else a.cr -= cr_.ref_steps;
+                if (cr_.qry_steps > a.cq) { a.cq = 0; a.qso = 0; } else a.cq -= cr_.qry_steps;
+                a.nleft += cr_.consumed;
+            } else {                                                             // extender.cpp:433-459
+                a.cr = min(a.cr + cr_.ref_steps, a.RL);
+                a.cq = min(a.cq + cr_.qry_steps, a.QL);
+                a.nright += cr_.consumed;
+            }
+            if (tfl & 1) a.flags |= DARWIN_ALN_LONG_INS_PATH;
+            if (tfl & 0x100) overflow = 1;
             if (ea.dbg && lane == 0 && a.n_tiles <= 128) {
                 uint32_t* d = ea.dbg + ((size_t)idx * 128 + (a.n_tiles - 1)) * 8;
                 d[0] = t.R; d[1] = t.Q; d[2] = len; d[3] = a.cr; d[4] = a.cq; d[5] = a.rso; d[6] = a.qso; d[7] = a.large | (left << 1);
@@ -443,17 +450,15 @@ static int pick_k(const DarwinGpu* h, int maxdim, int do_traceback) {
 
 template <int K>
 static int configure_variant(DarwinGpu* h) {
-    const size_t smem = KernelGeom<K>::kSmem;
+    const size_t smem_t = KernelGeom<K>::kSmem, smem_e = KernelGeom<K>::kSmemExtend;
     const int threads = KernelGeom<K>::kWarps * 32;
     CK(cudaFuncSetAttribute(tiles_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(extend_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (smem > 48 * 1024) {
-        CK(cudaFuncSetAttribute(tiles_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(extend_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(tiles_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    if (smem_e > 48 * 1024) CK(cudaFuncSetAttribute(extend_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
     int a = 0, b = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, tiles_kernel<K>, threads, smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, extend_kernel<K>, threads, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, tiles_kernel<K>, threads, smem_t));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, extend_kernel<K>, threads, smem_e));
     const int cap = h->max_warps / h->sm_count / KernelGeom<K>::kWarps;       // scratch bound
     a = std::max(1, std::min(a, cap)); b = std::max(1, std::min(b, cap));
     h->ctas_tiles[variant_index(K)] = h->sm_count * a;                        // persistent grids: multiples of the SM count
@@ -753,7 +758,7 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     CK(cudaEventRecord(h->ev0, h->stream));
     const int K = pick_k(h, p->tile_size, 1);
     const int ctas = h->ctas_extend[variant_index(K)];
-#define LAUNCH_EXTEND(KK) extend_kernel<KK><<<ctas, KernelGeom<KK>::kWarps * 32, KernelGeom<KK>::kSmem, h->stream>>>( \
+#define LAUNCH_EXTEND(KK) extend_kernel<KK><<<ctas, KernelGeom<KK>::kWarps * 32, KernelGeom<KK>::kSmemExtend, h->stream>>>( \
         h->ks, ea, h->d_trace, h->trace_stride, h->d_bound)
     switch (K) {
         case 4: LAUNCH_EXTEND(4); break;

@@ -38,37 +38,48 @@ struct AnchorState {
     uint64_t cells;
 };
 
-// Consumption of one tile's ops by lane 0 (extender.cpp:280-331 / :427-466 and the rc twins).
-struct ConsumeSink {
-    uint32_t cr, cq, rso, qso;      // running offsets
-    uint32_t RL, QL;
-    int left, S, steps, pos_in_word, skipping;
-    uint8_t* lptr;                  // next left op goes to *--lptr
-    uint8_t* rptr;                  // next right op goes to *rptr++
-    uint32_t lroom, rroom, nl, nr, overflow;
-    int emitted;                    // ops seen (consumed or skipped) == total_TB_pointers of the tile
-    __device__ __forceinline__ int count() const { return emitted; }
-
-    __device__ __forceinline__ void operator()(uint32_t d) {
-        // ops arrive in traceback order; a new 32-op word clears the `break`
-        if (pos_in_word == 32) { pos_in_word = 0; skipping = 0; }
-        pos_in_word++; emitted++;
-        if (skipping) return;
-        if (left) {
-            if (nl < lroom) *--lptr = (uint8_t)d; else overflow = 1;
-            nl++;
-            if (d != DARWIN_OP_I) { if (cr > 0) cr--; else rso = 0; }
-            if (d != DARWIN_OP_D) { if (cq > 0) cq--; else qso = 0; }
-        } else {
-            if (nr < rroom) *rptr++ = (uint8_t)d; else overflow = 1;
-            nr++;
-            if (d != DARWIN_OP_I) { if (cr < RL) cr++; }
-            if (d != DARWIN_OP_D) { if (cq < QL) cq++; }
-        }
-        steps++;
-        if (steps >= S && d == DARWIN_OP_M) skipping = 1;          // leaves only the 32-op loop
-    }
+// The traceback (one lane) only records the tile's ops, one byte each, in shared memory ...
+struct SmemOpSink {
+    uint8_t* buf; int n; int cap; int overflow;
+    __device__ __forceinline__ void operator()(uint32_t d) { if (n < cap) buf[n] = (uint8_t)d; else overflow = 1; n++; }
+    __device__ __forceinline__ int count() const { return n; }
 };
+constexpr int kOpsSmemBytes = 4096;                 // >= 4 * tile_size ops of one traceback (i_steps + j_steps <= 2 * max_tb_steps)
+
+// ... and the whole warp consumes them (extender.cpp:280-331 / :427-466 and the rc twins): one 32-op TB word per
+// iteration, one lane per op.  The reference's `break` leaves only the 32-op loop, so inside word w the ops up to and
+// including the first M at or after step S are taken; ballots find that M, pop-counts give the number of
+// reference / query bases consumed, and the taken ops are stored with one coalesced store per word.
+struct ConsumeResult { uint32_t consumed, ref_steps, qry_steps; };
+
+__device__ __forceinline__ ConsumeResult consume_ops_warp(const uint8_t* ops, int total, int S, bool left,
+                                                          uint8_t* slot, uint32_t lcap, uint32_t rcap,
+                                                          uint32_t nleft, uint32_t nright, uint32_t& overflow) {
+    const int lane = lane_id();
+    int steps = 0;
+    uint32_t consumed = 0, ref_c = 0, qry_c = 0;
+    for (int w0 = 0; w0 < total; w0 += 32) {
+        const int k = w0 + lane;
+        const bool valid = k < total;
+        const uint32_t d = valid ? ops[k] : 0u;
+        const int np = min(32, total - w0);
+        const uint32_t mM = __ballot_sync(0xffffffffu, valid && d == DARWIN_OP_M);
+        const int thr = S - steps - 1;                              // first position p with steps + p + 1 >= S
+        const uint32_t cand = thr <= 0 ? mM : (thr >= 32 ? 0u : (mM & (0xFFFFFFFFu << thr)));
+        const int c = cand ? __ffs(cand) : np;                      // ops taken from this word
+        const uint32_t low = c >= 32 ? 0xFFFFFFFFu : ((1u << c) - 1u);
+        const uint32_t mR = __ballot_sync(0xffffffffu, valid && d != DARWIN_OP_I) & low;
+        const uint32_t mQ = __ballot_sync(0xffffffffu, valid && d != DARWIN_OP_D) & low;
+        if (lane < c) {
+            const uint32_t pos = consumed + (uint32_t)lane;
+            if (left) { if (nleft + pos < lcap) slot[lcap - nleft - 1 - pos] = (uint8_t)d; else overflow = 1; }   // prepended
+            else      { if (nright + pos < rcap) slot[lcap + nright + pos] = (uint8_t)d; else overflow = 1; }
+        }
+        steps += c; consumed += (uint32_t)c; ref_c += __popc(mR); qry_c += __popc(mQ);
+    }
+    overflow = __any_sync(0xffffffffu, overflow != 0) ? 1u : 0u;
+    return ConsumeResult{consumed, ref_c, qry_c};
+}
 
 // Build the next tile request of an anchor (extender.cpp:58-207 / :573-722).  Returns rt/qt through refs.
 __device__ __forceinline__ void next_tile(const AnchorState& a, int T, TileJob& t, int& rt, int& qt) {
