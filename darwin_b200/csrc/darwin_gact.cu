@@ -709,16 +709,9 @@ int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, i
     return DARWIN_OK;
 }
 
-int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n,
-                      const uint64_t* hit_pool, uint64_t n_hits,
-                      DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes) {
-    if (!h || !p || n < 0 || (n && (!anchors || !res))) return DARWIN_ERR_INVALID;
-    if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
-    if (p->tile_size < 16 || p->tile_size > 1024 || p->tile_overlap < 0 || p->tile_overlap >= p->tile_size) {
-        h->err = "tile_size must be in [16,1024] and 0 <= tile_overlap < tile_size"; return DARWIN_ERR_INVALID;
-    }
-    if (n == 0) return DARWIN_OK;
-    CK(cudaSetDevice(h->device));
+// One chunk of anchors (the hit pool is already resident in d_buf[2]).  *used_out = op bytes written to ops_pool.
+static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n, uint64_t n_hits,
+                        DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes, uint64_t* used_out, float* kernel_ms) {
     // op slots: left part holds the (reversed) left extension, right part the right extension
     std::vector<uint64_t> base(n); std::vector<uint32_t> lcap(n), size(n);
     uint64_t total = 0;
@@ -736,12 +729,10 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     }
     int rc;
     const size_t an_b = (size_t)n * sizeof(DarwinAnchor), res_b = (size_t)n * sizeof(DarwinAlnRes);
-    const size_t hit_b = (size_t)std::max<uint64_t>(n_hits, 1) * 8;
-    if ((rc = grow_dev(h, 0, an_b)) || (rc = grow_dev(h, 1, res_b)) || (rc = grow_dev(h, 2, hit_b)) ||
+    if ((rc = grow_dev(h, 0, an_b)) || (rc = grow_dev(h, 1, res_b)) ||
         (rc = grow_dev(h, 3, total + 16)) || (rc = grow_dev(h, 4, (size_t)n * 8)) || (rc = grow_dev(h, 5, (size_t)n * 4)) ||
         (rc = grow_dev(h, 6, (size_t)n * 4)) || (rc = grow_dev(h, 7, (size_t)n * 8))) return rc;
     CK(cudaMemcpyAsync(h->d_buf[0], anchors, an_b, cudaMemcpyHostToDevice, h->stream));
-    if (n_hits) CK(cudaMemcpyAsync(h->d_buf[2], hit_pool, n_hits * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[4], base.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[5], lcap.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[6], size.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
@@ -773,7 +764,7 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     // first D2H: op counts -> dense offsets (host prefix sum), then score + compaction on the device
     CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
     if ((rc = read_counters(h))) return rc;
-    CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
+    { float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); *kernel_ms += ms; }
     std::vector<uint64_t> dense(n);
     uint64_t used = 0; int overflow = 0;
     for (int i = 0; i < n; i++) {
@@ -796,12 +787,49 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     CK(cudaFreeAsync(d_dense, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     (void)overflow;
+    *used_out = used;
     if (ea.dbg) {
         std::vector<uint32_t> hd((size_t)n * 128 * 8);
         CK(cudaMemcpy(hd.data(), ea.dbg, hd.size() * 4, cudaMemcpyDeviceToHost));
         FILE* f = fopen(getenv("DARWIN_GPU_DEBUG"), "wb"); if (f) { fwrite(hd.data(), 4, hd.size(), f); fclose(f); }
         cudaFree(ea.dbg);
     }
+    return DARWIN_OK;
+}
+
+int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n,
+                      const uint64_t* hit_pool, uint64_t n_hits,
+                      DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes) {
+    if (!h || !p || n < 0 || (n && (!anchors || !res))) return DARWIN_ERR_INVALID;
+    if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
+    if (p->tile_size < 16 || p->tile_size > 1024 || p->tile_overlap < 0 || p->tile_overlap >= p->tile_size) {
+        h->err = "tile_size must be in [16,1024] and 0 <= tile_overlap < tile_size"; return DARWIN_ERR_INVALID;
+    }
+    if (n == 0) return DARWIN_OK;
+    CK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = grow_dev(h, 2, (size_t)std::max<uint64_t>(n_hits, 1) * 8))) return rc;
+    if (n_hits) CK(cudaMemcpyAsync(h->d_buf[2], hit_pool, n_hits * 8, cudaMemcpyHostToDevice, h->stream));
+    // Anchors go to the device in chunks so that the op slots (about 2 bytes per read base per anchor) stay bounded.
+    const uint64_t kSlotBudget = 6ull << 30;
+    uint64_t used_total = 0;
+    float kernel_ms = 0.f;
+    for (int lo = 0; lo < n;) {
+        int hi = lo; uint64_t bytes = 0;
+        while (hi < n && hi - lo < (1 << 20)) {
+            const uint64_t sz = 2ull * anchors[hi].read_len + 4ull * (uint64_t)p->tile_size + 512ull;
+            if (hi > lo && bytes + sz > kSlotBudget) break;
+            bytes += sz; hi++;
+        }
+        uint64_t used = 0;
+        rc = extend_chunk(h, p, anchors + lo, hi - lo, n_hits, res + lo, ops_pool ? ops_pool + used_total : nullptr,
+                          ops_pool_bytes - used_total, &used, &kernel_ms);
+        if (rc) return rc;
+        for (int i = lo; i < hi; i++) res[i].ops_offset += used_total;
+        used_total += used;
+        lo = hi;
+    }
+    h->stats.last_kernel_ms = kernel_ms;
     return DARWIN_OK;
 }
 
