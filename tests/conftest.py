@@ -19,9 +19,13 @@ def pytest_configure(config):
 def _build_native():
     """Build the oracle libraries (gcc) once per session; the CUDA library is built by __graft_entry__.build()."""
     import oracle
-    oracle.build("port")
-    if os.path.isdir("/root/reference/software"):
-        oracle.build("ref")
+    import __graft_entry__ as entry
+    try:
+        entry.build()                      # nvcc (no-op when the library is up to date) + oracle libraries
+    except Exception:
+        oracle.build("port")               # no nvcc here: the prebuilt libdarwin_gact.so (if any) is used as is
+        if os.path.isdir("/root/reference/software"):
+            oracle.build("ref")
 
 
 @pytest.fixture(scope="session")

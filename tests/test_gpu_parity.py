@@ -109,7 +109,7 @@ def test_extend_random_vs_oracle(gpu):
     arena, anchors, hits = synthetic_anchor_set(seed=21, n_reads=24, read_len=3000)
     p = gpu(len(arena), sc)
     p.InitializeReferenceMemory(0, arena)
-    for (T, O) in ((384, 64), (320, 128), (128, 32)):
+    for (T, O) in ((384, 64), (320, 128), (128, 32), (512, 64), (1024, 64)):     # 512: multi-strip fast; 1024: exact path
         res, ops = p.extender_body(anchors, hits, T, O, 0)
         pres, pops = oracle.port(sc).extend(arena, abi.ExtendParams(T, O, 0, 0), anchors, hits, oracle.Port.STREAM)
         assert alignments_equal(pres, pops, res, ops, ALN_FIELDS_OURS) == []

@@ -54,3 +54,43 @@ def test_general_matrix_port_equals_reference():
     rres, rtb = ref.tiles(arena, req, 1, tb_words_per_req=80)
     pres, ptb, _ = port.tiles(arena, req, 1, oracle.Port.STREAM, tb_words_per_req=80)
     assert tiles_equal(rres, rtb, pres, ptb) == []
+
+
+SAMPLE_REF = "/root/reference/software/data/sample_ref.fa"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(SAMPLE_REF), reason="reference data not present")
+def test_config1_sample_reference_plumbing():
+    """BASELINE.json configs[0]: the reference's own sample reference (sacCer3 chrI) with stock params.cfg; the reads
+    file is missing from the reference tree (.MISSING_LARGE_BLOBS), so reads are simulated (seeded, 15 % error).
+    Reference pipeline (D-SOFT, filter, extender_body) vs the restatement on the same anchors."""
+    from conftest import alignments_equal, ALN_FIELDS
+    seq = b"".join(l.strip() for l in open(SAMPLE_REF, "rb") if not l.startswith(b">"))
+    ref = oracle.reference("patched")
+    ref.load_cfg("/root/reference/software/params.cfg", 0)
+    ref.reset_arena()
+    ref.add_chr("chrI", seq, True)
+    ref.build_index()
+    rng = np.random.default_rng(1)
+    g = np.frombuffer(seq, np.uint8)
+    for k in range(6):
+        L = int(rng.integers(6000, 9000))
+        p = int(rng.integers(0, len(g) - L))
+        r = synth.mutate_fast(rng, np.char.upper(g[p:p + L].view("S1")).view(np.uint8), 0.05, 0.05, 0.05)
+        ref.add_read("r%d" % k, np.ascontiguousarray(synth.revcomp(r) if k % 2 else r).tobytes())
+    A, H, hb = [], [], 0
+    for k in range(6):
+        a, h = ref.seed_filter(k, 1)
+        a = a.copy()
+        a["left_hits_off"] += hb
+        a["right_hits_off"] += hb
+        hb += len(h)
+        A.append(a)
+        H.append(h)
+    anchors, hits = np.concatenate(A), np.concatenate(H)
+    assert len(anchors) >= 6
+    want, wops = ref.extend(anchors, hits)
+    port = oracle.port(abi.Scoring.from_values())
+    for rule in (oracle.Port.STREAM, oracle.Port.CLEAN):
+        got, gops = port.extend(ref.arena(), abi.ExtendParams(384, 64, 0, 0), anchors, hits, rule)
+        assert alignments_equal(want, wops, got, gops, ALN_FIELDS) == []
