@@ -40,14 +40,16 @@ def local_shard(anchors, hit_pool, rank, world):
     a = anchors[lo:hi].copy()
     if len(a) == 0:
         return a, np.zeros(0, np.uint64), (lo, hi)
-    parts, pos = [], 0
-    for k in range(len(a)):
-        for side in ("left", "right"):
-            off, cnt = int(a[k][side + "_hits_off"]), int(a[k][side + "_hits_n"])
-            parts.append(hit_pool[off:off + cnt])
-            a[k][side + "_hits_off"] = pos
-            pos += cnt
-    return a, (np.concatenate(parts) if parts else np.zeros(0, np.uint64)), (lo, hi)
+    # vectorised gather of the shard's hit lists: [left_0 | right_0 | left_1 | right_1 | ...]
+    off = np.stack([a["left_hits_off"], a["right_hits_off"]], 1).reshape(-1).astype(np.int64)
+    cnt = np.stack([a["left_hits_n"], a["right_hits_n"]], 1).reshape(-1).astype(np.int64)
+    start = np.cumsum(cnt) - cnt
+    total = int(cnt.sum())
+    idx = np.repeat(off - start, cnt) + np.arange(total, dtype=np.int64)
+    hp = hit_pool[idx] if total else np.zeros(0, np.uint64)
+    a["left_hits_off"] = start[0::2]
+    a["right_hits_off"] = start[1::2]
+    return a, hp, (lo, hi)
 
 
 def extend_sharded(compute, anchors, hit_pool, rank=0, world=1, group=None):
