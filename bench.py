@@ -288,7 +288,7 @@ def main():
                 # dram__bytes_read+write of tiles_kernel<5> from the committed ncu capture (profiles/r1_fast_*: 88.44 MB per
                 # 200k-tile launch = 442 B per tile), scaled to this launch's tile count; algorithmic bytes: 468 B per tile
                 "traffic": 442.2 * n,
-                "peak_detail_glaneops": dict(zip(["vimnmx_u16x2", "viaddmnmx_u16x2", "vimnmx3_u16x2", "iadd3", "lop3", "imad"], int_detail)) if int_detail else None,
+                "peak_detail_glaneops": dict(zip(["vimnmx_u16x2", "viaddmnmx_u16x2", "vimnmx3_u16x2", "iadd3", "lop3_3reg", "imad", "lop3_2reg", "lop3_imm", "prmt", "shfl_idx"], int_detail)) if int_detail else None,
                 "note": "SURVEY 8(d) integer-pipe roofline: 32 algorithmic int-ops per cell; peak = measured packed "
                         "s16x2 DPX/ALU issue rate (2 cells per lane-op) of this GPU; HBM is not the bound "
                         "(%.3f B/cell algorithmic)" % ((2 * TILE / 2 + 32 + 16 + tbw * 8) / (TILE * TILE)),

@@ -93,6 +93,7 @@ struct WarpCtx {
     unsigned char* wsmem;         // this warp's dynamic shared memory (fast view and ExactSmem alias each other)
     WarpScratch ws;
     uint32_t n_fast, n_exact, n_rerun;
+    unsigned long long cells_exact;
 };
 
 // One tile for one warp: packed fast path when the tile qualifies, exact path otherwise or when the fast
@@ -151,7 +152,7 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
         if (se) exact_forward<true, false>(cx.ssub, go, ge, lgo, lge, t, sm, cx.ws, out);
         else    exact_forward<false, false>(cx.ssub, go, ge, lgo, lge, t, sm, cx.ws, out);
     }
-    cx.n_exact++;
+    cx.n_exact++; cx.cells_exact += (unsigned long long)t.Q * (unsigned long long)t.R;
 }
 
 template <int K>
@@ -162,7 +163,7 @@ __device__ __forceinline__ WarpCtx make_ctx(const uint8_t* arena, const int* ssu
     WarpCtx cx;
     cx.arena = arena; cx.ssub = ssub; cx.wsmem = dyn + (size_t)warp * per_warp;
     cx.ws = WarpScratch{trace_base + (size_t)gw * trace_stride, bound_base + (size_t)gw * kMaxTile};
-    cx.n_fast = cx.n_exact = cx.n_rerun = 0;
+    cx.n_fast = cx.n_exact = cx.n_rerun = 0; cx.cells_exact = 0;
     return cx;
 }
 
@@ -171,6 +172,7 @@ __device__ __forceinline__ void flush_counters(const WarpCtx& cx, unsigned int* 
         if (cx.n_fast) atomicAdd(counter + 1, cx.n_fast);
         if (cx.n_exact) atomicAdd(counter + 2, cx.n_exact);
         if (cx.n_rerun) atomicAdd(counter + 3, cx.n_rerun);
+        if (cx.cells_exact) atomicAdd(reinterpret_cast<unsigned long long*>(counter + 4), cx.cells_exact);
     }
 }
 
@@ -367,7 +369,11 @@ __global__ void int_peak_kernel(uint32_t* out, const uint32_t* in, int iters) {
                 else if (KIND == 2) a[k] = __vimax3_u16x2(a[k], o, c);
                 else if (KIND == 3) a[k] = a[k] + o + c;
                 else if (KIND == 4) a[k] = (a[k] & o) ^ c;
-                else a[k] = a[k] * c + o;
+                else if (KIND == 5) a[k] = a[k] * c + o;
+                else if (KIND == 6) a[k] = a[k] ^ o;                        // 2-input LOP3
+                else if (KIND == 7) a[k] = (a[k] | 0x00010001u) ^ o;       // LOP3 with an immediate
+                else if (KIND == 8) a[k] = __byte_perm(a[k], o, 0x5410 + rep);   // PRMT
+                else a[k] = __shfl_sync(0xffffffffu, a[k], (threadIdx.x + 31) & 31);   // SHFL.IDX
             }
         }
     }
@@ -474,10 +480,11 @@ static int configure_kernels(DarwinGpu* h) {
 }
 
 static int read_counters(DarwinGpu* h) {
-    unsigned int c[4] = {0, 0, 0, 0};
+    unsigned int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CK(cudaMemcpyAsync(c, h->d_counter, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->stats.tiles_fast += c[1]; h->stats.tiles_exact += c[2]; h->stats.tiles_rerun += c[3];
+    h->stats.cells_exact += ((uint64_t)c[5] << 32) | c[4];
     return DARWIN_OK;
 }
 
@@ -512,7 +519,7 @@ int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) {
         CK(cudaEventCreateWithFlags(&h->ev_chunk[b], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
     }
-    CK(cudaMalloc(&h->d_counter, sizeof(unsigned int) * 4));
+    CK(cudaMalloc(&h->d_counter, sizeof(unsigned int) * 8));
     h->max_warps = h->sm_count * 16;                                           // scratch is sized for this many resident warps
     int rc = configure_kernels(h);
     if (rc) return rc;
@@ -648,7 +655,7 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
     const size_t tb_row = do_traceback ? (size_t)tb_words_per_req * sizeof(uint64_t) : 0;
     int rc;
     if ((rc = grow_dev(h, 0, req_b)) || (rc = grow_dev(h, 1, res_b)) || (rc = grow_dev(h, 2, tb_row * n + 8))) return rc;
-    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 8, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[0], req, req_b, cudaMemcpyHostToDevice, h->stream));
     // Chunked pipeline: kernel(c+1) on the compute stream overlaps the D2H of chunk c on the copy stream.  Page-locked
     // caller buffers receive the DMA directly; pageable ones go through the two pinned staging buffers.
@@ -698,7 +705,7 @@ int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, i
     if (max_ref_size <= 0 || max_query_size <= 0 || max_ref_size > kMaxTile || max_query_size > kMaxTile) return DARWIN_ERR_INVALID;
     if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
     CK(cudaSetDevice(h->device));
-    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 8, h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
     int rc = launch_tiles(h, do_traceback, (const DarwinTileReq*)d_req, n, (DarwinTileRes*)d_res,
                           (uint64_t*)d_tb_words, tb_words_per_req, max_query_size, max_ref_size);
@@ -738,7 +745,7 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     CK(cudaMemcpyAsync(h->d_buf[6], size.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     if ((rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(1984, 960), exact_trace_bytes(960, 1984)),
                                          std::max(exact_trace_bytes(p->tile_size, p->tile_size), multi_band_bytes<4>(kMaxTile)))))) return rc;
-    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 4, h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 8, h->stream));
     ExtendArgs ea;
     ea.arena = h->d_arena; ea.anchors = (const DarwinAnchor*)h->d_buf[0]; ea.hit_pool = (const uint64_t*)h->d_buf[2];
     ea.res = (DarwinAlnRes*)h->d_buf[1]; ea.ops = (uint8_t*)h->d_buf[3];
@@ -833,7 +840,7 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     return DARWIN_OK;
 }
 
-int darwin_gpu_int_peak(DarwinGpu* h, double out[6]) {
+int darwin_gpu_int_peak(DarwinGpu* h, double out[10]) {
     if (!h || !out) return DARWIN_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     uint32_t host_in[16];
@@ -842,7 +849,7 @@ int darwin_gpu_int_peak(DarwinGpu* h, double out[6]) {
     CK(cudaMalloc(&d, 64 * sizeof(uint32_t)));
     CK(cudaMemcpy(d, host_in, sizeof(host_in), cudaMemcpyHostToDevice));
     const int iters = 4096, blocks = h->sm_count * 8, threads = 256;
-    for (int kind = 0; kind < 6; kind++) {
+    for (int kind = 0; kind < 10; kind++) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; rep++) {
             CK(cudaEventRecord(h->ev0, h->stream));
@@ -852,7 +859,11 @@ int darwin_gpu_int_peak(DarwinGpu* h, double out[6]) {
                 case 2: int_peak_kernel<2><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
                 case 3: int_peak_kernel<3><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
                 case 4: int_peak_kernel<4><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
-                default: int_peak_kernel<5><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                case 5: int_peak_kernel<5><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                case 6: int_peak_kernel<6><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                case 7: int_peak_kernel<7><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                case 8: int_peak_kernel<8><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
+                default: int_peak_kernel<9><<<blocks, threads, 0, h->stream>>>(d + 32, d, iters); break;
             }
             CK(cudaGetLastError());
             CK(cudaEventRecord(h->ev1, h->stream));

@@ -134,8 +134,9 @@ class Processor:
         return res, ops
 
     def int_peak(self):
-        """Measured issue rates (G lane-ops/s): VIMNMX.U16x2, VIADDMNMX.U16x2, VIMNMX3.U16x2, IADD3, LOP3, IMAD."""
-        out = (C.c_double * 6)()
+        """Measured issue rates (G lane-ops/s): VIMNMX.U16x2, VIADDMNMX.U16x2, VIMNMX3.U16x2, IADD3, LOP3 (3 regs),
+        IMAD, LOP3 (2 regs), LOP3 (immediate), PRMT, SHFL.IDX."""
+        out = (C.c_double * 10)()
         self._check(self.lib.darwin_gpu_int_peak(self.h, out))
         return list(out)
 

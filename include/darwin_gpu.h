@@ -148,6 +148,7 @@ typedef struct DarwinGpuStats {
     uint64_t tiles_exact;       /* tiles (re)computed by the exact path */
     uint64_t tiles_rerun;       /* fast tiles whose traceback asked for the exact path (subset of tiles_exact) */
     uint64_t cells;             /* DP cells requested (algorithmic) */
+    uint64_t cells_exact;       /* DP cells computed by the exact path (incl. reruns) */
     float    last_kernel_ms;    /* CUDA-event time of the last tiles/extend kernel(s) */
     float    reserved;
 } DarwinGpuStats;
@@ -191,8 +192,9 @@ int darwin_gpu_stats(DarwinGpu* h, DarwinGpuStats* out);
 /* Roofline denominator: measured issue rate, in 1e9 32-bit lane-ops per second, of packed-int16 /
  * integer instructions on this GPU (8 independent chains per thread, operands all loop-variant):
  * out[0] VIMNMX.U16x2 (2-input min/max), out[1] VIADDMNMX.U16x2, out[2] VIMNMX3.U16x2, out[3] IADD3, out[4] LOP3,
- * out[5] IMAD (fma pipe).  Each packed lane-op updates two int16 cells. */
-int darwin_gpu_int_peak(DarwinGpu* h, double out_glaneops[6]);
+ * out[5] IMAD (fma pipe), out[6] 2-input LOP3, out[7] LOP3 with immediate, out[8] PRMT, out[9] SHFL.IDX.
+ * Each packed lane-op updates two int16 cells. */
+int darwin_gpu_int_peak(DarwinGpu* h, double out_glaneops[10]);
 const char* darwin_gpu_last_error(DarwinGpu* h);
 const char* darwin_gpu_version(void);
 
