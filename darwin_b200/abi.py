@@ -50,7 +50,7 @@ class ExtendParams(C.Structure):
 
 class GpuStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("tiles_fast", C.c_uint64), ("tiles_exact", C.c_uint64),
-                ("tiles_rerun", C.c_uint64), ("cells", C.c_uint64), ("cells_exact", C.c_uint64), ("last_kernel_ms", C.c_float), ("reserved", C.c_float)]
+                ("tiles_rerun", C.c_uint64), ("cells", C.c_uint64), ("cells_exact", C.c_uint64), ("tiles_xfast", C.c_uint64), ("last_kernel_ms", C.c_float), ("reserved", C.c_float)]
 
 
 TILE_REQ = np.dtype([

@@ -13,6 +13,7 @@
 #include "gact_common.cuh"
 #include "gact_exact.cuh"
 #include "gact_fast.cuh"
+#include "gact_xfast.cuh"
 #include "gact_extend.cuh"
 
 using namespace gact;
@@ -68,7 +69,7 @@ struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568
     }
 };
 
-struct KernelScoring { DevScoring sc; FastConst fc; };
+struct KernelScoring { DevScoring sc; FastConst fc; XConst xc; };
 
 __device__ __forceinline__ void load_scoring(const DevScoring& sc, int* ssub) {
     if (threadIdx.x < 25) ssub[threadIdx.x] = sc.sub[threadIdx.x];
@@ -80,6 +81,7 @@ template <int K> struct KernelGeom {
     static constexpr int kWarps = (K == 0) ? kWarpsPerCta : 1;
     static constexpr size_t kFast = (K == 0) ? 0 : FastGeom<(K == 0 ? 4 : K)>::kSmemBytes;
     static constexpr size_t kNeed = (K == 0) ? sizeof(ExactSmem) : (kFast > MultiSmemView::kBytes ? kFast : MultiSmemView::kBytes);
+    static_assert(XSmemView::kBytes <= MultiSmemView::kBytes, "xfast view must fit");
     static constexpr size_t kTileBytes = ((kNeed > sizeof(ExactSmem) ? kNeed : sizeof(ExactSmem)) + 15) & ~(size_t)15;
     static constexpr size_t kPerWarp = kTileBytes;                      // tiles kernel
     static constexpr size_t kPerWarpExtend = kTileBytes + kOpsSmemBytes; // + op buffer of the anchor walker
@@ -92,7 +94,7 @@ struct WarpCtx {
     const int* ssub;
     unsigned char* wsmem;         // this warp's dynamic shared memory (fast view and ExactSmem alias each other)
     WarpScratch ws;
-    uint32_t n_fast, n_exact, n_rerun;
+    uint32_t n_fast, n_exact, n_rerun, n_xfast;
     unsigned long long cells_exact;
 };
 
@@ -110,29 +112,45 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
         const FastConst& fc = ks.fc;
         const bool fast = fc.eligible && do_traceback && se && fc.match * min(t.Q, t.R) <= fc.max_score;
         const bool single = t.Q <= 64 * KK && t.R <= 64 * KK;
+        const bool xok = ks.xc.eligible && xfast_shape_ok(t.Q);          // the packed exact path can take this shape
         if (fast) {
             FastSmemView<KK> v(cx.wsmem);
             MultiSmemView mv(cx.wsmem);
-            const bool has_n = single ? stage_sequences(cx.arena, t, v.sref, v.sqry)
-                                      : stage_sequences(cx.arena, t, mv.sref, mv.sqry);
+            XSmemView xv(cx.wsmem);
+            bool has_n = single ? stage_sequences(cx.arena, t, v.sref, v.sqry)
+                                : stage_sequences(cx.arena, t, mv.sref, mv.sqry);
             if (!has_n) {
                 uint32_t* gband = reinterpret_cast<uint32_t*>(cx.ws.trace);
-                const int score = single ? fast_forward<KK>(fc, v, t.Q, t.R) : fast_forward_multi<KK>(fc, mv, gband, t.Q, t.R);
-                int rc = FAST_OK;
-                if (lane == 0) {
-                    Sink trial = sink;
-                    TileOut o2{};
-                    rc = single ? fast_traceback<KK, false>(v.band, t.Q, t.R, t.max_tb, o2, trial)
-                                : fast_traceback<KK, true>(gband, t.Q, t.R, t.max_tb, o2, trial);
-                    if (rc == FAST_OK) { sink = trial; out = o2; }
+                // large tiles bridge long gaps by construction: the clean rule would almost always be refused, so
+                // shapes the packed exact path accepts go there directly
+                if (single || !xok) {
+                    const int score = single ? fast_forward<KK>(fc, v, t.Q, t.R) : fast_forward_multi<KK>(fc, mv, gband, t.Q, t.R);
+                    int rc = FAST_OK;
+                    if (lane == 0) {
+                        Sink trial = sink;
+                        TileOut o2{};
+                        rc = single ? fast_traceback<KK, false>(v.band, t.Q, t.R, t.max_tb, o2, trial)
+                                    : fast_traceback<KK, true>(gband, t.Q, t.R, t.max_tb, o2, trial);
+                        if (rc == FAST_OK) { sink = trial; out = o2; }
+                    }
+                    rc = __shfl_sync(0xffffffffu, rc, 0);
+                    if (rc == FAST_OK) {
+                        out.score = score; out.ref_max_pos = t.R - 1; out.query_max_pos = t.Q - 1;
+                        cx.n_fast++;
+                        return;
+                    }
+                    cx.n_rerun++;
+                    __syncwarp();
+                    if (xok && single) stage_sequences(cx.arena, t, xv.sref, xv.sqry);   // the fast view kept them elsewhere
                 }
-                rc = __shfl_sync(0xffffffffu, rc, 0);
-                if (rc == FAST_OK) {
+                if (xok) {
+                    const int score = xfast_forward(ks.xc, xv, gband, reinterpret_cast<uint4*>(cx.ws.bound), t.Q, t.R);
+                    __syncwarp();
+                    if (lane == 0) xfast_traceback(gband, t.Q, t.R, t.max_tb, out, sink);
                     out.score = score; out.ref_max_pos = t.R - 1; out.query_max_pos = t.Q - 1;
-                    cx.n_fast++;
+                    cx.n_xfast++;
                     return;
                 }
-                cx.n_rerun++;
             }
             __syncwarp();
         }
@@ -163,7 +181,7 @@ __device__ __forceinline__ WarpCtx make_ctx(const uint8_t* arena, const int* ssu
     WarpCtx cx;
     cx.arena = arena; cx.ssub = ssub; cx.wsmem = dyn + (size_t)warp * per_warp;
     cx.ws = WarpScratch{trace_base + (size_t)gw * trace_stride, bound_base + (size_t)gw * kMaxTile};
-    cx.n_fast = cx.n_exact = cx.n_rerun = 0; cx.cells_exact = 0;
+    cx.n_fast = cx.n_exact = cx.n_rerun = cx.n_xfast = 0; cx.cells_exact = 0;
     return cx;
 }
 
@@ -173,6 +191,7 @@ __device__ __forceinline__ void flush_counters(const WarpCtx& cx, unsigned int* 
         if (cx.n_exact) atomicAdd(counter + 2, cx.n_exact);
         if (cx.n_rerun) atomicAdd(counter + 3, cx.n_rerun);
         if (cx.cells_exact) atomicAdd(reinterpret_cast<unsigned long long*>(counter + 4), cx.cells_exact);
+        if (cx.n_xfast) atomicAdd(counter + 6, cx.n_xfast);
     }
 }
 
@@ -485,6 +504,7 @@ static int read_counters(DarwinGpu* h) {
     CK(cudaStreamSynchronize(h->stream));
     h->stats.tiles_fast += c[1]; h->stats.tiles_exact += c[2]; h->stats.tiles_rerun += c[3];
     h->stats.cells_exact += ((uint64_t)c[5] << 32) | c[4];
+    h->stats.tiles_xfast += c[6];
     return DARWIN_OK;
 }
 
@@ -577,6 +597,7 @@ int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s) {
     d.uniform = (AA == CC && AA == GG && AA == TT && AC == AG && AC == AT && AC == CG && AC == CT && AC == GT);
     d.match = AA; d.mismatch = AC; d.subn = N;
     h->ks.fc = make_fast_const(d);
+    h->ks.xc = make_xconst(d, h->ks.fc);
     h->have_scoring = true;
     return DARWIN_OK;
 }
@@ -617,7 +638,8 @@ int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint
 static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_req, int n,
                         DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR) {
     // per-warp scratch: exact-path trace (1 B/cell) or the multi-strip fast path's band, whichever is larger
-    int rc = ensure_scratch(h, std::max(exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)), multi_band_bytes<4>(std::max(maxQ, 1))));
+    int rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)), multi_band_bytes<4>(std::max(maxQ, 1))),
+                                        xfast_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1))));
     if (rc) return rc;
     const int K = pick_k(h, std::max(maxQ, maxR), do_traceback);
     const int ctas = h->ctas_tiles[variant_index(K)];
@@ -744,7 +766,9 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     CK(cudaMemcpyAsync(h->d_buf[5], lcap.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[6], size.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     if ((rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(1984, 960), exact_trace_bytes(960, 1984)),
-                                         std::max(exact_trace_bytes(p->tile_size, p->tile_size), multi_band_bytes<4>(kMaxTile)))))) return rc;
+                                         std::max(std::max(exact_trace_bytes(p->tile_size, p->tile_size), multi_band_bytes<4>(kMaxTile)),
+                                                  std::max(std::max(xfast_trace_bytes(1984, 960), xfast_trace_bytes(960, 1984)),
+                                                           xfast_trace_bytes(p->tile_size, p->tile_size))))))) return rc;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 8, h->stream));
     ExtendArgs ea;
     ea.arena = h->d_arena; ea.anchors = (const DarwinAnchor*)h->d_buf[0]; ea.hit_pool = (const uint64_t*)h->d_buf[2];

@@ -145,10 +145,11 @@ typedef struct DarwinExtendParams {
 typedef struct DarwinGpuStats {
     uint64_t kernel_launches;   /* kernels of this library launched since create */
     uint64_t tiles_fast;        /* tiles finished by the packed fast path */
-    uint64_t tiles_exact;       /* tiles (re)computed by the exact path */
+    uint64_t tiles_exact;       /* tiles (re)computed by the unpacked exact path */
     uint64_t tiles_rerun;       /* fast tiles whose traceback asked for the exact path (subset of tiles_exact) */
     uint64_t cells;             /* DP cells requested (algorithmic) */
-    uint64_t cells_exact;       /* DP cells computed by the exact path (incl. reruns) */
+    uint64_t cells_exact;       /* DP cells computed by the unpacked exact path (incl. reruns) */
+    uint64_t tiles_xfast;       /* tiles computed by the packed exact path (large tiles, reruns) */
     float    last_kernel_ms;    /* CUDA-event time of the last tiles/extend kernel(s) */
     float    reserved;
 } DarwinGpuStats;

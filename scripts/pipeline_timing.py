@@ -39,7 +39,7 @@ large_cells = 0
 print("GPU darwin_gpu_extend: kernel %.2f ms (wall %.1f ms), %.3g cells, %d alignments -> %.1f GCUPS, %.0f reads/s (kernel)" % (
     st.last_kernel_ms, wall * 1e3, gc, int((res["flags"] & 1).sum()), gc / st.last_kernel_ms / 1e6, n_reads / st.last_kernel_ms * 1e3))
 print("tiles %d (large %d), fast %d exact %d rerun %d" % (int(res["n_tiles"].sum()), int(res["n_large_tiles"].sum()),
-      st.tiles_fast - st0.tiles_fast, st.tiles_exact - st0.tiles_exact, st.tiles_rerun - st0.tiles_rerun))
+      st.tiles_fast - st0.tiles_fast, st.tiles_exact - st0.tiles_exact, st.tiles_rerun - st0.tiles_rerun), "xfast", st.tiles_xfast - st0.tiles_xfast)
 print("cells on the exact path: %.3g of %.3g (%.1f %%)" % (st.cells_exact - st0.cells_exact, gc, 100.0 * (st.cells_exact - st0.cells_exact) / gc))
 want_res, want_ops = ref.extend(anchors[:100], hits)
 print("parity on first 100 anchors:", alignments_equal(want_res, want_ops, res[:100], ops, ALN_FIELDS) == [])
