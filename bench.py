@@ -253,8 +253,9 @@ def main():
         ex.InitializeScoringParameters(sc)
         ex.InitializeReferenceMemory(0, ex_arena)
         ex.extender_body(ex_anchors[:64], ex_hits, 384, 64, 0)                     # warm-up
+        ex_out = (pinned((len(ex_anchors),), abi.ALN_RES), pinned((int(ex_anchors["read_len"].sum()) * 2,), np.uint8))
         t0 = time.perf_counter()
-        ex_res, ex_ops = ex.extender_body(ex_anchors, ex_hits, 384, 64, 0)
+        ex_res, ex_ops = ex.extender_body(ex_anchors, ex_hits, 384, 64, 0, out=ex_out)   # anchors + hits H2D, ops D2H
         ex_wall = time.perf_counter() - t0
         ex_st = ex.stats()
         ex_cells = float(ex_res["cells"].sum())

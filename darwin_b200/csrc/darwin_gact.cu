@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <chrono>
 
 #include "gact_common.cuh"
 #include "gact_exact.cuh"
@@ -420,7 +421,7 @@ struct DarwinGpu {
     uint8_t* d_trace = nullptr; size_t trace_stride = 0; ChainRec* d_bound = nullptr;
     unsigned int* d_counter = nullptr;
     // growable device buffers
-    void* d_buf[8] = {nullptr}; size_t d_cap[8] = {0};
+    void* d_buf[10] = {nullptr}; size_t d_cap[10] = {0};
     void* h_buf[4] = {nullptr}; size_t h_cap[4] = {0};
     DarwinGpuStats stats{};
     std::string err;
@@ -551,7 +552,7 @@ int darwin_gpu_destroy(DarwinGpu* h) {
     if (!h) return DARWIN_ERR_INVALID;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < 8; i++) if (h->d_buf[i]) cudaFree(h->d_buf[i]);
+    for (int i = 0; i < 10; i++) if (h->d_buf[i]) cudaFree(h->d_buf[i]);
     for (int i = 0; i < 4; i++) if (h->h_buf[i]) cudaFreeHost(h->h_buf[i]);
     if (h->d_trace) cudaFree(h->d_trace);
     if (h->d_bound) cudaFree(h->d_bound);
@@ -739,8 +740,12 @@ int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, i
 }
 
 // One chunk of anchors (the hit pool is already resident in d_buf[2]).  *used_out = op bytes written to ops_pool.
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+#define TMARK(name) do { if (tdbg) { double t_ = now_ms(); fprintf(stderr, "  [extend] %-18s %.2f ms\n", name, t_ - tlast); tlast = t_; } } while (0)
+
 static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n, uint64_t n_hits,
                         DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes, uint64_t* used_out, float* kernel_ms) {
+    const bool tdbg = getenv("DARWIN_GPU_TIMING") != nullptr; double tlast = now_ms();
     // op slots: left part holds the (reversed) left extension, right part the right extension
     std::vector<uint64_t> base(n); std::vector<uint32_t> lcap(n), size(n);
     uint64_t total = 0;
@@ -756,6 +761,7 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
         size[i] = lcap[i] + 2u * (a.read_len - a.query_pos) + slack;
         base[i] = total; total += size[i];
     }
+    TMARK("slots");
     int rc;
     const size_t an_b = (size_t)n * sizeof(DarwinAnchor), res_b = (size_t)n * sizeof(DarwinAlnRes);
     if ((rc = grow_dev(h, 0, an_b)) || (rc = grow_dev(h, 1, res_b)) ||
@@ -792,10 +798,12 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev1, h->stream));
     h->stats.kernel_launches++;
+    TMARK("launch");
     // first D2H: op counts -> dense offsets (host prefix sum), then score + compaction on the device
     CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
     if ((rc = read_counters(h))) return rc;
     { float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); *kernel_ms += ms; }
+    TMARK("kernel+res D2H");
     std::vector<uint64_t> dense(n);
     uint64_t used = 0; int overflow = 0;
     for (int i = 0; i < n; i++) {
@@ -805,9 +813,10 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
         h->stats.cells += res[i].cells;
     }
     if (used > ops_pool_bytes) { h->err = "ops_pool too small: need " + std::to_string(used); return DARWIN_ERR_CAPACITY; }
+    TMARK("prefix");
     CK(cudaMemcpyAsync(h->d_buf[7], dense.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
-    uint8_t* d_dense = nullptr;
-    CK(cudaMallocAsync(&d_dense, used + 16, h->stream));
+    if ((rc = grow_dev(h, 8, used + 16))) return rc;
+    uint8_t* d_dense = (uint8_t*)h->d_buf[8];
     score_compact_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_arena, h->ks, (const DarwinAnchor*)h->d_buf[0],
                                                                 (DarwinAlnRes*)h->d_buf[1], n, (const uint8_t*)h->d_buf[3],
                                                                 (const uint64_t*)h->d_buf[7], d_dense);
@@ -815,8 +824,8 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     h->stats.kernel_launches++;
     CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
     if (used && ops_pool) CK(cudaMemcpyAsync(ops_pool, d_dense, used, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaFreeAsync(d_dense, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    TMARK("compact+D2H");
     (void)overflow;
     *used_out = used;
     if (ea.dbg) {

@@ -119,14 +119,21 @@ class Processor:
                                                      int(max_ref_size), int(max_query_size)))
 
     # extender_body::operator() (extender.cpp:9-1065) for a batch of anchors
-    def extender_body(self, anchors, hit_pool, tile_size=384, tile_overlap=64, do_overlap=0, ops_cap=None):
-        an = np.ascontiguousarray(anchors, dtype=abi.ANCHOR)
+    def extender_body(self, anchors, hit_pool, tile_size=384, tile_overlap=64, do_overlap=0, ops_cap=None, out=None):
+        """Returns (DarwinAlnRes array, op pool).  `out=(res, ops)` supplies caller-owned (ideally page-locked) buffers."""
+        an = anchors if (isinstance(anchors, np.ndarray) and anchors.dtype == abi.ANCHOR and anchors.flags["C_CONTIGUOUS"]) \
+            else np.ascontiguousarray(anchors, dtype=abi.ANCHOR)
         hp = np.ascontiguousarray(hit_pool, dtype=np.uint64)
         n = len(an)
-        res = np.zeros(n, abi.ALN_RES)
-        if ops_cap is None:
-            ops_cap = int(an["read_len"].astype(np.int64).sum()) * 3 + 65536
-        ops = np.zeros(ops_cap, np.uint8)
+        if out is not None:
+            res, ops = out
+            assert res.dtype == abi.ALN_RES and len(res) >= n and ops.dtype == np.uint8
+            ops_cap = len(ops)
+        else:
+            res = np.empty(n, abi.ALN_RES)
+            if ops_cap is None:
+                ops_cap = int(an["read_len"].astype(np.int64).sum()) * 3 + 65536
+            ops = np.empty(ops_cap, np.uint8)
         prm = abi.ExtendParams(int(tile_size), int(tile_overlap), int(do_overlap), 0)
         self._check(self.lib.darwin_gpu_extend(self.h, C.byref(prm), abi.ptr(an), n,
                                                abi.ptr(hp) if len(hp) else None, C.c_uint64(len(hp)),
