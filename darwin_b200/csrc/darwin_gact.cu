@@ -84,8 +84,16 @@ template <int K> struct KernelGeom {
     static constexpr size_t kNeed = (K == 0) ? sizeof(ExactSmem) : (kFast > MultiSmemView::kBytes ? kFast : MultiSmemView::kBytes);
     static_assert(XSmemView::kBytes <= MultiSmemView::kBytes, "xfast view must fit");
     static constexpr size_t kTileBytes = ((kNeed > sizeof(ExactSmem) ? kNeed : sizeof(ExactSmem)) + 15) & ~(size_t)15;
-    static constexpr size_t kPerWarp = kTileBytes;                      // tiles kernel
-    static constexpr size_t kPerWarpExtend = kTileBytes + kOpsSmemBytes; // + op buffer of the anchor walker
+    // raw packed windows for the TMA staging: single-strip fast tiles use a small pair behind the tile region; bigger
+    // tiles (multi-strip / packed exact / unpacked exact) use the spare space of the tile region (K > 0) or a big pair (K = 0)
+    static constexpr int kRawSmallStride = (K == 0) ? kRawBig : ((32 * K + 32 + 15) & ~15);
+    static constexpr size_t kRawOff = kTileBytes;                        // offset of the small raw pair
+    static constexpr size_t kMbarOff = kRawOff + 2 * kRawSmallStride;
+    static constexpr size_t kBigRawOff = (K == 0) ? kRawOff : 16000;     // MultiSmemView / XSmemView / ExactSmem end below 16000
+    static_assert(K == 0 || 16000 + 2 * (size_t)kRawBig <= kTileBytes, "spare space for the big raw windows");
+    static constexpr size_t kPerWarp = kMbarOff + 16;                    // tiles kernel
+    static constexpr size_t kOpsOff = kPerWarp;
+    static constexpr size_t kPerWarpExtend = kPerWarp + kOpsSmemBytes;   // + op buffer of the anchor walker
     static constexpr size_t kSmemExtend = kPerWarpExtend * kWarps;
     static constexpr size_t kSmem = kPerWarp * kWarps;
 };
@@ -94,10 +102,20 @@ struct WarpCtx {
     const uint8_t* arena;
     const int* ssub;
     unsigned char* wsmem;         // this warp's dynamic shared memory (fast view and ExactSmem alias each other)
+    TmaStage ts_small, ts_big;    // TMA staging windows (small: single-strip fast tiles; big: everything else)
     WarpScratch ws;
     uint32_t n_fast, n_exact, n_rerun, n_xfast;
     unsigned long long cells_exact;
 };
+
+// TMA staging through the warp's small or big raw windows (one mbarrier, one phase bit for both).
+__device__ __forceinline__ bool stage_tile(WarpCtx& cx, const TileJob& t, uint8_t* sref, uint8_t* sqry, bool small) {
+    TmaStage& ts = small ? cx.ts_small : cx.ts_big;
+    ts.phase = cx.ts_small.phase;
+    const bool has_n = stage_sequences(cx.arena, t, sref, sqry, ts);
+    cx.ts_small.phase = ts.phase;
+    return has_n;
+}
 
 // One tile for one warp: packed fast path when the tile qualifies, exact path otherwise or when the fast
 // traceback asks for it.  `out` offsets/total and the sink are meaningful in lane 0 only.
@@ -118,8 +136,7 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
             FastSmemView<KK> v(cx.wsmem);
             MultiSmemView mv(cx.wsmem);
             XSmemView xv(cx.wsmem);
-            bool has_n = single ? stage_sequences(cx.arena, t, v.sref, v.sqry)
-                                : stage_sequences(cx.arena, t, mv.sref, mv.sqry);
+            bool has_n = single ? stage_tile(cx, t, v.sref, v.sqry, true) : stage_tile(cx, t, mv.sref, mv.sqry, false);
             if (!has_n) {
                 uint32_t* gband = reinterpret_cast<uint32_t*>(cx.ws.trace);
                 // large tiles bridge long gaps by construction: the clean rule would almost always be refused, so
@@ -142,7 +159,7 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
                     }
                     cx.n_rerun++;
                     __syncwarp();
-                    if (xok && single) stage_sequences(cx.arena, t, xv.sref, xv.sqry);   // the fast view kept them elsewhere
+                    if (xok && single) stage_tile(cx, t, xv.sref, xv.sqry, false);        // the fast view kept them elsewhere
                 }
                 if (xok) {
                     const int score = xfast_forward(ks.xc, xv, gband, reinterpret_cast<uint4*>(cx.ws.bound), t.Q, t.R);
@@ -157,7 +174,7 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
         }
     }
     ExactSmem* sm = reinterpret_cast<ExactSmem*>(cx.wsmem);
-    stage_sequences(cx.arena, t, sm->ref, sm->qry);
+    stage_tile(cx, t, sm->ref, sm->qry, false);
     const int go = ks.sc.go, ge = ks.sc.ge, lgo = ks.sc.lgo, lge = ks.sc.lge;
     if (do_traceback) {
         if (se) exact_forward<true, true>(cx.ssub, go, ge, lgo, lge, t, sm, cx.ws, out);
@@ -181,6 +198,10 @@ __device__ __forceinline__ WarpCtx make_ctx(const uint8_t* arena, const int* ssu
     const int gw = blockIdx.x * KernelGeom<K>::kWarps + warp;
     WarpCtx cx;
     cx.arena = arena; cx.ssub = ssub; cx.wsmem = dyn + (size_t)warp * per_warp;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(cx.wsmem + KernelGeom<K>::kMbarOff);
+    cx.ts_small = TmaStage{cx.wsmem + KernelGeom<K>::kRawOff, KernelGeom<K>::kRawSmallStride, mbar, 0u};
+    cx.ts_big = TmaStage{cx.wsmem + KernelGeom<K>::kBigRawOff, kRawBig, mbar, 0u};
+    tma_stage_init(mbar);
     cx.ws = WarpScratch{trace_base + (size_t)gw * trace_stride, bound_base + (size_t)gw * kMaxTile};
     cx.n_fast = cx.n_exact = cx.n_rerun = cx.n_xfast = 0; cx.cells_exact = 0;
     return cx;
@@ -278,7 +299,7 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
             int crt = T, cqt = T;
             if (a.large && ea.do_overlap == 0) { crt = rt; cqt = qt; }           // extender.cpp:261 / :408
             // lane 0 walks the traceback and records the ops in shared memory; the warp then consumes them together
-            uint8_t* opbuf = cx.wsmem + KernelGeom<K>::kTileBytes;          // behind the tile's own shared memory
+            uint8_t* opbuf = cx.wsmem + KernelGeom<K>::kOpsOff;             // behind the tile's own shared memory
             SmemOpSink sink{opbuf, 0, kOpsSmemBytes, 0};
             TileOut out{};
             process_tile<K>(cx, ks, t, true, out, sink);
@@ -528,7 +549,7 @@ int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
     h->arena_bytes = arena_bytes;
-    const size_t packed = (arena_bytes + 1) / 2 + 16;
+    const size_t packed = (arena_bytes + 1) / 2 + 64;          // slack: TMA windows are rounded up to 16 bytes
     CK(cudaMalloc(&h->d_arena, packed));
     CK(cudaMemsetAsync(h->d_arena, 0x44, packed, h->stream));                  // all 'N' (Index.cpp:12 pads with 'N')
     h->stage_bytes = 32u << 20;

@@ -22,24 +22,71 @@ struct ExactSmem {                       // per warp
     ChainRec rec[2][32];                 // boundary records of the previous strip, 32 columns at a time
 };
 
+// ---- TMA staging of the packed sequences -----------------------------------------------------------------------
+// The 4-bit packed windows of the tile's reference and query are brought into shared memory by two bulk async copies
+// (cp.async.bulk, completion on an mbarrier); the lanes then unpack / reverse / complement out of shared memory.
+constexpr int kRawBig = (kMaxTile / 2 + 48 + 15) & ~15;          // bytes of one packed window of <= 1984 bases (16-byte rounded)
+
+struct TmaStage {
+    uint8_t*  raw;        // two windows, `stride` bytes apart, 16-byte aligned (shared memory)
+    int       stride;
+    uint64_t* mbar;       // shared-memory mbarrier of this warp
+    uint32_t  phase;      // parity of the next completion
+};
+
+__device__ __forceinline__ void tma_stage_init(uint64_t* mbar) {
+    if (lane_id() == 0) {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(mbar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(a));
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncwarp();
+}
+
 // Stage one tile's sequences into shared memory (Processor.cpp:105-106 and :276-277 index rules).
 // Returns (warp-uniform) whether any staged base is N.
 __device__ __forceinline__ bool stage_sequences(const uint8_t* __restrict__ arena, const TileJob& t,
-                                                uint8_t* sref, uint8_t* sqry) {
+                                                uint8_t* sref, uint8_t* sqry, TmaStage& ts) {
     const int lane = lane_id();
     const bool rr = t.flags & DARWIN_REVERSE_REF, cr = t.flags & DARWIN_COMPLEMENT_REF;
     const bool rq = t.flags & DARWIN_REVERSE_QUERY, cq = t.flags & DARWIN_COMPLEMENT_QUERY;
+    // 16-byte aligned packed windows [r0, r1) and [q0, q1) (byte offsets into the packed arena)
+    const uint64_t r0 = (t.ra >> 1) & ~(uint64_t)15, r1 = ((((t.ra + (uint64_t)t.R - 1) >> 1) + 16) & ~(uint64_t)15);
+    const uint64_t q0 = (t.qa >> 1) & ~(uint64_t)15, q1 = ((((t.qa + (uint64_t)t.Q - 1) >> 1) + 16) & ~(uint64_t)15);
+    __syncwarp();                                                   // nobody still reads the previous tile's windows
+    if (lane == 0) {
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(ts.mbar);
+        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(ts.raw), d1 = d0 + (uint32_t)ts.stride;
+        const uint32_t nr = (uint32_t)(r1 - r0), nq = (uint32_t)(q1 - q0);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic reads of raw[] before the async writes
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(mb), "r"(nr + nq) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(d0), "l"(arena + r0), "r"(nr), "r"(mb) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     ::"r"(d1), "l"(arena + q0), "r"(nq), "r"(mb) : "memory");
+    }
+    {   // every lane waits for the completion of this phase (bounded: a lost copy traps instead of hanging the GPU)
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(ts.mbar);
+        uint32_t done = 0;
+        for (int spin = 0; spin < (1 << 24) && !done; spin++)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done) : "r"(mb), "r"(ts.phase) : "memory");
+        if (!done) __trap();
+        ts.phase ^= 1u;
+    }
+    const uint8_t* wr = ts.raw;
+    const uint8_t* wq = ts.raw + ts.stride;
     uint32_t seen = 0;
     for (int k = lane; k < t.R; k += 32) {
-        uint64_t a = rr ? t.ra + (uint64_t)(t.R - 1 - k) : t.ra + (uint64_t)k;
-        uint32_t c = arena_code(arena, a);
+        const uint64_t a = rr ? t.ra + (uint64_t)(t.R - 1 - k) : t.ra + (uint64_t)k;
+        uint32_t c = (wr[(a >> 1) - r0] >> ((a & 1) * 4)) & 0xFu;
         if (cr && c < 4) c = 3 - c;
         seen |= c;
         sref[k] = (uint8_t)c;
     }
     for (int k = lane; k < t.Q; k += 32) {
-        uint64_t a = rq ? t.qa + (uint64_t)(t.Q - 1 - k) : t.qa + (uint64_t)k;
-        uint32_t c = arena_code(arena, a);
+        const uint64_t a = rq ? t.qa + (uint64_t)(t.Q - 1 - k) : t.qa + (uint64_t)k;
+        uint32_t c = (wq[(a >> 1) - q0] >> ((a & 1) * 4)) & 0xFu;
         if (cq && c < 4) c = 3 - c;
         seen |= c;
         sqry[k] = (uint8_t)c;
