@@ -48,9 +48,16 @@ class ExtendParams(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class FilterParams(C.Structure):
+    """params.cfg [GACT_first_tile] (software/params.cfg:29-34) as darwin_gpu_filter takes it."""
+    _fields_ = [("first_tile_size", C.c_int32), ("first_tile_score_threshold", C.c_int32), ("min_overlap", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
 class GpuStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("tiles_fast", C.c_uint64), ("tiles_exact", C.c_uint64),
-                ("tiles_rerun", C.c_uint64), ("cells", C.c_uint64), ("cells_exact", C.c_uint64), ("tiles_xfast", C.c_uint64), ("last_kernel_ms", C.c_float), ("reserved", C.c_float)]
+                ("tiles_rerun", C.c_uint64), ("cells", C.c_uint64), ("cells_exact", C.c_uint64), ("tiles_xfast", C.c_uint64), ("last_kernel_ms", C.c_float), ("reserved", C.c_float),
+                ("tiles_filter", C.c_uint64)]
 
 
 TILE_REQ = np.dtype([
@@ -63,6 +70,15 @@ TILE_RES = np.dtype([
     ("score", "<i4"), ("ref_offset", "<u2"), ("query_offset", "<u2"), ("ref_max_pos", "<u2"),
     ("query_max_pos", "<u2"), ("total_TB_pointers", "<u2"), ("index", "u1"), ("status", "u1")], align=False)
 assert TILE_RES.itemsize == 16
+
+FILTER_CAND = np.dtype([
+    ("read_addr", "<u8"), ("hit", "<u4"), ("offset", "<u4"), ("chr_start", "<u4"), ("chr_len", "<u4"),
+    ("read_len", "<u4"), ("strand", "u1"), ("reserved", "u1", (3,))], align=False)
+assert FILTER_CAND.itemsize == 32
+
+FILTER_RES = np.dtype([("score", "<i4"), ("reference_pos", "<u4"), ("query_pos", "<u4"), ("flags", "<u4")], align=False)
+assert FILTER_RES.itemsize == 16
+FILTER_SCORE_OK, FILTER_OVERLAP_OK = 1, 2
 
 ANCHOR = np.dtype([
     ("read_addr", "<u8"), ("reference_pos", "<u4"), ("query_pos", "<u4"), ("chr_start", "<u4"),

@@ -16,6 +16,7 @@
 #include "gact_fast.cuh"
 #include "gact_xfast.cuh"
 #include "gact_extend.cuh"
+#include "gact_filter.cuh"
 
 using namespace gact;
 
@@ -71,6 +72,7 @@ struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568
 };
 
 struct KernelScoring { DevScoring sc; FastConst fc; XConst xc; };
+
 
 __device__ __forceinline__ void load_scoring(const DevScoring& sc, int* ssub) {
     if (threadIdx.x < 25) ssub[threadIdx.x] = sc.sub[threadIdx.x];
@@ -224,18 +226,21 @@ __global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 4 : 11)
 tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
              const DarwinTileReq* __restrict__ req, int n, int do_traceback,
              DarwinTileRes* __restrict__ res, uint64_t* __restrict__ tb_words, int tb_words_per_req,
-             uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base, unsigned int* counter) {
+             uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base, unsigned int* counter,
+             const unsigned int* __restrict__ idx_list, const unsigned int* __restrict__ idx_count) {
     __shared__ int ssub[32];
     extern __shared__ __align__(16) unsigned char dyn_smem[];
     load_scoring(ks.sc, ssub);
     const int lane = lane_id();
     WarpCtx cx = make_ctx<K>(arena, ssub, dyn_smem, KernelGeom<K>::kPerWarp, trace_base, trace_stride, bound_base);
+    if (idx_list) n = (int)*idx_count;                       // tiles the packed filter path handed over (filter_kernel)
 
     for (;;) {
         unsigned int idx = 0;
         if (lane == 0) idx = atomicAdd(counter, 1u);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= (unsigned)n) break;
+        if (idx_list) idx = idx_list[idx];
         const DarwinTileReq rq = req[idx];
         TileJob t{rq.ref_bases_start_addr, rq.query_bases_start_addr, (int)rq.ref_size, (int)rq.query_size,
                   rq.align_fields, (int)rq.max_tb_steps};
@@ -255,6 +260,102 @@ tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelSc
         __syncwarp();
     }
     flush_counters(cx, counter);
+}
+
+// First-tile filter tiles (filter.cpp:28-122 / :131-223 -> BatchAlignmentSIMD with do_traceback = 0, max-cell mode):
+// persistent warps pull PAIRS of tiles and run them in the two 16-bit halves of the packed score-only path
+// (gact_filter.cuh).  Tiles the packed path cannot take (N bases, odd shapes, start_end, score range) are appended to
+// `fb_list` and finished by tiles_kernel<0> (exact path) right after this kernel.
+constexpr int kFilterWarps = 4;
+__global__ void __launch_bounds__(kFilterWarps * 32, 5)
+filter_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ FilterConst fc,
+              const DarwinTileReq* __restrict__ req, int n, DarwinTileRes* __restrict__ res,
+              unsigned int* counter, unsigned int* fb_list, unsigned int* fb_count) {
+    __shared__ FilterSmem smem[kFilterWarps];
+    FilterSmem& sm = smem[threadIdx.x >> 5];
+    const int lane = lane_id();
+    tma_stage_init(&sm.mbar);
+    TmaStage ts{&sm.raw[0][0], kFiltRaw, &sm.mbar, 0u};
+    const unsigned int npairs = ((unsigned)n + 1u) >> 1;
+    unsigned int n_done = 0;
+    for (;;) {
+        unsigned int p = 0;
+        if (lane == 0) p = atomicAdd(counter, 1u);
+        p = __shfl_sync(0xffffffffu, p, 0);
+        if (p >= npairs) break;
+        const unsigned int ia = 2u * p, ib = (2u * p + 1u < (unsigned)n) ? 2u * p + 1u : ia;
+        const DarwinTileReq ra = req[ia], rb = req[ib];
+        const TileJob ta{ra.ref_bases_start_addr, ra.query_bases_start_addr, (int)ra.ref_size, (int)ra.query_size, ra.align_fields, (int)ra.max_tb_steps};
+        const TileJob tb{rb.ref_bases_start_addr, rb.query_bases_start_addr, (int)rb.ref_size, (int)rb.query_size, rb.align_fields, (int)rb.max_tb_steps};
+        const bool oka = filter_tile_ok(fc, ta), okb = filter_tile_ok(fc, tb);
+        const bool together = oka && okb && ib != ia && ta.Q == tb.Q && ta.R == tb.R;
+        // rounds: one packed pair, or each tile alone (duplicated into both halves)
+        for (int round = 0; round < (together || ib == ia ? 1 : 2); round++) {
+            const bool second = round == 1;
+            const TileJob& t0 = second ? tb : ta;
+            const TileJob& t1 = together ? tb : t0;
+            const unsigned int i0 = second ? ib : ia;
+            bool fallback = !(second ? okb : oka);
+            FilterHit h0{}, h1{};
+            if (!fallback) {
+                bool has_n = stage_sequences(arena, t0, sm.sref[0], sm.sqry[0], ts);
+                if (together) has_n |= stage_sequences(arena, t1, sm.sref[1], sm.sqry[1], ts);
+                else {
+                    for (int k = lane; k < kFiltMax; k += 32) { sm.sref[1][k] = sm.sref[0][k]; sm.sqry[1][k] = sm.sqry[0][k]; }
+                    __syncwarp();
+                }
+                if (!has_n) filter_pair_forward(fc, sm, t0.Q, t0.R, h0, h1);
+                else fallback = true;                           // a pair with an N goes to the exact path as a whole
+            }
+            if (lane == 0) {
+                if (fallback) {
+                    const unsigned int k = atomicAdd(fb_count, together ? 2u : 1u);
+                    fb_list[k] = i0;
+                    if (together) fb_list[k + 1] = ib;
+                } else {
+                    DarwinTileRes r;
+                    r.score = h0.score; r.ref_offset = 0; r.query_offset = 0;
+                    r.ref_max_pos = (uint16_t)h0.ref_max_pos; r.query_max_pos = (uint16_t)h0.query_max_pos;
+                    r.total_TB_pointers = 0; r.index = (uint8_t)(second ? rb.index : ra.index); r.status = 0;
+                    res[i0] = r;
+                    if (together) {
+                        r.score = h1.score; r.ref_max_pos = (uint16_t)h1.ref_max_pos; r.query_max_pos = (uint16_t)h1.query_max_pos;
+                        r.index = (uint8_t)rb.index;
+                        res[ib] = r;
+                    }
+                }
+            }
+            if (!fallback) n_done += together ? 2u : 1u;
+            __syncwarp();
+        }
+    }
+    if (lane == 0 && n_done) atomicAdd(fb_count + 1, n_done);
+}
+
+// filter_body's request construction (filter.cpp:44-71, :154-181), one thread per candidate.
+__global__ void filter_build_kernel(const DarwinFilterCand* __restrict__ cands, int n, int fts, DarwinTileReq* __restrict__ req) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    DarwinTileReq rq; uint32_t rts, qts;
+    filter_make_request(cands[k], fts, rq, rts, qts);
+    rq.index = (uint16_t)(k & 63);                              // position inside the reference's 64-request batch (:62)
+    req[k] = rq;
+}
+
+// filter_body's use of the results (filter.cpp:83-116), one thread per candidate.
+__global__ void filter_finish_kernel(const DarwinFilterCand* __restrict__ cands, const DarwinTileRes* __restrict__ tres, int n,
+                                     int fts, int threshold, int min_overlap, DarwinFilterRes* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const DarwinFilterCand c = cands[k];
+    DarwinTileReq rq; uint32_t rts, qts;
+    filter_make_request(c, fts, rq, rts, qts);
+    const DarwinTileRes t = tres[k];
+    DarwinFilterRes r;
+    r.score = t.score; r.reference_pos = rts + t.ref_max_pos; r.query_pos = qts + t.query_max_pos;
+    const uint32_t ovl = c.offset + ((c.chr_start + c.chr_len) - c.hit);
+    r.flags = ((uint32_t)t.score >= (uint32_t)threshold ? DARWIN_FILTER_SCORE_OK : 0u) | (ovl > (uint32_t)(min_overlap / 2) ? DARWIN_FILTER_OVERLAP_OK : 0u);
+    out[k] = r;
 }
 
 // extender_body::operator() (extender.cpp:9-1065): persistent warps pull ANCHORS and walk their tiles.
@@ -427,6 +528,8 @@ __global__ void int_peak_kernel(uint32_t* out, const uint32_t* in, int iters) {
 // =====================================================================================================
 // Host side: handle + C-ABI
 // =====================================================================================================
+constexpr int kCounters = 16;    // [0] queue head, [1] fast, [2] exact, [3] rerun, [4,5] cells_exact, [6] xfast, [8] filter hand-over count, [9] filter tiles
+
 struct DarwinGpu {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -436,7 +539,8 @@ struct DarwinGpu {
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;         // D2H of finished chunks overlaps the next chunk's kernel
     cudaEvent_t ev_chunk[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
-    KernelScoring ks{}; bool have_scoring = false;
+    KernelScoring ks{}; FilterConst filt{}; bool have_scoring = false;
+    int ctas_filter = 0;
     int sm_count = 0, max_warps = 0;
     int ctas_tiles[4] = {0, 0, 0, 0}, ctas_extend[4] = {0, 0, 0, 0};   // persistent grid per kernel variant (K = 0,4,5,6)
     uint8_t* d_trace = nullptr; size_t trace_stride = 0; ChainRec* d_bound = nullptr;
@@ -517,16 +621,20 @@ static int configure_kernels(DarwinGpu* h) {
     int rc;
     if ((rc = configure_variant<0>(h)) || (rc = configure_variant<4>(h)) || (rc = configure_variant<5>(h)) ||
         (rc = configure_variant<6>(h))) return rc;
+    int f = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, filter_kernel, kFilterWarps * 32, 0));
+    h->ctas_filter = h->sm_count * std::max(1, f);
     return DARWIN_OK;
 }
 
 static int read_counters(DarwinGpu* h) {
-    unsigned int c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned int c[kCounters] = {0};
     CK(cudaMemcpyAsync(c, h->d_counter, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->stats.tiles_fast += c[1]; h->stats.tiles_exact += c[2]; h->stats.tiles_rerun += c[3];
     h->stats.cells_exact += ((uint64_t)c[5] << 32) | c[4];
     h->stats.tiles_xfast += c[6];
+    h->stats.tiles_filter += c[9];
     return DARWIN_OK;
 }
 
@@ -561,7 +669,7 @@ int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) {
         CK(cudaEventCreateWithFlags(&h->ev_chunk[b], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
     }
-    CK(cudaMalloc(&h->d_counter, sizeof(unsigned int) * 8));
+    CK(cudaMalloc(&h->d_counter, sizeof(unsigned int) * kCounters));
     h->max_warps = h->sm_count * 16;                                           // scratch is sized for this many resident warps
     int rc = configure_kernels(h);
     if (rc) return rc;
@@ -620,6 +728,7 @@ int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s) {
     d.match = AA; d.mismatch = AC; d.subn = N;
     h->ks.fc = make_fast_const(d);
     h->ks.xc = make_xconst(d, h->ks.fc);
+    h->filt = make_filter_const(d);
     h->have_scoring = true;
     return DARWIN_OK;
 }
@@ -658,16 +767,39 @@ int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint
 }
 
 static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_req, int n,
-                        DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR) {
+                        DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR,
+                        const unsigned int* idx_list = nullptr, const unsigned int* idx_count = nullptr);
+
+// Score-only tiles (do_traceback = 0): packed filter path first, then the exact path on whatever it handed over.
+static int launch_filter_tiles(DarwinGpu* h, const DarwinTileReq* d_req, int n, DarwinTileRes* d_res, int maxQ, int maxR) {
+    int rc;
+    if ((rc = grow_dev(h, 9, (size_t)n * sizeof(unsigned int) + 16))) return rc;
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));
+    CK(cudaMemsetAsync(h->d_counter + 8, 0, sizeof(unsigned int), h->stream));
+    const int pairs = (n + 1) / 2;
+    const int ctas = std::max(1, std::min(h->ctas_filter, (pairs + kFilterWarps - 1) / kFilterWarps));
+    filter_kernel<<<ctas, kFilterWarps * 32, 0, h->stream>>>(h->d_arena, h->filt, d_req, n, d_res, h->d_counter,
+                                                            (unsigned int*)h->d_buf[9], h->d_counter + 8);
+    CK(cudaGetLastError());
+    h->stats.kernel_launches++;
+    return launch_tiles(h, 0, d_req, n, d_res, nullptr, 0, maxQ, maxR, (const unsigned int*)h->d_buf[9], h->d_counter + 8);
+}
+
+static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_req, int n,
+                        DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR,
+                        const unsigned int* idx_list, const unsigned int* idx_count) {
+    if (!do_traceback && !idx_list && h->filt.eligible) return launch_filter_tiles(h, d_req, n, d_res, maxQ, maxR);
     // per-warp scratch: exact-path trace (1 B/cell) or the multi-strip fast path's band, whichever is larger
     int rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)), multi_band_bytes<4>(std::max(maxQ, 1))),
                                         xfast_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1))));
     if (rc) return rc;
     const int K = pick_k(h, std::max(maxQ, maxR), do_traceback);
-    const int ctas = h->ctas_tiles[variant_index(K)];
+    int ctas = h->ctas_tiles[variant_index(K)];
+    if (idx_list) ctas = std::min(ctas, h->sm_count);                           // hand-over lists are short
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));      // queue head; [1..3] accumulate
 #define LAUNCH_TILES(KK) tiles_kernel<KK><<<ctas, KernelGeom<KK>::kWarps * 32, KernelGeom<KK>::kSmem, h->stream>>>( \
-        h->d_arena, h->ks, d_req, n, do_traceback, d_res, d_tb, tb_words_per_req, h->d_trace, h->trace_stride, h->d_bound, h->d_counter)
+        h->d_arena, h->ks, d_req, n, do_traceback, d_res, d_tb, tb_words_per_req, h->d_trace, h->trace_stride, h->d_bound, h->d_counter, \
+        idx_list, idx_count)
     switch (K) {
         case 4: LAUNCH_TILES(4); break;
         case 5: LAUNCH_TILES(5); break;
@@ -699,7 +831,7 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
     const size_t tb_row = do_traceback ? (size_t)tb_words_per_req * sizeof(uint64_t) : 0;
     int rc;
     if ((rc = grow_dev(h, 0, req_b)) || (rc = grow_dev(h, 1, res_b)) || (rc = grow_dev(h, 2, tb_row * n + 8))) return rc;
-    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * kCounters, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[0], req, req_b, cudaMemcpyHostToDevice, h->stream));
     // Chunked pipeline: kernel(c+1) on the compute stream overlaps the D2H of chunk c on the copy stream.  Page-locked
     // caller buffers receive the DMA directly; pageable ones go through the two pinned staging buffers.
@@ -743,13 +875,53 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
     return DARWIN_OK;
 }
 
+int darwin_gpu_filter(DarwinGpu* h, const DarwinFilterParams* p, const DarwinFilterCand* cands, int n, DarwinFilterRes* res) {
+    if (!h || !p || n < 0 || (n && (!cands || !res))) return DARWIN_ERR_INVALID;
+    if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
+    if (p->first_tile_size < 1 || p->first_tile_size > kMaxTile) { h->err = "first_tile_size must be in [1,1984]"; return DARWIN_ERR_INVALID; }
+    if (n == 0) return DARWIN_OK;
+    CK(cudaSetDevice(h->device));
+    const uint32_t fts = (uint32_t)p->first_tile_size;
+    for (int i = 0; i < n; i++) {
+        const DarwinFilterCand& c = cands[i];
+        const uint64_t chr_end = (uint64_t)c.chr_start + c.chr_len;
+        // the reference falls back to arena offset 0 for chromosomes shorter than the tile (filter.cpp:57); everything a
+        // request can touch must lie inside the arena
+        if (chr_end > h->arena_bytes || c.read_addr + c.read_len > h->arena_bytes || c.hit < c.chr_start || c.hit >= chr_end ||
+            c.offset >= c.read_len || c.strand > 1) {
+            h->err = "filter candidate " + std::to_string(i) + " is inconsistent"; return DARWIN_ERR_INVALID;
+        }
+    }
+    int rc;
+    const size_t cand_b = (size_t)n * sizeof(DarwinFilterCand), req_b = (size_t)n * sizeof(DarwinTileReq);
+    const size_t tres_b = (size_t)n * sizeof(DarwinTileRes), out_b = (size_t)n * sizeof(DarwinFilterRes);
+    if ((rc = grow_dev(h, 0, req_b)) || (rc = grow_dev(h, 1, tres_b)) || (rc = grow_dev(h, 4, cand_b)) || (rc = grow_dev(h, 5, out_b))) return rc;
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * kCounters, h->stream));
+    CK(cudaMemcpyAsync(h->d_buf[4], cands, cand_b, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaEventRecord(h->ev0, h->stream));
+    filter_build_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>((const DarwinFilterCand*)h->d_buf[4], n, (int)fts, (DarwinTileReq*)h->d_buf[0]);
+    CK(cudaGetLastError());
+    const int tile = (int)std::min<uint32_t>(fts, kMaxTile);
+    if ((rc = launch_tiles(h, 0, (const DarwinTileReq*)h->d_buf[0], n, (DarwinTileRes*)h->d_buf[1], nullptr, 0, tile, tile))) return rc;
+    filter_finish_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>((const DarwinFilterCand*)h->d_buf[4], (const DarwinTileRes*)h->d_buf[1], n,
+                                                                (int)fts, p->first_tile_score_threshold, p->min_overlap, (DarwinFilterRes*)h->d_buf[5]);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev1, h->stream));
+    h->stats.kernel_launches += 2;
+    CK(cudaMemcpyAsync(res, h->d_buf[5], out_b, cudaMemcpyDeviceToHost, h->stream));
+    if ((rc = read_counters(h))) return rc;
+    CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
+    h->stats.cells += (uint64_t)n * std::min<uint32_t>(fts, kMaxTile) * std::min<uint32_t>(fts, kMaxTile);
+    return DARWIN_OK;
+}
+
 int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, int n,
                             void* d_res, void* d_tb_words, int tb_words_per_req, int max_ref_size, int max_query_size) {
     if (!h || n <= 0 || !d_req || !d_res) return DARWIN_ERR_INVALID;
     if (max_ref_size <= 0 || max_query_size <= 0 || max_ref_size > kMaxTile || max_query_size > kMaxTile) return DARWIN_ERR_INVALID;
     if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
     CK(cudaSetDevice(h->device));
-    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * kCounters, h->stream));
     CK(cudaEventRecord(h->ev0, h->stream));
     int rc = launch_tiles(h, do_traceback, (const DarwinTileReq*)d_req, n, (DarwinTileRes*)d_res,
                           (uint64_t*)d_tb_words, tb_words_per_req, max_query_size, max_ref_size);
@@ -796,7 +968,7 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
                                          std::max(std::max(exact_trace_bytes(p->tile_size, p->tile_size), multi_band_bytes<4>(kMaxTile)),
                                                   std::max(std::max(xfast_trace_bytes(1984, 960), xfast_trace_bytes(960, 1984)),
                                                            xfast_trace_bytes(p->tile_size, p->tile_size))))))) return rc;
-    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * 8, h->stream));
+    CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * kCounters, h->stream));
     ExtendArgs ea;
     ea.arena = h->d_arena; ea.anchors = (const DarwinAnchor*)h->d_buf[0]; ea.hit_pool = (const uint64_t*)h->d_buf[2];
     ea.res = (DarwinAlnRes*)h->d_buf[1]; ea.ops = (uint8_t*)h->d_buf[3];

@@ -41,6 +41,7 @@ def load_library():
         L.darwin_gpu_tiles_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.darwin_gpu_extend.argtypes = [C.c_void_p, C.POINTER(abi.ExtendParams), C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.darwin_gpu_filter.argtypes = [C.c_void_p, C.POINTER(abi.FilterParams), C.c_void_p, C.c_int, C.c_void_p]
         L.darwin_gpu_stats.argtypes = [C.c_void_p, C.POINTER(abi.GpuStats)]
         L.darwin_gpu_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _lib = L
@@ -48,7 +49,7 @@ def load_library():
 
 
 EXPORTS = ("darwin_gpu_create", "darwin_gpu_destroy", "darwin_gpu_set_scoring", "darwin_gpu_upload",
-           "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_stats", "darwin_gpu_int_peak",
+           "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_filter", "darwin_gpu_stats", "darwin_gpu_int_peak",
            "darwin_gpu_last_error", "darwin_gpu_version")
 
 
@@ -117,6 +118,19 @@ class Processor:
         self._check(self.lib.darwin_gpu_tiles_device(self.h, int(do_traceback), C.c_void_p(d_req), int(n),
                                                      C.c_void_p(d_res), C.c_void_p(d_tb), int(tb_words_per_req),
                                                      int(max_ref_size), int(max_query_size)))
+
+    # the tile part of filter_body::operator() (filter.cpp:28-122, :131-223) for a batch of D-SOFT candidates
+    def filter_body(self, cands, first_tile_size=128, first_tile_score_threshold=60, min_overlap=1000, out=None):
+        """Returns a DarwinFilterRes array (score, reference_pos, query_pos, flags) aligned with `cands`;
+        the slope filter (filter.cpp:227-289) is host work (darwin_b200.hostlogic.slope_filter)."""
+        cd = cands if (isinstance(cands, np.ndarray) and cands.dtype == abi.FILTER_CAND and cands.flags["C_CONTIGUOUS"]) \
+            else np.ascontiguousarray(cands, dtype=abi.FILTER_CAND)
+        n = len(cd)
+        res = out if out is not None else np.empty(n, abi.FILTER_RES)
+        assert res.dtype == abi.FILTER_RES and len(res) >= n
+        prm = abi.FilterParams(int(first_tile_size), int(first_tile_score_threshold), int(min_overlap), 0)
+        self._check(self.lib.darwin_gpu_filter(self.h, C.byref(prm), abi.ptr(cd), n, abi.ptr(res)))
+        return res
 
     # extender_body::operator() (extender.cpp:9-1065) for a batch of anchors
     def extender_body(self, anchors, hit_pool, tile_size=384, tile_overlap=64, do_overlap=0, ops_cap=None, out=None):

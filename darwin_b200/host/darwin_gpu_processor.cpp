@@ -1,6 +1,8 @@
 // See darwin_gpu_processor.h.  Host-side only; all arithmetic of the path runs in libdarwin_gact.so.
 #include "darwin_gpu_processor.h"
 
+#include <algorithm>
+#include <deque>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -189,6 +191,77 @@ void gpu_extender_body::operator()(extender_input input, extender_node::output_p
     }
     get<1>(op).try_put(token);                                                        // extender.cpp:1062-1063
     get<0>(op).try_put(printer_input(printer_payload(reads, output), token));
+}
+
+// filter_body::operator() (filter.cpp:8-225) with every first tile of the batch -- both strands, all reads -- in ONE
+// darwin_gpu_filter call instead of g_BatchAlignmentSIMD batches of 64 (filter.cpp:22, :75).  Request construction,
+// score and overlap tests run on the device; the ExtendLocations (chr_id / read_num lookups, chained hits) and the
+// slope filter -- the reference's own filter_body::slopeFilter, unchanged -- stay here.
+extender_input gpu_filter_body::operator()(filter_input input) {
+    auto& payload = get<0>(input);
+    auto& reads = get<0>(payload);
+    auto& data = get<1>(payload);
+    size_t token = get<1>(input);
+    DarwinGpu* h = handle_for_token(token);
+    filter_data output;
+
+    const size_t nf = data.fwAnchors.size(), nr = data.rcAnchors.size();
+    std::vector<DarwinFilterCand> cands(nf + nr);
+    std::vector<int> chr_of(nf + nr), read_of(nf + nr);
+    for (int strand = 0; strand < 2; strand++) {
+        const auto& anchors = strand ? data.rcAnchors : data.fwAnchors;
+        const auto& buckets = strand ? data.rcAnchorBuckets : data.fwAnchorBuckets;
+        const size_t base = strand ? nf : 0;
+        for (size_t c = 0; c < anchors.size(); c++) {
+            const uint32_t hit = (uint32_t)(anchors[c].hit_offset >> 32);
+            const uint32_t offset = (uint32_t)((anchors[c].hit_offset << 32) >> 32);
+            const size_t chr_id = std::upper_bound(Index::chr_coord.cbegin(), Index::chr_coord.cend(), hit) - Index::chr_coord.cbegin() - 1;   // filter.cpp:49
+            const size_t read_num = std::upper_bound(buckets.cbegin(), buckets.cend(), c) - buckets.cbegin() - 1;                                // filter.cpp:53
+            const Read& read = reads[read_num];
+            DarwinFilterCand& k = cands[base + c];
+            k = DarwinFilterCand{};
+            k.read_addr = (uint64_t)(read.seq.data() - g_DRAM->buffer);
+            k.hit = hit; k.offset = offset;
+            k.chr_start = Index::chr_coord[chr_id]; k.chr_len = Index::chr_len[chr_id];
+            k.read_len = (uint32_t)read.seq.size(); k.strand = (uint8_t)strand;
+            chr_of[base + c] = (int)chr_id; read_of[base + c] = (int)read_num;
+        }
+    }
+    std::vector<DarwinFilterRes> res(cands.size());
+    if (!cands.empty()) {
+        for (const auto& rd : reads) {                                                 // the reads of this batch must be resident
+            const uint64_t at = (uint64_t)(rd.seq.data() - g_DRAM->buffer);
+            int rc = darwin_gpu_upload(h, at, rd.seq.data(), rd.seq.size());
+            if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_upload(read)");
+        }
+        DarwinFilterParams prm{cfg.first_tile_size, cfg.first_tile_score_threshold, cfg.min_overlap, 0};
+        int rc = darwin_gpu_filter(h, &prm, cands.data(), (int)cands.size(), res.data());
+        if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_filter");
+    }
+    for (int strand = 0; strand < 2; strand++) {
+        const auto& anchors = strand ? data.rcAnchors : data.fwAnchors;
+        const size_t base = strand ? nf : 0;
+        std::deque<ExtendLocations> read_extend_locations;
+        filter_body::num_filter_tiles += (int)anchors.size();                          // filter.cpp:80
+        for (size_t c = 0; c < anchors.size(); c++) {
+            const DarwinFilterRes& r = res[base + c];
+            if (!(r.flags & DARWIN_FILTER_SCORE_OK)) continue;                         // filter.cpp:87
+            if (r.flags & DARWIN_FILTER_OVERLAP_OK) {                                  // filter.cpp:104
+                ExtendLocations loc;
+                loc.read_num = read_of[base + c];
+                loc.chr_id = chr_of[base + c];
+                loc.score = r.score;
+                loc.reference_pos = r.reference_pos;
+                loc.query_pos = r.query_pos;
+                loc.left_hit_offsets.assign(anchors[c].left_chained_hits.begin(), anchors[c].left_chained_hits.end());
+                loc.right_hit_offsets.assign(anchors[c].right_chained_hits.begin(), anchors[c].right_chained_hits.end());
+                read_extend_locations.push_back(loc);
+            }
+            filter_body::num_extend_requests += 1;                                     // filter.cpp:117
+        }
+        filter_body().slopeFilter(read_extend_locations, strand ? output.rcLocations : output.fwLocations);   // filter.cpp:124 / :223
+    }
+    return extender_input(extender_payload(reads, output), token);
 }
 
 } // namespace darwin_gpu_host

@@ -34,6 +34,12 @@ struct gpu_extender_body {
     void operator()(extender_input input, extender_node::output_ports_type& op);
 };
 
+// == filter_body (software/graph.h:205-217, filter.cpp:8-225): same input/output tuples; the first tiles of the whole
+// batch (both strands) go to the GPU in one darwin_gpu_filter call; the slope filter is the reference's own.
+struct gpu_filter_body {
+    extender_input operator()(filter_input input);
+};
+
 // install the functions above into the reference's table (g_InitializeScoringParameters, ...).
 void InstallProcessorTable();
 

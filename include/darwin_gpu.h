@@ -12,6 +12,8 @@
  *   InitializeReferenceMemory_ptr     (:52)            darwin_gpu_upload
  *   InitializeReadMemory_ptr          (:53)            darwin_gpu_upload
  *   BatchAlignmentSIMD_ptr            (:55)            darwin_gpu_tiles
+ *   filter_body::operator()  (software/filter.cpp:8-225, graph.h:205-217)
+ *                                                      darwin_gpu_filter
  *   extender_body::operator()  (software/extender.cpp:9, graph.h:219-229)
  *                                                      darwin_gpu_extend
  *
@@ -142,6 +144,37 @@ typedef struct DarwinExtendParams {
     int32_t reserved;
 } DarwinExtendParams;
 
+/* One first-tile candidate == one element of seeder_data::fwAnchors / rcAnchors (software/graph.h:131-138,
+ * Anchors::hit_offset, software/seed_pos_table.h:30-40) plus what filter_body looks up for it (filter.cpp:44-56). */
+typedef struct DarwinFilterCand {
+    uint64_t read_addr;        /* arena offset of the FORWARD read (read.seq.data() - g_DRAM->buffer) */
+    uint32_t hit;              /* hit_offset >> 32: absolute arena offset of the seed hit on the reference */
+    uint32_t offset;           /* hit_offset & 0xffffffff: strand-local read offset of the seed hit */
+    uint32_t chr_start;        /* Index::chr_coord[chr_id] */
+    uint32_t chr_len;          /* Index::chr_len[chr_id] (padded) */
+    uint32_t read_len;
+    uint8_t  strand;           /* 0 = fwAnchors, 1 = rcAnchors (reverse_query + complement_query, filter.cpp:181) */
+    uint8_t  reserved[3];
+} DarwinFilterCand;
+
+#define DARWIN_FILTER_SCORE_OK   (1u << 0)  /* score >= first_tile_score_threshold (filter.cpp:87) */
+#define DARWIN_FILTER_OVERLAP_OK (1u << 1)  /* offset + (chr_end - hit) > min_overlap / 2 (filter.cpp:102-104) */
+
+/* What filter_body derives from one candidate's tile (filter.cpp:87-116): the ExtendLocations fields. */
+typedef struct DarwinFilterRes {
+    int32_t  score;            /* AlignmentResult.score of the first tile */
+    uint32_t reference_pos;    /* ref_tile_start + ref_max_pos   (absolute arena offset) */
+    uint32_t query_pos;        /* query_tile_start + query_max_pos (strand-local) */
+    uint32_t flags;            /* DARWIN_FILTER_* */
+} DarwinFilterRes;
+
+typedef struct DarwinFilterParams {
+    int32_t first_tile_size;              /* params.cfg [GACT_first_tile] first_tile_size */
+    int32_t first_tile_score_threshold;   /* first_tile_score_threshold */
+    int32_t min_overlap;                  /* min_overlap */
+    int32_t reserved;
+} DarwinFilterParams;
+
 typedef struct DarwinGpuStats {
     uint64_t kernel_launches;   /* kernels of this library launched since create */
     uint64_t tiles_fast;        /* tiles finished by the packed fast path */
@@ -150,8 +183,9 @@ typedef struct DarwinGpuStats {
     uint64_t cells;             /* DP cells requested (algorithmic) */
     uint64_t cells_exact;       /* DP cells computed by the unpacked exact path (incl. reruns) */
     uint64_t tiles_xfast;       /* tiles computed by the packed exact path (large tiles, reruns) */
-    float    last_kernel_ms;    /* CUDA-event time of the last tiles/extend kernel(s) */
+    float    last_kernel_ms;    /* CUDA-event time of the last tiles/extend/filter kernel(s) */
     float    reserved;
+    uint64_t tiles_filter;      /* score-only tiles finished by the packed filter path (two tiles per warp) */
 } DarwinGpuStats;
 
 typedef struct DarwinGpu DarwinGpu;   /* opaque */
@@ -181,6 +215,13 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p,
                       const DarwinAnchor* anchors, int n,
                       const uint64_t* hit_pool, uint64_t n_hits,
                       DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes);
+
+/* replaces the tile part of filter_body::operator() (filter.cpp:28-122 forward, :131-223 reverse complement) for n
+ * candidates of any number of reads: builds the first-tile requests (first_tile_size x first_tile_size, score-only,
+ * max-cell mode), runs them and applies the score and overlap tests.  The slope filter (filter.cpp:227-289) and the
+ * copying of the chained hits stay on the host (darwin_b200/host: gpu_filter_body). */
+int darwin_gpu_filter(DarwinGpu* h, const DarwinFilterParams* p, const DarwinFilterCand* cands, int n,
+                      DarwinFilterRes* res);
 
 /* device-resident variants used by bench.py's `value` leg: same work, inputs and
  * outputs stay in HBM (pointers are device pointers of this handle's device). */

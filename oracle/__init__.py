@@ -55,6 +55,28 @@ class Port:
             raise RuntimeError("gact_tiles rc=%d" % rc)
         return res, tb, flags
 
+    def filter(self, dram, cands, first_tile_size=128, threshold=60, min_overlap=1000):
+        """The tile part of filter_body (filter.cpp:28-122, :131-223) for a candidate array."""
+        cd = np.ascontiguousarray(cands, dtype=abi.FILTER_CAND)
+        res = np.zeros(len(cd), abi.FILTER_RES)
+        prm = abi.FilterParams(int(first_tile_size), int(threshold), int(min_overlap), 0)
+        rc = self.lib.gact_filter(self.sc, abi.ptr(dram), C.byref(prm), abi.ptr(cd), len(cd), abi.ptr(res))
+        if rc:
+            raise RuntimeError("gact_filter rc=%d" % rc)
+        return res
+
+    def slope_filter(self, read_num, score, reference_pos, query_pos, slope_threshold=0.05):
+        """filter_body::slopeFilter (filter.cpp:227-289) for one strand; returns the kept indices in output order."""
+        rn = np.ascontiguousarray(read_num, np.int32)
+        sc = np.ascontiguousarray(score, np.int32)
+        rp = np.ascontiguousarray(reference_pos, np.uint32)
+        qp = np.ascontiguousarray(query_pos, np.uint32)
+        order = np.zeros(max(len(rn), 1), np.int32)
+        self.lib.gact_slope_filter.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_void_p]
+        n = self.lib.gact_slope_filter(abi.ptr(rn), abi.ptr(sc), abi.ptr(rp), abi.ptr(qp), len(rn), C.c_float(slope_threshold),
+                                       abi.ptr(order))
+        return order[:n].copy()
+
     def extend(self, dram, params, anchors, hit_pool, rule=1, ops_cap=None):
         n = len(anchors)
         res = np.zeros(n, abi.ALN_RES)
@@ -153,6 +175,55 @@ class Reference:
         got = self.lib.dref_get_anchors(abi.ptr(anchors), n, abi.ptr(hits), C.c_uint64(nh), C.c_uint64(0))
         assert got == n
         return anchors[:n], hits[:nh]
+
+    def _fetch_anchors(self, n):
+        nh = self.lib.dref_anchor_hits_total()
+        anchors = np.zeros(max(n, 1), abi.ANCHOR)
+        hits = np.zeros(max(nh, 1), np.uint64)
+        got = self.lib.dref_get_anchors(abi.ptr(anchors), n, abi.ptr(hits), C.c_uint64(nh), C.c_uint64(0))
+        assert got == n
+        return anchors[:n], hits[:nh]
+
+    def seed(self, first, count):
+        """seeder_body alone on reads [first, first+count): returns (candidates, read_num per candidate) as
+        filter_body would see them (forward strand first)."""
+        n = self.lib.dref_seed(int(first), int(count))
+        if n < 0:
+            raise RuntimeError("index not built")
+        cands = np.zeros(max(n, 1), abi.FILTER_CAND)
+        rn = np.zeros(max(n, 1), np.int32)
+        got = self.lib.dref_get_candidates(abi.ptr(cands), abi.ptr(rn), n)
+        assert got == n
+        return cands[:n], rn[:n]
+
+    def _fetch_candidates(self, n):
+        cands = np.zeros(max(n, 1), abi.FILTER_CAND)
+        rn = np.zeros(max(n, 1), np.int32)
+        got = self.lib.dref_get_candidates(abi.ptr(cands), abi.ptr(rn), n)
+        assert got == n
+        return cands[:n], rn[:n]
+
+    def seed_custom(self, first, count, hit, offset, read_num, strand):
+        """Hand-made seeder output (sorted by read within each strand): returns (candidates, read_num) like seed()."""
+        ho = (np.asarray(hit, np.uint64) << np.uint64(32)) | np.asarray(offset, np.uint64)
+        rn = np.ascontiguousarray(read_num, np.int32)
+        st = np.ascontiguousarray(strand, np.uint8)
+        n = self.lib.dref_seed_custom(int(first), int(count), abi.ptr(np.ascontiguousarray(ho)), abi.ptr(rn), abi.ptr(st), len(rn))
+        if n != len(rn):
+            raise RuntimeError("dref_seed_custom rc=%d" % n)
+        return self._fetch_candidates(n)
+
+    def set_first_tile(self, first_tile_size=128, threshold=60, min_overlap=1000, slope_threshold=0.05):
+        """params.cfg [GACT_first_tile]; the D-SOFT parameters stay at the stock values (software/params.cfg:18-35)."""
+        self.lib.dref_set_dsoft(14, 3, 64, 26, 1000, 40, 1000, 4, int(first_tile_size), int(threshold), 64, int(min_overlap),
+                                C.c_float(slope_threshold))
+
+    def filter_last(self, gpu=False):
+        """filter_body (the reference's, or the GPU host adapter's with gpu=True) on the last seed() output."""
+        n = self.lib.dref_filter_last_gpu() if gpu else self.lib.dref_filter_last()
+        if n < 0:
+            raise RuntimeError("filter_last rc=%d" % n)
+        return self._fetch_anchors(n)
 
     def extend(self, anchors, hit_pool, ops_cap=None):
         n = len(anchors)

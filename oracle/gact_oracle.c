@@ -606,3 +606,83 @@ int gact_extend(const GactScoring* sc, const char* dram, const DarwinExtendParam
     }
     return 0;
 }
+
+/* ---- first-tile filter (filter.cpp) ------------------------------------------------------------------------------ */
+
+/* Request construction of filter_body for one candidate: filter.cpp:44-71 (forward), :154-181 (reverse complement).
+ * All arithmetic in the reference's own types (uint32_t hit/offset/chr_*, size_t read_len, int cfg.first_tile_size). */
+static void filter_request(const DarwinFilterCand* c, int fts, DarwinTileReq* rq, uint32_t* rts_out, uint32_t* qts_out) {
+    uint32_t hit = c->hit, offset = c->offset, chr_start = c->chr_start;
+    uint32_t chr_end = chr_start + c->chr_len;                                                     /* :51 */
+    size_t read_len = c->read_len;
+    uint32_t ref_tile_start = (hit + fts < chr_end) ? hit : ((chr_end > (uint32_t)fts) ? chr_end - fts : 0);             /* :57 */
+    uint32_t query_tile_start = (offset + fts < read_len) ? offset : ((read_len > (size_t)fts) ? (uint32_t)(read_len - fts) : 0);   /* :58 */
+    uint32_t ref_tile_size = ((uint32_t)fts < (chr_end - chr_start)) ? (uint32_t)fts : (chr_end - chr_start);             /* :59 */
+    uint32_t query_tile_size = ((size_t)fts < read_len) ? (uint32_t)fts : (uint32_t)read_len;                            /* :60 */
+    memset(rq, 0, sizeof(*rq));
+    rq->ref_size = (uint16_t)ref_tile_size; rq->query_size = (uint16_t)query_tile_size;
+    rq->ref_bases_start_addr = ref_tile_start;                                                                           /* :66 */
+    rq->query_bases_start_addr = c->strand ? c->read_addr + read_len - (query_tile_start + query_tile_size)              /* :176 */
+                                           : c->read_addr + query_tile_start;                                            /* :67 */
+    rq->max_tb_steps = (uint16_t)(2 * fts); rq->score_threshold = 0;                                                     /* :69-70 */
+    rq->align_fields = c->strand ? (DARWIN_REVERSE_QUERY | DARWIN_COMPLEMENT_QUERY) : 0;                                 /* :72 / :181 */
+    *rts_out = ref_tile_start; *qts_out = query_tile_start;
+}
+
+/* The tile part of filter_body::operator() for n candidates (filter.cpp:28-122, :131-223): score-only max-cell tiles
+ * (do_traceback = 0), then the score test (:87) and the overlap test (:102-104). */
+int gact_filter(const GactScoring* sc, const char* dram, const DarwinFilterParams* p, const DarwinFilterCand* cands, int n,
+                DarwinFilterRes* res) {
+    for (int k = 0; k < n; k++) {
+        const DarwinFilterCand* c = &cands[k];
+        DarwinTileReq rq; uint32_t rts, qts;
+        filter_request(c, p->first_tile_size, &rq, &rts, &qts);
+        rq.index = (uint16_t)(k & 63);                                                              /* :62 (c - b) */
+        DarwinTileRes tr;
+        int rc = gact_tile(sc, dram, &rq, 0, GACT_RULE_STREAM, &tr, NULL, 0, NULL, 0, NULL);
+        if (rc) return rc;
+        uint32_t chr_end = c->chr_start + c->chr_len;
+        uint32_t ovl = c->offset + (chr_end - c->hit);                                              /* :102 */
+        res[k].score = tr.score;
+        res[k].reference_pos = rts + tr.ref_max_pos;                                                /* :109 */
+        res[k].query_pos = qts + tr.query_max_pos;                                                  /* :110 */
+        res[k].flags = ((uint32_t)tr.score >= (uint32_t)p->first_tile_score_threshold ? DARWIN_FILTER_SCORE_OK : 0u) |   /* :87: uint32 score vs int */
+                       (ovl > (uint32_t)(p->min_overlap / 2) ? DARWIN_FILTER_OVERLAP_OK : 0u);      /* :104 */
+    }
+    return 0;
+}
+
+/* filter_body::slopeFilter (filter.cpp:227-289) on the locations of ONE strand of one batch.
+ * in: read_num / score / reference_pos / query_pos per location (any order); order_out receives the indices of the
+ * surviving locations in output order; returns their number.  The sort predicate is the reference's (:232-234):
+ * read_num asc, score desc, reference_pos asc, query_pos asc; std::sort is not stable but the key is total up to exact
+ * duplicates.  The slope test is evaluated in float like the reference (:266-271). */
+typedef struct { int read_num, score; uint32_t rpos, qpos; int idx; } SlopeLoc;
+static int slope_cmp(const void* a_, const void* b_) {
+    const SlopeLoc* a = (const SlopeLoc*)a_; const SlopeLoc* b = (const SlopeLoc*)b_;
+    if (a->read_num != b->read_num) return a->read_num < b->read_num ? -1 : 1;
+    if (a->score != b->score) return a->score > b->score ? -1 : 1;
+    if (a->rpos != b->rpos) return a->rpos < b->rpos ? -1 : 1;
+    if (a->qpos != b->qpos) return a->qpos < b->qpos ? -1 : 1;
+    return a->idx < b->idx ? -1 : (a->idx > b->idx);
+}
+int gact_slope_filter(const int* read_num, const int* score, const uint32_t* reference_pos, const uint32_t* query_pos, int n,
+                      float slope_threshold, int* order_out) {
+    SlopeLoc* v = (SlopeLoc*)malloc(sizeof(SlopeLoc) * (size_t)(n > 0 ? n : 1));
+    for (int k = 0; k < n; k++) { v[k].read_num = read_num[k]; v[k].score = score[k]; v[k].rpos = reference_pos[k]; v[k].qpos = query_pos[k]; v[k].idx = k; }
+    qsort(v, (size_t)n, sizeof(SlopeLoc), slope_cmp);
+    int kept = 0;
+    for (int a = 0; a < n; a++) {
+        if (v[a].read_num == -1) continue;                                                          /* :240-241 */
+        order_out[kept++] = v[a].idx;                                                               /* :243 */
+        for (int b = a + 1; b < n; b++) {
+            if (v[b].read_num == -1) continue;
+            if (v[b].read_num != v[a].read_num) break;                                              /* :250-251 */
+            float r1 = (float)v[a].rpos, q1 = (float)v[a].qpos, r2 = (float)v[b].rpos, q2 = (float)v[b].qpos;
+            float s = (r1 - r2) / (q1 - q2) - 1;                                                    /* :270 */
+            if ((s < 0 ? -s : s) <= slope_threshold) v[b].read_num = -1;                            /* :271-274 */
+        }
+    }
+    free(v);
+    return kept;
+}

@@ -65,6 +65,15 @@ int gact_alignment_score(const GactScoring* sc, const char* ref_str, const char*
 int gact_build_strings(const char* dram, const DarwinAnchor* a, const DarwinAlnRes* r, const uint8_t* ops,
                        char* ref_str, char* query_str);
 
+/* The tile part of filter_body::operator() (filter.cpp:28-122, :131-223) for n candidates. */
+int gact_filter(const GactScoring* sc, const char* dram, const DarwinFilterParams* p, const DarwinFilterCand* cands, int n,
+                DarwinFilterRes* res);
+
+/* filter_body::slopeFilter (filter.cpp:227-289) for the locations of one strand; returns the number kept and their
+ * indices in output order. */
+int gact_slope_filter(const int* read_num, const int* score, const uint32_t* reference_pos, const uint32_t* query_pos, int n,
+                      float slope_threshold, int* order_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@
 // bench.py's cpu_baseline / --impl reference leg may load it.
 #include "../include/darwin_gpu.h"
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -314,6 +315,90 @@ int dref_seed_filter(int first, int count) {
     return (int)(g_last_filter.fwLocations.size() + g_last_filter.rcLocations.size());
 }
 
+// ---- seeder alone, then the reference's filter_body on the kept seeder output (first-tile filter parity) ----------
+static filter_input* g_last_seed = nullptr;
+static int g_last_seed_first = 0;
+
+int dref_seed(int first, int count) {
+    if (!sa) return -1;
+    reader_output reads(g_reads.begin() + first, g_reads.begin() + first + count);
+    seeder_input sin(reads, 0);
+    delete g_last_seed;
+    g_last_seed = new filter_input(seeder_body()(sin));
+    g_last_seed_first = first;
+    auto& d = std::get<1>(std::get<0>(*g_last_seed));
+    return (int)(d.fwAnchors.size() + d.rcAnchors.size());
+}
+
+// Hand-made seeder output for reads [first, first+count): candidate k = (hit_offset[k], read read_num[k] (absolute),
+// strand[k]); within each strand the candidates must be sorted by read (seeder.cpp:38-50 appends read by read).
+// Lets the tests drive the reference's filter_body with candidates D-SOFT would rarely propose (tiles clamped at
+// chromosome / read ends, low scores).
+int dref_seed_custom(int first, int count, const uint64_t* hit_offset, const int* read_num, const uint8_t* strand, int n) {
+    reader_output reads(g_reads.begin() + first, g_reads.begin() + first + count);
+    seeder_data d;
+    for (int s = 0; s < 2; s++) {
+        auto& anchors = s ? d.rcAnchors : d.fwAnchors;
+        auto& buckets = s ? d.rcAnchorBuckets : d.fwAnchorBuckets;
+        buckets.push_back(0ull);
+        int k = 0;
+        for (int r = 0; r < count; r++) {
+            for (; k < n; k++) {
+                if (strand[k] != s) continue;
+                if (read_num[k] - first < r) return -3;                      // not sorted by read
+                if (read_num[k] - first > r) break;
+                Anchors a(hit_offset[k]);
+                a.num_chained_hits = 1; a.anchor_score = 0;
+                a.left_chained_hits.push_back(hit_offset[k]); a.right_chained_hits.push_back(hit_offset[k]);
+                anchors.push_back(a);
+            }
+            buckets.push_back(anchors.size());
+        }
+    }
+    delete g_last_seed;
+    g_last_seed = new filter_input(filter_payload(reads, d), 0);
+    g_last_seed_first = first;
+    return (int)(d.fwAnchors.size() + d.rcAnchors.size());
+}
+
+// the candidates of the last dref_seed as filter_body sees them (filter.cpp:44-56): forward strand first
+int dref_get_candidates(DarwinFilterCand* out, int* read_num_out, int cap) {
+    if (!g_last_seed) return -1;
+    auto& reads = std::get<0>(std::get<0>(*g_last_seed));
+    auto& d = std::get<1>(std::get<0>(*g_last_seed));
+    int n = 0;
+    for (int strand = 0; strand < 2; strand++) {
+        auto& anchors = strand ? d.rcAnchors : d.fwAnchors;
+        auto& buckets = strand ? d.rcAnchorBuckets : d.fwAnchorBuckets;
+        for (size_t c = 0; c < anchors.size(); c++) {
+            if (n >= cap) return DARWIN_ERR_CAPACITY;
+            uint32_t hit = (uint32_t)(anchors[c].hit_offset >> 32), offset = (uint32_t)((anchors[c].hit_offset << 32) >> 32);
+            size_t chr_id = std::upper_bound(Index::chr_coord.cbegin(), Index::chr_coord.cend(), hit) - Index::chr_coord.cbegin() - 1;
+            size_t read_num = std::upper_bound(buckets.cbegin(), buckets.cend(), c) - buckets.cbegin() - 1;
+            const Read& rd = reads[read_num];
+            DarwinFilterCand& k = out[n];
+            memset(&k, 0, sizeof(k));
+            k.read_addr = (uint64_t)(rd.seq.data() - g_DRAM->buffer);
+            k.hit = hit; k.offset = offset; k.chr_start = Index::chr_coord[chr_id]; k.chr_len = Index::chr_len[chr_id];
+            k.read_len = (uint32_t)rd.seq.size(); k.strand = (uint8_t)strand;
+            if (read_num_out) read_num_out[n] = (int)read_num + g_last_seed_first;
+            n++;
+        }
+    }
+    return n;
+}
+
+// the reference's filter_body (first tiles through g_BatchAlignmentSIMD + slopeFilter) on the last dref_seed output;
+// fetch the locations with dref_get_anchors
+int dref_filter_last(void) {
+    if (!g_last_seed) return -1;
+    extender_input ein = filter_body()(*g_last_seed);
+    g_last_filter = std::get<1>(std::get<0>(ein));
+    for (auto& l : g_last_filter.fwLocations) l.read_num += g_last_seed_first;
+    for (auto& l : g_last_filter.rcLocations) l.read_num += g_last_seed_first;
+    return (int)(g_last_filter.fwLocations.size() + g_last_filter.rcLocations.size());
+}
+
 uint64_t dref_anchor_hits_total(void) {
     uint64_t n = 0;
     for (auto& l : g_last_filter.fwLocations) n += l.left_hit_offsets.size() + l.right_hit_offsets.size();
@@ -441,6 +526,9 @@ double dref_extend_mt(const DarwinAnchor* anchors, int n, const uint64_t* hit_po
 }
 
 int dref_num_reads(void) { return (int)g_reads.size(); }
+int dref_read_len(int k) { return (k >= 0 && k < (int)g_reads.size()) ? (int)g_reads[k].seq.size() : -1; }
+unsigned dref_chr_start(int k) { return Index::chr_coord[k]; }
+unsigned dref_chr_len(int k) { return Index::chr_len[k]; }
 int dref_num_chr(void) { return (int)Index::chr_id.size(); }
 int dref_hw_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
@@ -496,15 +584,28 @@ void dref_gpu_shutdown(void) {
     darwin_gpu_host::ShutdownProcessor();
 }
 
-// seeder -> filter -> extender for reads [first, first+count); use_gpu selects gpu_extender_body (the filter always
-// goes through g_BatchAlignmentSIMD, i.e. through the GPU once dref_gpu_init has installed the table).
+// GPU filter stage on the last dref_seed output (darwin_gpu_host::gpu_filter_body); fetch with dref_get_anchors
+int dref_filter_last_gpu(void) {
+    if (!g_last_seed) return -1;
+    try {
+        extender_input ein = darwin_gpu_host::gpu_filter_body()(*g_last_seed);
+        g_last_filter = std::get<1>(std::get<0>(ein));
+    } catch (const std::exception& e) { fprintf(stderr, "dref_filter_last_gpu: %s\n", e.what()); return -2; }
+    for (auto& l : g_last_filter.fwLocations) l.read_num += g_last_seed_first;
+    for (auto& l : g_last_filter.rcLocations) l.read_num += g_last_seed_first;
+    return (int)(g_last_filter.fwLocations.size() + g_last_filter.rcLocations.size());
+}
+
+// seeder -> filter -> extender for reads [first, first+count); use_gpu = 1 selects gpu_extender_body, use_gpu = 2 also
+// gpu_filter_body (with use_gpu <= 1 the filter still goes through g_BatchAlignmentSIMD, i.e. through the GPU once
+// dref_gpu_init has installed the table).
 // Writes one canonical text line per alignment, sorted; returns the number of alignments or <0.
 int dref_pipeline(int first, int count, int use_gpu, char* out, uint64_t cap) {
     try {
         reader_output reads(g_reads.begin() + first, g_reads.begin() + first + count);
         seeder_input sin(reads, 0);
         filter_input fin = seeder_body()(sin);
-        extender_input ein = filter_body()(fin);
+        extender_input ein = (use_gpu >= 2) ? darwin_gpu_host::gpu_filter_body()(fin) : filter_body()(fin);
         extender_node::output_ports_type ports;
         if (getenv("DREF_DEBUG")) fprintf(stderr, "dref_pipeline: %zu fw + %zu rc anchors\n", std::get<1>(std::get<0>(ein)).fwLocations.size(), std::get<1>(std::get<0>(ein)).rcLocations.size());
         if (use_gpu) darwin_gpu_host::gpu_extender_body()(ein, ports);

@@ -8,6 +8,9 @@ Fixtures (all seeded; inputs are synthetic, expected outputs come from the refer
                  `asis_same` marks tiles where the as-is flavour gave the identical answer)
   extend_v1.npz  synthetic 150 kbp reference + 10 reads, anchors from the reference's own D-SOFT + filter,
                  extender_body results for T/O = 384/64 and 320/128 (+ do_overlap=1)
+  filter_v1.npz  3 chromosomes (one 5 kbp) + 48 reads (some hanging over chromosome ends): the candidates of the reference's
+                 seeder_body, the first-tile results of its BatchAlignmentSIMD on filter_body's requests, and the
+                 ExtendLocations its filter_body (tiles + slope filter) returns
   rtl_kat.npz    the RTL testbench's 10 known-answer pairs (RTL/GACT/test_data/{ref,query}_320.txt) and
                  their "Total score" lines (test_align.txt) -- score-level vectors only
 """
@@ -159,6 +162,82 @@ def gen_extend():
     np.savez_compressed(os.path.join(OUT, "extend_v1.npz"), **out)
 
 
+def filter_case(seed=11, n_reads=48):
+    """Shared by the generator and the live tests: (reference driver with arena + index + reads loaded)."""
+    rng = np.random.default_rng(seed)
+    ref = oracle.reference("patched")
+    ref.set_scoring(abi.Scoring.from_values(*SCHEMES["stock"]))
+    ref.set_dsoft_defaults()
+    ref.reset_arena()
+    chrs = [synth.random_seq(rng, 100), synth.random_seq(rng, 180000), synth.random_seq(rng, 5000), synth.random_seq(rng, 90000)]
+    chrs[0][:] = chrs[3][500:600]            # the first chromosome is SHORTER than a first tile (filter.cpp:57 falls back to 0)
+    a = chrs[1]
+    for _ in range(5):                       # diverged repeats -> secondary candidates, slope-filter work
+        x, y = int(rng.integers(0, 170000)), int(rng.integers(0, 170000))
+        rep = synth.mutate_fast(rng, a[x:x + 3000], 0.03, 0.01, 0.01)[:2900]
+        a[y:y + len(rep)] = rep
+    for k, c in enumerate(chrs):
+        ref.add_chr("chr%d" % k, c.tobytes(), True)
+    ref.build_index()
+    for k in range(n_reads):
+        c = chrs[1 + k % 3]
+        L = int(rng.integers(600, min(9000, len(c) - 10))) if k % 8 != 7 else int(rng.integers(70, 128))   # reads shorter than a tile
+        if k % 6 == 0:
+            p = len(c) - L                   # ends exactly at the chromosome end: tiles clamp to chr_end - first_tile_size
+        elif k % 6 == 1:
+            p = 0
+        else:
+            p = int(rng.integers(0, len(c) - L))
+        r = synth.mutate_fast(rng, c[p:p + L], 0.05, 0.05, 0.05)
+        if k % 2:
+            r = synth.revcomp(r)
+        ref.add_read("r%d" % k, np.ascontiguousarray(r).tobytes())
+    return ref, n_reads
+
+
+def custom_candidates(ref, n_reads, seed=5, per_read=6):
+    """Candidates D-SOFT would rarely propose: random loci (low scores), hits within a tile of a chromosome end, offsets
+    within a tile of the read end, the sub-tile chromosome, both strands.  Sorted by read within each strand."""
+    rng = np.random.default_rng(seed)
+    arena_chr = [(int(ref.lib.dref_chr_start(k)), int(ref.lib.dref_chr_len(k))) for k in range(ref.lib.dref_num_chr())]
+    hit, off, rn, st = [], [], [], []
+    for strand in (0, 1):
+        for r in range(n_reads):
+            rl = int(ref.lib.dref_read_len(r))
+            for j in range(per_read):
+                cs, cl = arena_chr[int(rng.integers(0, len(arena_chr)))]
+                mode = (r + j) % 4
+                h = cs + (int(rng.integers(0, cl)) if mode < 2 else max(0, cl - 1 - int(rng.integers(0, 140))))
+                o = int(rng.integers(0, rl)) if mode % 2 == 0 else max(0, rl - 1 - int(rng.integers(0, 140)))
+                hit.append(h); off.append(o); rn.append(r); st.append(strand)
+    return np.array(hit, np.uint64), np.array(off, np.uint64), np.array(rn, np.int32), np.array(st, np.uint8)
+
+
+def gen_filter():
+    ref, n_reads = filter_case()
+    # part 2 first (it only needs the arena): hand-made candidates through the reference's filter_body with thresholds
+    # that let EVERY candidate through (score >= 0, min_overlap 0, slope filter off) -> per-candidate reference values
+    hit, off, rn2, st = custom_candidates(ref, n_reads)
+    ref.set_first_tile(128, 0, 0, -1.0)
+    cands2, crn2 = ref.seed_custom(0, n_reads, hit, off, rn2, st)
+    all_loc, _ = ref.filter_last()
+    ref.set_first_tile(96, 0, 0, -1.0)                       # a first_tile_size other than 128 (ragged lanes on the GPU)
+    all_loc96, _ = ref.filter_last()
+    ref.set_first_tile()
+    cands, rn = ref.seed(0, n_reads)
+    anchors, hits = ref.filter_last()
+    arena = ref.arena().copy()
+    # the reference's own BatchAlignmentSIMD on the requests filter_body builds (restated by the port; equality of the
+    # final ExtendLocations above pins that restatement)
+    port = oracle.port(abi.Scoring.from_values(*SCHEMES["stock"]))
+    pres = port.filter(arena, cands)
+    np.savez_compressed(os.path.join(OUT, "filter_v1.npz"), arena=arena, cands=cands, cand_read_num=rn, anchors=anchors,
+                        hits=hits, port_res=pres, scoring=np.array(SCHEMES["stock"], np.int32),
+                        custom_cands=cands2, custom_read_num=crn2, custom_locations=all_loc, custom_locations96=all_loc96)
+    print("filter: candidates", len(cands), "rc", int(cands["strand"].sum()), "locations", len(anchors),
+          "| custom", len(cands2), "locations", len(all_loc), len(all_loc96), "score<60:", int((all_loc["score"] < 60).sum()))
+
+
 def gen_rtl():
     d = os.path.join(REF, "RTL", "GACT", "test_data")
     refs = open(os.path.join(d, "ref_320.txt")).read().split()
@@ -174,4 +253,5 @@ if __name__ == "__main__":
     oracle.build()
     gen_tiles()
     gen_extend()
+    gen_filter()
     gen_rtl()
