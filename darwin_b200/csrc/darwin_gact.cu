@@ -444,52 +444,75 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
 }
 
 // AlignmentScore (extender.cpp:1161-1200) + compaction of the op slots into a dense pool.
-// One thread per alignment: walks its ops left to right exactly as the reference walks the strings.
-__global__ void score_compact_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
-                                     const DarwinAnchor* __restrict__ anchors, DarwinAlnRes* __restrict__ res, int n,
-                                     const uint8_t* __restrict__ slots, const uint64_t* __restrict__ dense_off,
-                                     uint8_t* __restrict__ dense) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per alignment, 32 ops per iteration.  The reference walks the two gapped strings left to right; per aligned
+// column it adds sub(r, q) and, if a run of gap columns (I and D mixed) precedes it, max(go + (L-1) ge, lgo + (L-1) lge)
+// for the run length L; a trailing run is never charged.  Here the sequence positions of every op come from ballots +
+// pop-counts, the run length from the position of the previous M (carried across iterations), so the walk is parallel.
+__global__ void __launch_bounds__(128)
+score_compact_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
+                     const DarwinAnchor* __restrict__ anchors, DarwinAlnRes* __restrict__ res, int n,
+                     const uint8_t* __restrict__ slots, const uint64_t* __restrict__ dense_off,
+                     uint8_t* __restrict__ dense) {
+    const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = lane_id();
     if (k >= n) return;
     DarwinAlnRes r = res[k];
     const uint64_t dst = dense_off[k];
-    if (!(r.flags & DARWIN_ALN_EMITTED) || (r.flags & DARWIN_ALN_OPS_OVERFLOW)) { r.ops_offset = dst; if (r.flags & DARWIN_ALN_OPS_OVERFLOW) r.n_ops = 0; res[k] = r; return; }
+    if (!(r.flags & DARWIN_ALN_EMITTED) || (r.flags & DARWIN_ALN_OPS_OVERFLOW)) {
+        r.ops_offset = dst; if (r.flags & DARWIN_ALN_OPS_OVERFLOW) r.n_ops = 0;
+        if (lane == 0) res[k] = r;
+        return;
+    }
     const DarwinAnchor an = anchors[k];
     const DevScoring& sc = ks.sc;
-    // string position p corresponds to: left part ops[0..n_left) end at the anchor, right part starts at anchor+1
-    // left-to-right walk: the first left op consumed LAST, so start offsets are derived from the op counts.
-    uint32_t nl = r.n_left_ops;
+    const uint8_t* ops = slots + r.ops_offset;
+    // bases consumed by the left part: the first left op was consumed LAST, so the start offsets follow from the counts
     uint32_t ref_cons = 0, qry_cons = 0;
-    for (uint32_t p = 0; p < nl; p++) { const uint8_t d = slots[r.ops_offset + p]; ref_cons += (d != DARWIN_OP_I); qry_cons += (d != DARWIN_OP_D); }
+    for (uint32_t p = lane; p < r.n_left_ops; p += 32) { const uint8_t d = ops[p]; ref_cons += (d != DARWIN_OP_I); qry_cons += (d != DARWIN_OP_D); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ref_cons += __shfl_xor_sync(0xffffffffu, ref_cons, o); qry_cons += __shfl_xor_sync(0xffffffffu, qry_cons, o); }
     const uint32_t ar = an.reference_pos - an.chr_start, aq = an.query_pos;
     // The reference clamps at offset 0 (extender.cpp:289-300); a left walk never consumes more than ar+1 / aq+1 bases.
     int64_t cr = (int64_t)ar + 1 - ref_cons, cq = (int64_t)aq + 1 - qry_cons;
-    int score = 0, open = 0, sgp = 0, lgp = 0;
-    const int mat_offset[4] = {0, 1, 3, 6};
-    for (uint32_t p = 0; p < r.n_ops; p++) {
-        const uint8_t d = slots[r.ops_offset + p];
-        dense[dst + p] = d;
-        if (d != DARWIN_OP_M) {
-            sgp += open ? sc.ge : sc.go; lgp += open ? sc.lge : sc.lgo; open = 1;
-            if (d == DARWIN_OP_D) cr++; else cq++;
-        } else {
-            const int64_t rclamp = cr < 0 ? 0 : cr, qclamp = cq < 0 ? 0 : cq;
-            uint32_t rn = arena_code(arena, an.chr_start + (uint64_t)rclamp);
+    const uint32_t lt = (1u << lane) - 1u;
+    int score = 0;
+    uint32_t run_in = 0;                                       // gap columns pending since the last M (warp-uniform)
+    for (uint32_t base = 0; base < r.n_ops; base += 32) {
+        const uint32_t p = base + lane;
+        const bool valid = p < r.n_ops;
+        const uint8_t d = valid ? ops[p] : 0;
+        if (valid) dense[dst + p] = d;
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        const uint32_t mM = __ballot_sync(0xffffffffu, d == DARWIN_OP_M);
+        const uint32_t mD = __ballot_sync(0xffffffffu, d == DARWIN_OP_D);
+        const uint32_t mI = vmask & ~mM & ~mD;
+        if (d == DARWIN_OP_M) {
+            const int64_t pr = cr + __popc((mM | mD) & lt), pq = cq + __popc((mM | mI) & lt);
+            const int64_t rclamp = pr < 0 ? 0 : pr, qclamp = pq < 0 ? 0 : pq;
+            const uint32_t rn = arena_code(arena, an.chr_start + (uint64_t)rclamp);
             uint32_t qn;
             if (!an.strand) qn = arena_code(arena, an.read_addr + (uint64_t)qclamp);
             else if ((uint64_t)qclamp >= an.read_len) qn = 4;
             else { qn = arena_code(arena, an.read_addr + (an.read_len - 1 - (uint64_t)qclamp)); if (qn < 4) qn = 3 - qn; }
             if (rn <= 3 && qn <= 3) {
-                const int idx = (rn > qn) ? qn * 4 + rn - mat_offset[qn] : rn * 4 + qn - mat_offset[rn];
-                score += sc.tri[idx];
+                const int mo = (rn > qn) ? (int)qn : (int)rn, hi = (rn > qn) ? (int)rn : (int)qn;
+                score += sc.tri[mo * 4 + hi - ((mo * (mo + 1)) >> 1)];              // mat_offset = {0, 1, 3, 6}
             } else score += sc.tri[10];
-            score += (lgp < sgp) ? sgp : lgp;
-            open = 0; sgp = 0; lgp = 0;
-            cr++; cq++;
+            const uint32_t below = mM & lt;                                    // previous M inside this word?
+            const uint32_t run = below ? (uint32_t)(lane - 1 - (31 - __clz(below))) : (uint32_t)lane + run_in;
+            if (run) {
+                const int sgp = sc.go + (int)(run - 1) * sc.ge, lgp = sc.lgo + (int)(run - 1) * sc.lge;
+                score += (lgp < sgp) ? sgp : lgp;
+            }
         }
+        const uint32_t nvalid = __popc(vmask);
+        run_in = mM ? nvalid - 1u - (31u - __clz(mM)) : run_in + nvalid;
+        cr += __popc(mM | mD); cq += __popc(mM | mI);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) score += __shfl_xor_sync(0xffffffffu, score, o);
     r.score = score; r.ops_offset = dst;
-    res[k] = r;
+    if (lane == 0) res[k] = r;
 }
 
 // Integer-pipe microbenchmark: 8 accumulators per thread, 16 ops per loop trip, no memory traffic.  Every op takes a
@@ -534,7 +557,7 @@ struct DarwinGpu {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    uint8_t* d_arena = nullptr; uint64_t arena_bytes = 0;
+    uint8_t* d_arena = nullptr; uint64_t arena_bytes = 0; bool owns_arena = true;
     char* h_stage[2] = {nullptr, nullptr}; char* d_stage[2] = {nullptr, nullptr}; size_t stage_bytes = 0;
     cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     cudaStream_t copy_stream = nullptr;         // D2H of finished chunks overlaps the next chunk's kernel
@@ -642,7 +665,16 @@ extern "C" {
 
 const char* darwin_gpu_version(void) { return "darwin-gact-b200 0.1 (sm_100a)"; }
 
-int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) {
+static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, DarwinGpu* parent);
+
+int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) { return create_handle(out, device, arena_bytes, nullptr); }
+
+int darwin_gpu_create_shared(DarwinGpu** out, DarwinGpu* parent) {
+    if (!parent) return DARWIN_ERR_INVALID;
+    return create_handle(out, parent->device, parent->arena_bytes, parent);
+}
+
+static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, DarwinGpu* parent) {
     if (!out) return DARWIN_ERR_INVALID;
     *out = nullptr;
     int ndev = 0;
@@ -657,9 +689,14 @@ int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) {
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
     h->arena_bytes = arena_bytes;
-    const size_t packed = (arena_bytes + 1) / 2 + 64;          // slack: TMA windows are rounded up to 16 bytes
-    CK(cudaMalloc(&h->d_arena, packed));
-    CK(cudaMemsetAsync(h->d_arena, 0x44, packed, h->stream));                  // all 'N' (Index.cpp:12 pads with 'N')
+    if (parent) {                                                              // another lane of the same device: one arena replica
+        h->d_arena = parent->d_arena; h->owns_arena = false;
+        if (parent->have_scoring) { h->ks = parent->ks; h->filt = parent->filt; h->have_scoring = true; }
+    } else {
+        const size_t packed = (arena_bytes + 1) / 2 + 64;      // slack: TMA windows are rounded up to 16 bytes
+        CK(cudaMalloc(&h->d_arena, packed));
+        CK(cudaMemsetAsync(h->d_arena, 0x44, packed, h->stream));              // all 'N' (Index.cpp:12 pads with 'N')
+    }
     h->stage_bytes = 32u << 20;
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     for (int b = 0; b < 2; b++) {
@@ -694,7 +731,7 @@ int darwin_gpu_destroy(DarwinGpu* h) {
         if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    if (h->d_arena) cudaFree(h->d_arena);
+    if (h->d_arena && h->owns_arena) cudaFree(h->d_arena);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1010,7 +1047,7 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     CK(cudaMemcpyAsync(h->d_buf[7], dense.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
     if ((rc = grow_dev(h, 8, used + 16))) return rc;
     uint8_t* d_dense = (uint8_t*)h->d_buf[8];
-    score_compact_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(h->d_arena, h->ks, (const DarwinAnchor*)h->d_buf[0],
+    score_compact_kernel<<<(n + 3) / 4, 128, 0, h->stream>>>(h->d_arena, h->ks, (const DarwinAnchor*)h->d_buf[0],
                                                                 (DarwinAlnRes*)h->d_buf[1], n, (const uint8_t*)h->d_buf[3],
                                                                 (const uint64_t*)h->d_buf[7], d_dense);
     CK(cudaGetLastError());

@@ -34,6 +34,7 @@ def load_library():
         L.darwin_gpu_last_error.restype = C.c_char_p
         L.darwin_gpu_last_error.argtypes = [C.c_void_p]
         L.darwin_gpu_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint64]
+        L.darwin_gpu_create_shared.argtypes = [C.POINTER(C.c_void_p), C.c_void_p]
         L.darwin_gpu_destroy.argtypes = [C.c_void_p]
         L.darwin_gpu_set_scoring.argtypes = [C.c_void_p, C.POINTER(abi.Scoring)]
         L.darwin_gpu_upload.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
@@ -48,7 +49,7 @@ def load_library():
     return _lib
 
 
-EXPORTS = ("darwin_gpu_create", "darwin_gpu_destroy", "darwin_gpu_set_scoring", "darwin_gpu_upload",
+EXPORTS = ("darwin_gpu_create", "darwin_gpu_create_shared", "darwin_gpu_destroy", "darwin_gpu_set_scoring", "darwin_gpu_upload",
            "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_filter", "darwin_gpu_stats", "darwin_gpu_int_peak",
            "darwin_gpu_last_error", "darwin_gpu_version")
 
@@ -56,15 +57,21 @@ EXPORTS = ("darwin_gpu_create", "darwin_gpu_destroy", "darwin_gpu_set_scoring", 
 class Processor:
     """One GPU-backed Processor (== one `token` of the reference, main.cpp:615-624)."""
 
-    def __init__(self, arena_bytes, device=0):
+    def __init__(self, arena_bytes, device=0, parent=None):
+        """`parent`: another Processor of the same device whose arena replica this one shares (a further lane)."""
         self.lib = load_library()
         self.h = C.c_void_p()
-        rc = self.lib.darwin_gpu_create(C.byref(self.h), int(device), C.c_uint64(int(arena_bytes)))
+        if parent is not None:
+            rc = self.lib.darwin_gpu_create_shared(C.byref(self.h), parent.h)
+            arena_bytes, device = parent.arena_bytes, parent.device
+        else:
+            rc = self.lib.darwin_gpu_create(C.byref(self.h), int(device), C.c_uint64(int(arena_bytes)))
         if rc:
             msg = self.lib.darwin_gpu_last_error(self.h).decode() if self.h else "no usable CUDA device"
             raise DarwinGpuError(rc, msg)
         self.arena_bytes = int(arena_bytes)
         self.device = device
+        self._parent = parent                  # keeps the arena owner alive
 
     def close(self):
         if getattr(self, "h", None):

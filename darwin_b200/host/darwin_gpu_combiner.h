@@ -1,0 +1,231 @@
+// Cross-read batching for the GPU stages ("flat combining" / group commit).
+//
+// The reference runs one read batch per TBB token (main.cpp:590-702: the reader emits a batch as soon as it holds more
+// than readBufferLimit = 64 bytes, i.e. ONE read; cfg.num_threads tokens are in flight, main.cpp:615-624) and every
+// stage body talks to the Processor on its own.  A GPU wants thousands of anchors per launch, not the one or two of a
+// single read, and a DarwinGpu handle is single-threaded.  GpuCombiner sits between the stage bodies and the C-ABI:
+// every host thread submits its own request (first-tile candidates, anchors, tiles -- plus the read spans that must be
+// resident first) and blocks; whichever thread finds the device idle becomes the combiner, concatenates EVERYTHING
+// queued so far into one darwin_gpu_filter / darwin_gpu_extend / darwin_gpu_tiles call, scatters the results and wakes
+// the owners.  While that call runs the other threads keep seeding and queue up behind it, so the batch size adapts
+// itself to the device latency; no timers, no extra thread.
+//
+// Only include/darwin_gpu.h is needed here (no reference headers), so the merge / scatter logic is unit-tested on the
+// CPU with stand-in entry points (tests/cpp/test_combiner.cpp).
+#pragma once
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "darwin_gpu.h"
+
+namespace darwin_gpu_host {
+
+// The C-ABI entry points the combiner drives; tests inject CPU stand-ins.
+struct GpuCalls {
+    int (*upload)(DarwinGpu*, uint64_t, const char*, uint64_t);
+    int (*tiles)(DarwinGpu*, int, const DarwinTileReq*, int, DarwinTileRes*, uint64_t*, int);
+    int (*filter)(DarwinGpu*, const DarwinFilterParams*, const DarwinFilterCand*, int, DarwinFilterRes*);
+    int (*extend)(DarwinGpu*, const DarwinExtendParams*, const DarwinAnchor*, int, const uint64_t*, uint64_t,
+                  DarwinAlnRes*, uint8_t*, uint64_t);
+    const char* (*last_error)(DarwinGpu*);
+    static GpuCalls library() {
+        return GpuCalls{darwin_gpu_upload, darwin_gpu_tiles, darwin_gpu_filter, darwin_gpu_extend, darwin_gpu_last_error};
+    }
+};
+
+struct UploadSpan { uint64_t arena_addr; const char* ascii; uint64_t n; };
+
+struct CombinerStats {
+    uint64_t device_calls[3];   // [0] tiles, [1] filter, [2] extend: calls that reached the device
+    uint64_t requests[3];       // requests submitted by host threads
+    uint64_t items[3];          // tiles / candidates / anchors
+    uint64_t max_merged[3];     // largest number of requests served by one device call
+};
+
+class GpuCombiner {
+public:
+    GpuCombiner(DarwinGpu* h, const GpuCalls& calls) : h_(h), c_(calls) { memset(&st_, 0, sizeof(st_)); }
+
+    // == g_BatchAlignmentSIMD for one caller; merged with other callers using the same do_traceback
+    int tiles(int do_traceback, const DarwinTileReq* req, int n, DarwinTileRes* res, uint64_t* tb_words, int tb_words_per_req,
+              std::string* err) {
+        Request r; r.kind = TILES; r.do_tb = do_traceback; r.treq = req; r.n = n; r.tres = res; r.tb = tb_words; r.words = tb_words_per_req;
+        return run(r, err);
+    }
+    // == the tile part of filter_body for one caller's candidates
+    int filter(const DarwinFilterParams& p, const std::vector<UploadSpan>& up, const DarwinFilterCand* cands, int n,
+               DarwinFilterRes* res, std::string* err) {
+        Request r; r.kind = FILTER; r.fp = p; r.up = &up; r.cands = cands; r.n = n; r.fres = res;
+        return run(r, err);
+    }
+    // == extender_body for one caller's anchors; `ops` receives this caller's op strings, res[i].ops_offset index into it
+    int extend(const DarwinExtendParams& p, const std::vector<UploadSpan>& up, const DarwinAnchor* anchors, int n,
+               const uint64_t* pool, uint64_t n_pool, DarwinAlnRes* res, std::vector<uint8_t>* ops, std::string* err) {
+        Request r; r.kind = EXTEND; r.ep = p; r.up = &up; r.anchors = anchors; r.n = n; r.pool = pool; r.n_pool = n_pool;
+        r.ares = res; r.ops = ops;
+        return run(r, err);
+    }
+    // == g_InitializeReferenceMemory / g_InitializeReadMemory from any thread (rides along with the next tile batch)
+    int upload(const std::vector<UploadSpan>& up, std::string* err) {
+        Request r; r.kind = TILES; r.do_tb = 0; r.up = &up; r.n = 0;
+        return run(r, err);
+    }
+    CombinerStats stats() { std::lock_guard<std::mutex> g(m_); return st_; }
+    DarwinGpu* handle() const { return h_; }
+
+private:
+    enum Kind { TILES = 0, FILTER = 1, EXTEND = 2 };
+    struct Request {
+        Kind kind; int n = 0; bool done = false; int rc = 0; std::string err;
+        const std::vector<UploadSpan>* up = nullptr;
+        // tiles
+        int do_tb = 0, words = 0; const DarwinTileReq* treq = nullptr; DarwinTileRes* tres = nullptr; uint64_t* tb = nullptr;
+        // filter
+        DarwinFilterParams fp{}; const DarwinFilterCand* cands = nullptr; DarwinFilterRes* fres = nullptr;
+        // extend
+        DarwinExtendParams ep{}; const DarwinAnchor* anchors = nullptr; const uint64_t* pool = nullptr; uint64_t n_pool = 0;
+        DarwinAlnRes* ares = nullptr; std::vector<uint8_t>* ops = nullptr;
+    };
+
+    static bool mergeable(const Request& a, const Request& b) {
+        if (a.kind != b.kind) return false;
+        if (a.kind == TILES) return a.do_tb == b.do_tb;
+        if (a.kind == FILTER) return memcmp(&a.fp, &b.fp, sizeof(a.fp)) == 0;
+        return memcmp(&a.ep, &b.ep, sizeof(a.ep)) == 0;
+    }
+
+    int run(Request& r, std::string* err) {
+        std::unique_lock<std::mutex> lk(m_);
+        st_.requests[r.kind]++; st_.items[r.kind] += (uint64_t)r.n;
+        q_.push_back(&r);
+        while (!r.done) {
+            if (busy_) { cv_.wait(lk); continue; }
+            // become the combiner: take the oldest request and everything queued that can ride along with it
+            busy_ = true;
+            std::vector<Request*> batch;
+            batch.push_back(q_.front()); q_.pop_front();
+            for (auto it = q_.begin(); it != q_.end();) {
+                if (mergeable(*batch[0], **it)) { batch.push_back(*it); it = q_.erase(it); } else ++it;
+            }
+            lk.unlock();
+            execute(batch);
+            lk.lock();
+            const Kind k = batch[0]->kind;
+            st_.device_calls[k]++;
+            if (batch.size() > st_.max_merged[k]) st_.max_merged[k] = batch.size();
+            for (auto* b : batch) b->done = true;
+            busy_ = false;
+            cv_.notify_all();
+        }
+        if (r.rc && err) *err = r.err;
+        return r.rc;
+    }
+
+    void fail_all(std::vector<Request*>& batch, int rc, const char* what) {
+        const std::string msg = std::string(what) + ": " + (c_.last_error ? c_.last_error(h_) : "");
+        for (auto* b : batch) { b->rc = rc; b->err = msg; }
+    }
+
+    void execute(std::vector<Request*>& batch) {
+        for (auto* b : batch)
+            if (b->up)
+                for (const auto& s : *b->up) {
+                    const int rc = c_.upload(h_, s.arena_addr, s.ascii, s.n);
+                    if (rc) { fail_all(batch, rc, "darwin_gpu_upload"); return; }
+                }
+        size_t total = 0;
+        for (auto* b : batch) total += (size_t)b->n;
+        const Kind k = batch[0]->kind;
+        if (k == TILES) {
+            int words = 1;
+            for (auto* b : batch) if (b->words > words) words = b->words;
+            const bool tb = batch[0]->do_tb != 0;
+            if (batch.size() == 1) {
+                Request* b = batch[0];
+                b->rc = b->n ? c_.tiles(h_, b->do_tb, b->treq, b->n, b->tres, b->tb, b->words) : 0;
+                if (b->rc) fail_all(batch, b->rc, "darwin_gpu_tiles");
+                return;
+            }
+            std::vector<DarwinTileReq> req; req.reserve(total);
+            for (auto* b : batch) req.insert(req.end(), b->treq, b->treq + b->n);
+            std::vector<DarwinTileRes> res(total);
+            std::vector<uint64_t> tbw(tb ? total * (size_t)words : 1);
+            const int rc = total ? c_.tiles(h_, tb, req.data(), (int)total, res.data(), tb ? tbw.data() : nullptr, words) : 0;
+            if (rc) { fail_all(batch, rc, "darwin_gpu_tiles"); return; }
+            size_t at = 0;
+            for (auto* b : batch) {
+                for (int i = 0; i < b->n; i++) {
+                    b->tres[i] = res[at + i];
+                    if (tb) memcpy(b->tb + (size_t)i * b->words, tbw.data() + (at + i) * (size_t)words, sizeof(uint64_t) * (size_t)b->words);
+                }
+                at += (size_t)b->n;
+            }
+        } else if (k == FILTER) {
+            if (batch.size() == 1) {
+                Request* b = batch[0];
+                b->rc = c_.filter(h_, &b->fp, b->cands, b->n, b->fres);
+                if (b->rc) fail_all(batch, b->rc, "darwin_gpu_filter");
+                return;
+            }
+            std::vector<DarwinFilterCand> cands; cands.reserve(total);
+            for (auto* b : batch) cands.insert(cands.end(), b->cands, b->cands + b->n);
+            std::vector<DarwinFilterRes> res(total);
+            const int rc = c_.filter(h_, &batch[0]->fp, cands.data(), (int)total, res.data());
+            if (rc) { fail_all(batch, rc, "darwin_gpu_filter"); return; }
+            size_t at = 0;
+            for (auto* b : batch) { if (b->n) memcpy(b->fres, res.data() + at, sizeof(DarwinFilterRes) * (size_t)b->n); at += (size_t)b->n; }
+        } else {
+            // anchors of all callers back to back; their hit lists are rebased into one pool
+            std::vector<DarwinAnchor> anchors; anchors.reserve(total);
+            std::vector<uint64_t> pool;
+            uint64_t cap = 65536;
+            for (auto* b : batch) {
+                const uint64_t base = pool.size();
+                if (b->n_pool) pool.insert(pool.end(), b->pool, b->pool + b->n_pool);
+                for (int i = 0; i < b->n; i++) {
+                    DarwinAnchor a = b->anchors[i];
+                    a.left_hits_off += (uint32_t)base; a.right_hits_off += (uint32_t)base;
+                    cap += 3ull * a.read_len;
+                    anchors.push_back(a);
+                }
+            }
+            std::vector<DarwinAlnRes> res(total);
+            std::vector<uint8_t> ops(cap);
+            const int rc = c_.extend(h_, &batch[0]->ep, anchors.data(), (int)total, pool.empty() ? nullptr : pool.data(), pool.size(),
+                                     res.data(), ops.data(), cap);
+            if (rc) { fail_all(batch, rc, "darwin_gpu_extend"); return; }
+            // op strings are dense and in anchor order: each caller owns one contiguous slice of the pool
+            size_t at = 0;
+            for (auto* b : batch) {
+                uint64_t lo = UINT64_MAX, hi = 0;
+                for (int i = 0; i < b->n; i++) {
+                    const DarwinAlnRes& r = res[at + i];
+                    if (!(r.flags & DARWIN_ALN_EMITTED) || (r.flags & DARWIN_ALN_OPS_OVERFLOW) || r.n_ops == 0) continue;
+                    if (r.ops_offset < lo) lo = r.ops_offset;
+                    if (r.ops_offset + r.n_ops > hi) hi = r.ops_offset + r.n_ops;
+                }
+                if (lo == UINT64_MAX) { lo = 0; hi = 0; }
+                if (b->ops) b->ops->assign(ops.begin() + lo, ops.begin() + hi);
+                for (int i = 0; i < b->n; i++) {
+                    b->ares[i] = res[at + i];
+                    b->ares[i].ops_offset = (res[at + i].ops_offset >= lo) ? res[at + i].ops_offset - lo : 0;
+                }
+                at += (size_t)b->n;
+            }
+        }
+    }
+
+    DarwinGpu* h_;
+    GpuCalls c_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Request*> q_;
+    bool busy_ = false;
+    CombinerStats st_;
+};
+
+} // namespace darwin_gpu_host

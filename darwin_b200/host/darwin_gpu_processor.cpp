@@ -2,6 +2,7 @@
 #include "darwin_gpu_processor.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <deque>
 #include <mutex>
 #include <stdexcept>
@@ -11,12 +12,20 @@
 namespace darwin_gpu_host {
 
 static std::vector<DarwinGpu*> g_handles;
+static std::vector<GpuCombiner*> g_combiners;                            // one per GPU: merges the requests of all host threads
 static std::string g_error;
+static std::mutex g_error_mutex;
 static uint64_t g_arena_bytes = 4ull * 1024ull * 1024ull * 1024ull;       // DRAM.cpp:8
 
 static void fail(DarwinGpu* h, int rc, const char* what) {
-    g_error = std::string(what) + ": " + (h ? darwin_gpu_last_error(h) : "no handle") + " (" + std::to_string(rc) + ")";
-    throw std::runtime_error(g_error);                                   // no silent CPU fallback
+    std::string msg = std::string(what) + ": " + (h ? darwin_gpu_last_error(h) : "no handle") + " (" + std::to_string(rc) + ")";
+    { std::lock_guard<std::mutex> g(g_error_mutex); g_error = msg; }
+    throw std::runtime_error(msg);                                       // no silent CPU fallback
+}
+static void fail_msg(int rc, const char* what, const std::string& detail) {
+    std::string msg = std::string(what) + ": " + detail + " (" + std::to_string(rc) + ")";
+    { std::lock_guard<std::mutex> g(g_error_mutex); g_error = msg; }
+    throw std::runtime_error(msg);
 }
 
 const char* last_error() { return g_error.c_str(); }
@@ -26,22 +35,80 @@ DarwinGpu* handle_for_token(size_t token) {
     return g_handles[token % g_handles.size()];
 }
 
+GpuCombiner& combiner_for_token(size_t token) {
+    if (g_combiners.empty()) { g_error = "InitializeProcessor was not called"; throw std::runtime_error(g_error); }
+    return *g_combiners[token % g_combiners.size()];
+}
+
+// The reads of one batch as arena spans.  The reader lays the reads of a batch out back to back, WORD_SIZE-aligned with
+// 'N' padding in between (main.cpp:645-686), so they normally merge into ONE span; a wrap of the arena (main.cpp:652-655)
+// simply starts a second one.
+static std::vector<UploadSpan> read_spans(const std::vector<Read>& reads) {
+    std::vector<UploadSpan> spans;
+    for (const auto& rd : reads) {
+        const uint64_t at = (uint64_t)(rd.seq.data() - g_DRAM->buffer), n = rd.seq.size();
+        if (!spans.empty()) {
+            UploadSpan& s = spans.back();
+            const uint64_t end = s.arena_addr + s.n;
+            if (at >= end && at - end < 2 * WORD_SIZE) { s.n = at + n - s.arena_addr; continue; }
+        }
+        spans.push_back(UploadSpan{at, rd.seq.data(), n});
+    }
+    return spans;
+}
+
+// Layout of g_handles / g_combiners: lane-major, g_handles[lane * g_gpus + gpu]; lane 0 of every GPU owns the arena replica.
+static int g_gpus = 0, g_lanes = 0;
+
 size_t InitializeProcessor(int threads, int gpus, std::string /*chip_ids*/) {
-    (void)threads;
     if (gpus < 1) gpus = 1;
     if (g_DRAM) g_arena_bytes = g_DRAM->size;
+    // lanes per GPU: independent handles (stream + scratch) sharing the GPU's arena replica, so that the latency-bound
+    // kernels of small batches and the host-side pre/post work of different host threads overlap
+    int lanes = 4;
+    if (const char* e = getenv("DARWIN_GPU_LANES")) lanes = atoi(e);
+    if (threads > 0 && lanes > (threads + gpus - 1) / gpus) lanes = (threads + gpus - 1) / gpus;
+    if (lanes < 1) lanes = 1;
     for (int d = 0; d < gpus; d++) {
         DarwinGpu* h = nullptr;
         int rc = darwin_gpu_create(&h, d, g_arena_bytes);
         if (rc != DARWIN_OK) { if (d == 0) fail(h, rc, "darwin_gpu_create"); break; }
         g_handles.push_back(h);
     }
+    g_gpus = (int)g_handles.size(); g_lanes = 1;
+    for (int l = 1; l < lanes; l++) {
+        for (int d = 0; d < g_gpus; d++) {
+            DarwinGpu* h = nullptr;
+            int rc = darwin_gpu_create_shared(&h, g_handles[d]);
+            if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_create_shared");
+            g_handles.push_back(h);
+        }
+        g_lanes = l + 1;
+    }
+    for (auto h : g_handles) g_combiners.push_back(new GpuCombiner(h, GpuCalls::library()));
     return g_handles.size();
 }
 
 void ShutdownProcessor() {
-    for (auto h : g_handles) darwin_gpu_destroy(h);
+    for (auto c : g_combiners) delete c;
+    g_combiners.clear();
+    for (size_t k = g_handles.size(); k-- > 0;) darwin_gpu_destroy(g_handles[k]);       // arena owners (lane 0) last
     g_handles.clear();
+    g_gpus = g_lanes = 0;
+}
+
+CombinerStats combiner_stats(size_t token) { return combiner_for_token(token).stats(); }
+
+CombinerStats combiner_stats_total() {
+    CombinerStats t; memset(&t, 0, sizeof(t));
+    for (auto c : g_combiners) {
+        const CombinerStats s = c->stats();
+        for (int k = 0; k < 3; k++) {
+            t.device_calls[k] += s.device_calls[k]; t.requests[k] += s.requests[k]; t.items[k] += s.items[k];
+            if (s.max_merged[k] > t.max_merged[k]) t.max_merged[k] = s.max_merged[k];
+        }
+    }
+    return t;
 }
 
 void InitializeScoringParameters(size_t /*token*/, Darwin::AlignmentScoringParams& r,
@@ -58,16 +125,16 @@ static void upload(size_t token, Darwin::InitializeDRAMMessage& m, Darwin::Initi
     response.status = Darwin::Status::OK;
     if (m.data.size() * 8 < m.num_bytes) { response.status = Darwin::Status::InvalidData; return; }
     (void)token;
-    for (auto h : g_handles)                                             // every GPU keeps a replica of the arena
-        if (darwin_gpu_upload(h, m.start_addr, reinterpret_cast<const char*>(m.data.data()), m.num_bytes) != DARWIN_OK)
-            response.status = Darwin::Status::InvalidData;
+    const std::vector<UploadSpan> span{UploadSpan{m.start_addr, reinterpret_cast<const char*>(m.data.data()), m.num_bytes}};
+    for (int d = 0; d < g_gpus; d++)                                     // every GPU keeps ONE replica of the arena (its lanes share it)
+        if (g_combiners[d]->upload(span, nullptr) != DARWIN_OK) response.status = Darwin::Status::InvalidData;
 }
 void InitializeReferenceMemory(size_t token, char*, Darwin::InitializeDRAMMessage& m, Darwin::InitializeDRAMMessageResponse& r) { upload(token, m, r); }
 void InitializeReadMemory(size_t token, char*, Darwin::InitializeDRAMMessage& m, Darwin::InitializeDRAMMessageResponse& r) { upload(token, m, r); }
 
 void BatchAlignmentSIMD(size_t token, char* /*dram*/, Darwin::BatchAlignmentInputFieldsDRAM& request,
                         Darwin::BatchAlignmentResultDRAM& result) {
-    DarwinGpu* h = handle_for_token(token);
+    GpuCombiner& gc = combiner_for_token(token);
     const size_t n = request.requests.size();
     result.results.resize(n);
     if (n == 0) return;
@@ -82,8 +149,9 @@ void BatchAlignmentSIMD(size_t token, char* /*dram*/, Darwin::BatchAlignmentInpu
     const int words = max_tb / 16 + 2;
     std::vector<DarwinTileRes> res(n);
     std::vector<uint64_t> tb(request.do_traceback ? n * words : 1);
-    int rc = darwin_gpu_tiles(h, request.do_traceback, req.data(), (int)n, res.data(), tb.data(), words);
-    if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_tiles");
+    std::string err;
+    int rc = gc.tiles(request.do_traceback, req.data(), (int)n, res.data(), tb.data(), words, &err);
+    if (rc != DARWIN_OK) fail_msg(rc, "BatchAlignmentSIMD", err);
     for (size_t i = 0; i < n; i++) {
         auto& o = result.results[i];
         o.index = res[i].index; o.score = (uint32_t)res[i].score;
@@ -102,6 +170,9 @@ void InstallProcessorTable() {
     g_InitializeReadMemory = InitializeReadMemory;
     g_BatchAlignmentSIMD = BatchAlignmentSIMD;
 }
+
+// arena range this thread's last gpu_filter_body call made resident (lets gpu_extender_body skip the same upload)
+static thread_local uint64_t t_resident_addr = ~0ull, t_resident_end = 0;
 
 // ExtendLocations (graph.h:83-91) -> DarwinAnchor (what makeForward/BackwardAlignment look up, extender.cpp:1067-1159)
 static void to_anchor(const ExtendLocations& l, const Read& rd, int strand, std::vector<uint64_t>& pool, DarwinAnchor& a) {
@@ -122,7 +193,7 @@ void gpu_extender_body::operator()(extender_input input, extender_node::output_p
     auto& reads = get<0>(payload);
     auto& data = get<1>(payload);
     size_t token = get<1>(input);
-    DarwinGpu* h = handle_for_token(token);
+    GpuCombiner& gc = combiner_for_token(token);
     extend_data output;
 
     std::vector<DarwinAnchor> anchors;
@@ -134,23 +205,20 @@ void gpu_extender_body::operator()(extender_input input, extender_node::output_p
         }
     const int n = (int)anchors.size();
     if (n > 0) {
-        // the reads of this batch must be resident: upload them (the software reference reads g_DRAM directly)
-        for (const auto& rd : reads) {
-            const uint64_t at = (uint64_t)(rd.seq.data() - g_DRAM->buffer);
-            int rc = darwin_gpu_upload(h, at, rd.seq.data(), rd.seq.size());
-            if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_upload(read)");
-        }
+        // the reads of this batch must be resident (the software reference reads g_DRAM directly); gpu_filter_body has
+        // normally sent them already when it ran on this thread
+        std::vector<UploadSpan> spans = read_spans(reads);
+        if (!spans.empty() && t_resident_addr == spans[0].arena_addr && t_resident_end == spans.back().arena_addr + spans.back().n) spans.clear();
         DarwinExtendParams prm{cfg.tile_size, cfg.tile_overlap, cfg.do_overlap, 0};
         std::vector<DarwinAlnRes> res(n);
-        uint64_t cap = 65536;
-        for (const auto& a : anchors) cap += 3ull * a.read_len;
-        std::vector<uint8_t> ops(cap);
-        int rc = darwin_gpu_extend(h, &prm, anchors.data(), n, pool.data(), pool.size(), res.data(), ops.data(), cap);
-        if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_extend");
+        std::vector<uint8_t> ops;
+        std::string err;
+        int rc = gc.extend(prm, spans, anchors.data(), n, pool.data(), pool.size(), res.data(), &ops, &err);
+        if (rc != DARWIN_OK) fail_msg(rc, "gpu_extender_body", err);
         for (int k = 0; k < n; k++) {
             const DarwinAlnRes& r = res[k];
             if (!(r.flags & DARWIN_ALN_EMITTED)) continue;
-            if (r.flags & DARWIN_ALN_OPS_OVERFLOW) fail(h, DARWIN_ERR_CAPACITY, "op string overflow");
+            if (r.flags & DARWIN_ALN_OPS_OVERFLOW) fail_msg(DARWIN_ERR_CAPACITY, "gpu_extender_body", "op string overflow");
             const DarwinAnchor& a = anchors[k];
             const Read& rd = reads[a.read_num];
             const char* qchars = a.strand ? rd.rc_seq.data() : rd.seq.data();        // extender.cpp:243 / :758
@@ -202,7 +270,7 @@ extender_input gpu_filter_body::operator()(filter_input input) {
     auto& reads = get<0>(payload);
     auto& data = get<1>(payload);
     size_t token = get<1>(input);
-    DarwinGpu* h = handle_for_token(token);
+    GpuCombiner& gc = combiner_for_token(token);
     filter_data output;
 
     const size_t nf = data.fwAnchors.size(), nr = data.rcAnchors.size();
@@ -229,14 +297,12 @@ extender_input gpu_filter_body::operator()(filter_input input) {
     }
     std::vector<DarwinFilterRes> res(cands.size());
     if (!cands.empty()) {
-        for (const auto& rd : reads) {                                                 // the reads of this batch must be resident
-            const uint64_t at = (uint64_t)(rd.seq.data() - g_DRAM->buffer);
-            int rc = darwin_gpu_upload(h, at, rd.seq.data(), rd.seq.size());
-            if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_upload(read)");
-        }
+        const std::vector<UploadSpan> spans = read_spans(reads);                       // the reads of this batch must be resident
         DarwinFilterParams prm{cfg.first_tile_size, cfg.first_tile_score_threshold, cfg.min_overlap, 0};
-        int rc = darwin_gpu_filter(h, &prm, cands.data(), (int)cands.size(), res.data());
-        if (rc != DARWIN_OK) fail(h, rc, "darwin_gpu_filter");
+        std::string err;
+        int rc = gc.filter(prm, spans, cands.data(), (int)cands.size(), res.data(), &err);
+        if (rc != DARWIN_OK) fail_msg(rc, "gpu_filter_body", err);
+        if (!spans.empty()) { t_resident_addr = spans[0].arena_addr; t_resident_end = spans.back().arena_addr + spans.back().n; }
     }
     for (int strand = 0; strand < 2; strand++) {
         const auto& anchors = strand ? data.rcAnchors : data.fwAnchors;

@@ -7,11 +7,14 @@
 #pragma once
 #include "graph.h"               // reference: software/graph.h
 #include "darwin_gpu.h"          // include/darwin_gpu.h
+#include "darwin_gpu_combiner.h" // cross-read batching of the GPU calls
 
 namespace darwin_gpu_host {
 
 // == InitializeProcessor_ptr (software/Processor.h:50): one GPU handle per token (token -> device round-robin).
-// `fpgas` is read as the number of GPUs to use (params.cfg [FPGA] num_fpgas), `chip_ids` is ignored.
+// `fpgas` is read as the number of GPUs to use (params.cfg [FPGA] num_fpgas), `chip_ids` is ignored.  Every GPU gets
+// up to DARWIN_GPU_LANES (default 4, at most threads / gpus) handles sharing one arena replica; token t is served by
+// GPU t % gpus, lane (t / gpus) % lanes.
 // Returns the number of processors created.  arena_bytes defaults to the reference's 4 GiB arena (DRAM.cpp:8).
 size_t InitializeProcessor(int threads, int gpus, std::string chip_ids);
 void   ShutdownProcessor();
@@ -44,6 +47,9 @@ struct gpu_filter_body {
 void InstallProcessorTable();
 
 DarwinGpu* handle_for_token(size_t token);
+GpuCombiner& combiner_for_token(size_t token);       // the per-GPU batcher all stage bodies go through
+CombinerStats combiner_stats(size_t token);
+CombinerStats combiner_stats_total();              // summed over all GPUs and lanes
 const char* last_error();
 
 } // namespace darwin_gpu_host

@@ -194,6 +194,11 @@ typedef struct DarwinGpu DarwinGpu;   /* opaque */
  * arena_bytes = size of the byte-addressed sequence arena this handle mirrors
  * (the reference's g_DRAM, DRAM.cpp:8); the device keeps it 4-bit packed. */
 int darwin_gpu_create(DarwinGpu** h, int device, uint64_t arena_bytes);
+/* A further handle ("lane") on the parent's device that SHARES the parent's arena replica: own stream, own scratch,
+ * own result buffers.  Lets several host threads keep kernels of independent batches in flight on one GPU (the
+ * reference's tokens, main.cpp:615-624) without one arena copy per thread.  Uploads through any lane are visible to
+ * all of them once darwin_gpu_upload returns.  The parent must be destroyed last. */
+int darwin_gpu_create_shared(DarwinGpu** h, DarwinGpu* parent);
 int darwin_gpu_destroy(DarwinGpu* h);
 
 /* replaces g_InitializeScoringParameters (Processor.cpp:48-80). */

@@ -634,6 +634,88 @@ int dref_pipeline(int first, int count, int use_gpu, char* out, uint64_t cap) {
     } catch (const std::exception& e) { fprintf(stderr, "dref_pipeline: %s\n", e.what()); return -1; }
 }
 
+// ---- multi-threaded end-to-end run: `threads` host threads play the reference's tokens
+// (main.cpp:615-624); each pulls batches of `reads_per_batch` reads and runs seeder_body -> filter -> extender on them.
+// mode 0: the reference's CPU stages; mode 1: GPU extender only (filter tiles through g_BatchAlignmentSIMD);
+// mode 2: gpu_filter_body + gpu_extender_body.  With the GPU stages all threads share the per-GPU combiner
+// (darwin_b200/host/darwin_gpu_combiner.h).  Output: canonical sorted lines like dref_pipeline (out may be NULL);
+// stats[0] = wall seconds, [1] = alignments, [2] = seconds inside seeder_body (summed over threads), [3] = filter stage,
+// [4] = extender stage, [5] = DP cells of the alignments' tile requests when dref_count_cells(1) was set (CPU modes).
+int dref_pipeline_mt(int first, int count, int threads, int reads_per_batch, int mode, char* out, uint64_t cap, double* stats) {
+    if (threads < 1) threads = 1;
+    if (reads_per_batch < 1) reads_per_batch = 1;
+    const int nbatches = (count + reads_per_batch - 1) / reads_per_batch;
+    std::atomic<int> next(0);
+    std::atomic<int> failed(0);
+    std::mutex out_mutex;
+    std::vector<std::string> lines;
+    std::atomic<uint64_t> n_aln(0);
+    std::vector<double> t_seed(threads, 0.0), t_filter(threads, 0.0), t_extend(threads, 0.0);
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t0 = now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) {
+        th.emplace_back([&, t] {
+            try {
+                for (;;) {
+                    const int b = next.fetch_add(1);
+                    if (b >= nbatches || failed.load()) break;
+                    const int lo = first + b * reads_per_batch, hi = std::min(first + count, lo + reads_per_batch);
+                    reader_output reads(g_reads.begin() + lo, g_reads.begin() + hi);
+                    const auto a0 = now();
+                    filter_input fin = seeder_body()(seeder_input(reads, (size_t)t));
+                    const auto a1 = now();
+                    extender_input ein = (mode >= 2) ? darwin_gpu_host::gpu_filter_body()(fin) : filter_body()(fin);
+                    const auto a2 = now();
+                    extender_node::output_ports_type ports;
+                    if (mode >= 1) darwin_gpu_host::gpu_extender_body()(ein, ports);
+                    else extender_body()(ein, ports);
+                    const auto a3 = now();
+                    t_seed[t] += secs(a0, a1); t_filter[t] += secs(a1, a2); t_extend[t] += secs(a2, a3);
+                    auto& al = std::get<1>(std::get<0>(std::get<0>(ports).items[0])).extend_alignments;
+                    n_aln += al.size();
+                    if (out) {
+                        std::vector<std::string> mine;
+                        for (auto& e : al)
+                            mine.push_back(std::to_string(e.read_num + lo) + " " + std::to_string(e.chr_id) + " " + std::string(1, e.strand) + " " +
+                                           std::to_string(e.reference_start_offset) + " " + std::to_string(e.reference_end_offset) + " " +
+                                           std::to_string(e.query_start_offset) + " " + std::to_string(e.query_end_offset) + " " +
+                                           std::to_string(e.score) + " " + e.aligned_reference_str + " " + e.aligned_query_str);
+                        std::lock_guard<std::mutex> g(out_mutex);
+                        for (auto& l : mine) lines.push_back(std::move(l));
+                    }
+                }
+            } catch (const std::exception& e) { fprintf(stderr, "dref_pipeline_mt: %s\n", e.what()); failed = 1; }
+        });
+    }
+    for (auto& x : th) x.join();
+    const double wall = secs(t0, now());
+    if (stats) {
+        stats[0] = wall; stats[1] = (double)n_aln.load(); stats[2] = stats[3] = stats[4] = 0;
+        for (int t = 0; t < threads; t++) { stats[2] += t_seed[t]; stats[3] += t_filter[t]; stats[4] += t_extend[t]; }
+        stats[5] = (double)g_cells.load();
+    }
+    if (failed.load()) return -1;
+    if (out) {
+        std::sort(lines.begin(), lines.end());
+        uint64_t pos = 0;
+        for (auto& l : lines) {
+            if (pos + l.size() + 2 > cap) return -2;
+            memcpy(out + pos, l.data(), l.size()); pos += l.size(); out[pos++] = '\n';
+        }
+        out[pos] = 0;
+    }
+    return (int)n_aln.load();
+}
+
+// merged-call statistics summed over all combiners (GPUs x lanes): out[0..2] device calls (tiles, filter, extend), [3..5] requests, [6..8] items,
+// [9..11] largest number of requests merged into one call
+void dref_combiner_stats(uint64_t* out) {
+    darwin_gpu_host::CombinerStats s = darwin_gpu_host::combiner_stats_total();
+    for (int k = 0; k < 3; k++) { out[k] = s.device_calls[k]; out[3 + k] = s.requests[k]; out[6 + k] = s.items[k]; out[9 + k] = s.max_merged[k]; }
+}
+
 // back to the software Processor (the reference's defaults, Processor.cpp:1063-1069)
 void dref_use_cpu_table(void) {
     g_InitializeScoringParameters = InitializeScoringParams;

@@ -1,0 +1,125 @@
+// CPU unit test of darwin_b200/host/darwin_gpu_combiner.h: the merge / scatter logic of the cross-read batcher, driven
+// by several host threads, with the oracle's CPU functions standing in for the GPU entry points.  Built and called by
+// tests/test_combiner.py (g++ -shared, linked against oracle/libgact_oracle.so).  TEST CODE ONLY.
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../darwin_b200/host/darwin_gpu_combiner.h"
+#include "../../oracle/gact_oracle.h"
+
+using namespace darwin_gpu_host;
+
+struct Fake { GactScoring sc; char* dram; uint64_t dram_bytes; std::atomic<int> device_calls; int fail_filter; };
+static Fake* fake(DarwinGpu* h) { return reinterpret_cast<Fake*>(h); }
+static void device_latency() { std::this_thread::sleep_for(std::chrono::milliseconds(2)); }
+
+static int f_upload(DarwinGpu* h, uint64_t addr, const char* a, uint64_t n) {
+    if (addr + n > fake(h)->dram_bytes) return DARWIN_ERR_INVALID;
+    memcpy(fake(h)->dram + addr, a, n);
+    return 0;
+}
+static int f_tiles(DarwinGpu* h, int tb, const DarwinTileReq* req, int n, DarwinTileRes* res, uint64_t* w, int words) {
+    fake(h)->device_calls++; device_latency();
+    if (tb) memset(w, 0, sizeof(uint64_t) * (size_t)n * words);
+    return gact_tiles(&fake(h)->sc, fake(h)->dram, tb, GACT_RULE_STREAM, req, n, res, tb ? w : nullptr, words, nullptr);
+}
+static int f_filter(DarwinGpu* h, const DarwinFilterParams* p, const DarwinFilterCand* c, int n, DarwinFilterRes* res) {
+    fake(h)->device_calls++; device_latency();
+    if (fake(h)->fail_filter) return DARWIN_ERR_CUDA;
+    return gact_filter(&fake(h)->sc, fake(h)->dram, p, c, n, res);
+}
+static int f_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* a, int n, const uint64_t* pool, uint64_t,
+                    DarwinAlnRes* res, uint8_t* ops, uint64_t cap) {
+    fake(h)->device_calls++; device_latency();
+    memset(res, 0, sizeof(DarwinAlnRes) * (size_t)n);
+    return gact_extend(&fake(h)->sc, fake(h)->dram, p, GACT_RULE_STREAM, a, n, pool, res, ops, cap);
+}
+static const char* f_err(DarwinGpu*) { return "stand-in failure"; }
+
+static bool same_aln(const DarwinAlnRes& a, const uint8_t* oa, const DarwinAlnRes& b, const uint8_t* ob) {
+    if (a.n_ops != b.n_ops || a.cells != b.cells || a.reference_start_offset != b.reference_start_offset ||
+        a.reference_end_offset != b.reference_end_offset || a.query_start_offset != b.query_start_offset ||
+        a.query_end_offset != b.query_end_offset || a.n_tiles != b.n_tiles || a.score != b.score || a.flags != b.flags) return false;
+    if ((a.flags & DARWIN_ALN_EMITTED) && memcmp(oa + a.ops_offset, ob + b.ops_offset, a.n_ops)) return false;
+    return true;
+}
+
+extern "C" int combiner_selftest(const DarwinScoring* s, const char* dram, uint64_t dram_bytes,
+                                 const DarwinTileReq* req, int n_req, const DarwinFilterCand* cands, int n_cands,
+                                 const DarwinAnchor* anchors, int n_anchors, const uint64_t* pool, uint64_t n_pool,
+                                 int T, int O, int threads, uint64_t* stats_out) {
+    Fake fk; gact_scoring_init(&fk.sc, s);
+    std::vector<char> arena(dram_bytes, 'N');                         // the stand-in device starts empty: uploads must fill it
+    fk.dram = arena.data(); fk.dram_bytes = dram_bytes; fk.device_calls = 0; fk.fail_filter = 0;
+    DarwinGpu* h = reinterpret_cast<DarwinGpu*>(&fk);
+    GpuCalls calls{f_upload, f_tiles, f_filter, f_extend, f_err};
+    GpuCombiner gc(h, calls);
+
+    // ground truth: one direct call each on the real arena
+    Fake truth; truth.sc = fk.sc; truth.dram = const_cast<char*>(dram); truth.dram_bytes = dram_bytes; truth.device_calls = 0; truth.fail_filter = 0;
+    DarwinGpu* ht = reinterpret_cast<DarwinGpu*>(&truth);
+    const int words = 50;
+    std::vector<DarwinTileRes> t_res(n_req); std::vector<uint64_t> t_tb((size_t)n_req * words);
+    if (f_tiles(ht, 1, req, n_req, t_res.data(), t_tb.data(), words)) return 1;
+    DarwinFilterParams fp{128, 60, 1000, 0};
+    std::vector<DarwinFilterRes> f_res(n_cands);
+    if (f_filter(ht, &fp, cands, n_cands, f_res.data())) return 2;
+    DarwinExtendParams ep{T, O, 0, 0};
+    std::vector<DarwinAlnRes> a_res(n_anchors); uint64_t cap = 65536;
+    for (int i = 0; i < n_anchors; i++) cap += 3ull * anchors[i].read_len;
+    std::vector<uint8_t> a_ops(cap);
+    if (f_extend(ht, &ep, anchors, n_anchors, pool, n_pool, a_res.data(), a_ops.data(), cap)) return 3;
+
+    // the whole arena travels as upload spans attached to the FIRST request of every thread (in 3 pieces)
+    std::atomic<int> bad(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) {
+        th.emplace_back([&, t] {
+            std::string err;
+            std::vector<UploadSpan> up;
+            const uint64_t third = dram_bytes / 3;
+            up.push_back(UploadSpan{0, dram, third}); up.push_back(UploadSpan{third, dram + third, third});
+            up.push_back(UploadSpan{2 * third, dram + 2 * third, dram_bytes - 2 * third});
+            if (gc.upload(up, &err)) { bad |= 1; return; }
+            const std::vector<UploadSpan> none;
+            for (int round = 0; round < 3; round++) {
+                // this thread's slice of every kind of work
+                {   const int lo = (int)((int64_t)n_cands * t / threads), hi = (int)((int64_t)n_cands * (t + 1) / threads);
+                    std::vector<DarwinFilterRes> r(hi - lo);
+                    if (gc.filter(fp, none, cands + lo, hi - lo, r.data(), &err)) bad |= 2;
+                    else if (hi > lo && memcmp(r.data(), f_res.data() + lo, sizeof(DarwinFilterRes) * (hi - lo))) bad |= 4; }
+                {   const int lo = (int)((int64_t)n_anchors * t / threads), hi = (int)((int64_t)n_anchors * (t + 1) / threads);
+                    std::vector<DarwinAlnRes> r(hi - lo); std::vector<uint8_t> ops;
+                    if (gc.extend(ep, none, anchors + lo, hi - lo, pool, n_pool, r.data(), &ops, &err)) bad |= 8;
+                    else for (int i = lo; i < hi; i++) if (!same_aln(r[i - lo], ops.data(), a_res[i], a_ops.data())) bad |= 16; }
+                {   const int lo = (int)((int64_t)n_req * t / threads), hi = (int)((int64_t)n_req * (t + 1) / threads);
+                    const int w = words - (t % 3);                      // callers may size their TB rows differently
+                    std::vector<DarwinTileRes> r(hi - lo); std::vector<uint64_t> tb((size_t)(hi - lo) * w + 1);
+                    if (gc.tiles(1, req + lo, hi - lo, r.data(), tb.data(), w, &err)) bad |= 32;
+                    else for (int i = lo; i < hi; i++) {
+                        if (memcmp(&r[i - lo], &t_res[i], sizeof(DarwinTileRes))) bad |= 64;
+                        const int nw = (t_res[i].total_TB_pointers + 31) / 32;
+                        if (memcmp(tb.data() + (size_t)(i - lo) * w, t_tb.data() + (size_t)i * words, sizeof(uint64_t) * nw)) bad |= 128;
+                    } }
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    CombinerStats st = gc.stats();
+    for (int k = 0; k < 3; k++) { stats_out[k] = st.device_calls[k]; stats_out[3 + k] = st.requests[k]; stats_out[6 + k] = st.max_merged[k]; }
+    if (bad.load()) return 100 + bad.load();
+    // errors reach every merged caller
+    fk.fail_filter = 1;
+    std::atomic<int> errs(0);
+    std::vector<std::thread> th2;
+    for (int t = 0; t < threads; t++) th2.emplace_back([&] {
+        std::string err; std::vector<DarwinFilterRes> r(n_cands); const std::vector<UploadSpan> none;
+        if (gc.filter(fp, none, cands, n_cands, r.data(), &err) == DARWIN_ERR_CUDA && err.find("stand-in failure") != std::string::npos) errs++;
+    });
+    for (auto& x : th2) x.join();
+    return errs.load() == threads ? 0 : 50;
+}

@@ -1,0 +1,75 @@
+"""GPU: the whole reference-guided pipeline, multi-threaded -- the reference's own seeder_body on every host thread,
+gpu_filter_body + gpu_extender_body behind the per-GPU combiner (cross-read batches) -- against the reference's CPU
+pipeline on the same reads: byte-identical alignments (offsets, strand, AlignmentScore, gapped strings)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from darwin_b200 import abi, synth
+
+pytestmark = pytest.mark.gpu
+LIB = os.path.join(os.path.dirname(os.path.abspath(oracle.__file__)), "_ref", "libdarwin_ref_gpu.so")
+
+
+def load_driver():
+    ref = oracle.Reference.__new__(oracle.Reference)
+    ref.lib = C.CDLL(LIB)
+    L = ref.lib
+    L.dref_arena.restype = C.c_void_p
+    L.dref_arena_position.restype = C.c_uint64
+    L.dref_add_chr.restype = C.c_uint64
+    L.dref_anchor_hits_total.restype = C.c_uint64
+    return ref, L
+
+
+def load_case(ref, seed, genome_len, n_reads, read_len, err=(0.015, 0.09, 0.045)):
+    rng = np.random.default_rng(seed)
+    ref.set_scoring(abi.Scoring.from_values())
+    ref.set_dsoft_defaults()
+    ref.set_extend(384, 64, 2, 0)
+    ref.reset_arena()
+    genome = synth.random_seq(rng, genome_len)
+    for _ in range(max(2, genome_len // 500000)):
+        a, b = int(rng.integers(0, genome_len - 4000)), int(rng.integers(0, genome_len - 4000))
+        rep = synth.mutate_fast(rng, genome[a:a + 3000], 0.03, 0.01, 0.01)[:2900]
+        genome[b:b + len(rep)] = rep
+    ref.add_chr("chrS", genome.tobytes(), True)
+    ref.build_index()
+    for k in range(n_reads):
+        L = int(rng.integers(read_len // 2, read_len))
+        p = int(rng.integers(0, genome_len - L))
+        src = genome[p:p + L]
+        if k % 7 == 3:
+            src = np.concatenate([src[:L // 2], synth.random_seq(rng, 400), src[L // 2:]])      # stalls -> large tiles
+        r = synth.mutate_fast(rng, src, *err)
+        if k % 2:
+            r = synth.revcomp(r)
+        ref.add_read("r%d" % k, np.ascontiguousarray(r).tobytes())
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libdarwin_ref_gpu.so not built (needs /root/reference at build time)")
+def test_multithreaded_pipeline_matches_cpu_pipeline():
+    ref, L = load_driver()
+    n_reads = 96
+    load_case(ref, 5, 600000, n_reads, 6000)
+    cap = 256 << 20
+    buf_cpu, buf_gpu = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    stats = (C.c_double * 8)()
+    threads = min(8, os.cpu_count() or 1)
+    n_cpu = L.dref_pipeline_mt(0, n_reads, threads, 4, 0, buf_cpu, C.c_uint64(cap), stats)
+    assert n_cpu > n_reads // 2
+    assert L.dref_gpu_init(1) == 0
+    try:
+        for mode, per_batch in ((2, 4), (1, 7), (2, 1)):
+            n_gpu = L.dref_pipeline_mt(0, n_reads, threads, per_batch, mode, buf_gpu, C.c_uint64(cap), stats)
+            assert n_gpu == n_cpu and buf_gpu.value == buf_cpu.value, (mode, per_batch, n_gpu, n_cpu)
+        cs = (C.c_uint64 * 12)()
+        L.dref_combiner_stats(cs)
+        # requests of different host threads really shared device calls
+        assert cs[2] < cs[5] and cs[11] >= 2, list(cs)
+    finally:
+        L.dref_use_cpu_table()
+        L.dref_gpu_shutdown()
