@@ -71,7 +71,7 @@ struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568
     }
 };
 
-struct KernelScoring { DevScoring sc; FastConst fc; XConst xc; };
+struct KernelScoring { DevScoring sc; FastConst fc; XConst xc; FastConst fcw; };   // fcw: wide-score layout (4 tag bits)
 
 
 __device__ __forceinline__ void load_scoring(const DevScoring& sc, int* ssub) {
@@ -131,9 +131,14 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
     if (K > 0) {
         constexpr int KK = (K == 0 ? 4 : K);
         const FastConst& fc = ks.fc;
-        const bool fast = fc.eligible && do_traceback && se && fc.match * min(t.Q, t.R) <= fc.max_score;
+        const int smax = fc.match * min(t.Q, t.R);
+        const bool narrow = fc.eligible && do_traceback && se && smax <= fc.max_score;        // 11 score bits suffice
         const bool single = t.Q <= 64 * KK && t.R <= 64 * KK;
-        const bool xok = ks.xc.eligible && xfast_shape_ok(t.Q);          // the packed exact path can take this shape
+        const bool big = t.Q > 512 || t.R > 512;                         // beyond 512: wide band, wide scores (T = 1024)
+        const bool wide = !single && big && ks.fcw.eligible && do_traceback && se && smax <= ks.fcw.max_score;   // 12 score bits
+        const bool fast = narrow || wide;                                // `wide` also selects the variant when both hold
+        const bool xok = narrow && ks.xc.eligible && xfast_shape_ok(t.Q);   // the packed exact path can take this tile
+        const bool large = t.Q > 1024 || t.R > 1024;                     // 1984x960 / 960x1984 stall tiles (extender.cpp:70-75)
         if (fast) {
             FastSmemView<KK> v(cx.wsmem);
             MultiSmemView mv(cx.wsmem);
@@ -143,14 +148,17 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
                 uint32_t* gband = reinterpret_cast<uint32_t*>(cx.ws.trace);
                 // large tiles bridge long gaps by construction: the clean rule would almost always be refused, so
                 // shapes the packed exact path accepts go there directly
-                if (single || !xok) {
-                    const int score = single ? fast_forward<KK>(fc, v, t.Q, t.R) : fast_forward_multi<KK>(fc, mv, gband, t.Q, t.R);
+                if (single || !xok || !large) {
+                    const int score = single ? fast_forward<KK>(fc, v, t.Q, t.R)
+                                    : !wide ? fast_forward_multi<KK, 5, kBandHalf>(fc, mv, gband, t.Q, t.R)
+                                            : fast_forward_multi<KK, 4, kBandHalfWide>(ks.fcw, mv, gband, t.Q, t.R);
                     int rc = FAST_OK;
                     if (lane == 0) {
                         Sink trial = sink;
                         TileOut o2{};
                         rc = single ? fast_traceback<KK, false>(v.band, t.Q, t.R, t.max_tb, o2, trial)
-                                    : fast_traceback<KK, true>(gband, t.Q, t.R, t.max_tb, o2, trial);
+                                    : !wide ? fast_traceback<KK, true>(gband, t.Q, t.R, t.max_tb, o2, trial)
+                                            : fast_traceback<KK, true, Sink, kBandHalfWide>(gband, t.Q, t.R, t.max_tb, o2, trial);
                         if (rc == FAST_OK) { sink = trial; out = o2; }
                     }
                     rc = __shfl_sync(0xffffffffu, rc, 0);
@@ -162,6 +170,7 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
                     cx.n_rerun++;
                     __syncwarp();
                     if (xok && single) stage_tile(cx, t, xv.sref, xv.sqry, false);        // the fast view kept them elsewhere
+                    // (multi-strip tiles: MultiSmemView and XSmemView keep the sequences at the same offsets)
                 }
                 if (xok) {
                     const int score = xfast_forward(ks.xc, xv, gband, reinterpret_cast<uint4*>(cx.ws.bound), t.Q, t.R);
@@ -764,6 +773,7 @@ int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s) {
     d.uniform = (AA == CC && AA == GG && AA == TT && AC == AG && AC == AT && AC == CG && AC == CT && AC == GT);
     d.match = AA; d.mismatch = AC; d.subn = N;
     h->ks.fc = make_fast_const(d);
+    h->ks.fcw = make_fast_const(d, 4);
     h->ks.xc = make_xconst(d, h->ks.fc);
     h->filt = make_filter_const(d);
     h->have_scoring = true;
@@ -827,7 +837,7 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
                         const unsigned int* idx_list, const unsigned int* idx_count) {
     if (!do_traceback && !idx_list && h->filt.eligible) return launch_filter_tiles(h, d_req, n, d_res, maxQ, maxR);
     // per-warp scratch: exact-path trace (1 B/cell) or the multi-strip fast path's band, whichever is larger
-    int rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)), multi_band_bytes<4>(std::max(maxQ, 1))),
+    int rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)), multi_band_bytes<4, kBandHalfWide>(std::max(maxQ, 1))),
                                         xfast_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1))));
     if (rc) return rc;
     const int K = pick_k(h, std::max(maxQ, maxR), do_traceback);
@@ -1002,7 +1012,7 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     CK(cudaMemcpyAsync(h->d_buf[5], lcap.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[6], size.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     if ((rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(1984, 960), exact_trace_bytes(960, 1984)),
-                                         std::max(std::max(exact_trace_bytes(p->tile_size, p->tile_size), multi_band_bytes<4>(kMaxTile)),
+                                         std::max(std::max(exact_trace_bytes(p->tile_size, p->tile_size), multi_band_bytes<4, kBandHalfWide>(kMaxTile)),
                                                   std::max(std::max(xfast_trace_bytes(1984, 960), xfast_trace_bytes(960, 1984)),
                                                            xfast_trace_bytes(p->tile_size, p->tile_size))))))) return rc;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * kCounters, h->stream));

@@ -27,14 +27,15 @@
 namespace gact {
 
 constexpr int kBandHalf = 32;                       // +-steps around the corner diagonal kept per virtual lane
+constexpr int kBandHalfWide = 96;                   // multi-strip tiles beyond 512 (T = 1024): indel drift grows with the tile
 
 // Band layout: virtual lane v keeps the trace words of the 2*kBandHalf+1 steps centred on the step at which it
 // crosses the corner diagonal, contiguously: word(v, s) = band[v * kLp + t],  t = s - (K+1)*v - c2  in [0, kL).
 // For a cell (i, j), i = K*v + r:  t = j - K*v + c1  -- linear in v and j, so the traceback needs no division.
-template <int K> struct FastGeom {
+template <int K, int BH = kBandHalf> struct FastGeom {
     static constexpr int kRows  = 64 * K;           // max query rows (and reference columns) of a fast tile
     static constexpr int kSteps = kRows + 63;
-    static constexpr int kL     = 2 * kBandHalf + 1;
+    static constexpr int kL     = 2 * BH + 1;
     static constexpr int kLp    = kL + (((kL - K - 1) & 1) ? 0 : 1);   // lane stride kLp-(K+1) odd -> conflict-free stores
     static constexpr int kPWords = kRows + 128;     // packed reference pairs P[j + 32] = r[j] | r[j-32] << 16
     static constexpr size_t kBandWords = (size_t)64 * kLp;
@@ -65,7 +66,9 @@ struct FastConst {                                  // packed constants derived 
 constexpr uint32_t FT_DEL = 0, FT_INS = 1, FT_DIAG = 2, FT_ZERO = 3, FT_L = 4;
 constexpr uint32_t kMaskT = 0x001C001Cu, kMaskM = 0x00030003u, kMaskClean = 0xFFE0FFE0u;
 
-__host__ inline FastConst make_fast_const(const DevScoring& sc) {
+// S = tag bits below the score: 5 (bits 4:2 source, 1 "F extended", 0 "E extended"; scores up to 2047 - bias) or
+// 4 (bits 3:1 source, bit 0 "this gap chain was extended"; scores up to 4095 - bias: T = 1024 tiles at match = 2).
+__host__ inline FastConst make_fast_const(const DevScoring& sc, int S = 5) {
     FastConst f{};
     const int m = sc.match, mm = sc.mismatch, go = sc.go, ge = sc.ge, lgo = sc.lgo, lge = sc.lge;
     int B = -mm;
@@ -74,20 +77,21 @@ __host__ inline FastConst make_fast_const(const DevScoring& sc) {
     B += 1;
     f.eligible = sc.uniform && m > 0 && mm < 0 && go <= ge && ge < 0 && lgo <= lge && lge <= 0 && B < 512;
     auto pk = [](int v) { return (uint32_t)(v & 0xFFFF) * 0x00010001u; };
-    f.bias = B; f.match = m; f.max_score = 2047 - B - m; f.one[0] = f.one[1] = f.one[2] = f.one[3] = 1;
-    f.zeroc = pk((B << 5) | (FT_ZERO << 2));
-    f.hm_init = pk(((B + mm) << 5) | (FT_DIAG << 2));
-    f.e_init = pk((B + go) << 5);
-    f.el_init = pk(((B + lgo) << 5) | (FT_L << 2));
-    f.f_top = pk(((B + go) << 5) | (FT_INS << 2));
-    f.fl_top = pk(((B + lgo) << 5) | (FT_L << 2));
-    f.pkc32 = pk((m - mm) << 5);
-    f.negc32 = -((m - mm) << 5);
-    f.diaga = (mm * 32 + (int)(FT_DIAG << 2)) * 65537;
-    f.goa = (go * 32) * 65537; f.gofa = (go * 32 + (int)(FT_INS << 2)) * 65537;
-    f.gea = (ge * 32) * 65537;
-    f.lgoa = (lgo * 32 + (int)(FT_L << 2)) * 65537; f.lgea = (lge * 32) * 65537;
-    f.geh = pk(ge * 32); f.lgeh = pk(lge * 32);
+    const int U = 1 << S, ts = S - 3;                          // score unit, position of the 3-bit source field
+    f.bias = B; f.match = m; f.max_score = (65536 / U - 1) - B - m; f.one[0] = f.one[1] = f.one[2] = f.one[3] = 1;
+    f.zeroc = pk((B << S) | (FT_ZERO << ts));
+    f.hm_init = pk(((B + mm) << S) | (FT_DIAG << ts));
+    f.e_init = pk((B + go) << S);
+    f.el_init = pk(((B + lgo) << S) | (FT_L << ts));
+    f.f_top = pk(((B + go) << S) | (FT_INS << ts));
+    f.fl_top = pk(((B + lgo) << S) | (FT_L << ts));
+    f.pkc32 = pk((m - mm) << S);
+    f.negc32 = -((m - mm) << S);
+    f.diaga = (mm * U + (int)(FT_DIAG << ts)) * 65537;
+    f.goa = (go * U) * 65537; f.gofa = (go * U + (int)(FT_INS << ts)) * 65537;
+    f.gea = (ge * U) * 65537;
+    f.lgoa = (lgo * U + (int)(FT_L << ts)) * 65537; f.lgea = (lge * U) * 65537;
+    f.geh = pk(ge * U); f.lgeh = pk(lge * U);
     return f;
 }
 
@@ -106,12 +110,12 @@ template <int K> struct FastSmemView {
 };
 
 // Band addressing shared by the forward pass and the traceback.
-template <int K> struct BandMap {
+template <int K, int BH = kBandHalf> struct BandMap {
     int c1;               // t(i,j) = j - K*v + c1
     __device__ BandMap(int Q, int R) {
         // virtual lane v crosses the corner diagonal (i - j = Q - R) at its middle row K*v + K/2:
-        // step s_c(v) = (K+1)*v + K/2 - (Q - R); window t = s - s_c(v) + kBandHalf
-        c1 = (Q - R) - K / 2 + kBandHalf;
+        // step s_c(v) = (K+1)*v + K/2 - (Q - R); window t = s - s_c(v) + BH
+        c1 = (Q - R) - K / 2 + BH;
     }
     __device__ __forceinline__ int t_of(int j, int v) const { return j - K * v + c1; }
 };
@@ -127,6 +131,9 @@ struct FastRegs {
 
 // One packed cell pair (two int16 cells): recurrence of Processor.cpp:293-366 on tagged scores.
 // d = Hm of the row above at the previous column (in), Hm of this row at the previous column (out).
+// S = 5: the layout described above.  S = 4 (wide scores): source in bits 3:1, one shared "extended" bit 0; the 5-bit
+// trace code (same as S = 5) is assembled from Hk's source, E's bit 0 and F's bit 0 (one more ALU op per cell pair).
+template <int S = 5>
 __device__ __forceinline__ uint32_t fast_cell(const FastRegs& k, uint32_t rq, uint32_t qq, uint32_t& d, uint32_t& Hm,
                                               uint32_t& E, uint32_t& EL, uint32_t& F, uint32_t& FL) {
     const uint32_t x  = rq ^ qq;
@@ -135,14 +142,23 @@ __device__ __forceinline__ uint32_t fast_cell(const FastRegs& k, uint32_t rq, ui
     const uint32_t hd = __viaddmax_u16x2(d, sb, k.zeroc);        // max(Hdiag + s, 0)          :298-299
     const uint32_t h1 = __vimax3_u16x2(hd, E, F);
     const uint32_t Hk = __vimax3_u16x2(h1, EL, FL);              // H with the winner's tag      :300-303
-    const uint32_t em = E | F;
-    const uint32_t code = (Hk & kMaskT) | (em & kMaskM);
-    const uint32_t Hc = Hk & kMaskClean;
+    uint32_t code, Hc;
+    if (S == 5) {
+        const uint32_t em = E | F;
+        code = (Hk & kMaskT) | (em & kMaskM);
+        Hc = Hk & kMaskClean;
+    } else {
+        const uint32_t fm = F & 0x00010001u;                     // masked first: F's top score bit must not spill over
+        const uint32_t f2 = fm * k.one0 + fm, hk2 = Hk * k.one1 + Hk;          // x2 as IMADs
+        const uint32_t em = (E | f2) & kMaskM;                   // E's source bits are 0 (DEL): bit 0 is its marker
+        code = (hk2 & kMaskT) | em;
+        Hc = Hk & 0xFFF0FFF0u;
+    }
     d = Hm;
     Hm = Hc * k.one0 + k.diaga;                                  // IMADs: keeps the adds off the ALU pipe
     const uint32_t Ho = Hc * k.one1 + k.goa, HoF = Hc * k.one2 + k.gofa, HoL = Hc * k.one3 + k.lgoa;
     E  = __viaddmax_u16x2(E | 0x00010001u, k.geh, Ho);           // ties extend                  :336-337,:353
-    F  = __viaddmax_u16x2(F | 0x00020002u, k.geh, HoF);          //                              :363-364,:369
+    F  = __viaddmax_u16x2(F | (S == 5 ? 0x00020002u : 0x00010001u), k.geh, HoF);   //            :363-364,:369
     EL = __viaddmax_u16x2(EL, k.lgeh, HoL);                      //                              :339-340
     FL = __viaddmax_u16x2(FL, k.lgeh, HoL);                      //                              :365-366
     return code;
@@ -238,16 +254,16 @@ struct MultiSmemView {
     }
 };
 
-template <int K> __host__ __device__ inline size_t multi_band_bytes(int Q) {
-    return (size_t)((Q + K - 1) / K + 64) * FastGeom<K>::kLp * 4;
+template <int K, int BH = kBandHalf> __host__ __device__ inline size_t multi_band_bytes(int Q) {
+    return (size_t)((Q + K - 1) / K + 64) * FastGeom<K, BH>::kLp * 4;
 }
 
-template <int K>
+template <int K, int S = 5, int BH = kBandHalf>
 __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, uint32_t* gband, int Q, int R) {
-    using G = FastGeom<K>;
+    using G = FastGeom<K, BH>;
     const int lane = lane_id();
     const FastRegs kr(fc);
-    const BandMap<K> bm(Q, R);
+    const BandMap<K, BH> bm(Q, R);
     const int nstrips = (Q + 64 * K - 1) / (64 * K);
     const int vc = (Q - 1) / K, rc = (Q - 1) - vc * K;                   // global virtual lane / row of the corner
     const int sc_step = R - 1 + (vc & 63);                               // step of the corner inside the last strip
@@ -296,7 +312,7 @@ __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, u
             uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
             for (int r = 0; r < K; r++) {
-                const uint32_t code = fast_cell(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
+                const uint32_t code = fast_cell<S>(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
                 if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
             }
             if (strip == nstrips - 1 && s == sc_step) {
@@ -318,7 +334,7 @@ __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, u
     const int vl = vc & 63;
     uint32_t cw = __shfl_sync(0xffffffffu, corner, vl & 31);
     cw = (vl >= 32) ? (cw >> 16) : (cw & 0xFFFFu);
-    return (int)(cw >> 5) - fc.bias;
+    return (int)(cw >> S) - fc.bias;
 }
 
 enum : int { FAST_OK = 0, FAST_LFLAG = 1, FAST_BAND = 2 };
@@ -326,10 +342,10 @@ enum : int { FAST_OK = 0, FAST_LFLAG = 1, FAST_BAND = 2 };
 // Traceback over the band (Processor.cpp:585-716 with the clean rule), ONE lane.  GLOBAL: the band lives in the
 // warp's global scratch (multi-strip tiles) instead of shared memory.
 // Returns FAST_OK, or the reason the tile must be recomputed by the exact path.
-template <int K, bool GLOBAL, class Sink>
+template <int K, bool GLOBAL, class Sink, int BH = kBandHalf>
 __device__ int fast_traceback(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
-    using G = FastGeom<K>;
-    const BandMap<K> bm(Q, R);
+    using G = FastGeom<K, BH>;
+    const BandMap<K, BH> bm(Q, R);
     const int i0 = Q - 1, j0 = R - 1;
     int v = i0 / K, r = i0 - v * K;
     int t = bm.t_of(j0, v);                       // position inside virtual lane v's window

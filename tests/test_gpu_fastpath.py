@@ -146,3 +146,29 @@ def test_sharded_extend_matches_single(gpu):
         parts_ops.append(o[:used])
     assert alignments_equal(whole[0], whole[1], np.concatenate(parts_res), np.concatenate(parts_ops), ALN_FIELDS_OURS) == []
     p.close()
+
+
+@pytest.mark.parametrize("vals", [(2, -6, -1, -4, -2, -25, -1), (3, -2, -1, -5, -1, -30, 0), (1, -1, 0, -1, -1, -1, -1)])
+def test_wide_score_multistrip_T1024(gpu, vals):
+    """T = 1024: match * 1024 + bias needs 12 score bits -> the multi-strip fast path runs in its 4-tag-bit layout.
+    The batch mixes ragged tiles, low-error tiles and PERFECT 1024-base matches (score 2048 and 3072: the top score bit
+    of the low half is set, nothing may leak into the neighbouring half's markers)."""
+    sc = abi.Scoring.from_values(*vals)
+    arena, req = _ragged_batch(31 + vals[0], 40, 1024)
+    rng = np.random.default_rng(2)
+    extra, pos = [], len(arena)
+    req2 = np.zeros(6, abi.TILE_REQ)
+    for k in range(6):
+        r = synth.random_seq(rng, 1024)
+        q = r.copy() if k < 3 else synth.mutate(rng, r, 0.01, 0.005, 0.005)[:1024]
+        req2[k]["ref_bases_start_addr"], req2[k]["ref_size"] = pos, len(r)
+        req2[k]["query_bases_start_addr"], req2[k]["query_size"] = pos + len(r), len(q)
+        extra += [r, q]
+        pos += len(r) + len(q)
+        req2[k]["max_tb_steps"], req2[k]["align_fields"], req2[k]["index"] = 2048, (1 if k % 2 else 21), k
+    arena = np.concatenate([arena] + extra + [np.full(64, ord("N"), np.uint8)])
+    req = np.concatenate([req, req2])
+    fast, exact, rerun = _run(gpu, sc, arena, req)
+    assert fast + exact == len(req)
+    if vals[0] * 1024 > 2047:
+        assert fast >= 20                    # beyond the 11-bit layout, yet mostly on the fast path
