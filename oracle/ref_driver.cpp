@@ -539,6 +539,8 @@ int dref_hw_threads(void) { return (int)std::thread::hardware_concurrency(); }
 #ifdef DREF_WITH_GPU
 #include "../darwin_b200/host/darwin_gpu_processor.h"
 #include <algorithm>
+#include <iostream>
+#include <unistd.h>
 
 // software defaults of the reference (external linkage in Processor.cpp:48,:82; not declared in Processor.h)
 void InitializeScoringParams(size_t token, Darwin::AlignmentScoringParams& request, Darwin::AlignmentScoringParamsResponse& response);
@@ -602,20 +604,43 @@ int dref_filter_last_gpu(void) {
 // Writes one canonical text line per alignment, sorted; returns the number of alignments or <0.
 int dref_pipeline(int first, int count, int use_gpu, char* out, uint64_t cap) {
     try {
+        const bool sam = (use_gpu & 8) != 0;                   // bit 3: emit what the reference's printer_body prints
+        use_gpu &= 7;
         reader_output reads(g_reads.begin() + first, g_reads.begin() + first + count);
         seeder_input sin(reads, 0);
         filter_input fin = seeder_body()(sin);
         extender_input ein = (use_gpu >= 2) ? darwin_gpu_host::gpu_filter_body()(fin) : filter_body()(fin);
         extender_node::output_ports_type ports;
-        if (getenv("DREF_DEBUG")) fprintf(stderr, "dref_pipeline: %zu fw + %zu rc anchors\n", std::get<1>(std::get<0>(ein)).fwLocations.size(), std::get<1>(std::get<0>(ein)).rcLocations.size());
         if (use_gpu) darwin_gpu_host::gpu_extender_body()(ein, ports);
         else extender_body()(ein, ports);
-        if (getenv("DREF_DEBUG")) fprintf(stderr, "dref_pipeline: extender done\n");
+        if (sam) {
+            // printer.cpp:7-98 (SAM) / :100-180 (MHAP, cfg.do_overlap): the reference's own output stage, unmodified;
+            // its std::cout / printf output is captured through a pipe-less redirect of both streams into a file
+            printer_input pin = std::get<0>(ports).items[0];
+            fflush(stdout); std::cout.flush();
+            char path[] = "/tmp/dref_sam_XXXXXX";
+            int fd = mkstemp(path);
+            if (fd < 0) return -3;
+            int saved = dup(1);
+            dup2(fd, 1);
+            printer_body::done_header = 0;
+            printer_body()(pin);
+            std::cout.flush(); fflush(stdout);
+            dup2(saved, 1); close(saved);
+            off_t len = lseek(fd, 0, SEEK_END);
+            if ((uint64_t)len + 1 > cap) { close(fd); unlink(path); return -2; }
+            lseek(fd, 0, SEEK_SET);
+            ssize_t got = read(fd, out, (size_t)len);
+            close(fd); unlink(path);
+            if (got != len) return -3;
+            out[len] = 0;
+            int lines = 0;
+            for (off_t k = 0; k < len; k++) lines += out[k] == '\n';
+            return lines;
+        }
         auto& al = std::get<1>(std::get<0>(std::get<0>(ports).items[0])).extend_alignments;
         std::vector<std::string> lines;
-        if (getenv("DREF_DEBUG")) fprintf(stderr, "dref_pipeline: %zu alignments\n", al.size());
         for (auto& e : al) {
-            if (getenv("DREF_DEBUG")) fprintf(stderr, "  aln read %d chr %d len %zu %zu\n", e.read_num, e.chr_id, e.aligned_reference_str.size(), e.aligned_query_str.size());
             std::string o = std::to_string(e.read_num) + " " + std::to_string(e.chr_id) + " " + std::string(1, e.strand) + " " +
                             std::to_string(e.reference_start_offset) + " " + std::to_string(e.reference_end_offset) + " " +
                             std::to_string(e.query_start_offset) + " " + std::to_string(e.query_end_offset) + " " +
@@ -623,7 +648,6 @@ int dref_pipeline(int first, int count, int use_gpu, char* out, uint64_t cap) {
             lines.push_back(o);
         }
         std::sort(lines.begin(), lines.end());
-        if (getenv("DREF_DEBUG")) fprintf(stderr, "dref_pipeline: %zu lines, cap %llu out %p\n", lines.size(), (unsigned long long)cap, (void*)out);
         uint64_t pos = 0;
         for (auto& l : lines) {
             if (pos + l.size() + 2 > cap) return -2;

@@ -53,3 +53,48 @@ def test_reference_pipeline_with_gpu_processor():
     L.dref_gpu_shutdown()
     assert n_gpu == n_cpu
     assert buf_gpu.value == buf_cpu.value
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libdarwin_ref_gpu.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("do_overlap", [0, 1])
+def test_output_stage_bytes_are_identical(do_overlap):
+    """The reference's own printer_body (printer.cpp: SAM with CIGAR / overlap suppression, MHAP in overlap mode) fed by
+    the GPU stages prints byte-for-byte what it prints after the CPU stages."""
+    ref = oracle.Reference.__new__(oracle.Reference)
+    ref.lib = C.CDLL(LIB)
+    L = ref.lib
+    L.dref_arena.restype = C.c_void_p
+    L.dref_arena_position.restype = C.c_uint64
+    L.dref_add_chr.restype = C.c_uint64
+    ref.set_scoring(abi.Scoring.from_values())
+    ref.set_dsoft_defaults()
+    ref.set_extend(384, 64, 2, do_overlap)
+    ref.reset_arena()
+    rng = np.random.default_rng(43 + do_overlap)
+    genome = synth.random_seq(rng, 100000)
+    rep = synth.mutate_fast(rng, genome[1000:4000], 0.02, 0.01, 0.01)[:2900]
+    genome[60000:60000 + len(rep)] = rep                                   # secondary alignments -> overlap suppression
+    ref.add_chr("chrS", genome.tobytes(), True)
+    ref.build_index()
+    nreads = 10
+    for k in range(nreads):
+        Lr = int(rng.integers(3000, 5000))
+        p = int(rng.integers(0, len(genome) - Lr)) if k else 500
+        r = synth.mutate(rng, genome[p:p + Lr], 0.04, 0.04, 0.04)
+        if k % 2:
+            r = synth.revcomp(r)
+        ref.add_read("read_%d" % k, np.ascontiguousarray(r).tobytes())
+    cap = 64 << 20
+    buf_cpu, buf_gpu = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    n_cpu = L.dref_pipeline(0, nreads, 8, buf_cpu, C.c_uint64(cap))            # reference stages + reference printer
+    assert n_cpu > (0 if do_overlap else nreads)
+    assert L.dref_gpu_init(1) == 0
+    try:
+        n_gpu = L.dref_pipeline(0, nreads, 8 | 2, buf_gpu, C.c_uint64(cap))    # GPU filter + GPU extender + reference printer
+    finally:
+        L.dref_use_cpu_table()
+        L.dref_gpu_shutdown()
+    assert n_gpu == n_cpu and buf_gpu.value == buf_cpu.value
+    if not do_overlap:
+        text = buf_cpu.value.decode()
+        assert text.startswith("@HD\tVN:1.6") and "\tAS:i:" in text and "M" in text.split("\n")[2].split("\t")[5]
