@@ -149,6 +149,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extend-reads", type=int, default=4000,
                     help="secondary measurement: reads of 10 kbp through the in-kernel anchor walker (0 = skip)")
+    ap.add_argument("--filter-tiles", type=int, default=400000,
+                    help="secondary measurement: first-tile filter candidates through darwin_gpu_filter (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -268,6 +270,30 @@ def main():
                        "note": "one anchor per read at its true locus, synthetic chained hits; host D-SOFT not included"}
         ex.close()
 
+    # ---- secondary: first-tile filter (128x128 score-only, max-cell mode; filter.cpp:28-122) through darwin_gpu_filter ----
+    filter_info = None
+    if args.filter_tiles > 0 and rank == 0:
+        from darwin_b200 import synth
+        fa, freq = synth.tile_batch_fast(5, args.filter_tiles, 128, mode="filter")
+        fc = np.zeros(len(freq), abi.FILTER_CAND)
+        # one candidate per tile: a 256-base "chromosome" + 128-base "read" whose first tile is exactly the generated pair
+        fc["chr_start"] = freq["ref_bases_start_addr"]; fc["chr_len"] = 256; fc["hit"] = freq["ref_bases_start_addr"]
+        fc["read_addr"] = freq["query_bases_start_addr"]; fc["read_len"] = 128; fc["offset"] = 0
+        fc["strand"] = (np.arange(len(fc)) & 1).astype(np.uint8)
+        fp = darwin_b200.Processor(len(fa), local)
+        fp.InitializeScoringParameters(sc)
+        fp.InitializeReferenceMemory(0, fa)
+        fp.filter_body(fc[:1024])
+        t0 = time.perf_counter()
+        fres = fp.filter_body(fc)                                     # candidates H2D, 3 kernels, results D2H
+        fwall = time.perf_counter() - t0
+        fms = fp.stats().last_kernel_ms
+        filter_info = {"workload": "first_tile_128x128_score_only", "tiles": int(len(fc)), "kernel_ms": fms,
+                       "gcups_kernel": len(fc) * 16384 / (fms * 1e-3) / 1e9, "tiles_per_s_kernel": len(fc) / (fms * 1e-3),
+                       "tiles_per_s_e2e": len(fc) / fwall, "pass_rate": float((fres["flags"] & 1).mean()),
+                       "packed_tiles": int(fp.stats().tiles_filter)}
+        fp.close()
+
     # checksum of the last step (guards against "fast because wrong"): every tile must have produced a path
     assert int((res["total_TB_pointers"] > 0).sum()) > 0.99 * n, "tiles without traceback"
 
@@ -312,6 +338,8 @@ def main():
                           "rerun": int(st_end.tiles_rerun - st0.tiles_rerun)}}
         if extend_info:
             line["extend"] = extend_info
+        if filter_info:
+            line["filter"] = filter_info
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_leg(arena, req, args.cpu_seconds)
         print(json.dumps(line))
