@@ -54,6 +54,16 @@ class FilterParams(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class SeedParams(C.Structure):
+    """params.cfg [DSOFT_params] (software/params.cfg:18-27)."""
+    _fields_ = [(n, C.c_int32) for n in ("seed_size", "minimizer_window", "bin_size", "threshold", "num_seeds",
+                                         "seed_occurence_multiple", "max_stride", "do_overlap")]
+
+    @classmethod
+    def stock(cls, do_overlap=0):
+        return cls(14, 3, 64, 26, 1000, 40, 4, do_overlap)
+
+
 class GpuStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("tiles_fast", C.c_uint64), ("tiles_exact", C.c_uint64),
                 ("tiles_rerun", C.c_uint64), ("cells", C.c_uint64), ("cells_exact", C.c_uint64), ("tiles_xfast", C.c_uint64), ("last_kernel_ms", C.c_float), ("reserved", C.c_float),
@@ -79,6 +89,12 @@ assert FILTER_CAND.itemsize == 32
 FILTER_RES = np.dtype([("score", "<i4"), ("reference_pos", "<u4"), ("query_pos", "<u4"), ("flags", "<u4")], align=False)
 assert FILTER_RES.itemsize == 16
 FILTER_SCORE_OK, FILTER_OVERLAP_OK = 1, 2
+
+CHROM = np.dtype([("start", "<u4"), ("len_unpadded", "<u4")], align=False)
+SEED_READ = np.dtype([("read_addr", "<u8"), ("read_len", "<u4"), ("reserved", "<u4")], align=False)
+SEED_ANCHOR = np.dtype([("hit_offset", "<u8"), ("left_off", "<u8"), ("right_off", "<u8"), ("left_n", "<u4"), ("right_n", "<u4")],
+                       align=False)
+assert CHROM.itemsize == 8 and SEED_READ.itemsize == 16 and SEED_ANCHOR.itemsize == 32
 
 ANCHOR = np.dtype([
     ("read_addr", "<u8"), ("reference_pos", "<u4"), ("query_pos", "<u4"), ("chr_start", "<u4"),

@@ -175,6 +175,35 @@ typedef struct DarwinFilterParams {
     int32_t reserved;
 } DarwinFilterParams;
 
+/* D-SOFT parameters: params.cfg [DSOFT_params] (software/params.cfg:18-27) as SeedPosTable's constructor and
+ * seeder_body pass them on (seed_pos_table.cpp:41-57, seeder.cpp:27-33). */
+typedef struct DarwinSeedParams {
+    int32_t seed_size;                /* k, 4..15 */
+    int32_t minimizer_window;         /* w */
+    int32_t bin_size;
+    int32_t threshold;                /* dsoft_threshold: bases of one bin covered by seed hits */
+    int32_t num_seeds;                /* N: all minimizers up to index N+1, every max_stride-th afterwards */
+    int32_t seed_occurence_multiple;
+    int32_t max_stride;
+    int32_t do_overlap;               /* argv[3]: 1 = stop after N+1 seeds, SV window of one bin */
+} DarwinSeedParams;
+
+/* One chromosome for the index build (main.cpp:418-466): arena offset and UNPADDED length. */
+typedef struct DarwinChrom { uint32_t start; uint32_t len_unpadded; } DarwinChrom;
+
+/* One read to seed (both strands are seeded, seeder.cpp:35-49). */
+typedef struct DarwinSeedRead { uint64_t read_addr; uint32_t read_len; uint32_t reserved; } DarwinSeedRead;
+
+/* One D-SOFT candidate == Anchors (software/seed_pos_table.h:30-40): the hit that pushed its bin over the threshold and
+ * the collinear chained hits around it (left ascending incl. the anchor, right descending incl. the anchor). */
+typedef struct DarwinSeedAnchor {
+    uint64_t hit_offset;              /* (reference arena offset << 32) | strand-local read offset */
+    uint64_t left_off;                /* left_chained_hits  = pool[left_off  .. left_off  + left_n)  */
+    uint64_t right_off;               /* right_chained_hits = pool[right_off .. right_off + right_n) */
+    uint32_t left_n;
+    uint32_t right_n;
+} DarwinSeedAnchor;
+
 typedef struct DarwinGpuStats {
     uint64_t kernel_launches;   /* kernels of this library launched since create */
     uint64_t tiles_fast;        /* tiles finished by the packed fast path */
@@ -227,6 +256,18 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p,
  * copying of the chained hits stay on the host (darwin_b200/host: gpu_filter_body). */
 int darwin_gpu_filter(DarwinGpu* h, const DarwinFilterParams* p, const DarwinFilterCand* cands, int n,
                       DarwinFilterRes* res);
+
+/* replaces the SeedPosTable constructor + the minimizer pass over the reference (main.cpp:323-341, :508,
+ * seed_pos_table.cpp:41-160): builds the seed position table in HBM from the chromosomes already uploaded. */
+int darwin_gpu_seed_index(DarwinGpu* h, const DarwinSeedParams* p, const DarwinChrom* chroms, int n_chroms, uint64_t reference_size);
+
+/* replaces seeder_body::operator() (seeder.cpp:6-55) -> SeedPosTable::DSOFT (seed_pos_table.cpp:252-553) for n reads
+ * already resident in the arena: anchors of read r, strand s (0 = forward, 1 = reverse complement) are
+ * anchors[anchor_begin[2r+s] .. anchor_begin[2r+s+1]) in the reference's output order.  Capacities are in elements;
+ * DARWIN_ERR_CAPACITY reports the needed sizes in *n_anchors / *n_pool. */
+int darwin_gpu_seed(DarwinGpu* h, const DarwinSeedRead* reads, int n, uint32_t* anchor_begin /* 2n+1 */,
+                    DarwinSeedAnchor* anchors, uint64_t anchors_cap, uint64_t* n_anchors,
+                    uint64_t* pool, uint64_t pool_cap, uint64_t* n_pool);
 
 /* device-resident variants used by bench.py's `value` leg: same work, inputs and
  * outputs stay in HBM (pointers are device pointers of this handle's device). */

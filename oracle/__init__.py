@@ -91,6 +91,60 @@ class Port:
         return res, ops
 
 
+class DsoftPort:
+    """oracle/dsoft_oracle.c: the seed position table and SeedPosTable::DSOFT restated in C."""
+
+    class _Index(C.Structure):
+        _fields_ = [("k", C.c_int), ("w", C.c_int), ("max_stride", C.c_int), ("bin_size", C.c_uint32),
+                    ("kmer_max_occurence", C.c_uint32), ("n_buckets", C.c_uint64), ("n_positions", C.c_uint64),
+                    ("buckets", C.c_void_p), ("positions", C.c_void_p)]
+
+    def __init__(self, dram, chroms, reference_size, params):
+        self.lib = _load(os.path.join(_HERE, "libgact_oracle.so"))
+        self.ix = self._Index()
+        self.dram = np.ascontiguousarray(dram)
+        self.params = params
+        st = np.ascontiguousarray(chroms["start"], np.uint32)
+        ln = np.ascontiguousarray(chroms["len_unpadded"], np.uint32)
+        rc = self.lib.dsoft_index_build(C.byref(self.ix), abi.ptr(self.dram), abi.ptr(st), abi.ptr(ln), len(st),
+                                        C.c_uint32(int(reference_size)), params.seed_size, params.minimizer_window,
+                                        C.c_uint32(params.seed_occurence_multiple), C.c_uint32(params.bin_size), params.max_stride)
+        if rc:
+            raise MemoryError("dsoft_index_build")
+
+    def close(self):
+        if self.ix.buckets:
+            self.lib.dsoft_index_free(C.byref(self.ix))
+
+    def index_arrays(self):
+        b = np.frombuffer((C.c_uint32 * (self.ix.n_buckets + 1)).from_address(self.ix.buckets), np.uint32)
+        p = np.frombuffer((C.c_uint32 * max(self.ix.n_positions, 1)).from_address(self.ix.positions), np.uint32)
+        return b, p[:self.ix.n_positions]
+
+    def minimizers(self, seq):
+        s = np.concatenate([np.frombuffer(seq, np.uint8), np.full(64, ord("N"), np.uint8)])
+        out = np.zeros(len(s) + 32, np.uint64)
+        self.lib.dsoft_minimizers.restype = C.c_uint64
+        n = self.lib.dsoft_minimizers(abi.ptr(s), C.c_uint32(len(seq)), self.params.seed_size, self.params.minimizer_window, abi.ptr(out))
+        return out[:n]
+
+    def query(self, seq):
+        """seq: ASCII bytes/array of one strand (padded internally with 'N' like the reader does)."""
+        s = np.concatenate([np.frombuffer(seq, np.uint8) if not isinstance(seq, np.ndarray) else seq, np.full(160, ord("N"), np.uint8)])
+        n_seq = len(s) - 160
+        acap, pcap = 4096, 1 << 20
+        while True:
+            anchors = np.zeros(acap, abi.SEED_ANCHOR)
+            pool = np.zeros(pcap, np.uint64)
+            used = C.c_uint64(0)
+            n = self.lib.dsoft_query(C.byref(self.ix), abi.ptr(s), C.c_uint32(n_seq), self.params.num_seeds, self.params.threshold,
+                                     self.params.do_overlap, abi.ptr(anchors), acap, abi.ptr(pool), C.c_uint64(pcap), C.byref(used))
+            if n in (-2, -3):
+                acap, pcap = acap * 4, pcap * 4
+                continue
+            return anchors[:n].copy(), pool[:used.value].copy()
+
+
 class Reference:
     """The compiled reference (oracle/_ref) through oracle/ref_driver.cpp."""
 
@@ -190,6 +244,7 @@ class Reference:
         n = self.lib.dref_seed(int(first), int(count))
         if n < 0:
             raise RuntimeError("index not built")
+        self._last_seed_count = int(count)
         cands = np.zeros(max(n, 1), abi.FILTER_CAND)
         rn = np.zeros(max(n, 1), np.int32)
         got = self.lib.dref_get_candidates(abi.ptr(cands), abi.ptr(rn), n)
@@ -217,6 +272,39 @@ class Reference:
         """params.cfg [GACT_first_tile]; the D-SOFT parameters stay at the stock values (software/params.cfg:18-35)."""
         self.lib.dref_set_dsoft(14, 3, 64, 26, 1000, 40, 1000, 4, int(first_tile_size), int(threshold), 64, int(min_overlap),
                                 C.c_float(slope_threshold))
+
+    def seed_anchors(self):
+        """Full output of the last seed(): (anchor_begin[2n+1], anchors, pool) in the layout of darwin_gpu_seed."""
+        L = self.lib
+        L.dref_get_seed_anchors.restype = C.c_int64
+        n_reads = self._last_seed_count
+        acap, pcap = 1 << 16, 1 << 22
+        while True:
+            anchors = np.zeros(acap, abi.SEED_ANCHOR)
+            pool = np.zeros(pcap, np.uint64)
+            begin = np.zeros(2 * n_reads + 1, np.uint32)
+            used = C.c_uint64(0)
+            n = L.dref_get_seed_anchors(abi.ptr(anchors), C.c_uint64(acap), abi.ptr(begin), abi.ptr(pool), C.c_uint64(pcap), C.byref(used))
+            if n == abi.ERR_CAPACITY:
+                acap, pcap = acap * 4, pcap * 4
+                continue
+            if n < 0:
+                raise RuntimeError("dref_get_seed_anchors rc=%d" % n)
+            return begin, anchors[:n].copy(), pool[:used.value].copy()
+
+    def read_addr(self, k):
+        self.lib.dref_read_addr.restype = C.c_uint64
+        return int(self.lib.dref_read_addr(int(k)))
+
+    def chroms(self):
+        out = np.zeros(max(self.lib.dref_num_chr(), 1), abi.CHROM)
+        n = self.lib.dref_get_chroms(abi.ptr(out), len(out))
+        return out[:n]
+
+    def seed_params(self):
+        p = abi.SeedParams()
+        self.lib.dref_get_seed_params(C.byref(p))
+        return p
 
     def filter_last(self, gpu=False):
         """filter_body (the reference's, or the GPU host adapter's with gpu=True) on the last seed() output."""

@@ -388,6 +388,48 @@ int dref_get_candidates(DarwinFilterCand* out, int* read_num_out, int cap) {
     return n;
 }
 
+// the full output of the last dref_seed (SeedPosTable::DSOFT per read and strand): anchors with their chained hits in
+// the layout of darwin_gpu_seed -- anchors of read r (relative to `first`), strand s at [begin[2r+s], begin[2r+s+1])
+int64_t dref_get_seed_anchors(DarwinSeedAnchor* out, uint64_t cap, uint32_t* begin, uint64_t* pool, uint64_t pool_cap, uint64_t* pool_used) {
+    if (!g_last_seed) return -1;
+    auto& reads = std::get<0>(std::get<0>(*g_last_seed));
+    auto& d = std::get<1>(std::get<0>(*g_last_seed));
+    uint64_t n = 0, used = 0;
+    for (size_t r = 0; r < reads.size(); r++) {
+        for (int strand = 0; strand < 2; strand++) {
+            auto& anchors = strand ? d.rcAnchors : d.fwAnchors;
+            auto& buckets = strand ? d.rcAnchorBuckets : d.fwAnchorBuckets;
+            begin[2 * r + strand] = (uint32_t)n;
+            for (size_t c = buckets[r]; c < buckets[r + 1]; c++) {
+                const Anchors& a = anchors[c];
+                if (n >= cap || used + a.left_chained_hits.size() + a.right_chained_hits.size() > pool_cap) return DARWIN_ERR_CAPACITY;
+                DarwinSeedAnchor& o = out[n++];
+                o.hit_offset = a.hit_offset;
+                o.left_off = used; o.left_n = (uint32_t)a.left_chained_hits.size();
+                for (auto x : a.left_chained_hits) pool[used++] = x;
+                o.right_off = used; o.right_n = (uint32_t)a.right_chained_hits.size();
+                for (auto x : a.right_chained_hits) pool[used++] = x;
+            }
+        }
+    }
+    begin[2 * reads.size()] = (uint32_t)n;
+    if (pool_used) *pool_used = used;
+    return (int64_t)n;
+}
+
+// D-SOFT state of the driver: what SeedPosTable's constructor was given (dref_build_index) and the chromosomes
+int dref_get_chroms(DarwinChrom* out, int cap) {
+    int n = (int)Index::chr_id.size();
+    if (n > cap) return DARWIN_ERR_CAPACITY;
+    for (int k = 0; k < n; k++) { out[k].start = Index::chr_coord[k]; out[k].len_unpadded = (uint32_t)Index::chr_len_unpadded[k]; }
+    return n;
+}
+void dref_get_seed_params(DarwinSeedParams* p) {
+    p->seed_size = cfg.seed_size; p->minimizer_window = cfg.minimizer_window; p->bin_size = (int32_t)cfg.bin_size;
+    p->threshold = cfg.dsoft_threshold; p->num_seeds = cfg.num_seeds; p->seed_occurence_multiple = cfg.seed_occurence_multiple;
+    p->max_stride = cfg.max_stride; p->do_overlap = cfg.do_overlap;
+}
+
 // the reference's filter_body (first tiles through g_BatchAlignmentSIMD + slopeFilter) on the last dref_seed output;
 // fetch the locations with dref_get_anchors
 int dref_filter_last(void) {
@@ -527,6 +569,7 @@ double dref_extend_mt(const DarwinAnchor* anchors, int n, const uint64_t* hit_po
 
 int dref_num_reads(void) { return (int)g_reads.size(); }
 int dref_read_len(int k) { return (k >= 0 && k < (int)g_reads.size()) ? (int)g_reads[k].seq.size() : -1; }
+uint64_t dref_read_addr(int k) { return (k >= 0 && k < (int)g_reads.size()) ? (uint64_t)(g_reads[k].seq.data() - g_DRAM->buffer) : 0; }
 unsigned dref_chr_start(int k) { return Index::chr_coord[k]; }
 unsigned dref_chr_len(int k) { return Index::chr_len[k]; }
 int dref_num_chr(void) { return (int)Index::chr_id.size(); }
