@@ -17,6 +17,7 @@
 #include "gact_xfast.cuh"
 #include "gact_extend.cuh"
 #include "gact_filter.cuh"
+#include "dsoft.cuh"
 
 using namespace gact;
 
@@ -582,6 +583,7 @@ struct DarwinGpu {
     void* h_buf[4] = {nullptr}; size_t h_cap[4] = {0};
     DarwinGpuStats stats{};
     std::string err;
+    SeedIndex seed_ix;                          // D-SOFT seed position table (dsoft_host.cuh); lanes share the parent's
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DARWIN_ERR_CUDA; } } while (0)
@@ -604,6 +606,8 @@ static int grow_host(DarwinGpu* h, int slot, size_t bytes) {
     h->h_cap[slot] = want;
     return DARWIN_OK;
 }
+
+#include "dsoft_host.cuh"
 
 // per-warp exact-path scratch sized for the largest tile of the call
 static int ensure_scratch(DarwinGpu* h, size_t need) {
@@ -701,6 +705,7 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     if (parent) {                                                              // another lane of the same device: one arena replica
         h->d_arena = parent->d_arena; h->owns_arena = false;
         if (parent->have_scoring) { h->ks = parent->ks; h->filt = parent->filt; h->have_scoring = true; }
+        h->seed_ix = parent->seed_ix; h->seed_ix.owner = false;                // and one seed position table
     } else {
         const size_t packed = (arena_bytes + 1) / 2 + 64;      // slack: TMA windows are rounded up to 16 bytes
         CK(cudaMalloc(&h->d_arena, packed));
@@ -740,6 +745,7 @@ int darwin_gpu_destroy(DarwinGpu* h) {
         if (h->ev_copied[b]) cudaEventDestroy(h->ev_copied[b]);
     }
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    free_index(h->seed_ix);
     if (h->d_arena && h->owns_arena) cudaFree(h->d_arena);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -1110,6 +1116,45 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
         lo = hi;
     }
     h->stats.last_kernel_ms = kernel_ms;
+    return DARWIN_OK;
+}
+
+int darwin_gpu_seed_index(DarwinGpu* h, const DarwinSeedParams* p, const DarwinChrom* chroms, int n_chroms, uint64_t reference_size) {
+    if (!h || !p || n_chroms < 0 || (n_chroms && !chroms)) return DARWIN_ERR_INVALID;
+    if (!h->seed_ix.owner && h->seed_ix.ready) { h->err = "the seed position table belongs to the parent handle"; return DARWIN_ERR_INVALID; }
+    CK(cudaSetDevice(h->device));
+    return seed_index_build(h, h->seed_ix, p, chroms, n_chroms, reference_size);
+}
+
+int darwin_gpu_seed_index_share(DarwinGpu* h, DarwinGpu* parent) {
+    if (!h || !parent || !parent->seed_ix.ready) return DARWIN_ERR_INVALID;
+    free_index(h->seed_ix);
+    h->seed_ix = parent->seed_ix; h->seed_ix.owner = false;
+    return DARWIN_OK;
+}
+
+int darwin_gpu_seed(DarwinGpu* h, const DarwinSeedRead* reads, int n, uint32_t* anchor_begin,
+                    DarwinSeedAnchor* anchors, uint64_t anchors_cap, uint64_t* n_anchors,
+                    uint64_t* pool, uint64_t pool_cap, uint64_t* n_pool) {
+    if (!h || n < 0 || !anchor_begin || !n_anchors || !n_pool || (n && !reads)) return DARWIN_ERR_INVALID;
+    if (!h->seed_ix.ready) { h->err = "darwin_gpu_seed_index was not called"; return DARWIN_ERR_NOT_READY; }
+    *n_anchors = 0; *n_pool = 0; anchor_begin[0] = 0;
+    if (n == 0) return DARWIN_OK;
+    if ((anchors_cap && !anchors) || (pool_cap && !pool)) return DARWIN_ERR_INVALID;
+    CK(cudaSetDevice(h->device));
+    return seed_query(h, h->seed_ix, reads, n, anchor_begin, anchors, anchors_cap, n_anchors, pool, pool_cap, n_pool);
+}
+
+/* test / diagnostics: copy the table back (buckets: n_buckets + 1 entries) */
+int darwin_gpu_seed_index_read(DarwinGpu* h, uint32_t* buckets, uint64_t buckets_cap, uint32_t* positions, uint64_t positions_cap,
+                               uint64_t* n_buckets, uint64_t* n_positions, uint32_t* max_occ) {
+    if (!h || !h->seed_ix.ready) return DARWIN_ERR_NOT_READY;
+    if (n_buckets) *n_buckets = h->seed_ix.n_buckets;
+    if (n_positions) *n_positions = h->seed_ix.n_positions;
+    if (max_occ) *max_occ = h->seed_ix.sc.max_occ;
+    CK(cudaSetDevice(h->device));
+    if (buckets) { if (buckets_cap < h->seed_ix.n_buckets + 1) return DARWIN_ERR_CAPACITY; CK(cudaMemcpy(buckets, h->seed_ix.d_buckets, (h->seed_ix.n_buckets + 1) * 4, cudaMemcpyDeviceToHost)); }
+    if (positions) { if (positions_cap < h->seed_ix.n_positions) return DARWIN_ERR_CAPACITY; CK(cudaMemcpy(positions, h->seed_ix.d_positions, h->seed_ix.n_positions * 4, cudaMemcpyDeviceToHost)); }
     return DARWIN_OK;
 }
 

@@ -1,0 +1,223 @@
+// Host side of the GPU D-SOFT path (darwin_gpu_seed_index / darwin_gpu_seed); included by darwin_gact.cu after the
+// DarwinGpu handle is defined.  Kernels: dsoft.cuh.  CUB supplies the scans and the segmented sorts.
+#pragma once
+#include <cub/cub.cuh>
+#include "dsoft.cuh"
+
+#define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DARWIN_ERR_CUDA; } } while (0)
+
+struct DevBuf {                                      // scoped device allocation of the seeding calls
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static int seed_const_from(const DarwinSeedParams* p, uint64_t reference_size, dsoft::SeedConst& sc, std::string& err) {
+    if (p->seed_size < 4 || p->seed_size > 15) { err = "seed_size must be in [4,15] (seed_pos_table.cpp:51-52)"; return DARWIN_ERR_INVALID; }
+    if (p->minimizer_window < 1 || p->minimizer_window > 32) { err = "minimizer_window must be in [1,32]"; return DARWIN_ERR_INVALID; }
+    if (p->bin_size < 1 || p->max_stride < 1 || p->num_seeds < 0 || p->threshold < 0) { err = "bad D-SOFT parameters"; return DARWIN_ERR_INVALID; }
+    sc.k = p->seed_size; sc.w = p->minimizer_window; sc.N = p->num_seeds; sc.threshold = p->threshold;
+    sc.max_stride = p->max_stride; sc.overlap = p->do_overlap ? 1 : 0;
+    sc.bin_size = (uint32_t)p->bin_size;
+    sc.max_occ = (uint32_t)p->seed_occurence_multiple * (1u + (uint32_t)(reference_size >> (2 * p->seed_size)));   // seed_pos_table.cpp:57
+    sc.sv_bins = sc.overlap ? 1u : (uint32_t)((1u << 12) / sc.bin_size);                                           // :397
+    sc.kmask = (1u << (2 * p->seed_size)) - 1u;
+    return DARWIN_OK;
+}
+
+static uint32_t min_end(uint32_t len, int k) { const uint32_t c = (~0x0fu & (len + 15u)) - (uint32_t)k; return c < 16u ? 16u : c; }
+
+static void free_index(SeedIndex& ix) {
+    if (ix.owner) { if (ix.d_buckets) cudaFree(ix.d_buckets); if (ix.d_positions) cudaFree(ix.d_positions); }
+    ix = SeedIndex{};
+}
+
+static int seed_index_build(DarwinGpu* h, SeedIndex& ix, const DarwinSeedParams* p, const DarwinChrom* chroms, int n_chroms, uint64_t reference_size) {
+    using namespace dsoft;
+    free_index(ix);
+    int rc = seed_const_from(p, reference_size, ix.sc, h->err);
+    if (rc) return rc;
+    const SeedConst sc = ix.sc;
+    ix.n_buckets = 1ull << (2 * sc.k);
+    std::vector<MinJob> jobs(n_chroms);
+    uint64_t list_cap = 0; uint32_t max_chunks = 1;
+    for (int c = 0; c < n_chroms; c++) {
+        if ((uint64_t)chroms[c].start + chroms[c].len_unpadded > h->arena_bytes) { h->err = "chromosome outside arena"; return DARWIN_ERR_INVALID; }
+        jobs[c] = MinJob{chroms[c].start, chroms[c].len_unpadded, 0};
+        const uint32_t e = min_end(chroms[c].len_unpadded, sc.k);
+        list_cap += e;
+        max_chunks = std::max(max_chunks, (e + kChunk - 1) / kChunk);
+    }
+    CKS(cudaMalloc(&ix.d_buckets, (ix.n_buckets + 1) * sizeof(uint32_t)));
+    CKS(cudaMemsetAsync(ix.d_buckets, 0, (ix.n_buckets + 1) * sizeof(uint32_t), h->stream));
+    DevBuf d_jobs, d_list, d_carry, d_cursor, d_fill, d_tmp;
+    CKS(d_jobs.alloc(sizeof(MinJob) * n_chroms)); CKS(d_list.alloc(sizeof(uint64_t) * list_cap));
+    CKS(d_carry.alloc(sizeof(int) * (size_t)n_chroms * max_chunks)); CKS(d_cursor.alloc(sizeof(unsigned long long)));
+    CKS(cudaMemcpyAsync(d_jobs.p, jobs.data(), sizeof(MinJob) * n_chroms, cudaMemcpyHostToDevice, h->stream));
+    CKS(cudaMemsetAsync(d_cursor.p, 0, sizeof(unsigned long long), h->stream));
+    const dim3 grid(max_chunks, n_chroms);
+    minimizer_kernel<2><<<grid, kMinThreads, 0, h->stream>>>(h->d_arena, sc, d_jobs.as<MinJob>(), nullptr, nullptr, d_carry.as<int>(), nullptr, nullptr);
+    CKS(cudaGetLastError());
+    // pass A left the position of the last change of every chunk; turn it into the run start carried INTO every chunk
+    // (entries of chunks beyond a chromosome's end are never read)
+    carry_kernel<<<(n_chroms + 127) / 128, 128, 0, h->stream>>>(d_carry.as<int>(), n_chroms, (int)max_chunks);
+    CKS(cudaGetLastError());
+    minimizer_kernel<1><<<grid, kMinThreads, 0, h->stream>>>(h->d_arena, sc, d_jobs.as<MinJob>(), d_list.as<uint64_t>(), nullptr, d_carry.as<int>(),
+                                                            d_cursor.as<unsigned long long>(), ix.d_buckets);
+    CKS(cudaGetLastError());
+    h->stats.kernel_launches += 3;
+    unsigned long long n_min = 0;
+    CKS(cudaMemcpyAsync(&n_min, d_cursor.p, sizeof(n_min), cudaMemcpyDeviceToHost, h->stream));
+    CKS(cudaStreamSynchronize(h->stream));
+    if (n_min > 0xFFFFFFFFull) { h->err = "more than 2^32 minimizers"; return DARWIN_ERR_INVALID; }
+    ix.n_positions = n_min;
+    // buckets = prefix sums of the histogram (seed_pos_table.cpp:66-101); hist was counted at [m + 1]
+    size_t tmp_bytes = 0;
+    CKS(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, ix.d_buckets, ix.d_buckets, (int64_t)(ix.n_buckets + 1), h->stream));
+    CKS(d_tmp.alloc(tmp_bytes));
+    CKS(cub::DeviceScan::InclusiveSum(d_tmp.p, tmp_bytes, ix.d_buckets, ix.d_buckets, (int64_t)(ix.n_buckets + 1), h->stream));
+    CKS(cudaMalloc(&ix.d_positions, sizeof(uint32_t) * std::max<uint64_t>(n_min, 1)));
+    CKS(d_fill.alloc(sizeof(uint32_t) * ix.n_buckets));
+    CKS(cudaMemsetAsync(d_fill.p, 0, sizeof(uint32_t) * ix.n_buckets, h->stream));
+    if (n_min) scatter_kernel<<<(unsigned)((n_min + 255) / 256), 256, 0, h->stream>>>(d_list.as<uint64_t>(), n_min, ix.d_buckets, d_fill.as<uint32_t>(), ix.d_positions);
+    CKS(cudaGetLastError());
+    bucket_sort_kernel<<<(unsigned)((ix.n_buckets + 255) / 256), 256, 0, h->stream>>>(ix.d_buckets, ix.n_buckets, sc.max_occ, ix.d_positions);
+    CKS(cudaGetLastError());
+    h->stats.kernel_launches += 2;
+    CKS(cudaStreamSynchronize(h->stream));
+    ix.ready = true;
+    return DARWIN_OK;
+}
+
+template <class T>
+static int exclusive_sum(DarwinGpu* h, const T* in, T* out, int64_t n) {
+    size_t bytes = 0;
+    CKS(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, h->stream));
+    DevBuf tmp; CKS(tmp.alloc(bytes));
+    CKS(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, n, h->stream));
+    CKS(cudaStreamSynchronize(h->stream));           // tmp is freed on return
+    return DARWIN_OK;
+}
+
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, int n, uint32_t* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
+}
+__global__ void widen_kernel(const uint32_t* __restrict__ src, uint32_t n, uint64_t* __restrict__ dst) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* reads, int n, uint32_t* anchor_begin,
+                      DarwinSeedAnchor* anchors, uint64_t anchors_cap, uint64_t* n_anchors,
+                      uint64_t* pool, uint64_t pool_cap, uint64_t* n_pool) {
+    using namespace dsoft;
+    const SeedConst sc = ix.sc;
+    const int ns = 2 * n;
+    std::vector<MinJob> jobs(ns);
+    std::vector<uint32_t> seed_base(ns + 1);
+    uint32_t slots = 0, max_cap = 1;
+    for (int r = 0; r < n; r++) {
+        if (reads[r].read_addr + reads[r].read_len > h->arena_bytes || reads[r].read_len == 0) { h->err = "read outside arena"; return DARWIN_ERR_INVALID; }
+        const uint32_t e = min_end(reads[r].read_len, sc.k);
+        const uint32_t head = (uint32_t)sc.N + 2u;
+        const uint32_t cap = e <= head ? e : (sc.overlap ? head : head + (e - head) / (uint32_t)sc.max_stride + 1u);
+        for (int s = 0; s < 2; s++) {
+            seed_base[2 * r + s] = slots;
+            jobs[2 * r + s] = MinJob{reads[r].read_addr, reads[r].read_len, slots};
+            slots += cap;
+        }
+        max_cap = std::max(max_cap, cap);
+    }
+    seed_base[ns] = slots;
+    DevBuf d_jobs, d_base, d_seeds, d_nseeds, d_cnt, d_hoff, d_soff;
+    CKS(d_jobs.alloc(sizeof(MinJob) * ns)); CKS(d_base.alloc(sizeof(uint32_t) * (ns + 1))); CKS(d_seeds.alloc(sizeof(uint64_t) * slots));
+    CKS(d_nseeds.alloc(sizeof(uint32_t) * ns)); CKS(d_cnt.alloc(sizeof(uint32_t) * ((size_t)slots + 1))); CKS(d_hoff.alloc(sizeof(uint32_t) * ((size_t)slots + 1)));
+    CKS(d_soff.alloc(sizeof(uint32_t) * (ns + 1)));
+    CKS(cudaMemcpyAsync(d_jobs.p, jobs.data(), sizeof(MinJob) * ns, cudaMemcpyHostToDevice, h->stream));
+    CKS(cudaMemcpyAsync(d_base.p, seed_base.data(), sizeof(uint32_t) * (ns + 1), cudaMemcpyHostToDevice, h->stream));
+    CKS(cudaMemsetAsync(d_cnt.p, 0, sizeof(uint32_t) * ((size_t)slots + 1), h->stream));
+    CKS(cudaEventRecord(h->ev0, h->stream));
+    minimizer_kernel<0><<<ns, kMinThreads, 0, h->stream>>>(h->d_arena, sc, d_jobs.as<MinJob>(), d_seeds.as<uint64_t>(), d_nseeds.as<uint32_t>(), nullptr, nullptr, nullptr);
+    CKS(cudaGetLastError());
+    const uint64_t grid_threads = (uint64_t)ns * max_cap;
+    const unsigned gb = (unsigned)((grid_threads + 255) / 256);
+    hit_count_kernel<<<gb, 256, 0, h->stream>>>(sc, ix.d_buckets, ix.d_positions, d_seeds.as<uint64_t>(), d_base.as<uint32_t>(), d_nseeds.as<uint32_t>(), ns, max_cap, d_cnt.as<uint32_t>());
+    CKS(cudaGetLastError());
+    int rc;
+    if ((rc = exclusive_sum(h, d_cnt.as<uint32_t>(), d_hoff.as<uint32_t>(), (int64_t)slots + 1))) return rc;
+    gather_u32_kernel<<<(ns + 1 + 255) / 256, 256, 0, h->stream>>>(d_hoff.as<uint32_t>(), d_base.as<uint32_t>(), ns + 1, d_soff.as<uint32_t>());
+    CKS(cudaGetLastError());
+    uint32_t n_hits = 0;
+    CKS(cudaMemcpyAsync(&n_hits, d_hoff.as<uint32_t>() + slots, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CKS(cudaStreamSynchronize(h->stream));
+    DevBuf d_k0, d_k1, d_v0, d_v1, d_tmp;
+    CKS(d_k0.alloc(sizeof(uint64_t) * n_hits)); CKS(d_k1.alloc(sizeof(uint64_t) * n_hits));
+    CKS(d_v0.alloc(sizeof(uint32_t) * n_hits)); CKS(d_v1.alloc(sizeof(uint32_t) * n_hits));
+    hit_fill_kernel<<<gb, 256, 0, h->stream>>>(sc, ix.d_buckets, ix.d_positions, d_seeds.as<uint64_t>(), d_base.as<uint32_t>(), d_nseeds.as<uint32_t>(), ns, max_cap,
+                                              d_hoff.as<uint32_t>(), d_k0.as<uint64_t>(), d_v0.as<uint32_t>());
+    CKS(cudaGetLastError());
+    // std::stable_sort by bin_offset (seed_pos_table.cpp:338): ties (same seed) keep ascending hit order
+    size_t tmp_bytes = 0;
+    CKS(cub::DeviceSegmentedSort::StableSortPairs(nullptr, tmp_bytes, d_k0.as<uint64_t>(), d_k1.as<uint64_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(),
+                                                  (int64_t)n_hits, (int64_t)ns, d_soff.as<uint32_t>(), d_soff.as<uint32_t>() + 1, h->stream));
+    CKS(d_tmp.alloc(tmp_bytes));
+    CKS(cub::DeviceSegmentedSort::StableSortPairs(d_tmp.p, tmp_bytes, d_k0.as<uint64_t>(), d_k1.as<uint64_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(),
+                                                  (int64_t)n_hits, (int64_t)ns, d_soff.as<uint32_t>(), d_soff.as<uint32_t>() + 1, h->stream));
+    const uint64_t* keys = d_k1.as<uint64_t>(); const uint32_t* vals = d_v1.as<uint32_t>();
+    // candidate bins: count, scan, fill
+    DevBuf d_ncand, d_coff;
+    CKS(d_ncand.alloc(sizeof(uint32_t) * (ns + 1))); CKS(d_coff.alloc(sizeof(uint32_t) * (ns + 1)));
+    CKS(cudaMemsetAsync(d_ncand.p, 0, sizeof(uint32_t) * (ns + 1), h->stream));
+    candidate_kernel<false><<<(ns + 127) / 128, 128, 0, h->stream>>>(sc, keys, d_soff.as<uint32_t>(), ns, d_ncand.as<uint32_t>(), nullptr, nullptr);
+    CKS(cudaGetLastError());
+    if ((rc = exclusive_sum(h, d_ncand.as<uint32_t>(), d_coff.as<uint32_t>(), (int64_t)ns + 1))) return rc;
+    CKS(cudaMemcpyAsync(anchor_begin, d_coff.p, sizeof(uint32_t) * (ns + 1), cudaMemcpyDeviceToHost, h->stream));
+    CKS(cudaStreamSynchronize(h->stream));
+    const uint32_t n_cands = anchor_begin[ns];
+    *n_anchors = n_cands;
+    h->stats.kernel_launches += 6;
+    if (n_cands == 0) { *n_pool = 0; CKS(cudaEventRecord(h->ev1, h->stream)); CKS(cudaStreamSynchronize(h->stream)); CKS(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1)); return DARWIN_OK; }
+    DevBuf d_cidx, d_cstr, d_wlo, d_wn, d_wn64, d_woff;
+    CKS(d_cidx.alloc(sizeof(uint32_t) * n_cands)); CKS(d_cstr.alloc(sizeof(uint32_t) * n_cands)); CKS(d_wlo.alloc(sizeof(uint32_t) * n_cands));
+    CKS(d_wn.alloc(sizeof(uint32_t) * ((size_t)n_cands + 1))); CKS(d_wn64.alloc(sizeof(uint64_t) * ((size_t)n_cands + 1))); CKS(d_woff.alloc(sizeof(uint64_t) * ((size_t)n_cands + 1)));
+    candidate_kernel<true><<<(ns + 127) / 128, 128, 0, h->stream>>>(sc, keys, d_soff.as<uint32_t>(), ns, nullptr, d_coff.as<uint32_t>(), d_cidx.as<uint32_t>());
+    CKS(cudaGetLastError());
+    CKS(cudaMemsetAsync(d_wn.p, 0, sizeof(uint32_t) * ((size_t)n_cands + 1), h->stream));
+    window_size_kernel<<<(n_cands + 127) / 128, 128, 0, h->stream>>>(sc, keys, d_soff.as<uint32_t>(), d_coff.as<uint32_t>(), ns, d_cidx.as<uint32_t>(), n_cands,
+                                                                    d_cstr.as<uint32_t>(), d_wlo.as<uint32_t>(), d_wn.as<uint32_t>());
+    CKS(cudaGetLastError());
+    widen_kernel<<<(n_cands + 1 + 255) / 256, 256, 0, h->stream>>>(d_wn.as<uint32_t>(), n_cands + 1, d_wn64.as<uint64_t>());
+    CKS(cudaGetLastError());
+    if ((rc = exclusive_sum(h, d_wn64.as<uint64_t>(), d_woff.as<uint64_t>(), (int64_t)n_cands + 1))) return rc;
+    uint64_t n_win = 0;
+    CKS(cudaMemcpyAsync(&n_win, d_woff.as<uint64_t>() + n_cands, sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CKS(cudaStreamSynchronize(h->stream));
+    const uint64_t need_pool = n_win + n_cands;
+    *n_pool = need_pool;
+    if (n_cands > anchors_cap || need_pool > pool_cap) { h->err = "seed output capacity: need " + std::to_string(n_cands) + " anchors, " + std::to_string(need_pool) + " pool entries"; return DARWIN_ERR_CAPACITY; }
+    DevBuf d_w0, d_w1, d_pool, d_tanc, d_anc, d_tmp2;
+    CKS(d_w0.alloc(sizeof(uint64_t) * n_win)); CKS(d_w1.alloc(sizeof(uint64_t) * n_win)); CKS(d_pool.alloc(sizeof(uint64_t) * need_pool));
+    CKS(d_tanc.alloc(sizeof(DarwinSeedAnchor) * n_cands)); CKS(d_anc.alloc(sizeof(DarwinSeedAnchor) * n_cands));
+    window_copy_kernel<<<(unsigned)(((uint64_t)n_cands * 32 + 255) / 256), 256, 0, h->stream>>>(keys, vals, n_cands, d_wlo.as<uint32_t>(), d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w0.as<uint64_t>());
+    CKS(cudaGetLastError());
+    tmp_bytes = 0;
+    CKS(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, d_w0.as<uint64_t>(), d_w1.as<uint64_t>(), (int64_t)n_win, (int64_t)n_cands,
+                                           d_woff.as<uint64_t>(), d_woff.as<uint64_t>() + 1, h->stream));
+    CKS(d_tmp2.alloc(tmp_bytes));
+    CKS(cub::DeviceSegmentedSort::SortKeys(d_tmp2.p, tmp_bytes, d_w0.as<uint64_t>(), d_w1.as<uint64_t>(), (int64_t)n_win, (int64_t)n_cands,
+                                           d_woff.as<uint64_t>(), d_woff.as<uint64_t>() + 1, h->stream));
+    chain_kernel<<<(n_cands + 127) / 128, 128, 0, h->stream>>>(keys, vals, d_cidx.as<uint32_t>(), n_cands, d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w1.as<uint64_t>(),
+                                                              d_pool.as<uint64_t>(), d_tanc.as<DarwinSeedAnchor>());
+    CKS(cudaGetLastError());
+    order_kernel<<<(ns + 127) / 128, 128, 0, h->stream>>>(d_coff.as<uint32_t>(), ns, d_tanc.as<DarwinSeedAnchor>(), d_anc.as<DarwinSeedAnchor>());
+    CKS(cudaGetLastError());
+    CKS(cudaEventRecord(h->ev1, h->stream));
+    h->stats.kernel_launches += 7;
+    CKS(cudaMemcpyAsync(anchors, d_anc.p, sizeof(DarwinSeedAnchor) * n_cands, cudaMemcpyDeviceToHost, h->stream));
+    CKS(cudaMemcpyAsync(pool, d_pool.p, sizeof(uint64_t) * need_pool, cudaMemcpyDeviceToHost, h->stream));
+    CKS(cudaStreamSynchronize(h->stream));
+    CKS(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
+    return DARWIN_OK;
+}

@@ -43,6 +43,12 @@ def load_library():
         L.darwin_gpu_extend.argtypes = [C.c_void_p, C.POINTER(abi.ExtendParams), C.c_void_p, C.c_int, C.c_void_p,
                                         C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
         L.darwin_gpu_filter.argtypes = [C.c_void_p, C.POINTER(abi.FilterParams), C.c_void_p, C.c_int, C.c_void_p]
+        L.darwin_gpu_seed_index.argtypes = [C.c_void_p, C.POINTER(abi.SeedParams), C.c_void_p, C.c_int, C.c_uint64]
+        L.darwin_gpu_seed_index_share.argtypes = [C.c_void_p, C.c_void_p]
+        L.darwin_gpu_seed_index_read.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                                 C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.darwin_gpu_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
+                                      C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.darwin_gpu_stats.argtypes = [C.c_void_p, C.POINTER(abi.GpuStats)]
         L.darwin_gpu_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _lib = L
@@ -50,7 +56,8 @@ def load_library():
 
 
 EXPORTS = ("darwin_gpu_create", "darwin_gpu_create_shared", "darwin_gpu_destroy", "darwin_gpu_set_scoring", "darwin_gpu_upload",
-           "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_filter", "darwin_gpu_stats", "darwin_gpu_int_peak",
+           "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_filter", "darwin_gpu_seed_index",
+           "darwin_gpu_seed_index_share", "darwin_gpu_seed_index_read", "darwin_gpu_seed", "darwin_gpu_stats", "darwin_gpu_int_peak",
            "darwin_gpu_last_error", "darwin_gpu_version")
 
 
@@ -125,6 +132,41 @@ class Processor:
         self._check(self.lib.darwin_gpu_tiles_device(self.h, int(do_traceback), C.c_void_p(d_req), int(n),
                                                      C.c_void_p(d_res), C.c_void_p(d_tb), int(tb_words_per_req),
                                                      int(max_ref_size), int(max_query_size)))
+
+    # SeedPosTable construction (seed_pos_table.cpp:41-160) from the chromosomes already in the arena
+    def build_seed_index(self, params, chroms, reference_size):
+        ch = np.ascontiguousarray(chroms, dtype=abi.CHROM)
+        self._check(self.lib.darwin_gpu_seed_index(self.h, C.byref(params), abi.ptr(ch), len(ch), C.c_uint64(int(reference_size))))
+
+    def seed_index_arrays(self):
+        """(buckets, positions, max_occ) copied back from the device (tests)."""
+        nb, npos, mo = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        self._check(self.lib.darwin_gpu_seed_index_read(self.h, None, 0, None, 0, C.byref(nb), C.byref(npos), C.byref(mo)))
+        b = np.zeros(nb.value + 1, np.uint32)
+        p = np.zeros(max(npos.value, 1), np.uint32)
+        self._check(self.lib.darwin_gpu_seed_index_read(self.h, abi.ptr(b), C.c_uint64(len(b)), abi.ptr(p), C.c_uint64(len(p)), None, None, None))
+        return b, p[:npos.value], mo.value
+
+    # seeder_body::operator() (seeder.cpp:6-55) -> SeedPosTable::DSOFT (seed_pos_table.cpp:252-553) for resident reads
+    def seeder_body(self, reads):
+        """reads: SEED_READ array.  Returns (anchor_begin[2n+1], anchors, pool): anchors of read r, strand s are
+        anchors[anchor_begin[2r+s]:anchor_begin[2r+s+1]] in the reference's order."""
+        rd = np.ascontiguousarray(reads, dtype=abi.SEED_READ)
+        n = len(rd)
+        begin = np.zeros(2 * n + 1, np.uint32)
+        acap, pcap = max(64, 8 * n), max(1 << 16, 16384 * n)
+        for _ in range(3):
+            anchors = np.empty(acap, abi.SEED_ANCHOR)
+            pool = np.empty(pcap, np.uint64)
+            na, npool = C.c_uint64(0), C.c_uint64(0)
+            rc = self.lib.darwin_gpu_seed(self.h, abi.ptr(rd), n, abi.ptr(begin), abi.ptr(anchors), C.c_uint64(acap), C.byref(na),
+                                          abi.ptr(pool), C.c_uint64(pcap), C.byref(npool))
+            if rc == abi.ERR_CAPACITY:
+                acap, pcap = max(acap, int(na.value)), max(pcap, int(npool.value))
+                continue
+            self._check(rc)
+            return begin, anchors[:na.value], pool[:npool.value]
+        raise DarwinGpuError(abi.ERR_CAPACITY, "seed output capacity")
 
     # the tile part of filter_body::operator() (filter.cpp:28-122, :131-223) for a batch of D-SOFT candidates
     def filter_body(self, cands, first_tile_size=128, first_tile_score_threshold=60, min_overlap=1000, out=None):

@@ -261,6 +261,15 @@ int darwin_gpu_filter(DarwinGpu* h, const DarwinFilterParams* p, const DarwinFil
  * seed_pos_table.cpp:41-160): builds the seed position table in HBM from the chromosomes already uploaded. */
 int darwin_gpu_seed_index(DarwinGpu* h, const DarwinSeedParams* p, const DarwinChrom* chroms, int n_chroms, uint64_t reference_size);
 
+/* lanes created BEFORE the table was built adopt the parent's table with this call (lanes created afterwards share it
+ * automatically) */
+int darwin_gpu_seed_index_share(DarwinGpu* h, DarwinGpu* parent);
+
+/* diagnostics / tests: copy the table back (buckets: n_buckets + 1 prefix sums; positions of buckets larger than
+ * max_occ are unordered, D-SOFT never reads them) */
+int darwin_gpu_seed_index_read(DarwinGpu* h, uint32_t* buckets, uint64_t buckets_cap, uint32_t* positions, uint64_t positions_cap,
+                               uint64_t* n_buckets, uint64_t* n_positions, uint32_t* max_occ);
+
 /* replaces seeder_body::operator() (seeder.cpp:6-55) -> SeedPosTable::DSOFT (seed_pos_table.cpp:252-553) for n reads
  * already resident in the arena: anchors of read r, strand s (0 = forward, 1 = reverse complement) are
  * anchors[anchor_begin[2r+s] .. anchor_begin[2r+s+1]) in the reference's output order.  Capacities are in elements;

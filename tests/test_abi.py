@@ -55,4 +55,4 @@ def test_product_does_not_import_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) and f != "smoke.py":
                 txt = open(os.path.join(dirpath, f)).read()
-                assert "import oracle" not in txt and "oracle/" not in txt.replace("oracle/gact_oracle.c", ""), f
+                assert "import oracle" not in txt and "oracle/" not in txt.replace("oracle/gact_oracle.c", "").replace("oracle/dsoft_oracle.c", ""), f   # comments may NAME the CPU twins
