@@ -701,6 +701,11 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     *out = h;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+    {   // stream-ordered allocations (seeding scratch) stay in the device's pool instead of going back to the driver
+        cudaMemPool_t pool; uint64_t keep = ~0ull;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     h->arena_bytes = arena_bytes;
     if (parent) {                                                              // another lane of the same device: one arena replica
         h->d_arena = parent->d_arena; h->owns_arena = false;

@@ -6,10 +6,13 @@
 
 #define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DARWIN_ERR_CUDA; } } while (0)
 
-struct DevBuf {                                      // scoped device allocation of the seeding calls
-    void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+// Scoped device allocation of the seeding calls: stream-ordered (cudaMallocAsync on the handle's stream, the device's
+// default pool keeps the memory between calls), so neither the allocation nor the release synchronises the device --
+// cudaMalloc / cudaFree would stall the kernels of every other lane.
+struct DevBuf {
+    void* p = nullptr; cudaStream_t st = nullptr;
+    ~DevBuf() { if (p) cudaFreeAsync(p, st); }
+    cudaError_t alloc(size_t bytes, cudaStream_t stream) { st = stream; return cudaMallocAsync(&p, bytes ? bytes : 16, stream); }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -52,8 +55,8 @@ static int seed_index_build(DarwinGpu* h, SeedIndex& ix, const DarwinSeedParams*
     CKS(cudaMalloc(&ix.d_buckets, (ix.n_buckets + 1) * sizeof(uint32_t)));
     CKS(cudaMemsetAsync(ix.d_buckets, 0, (ix.n_buckets + 1) * sizeof(uint32_t), h->stream));
     DevBuf d_jobs, d_list, d_carry, d_cursor, d_fill, d_tmp;
-    CKS(d_jobs.alloc(sizeof(MinJob) * n_chroms)); CKS(d_list.alloc(sizeof(uint64_t) * list_cap));
-    CKS(d_carry.alloc(sizeof(int) * (size_t)n_chroms * max_chunks)); CKS(d_cursor.alloc(sizeof(unsigned long long)));
+    CKS(d_jobs.alloc(sizeof(MinJob) * n_chroms, h->stream)); CKS(d_list.alloc(sizeof(uint64_t) * list_cap, h->stream));
+    CKS(d_carry.alloc(sizeof(int) * (size_t)n_chroms * max_chunks, h->stream)); CKS(d_cursor.alloc(sizeof(unsigned long long), h->stream));
     CKS(cudaMemcpyAsync(d_jobs.p, jobs.data(), sizeof(MinJob) * n_chroms, cudaMemcpyHostToDevice, h->stream));
     CKS(cudaMemsetAsync(d_cursor.p, 0, sizeof(unsigned long long), h->stream));
     const dim3 grid(max_chunks, n_chroms);
@@ -75,10 +78,10 @@ static int seed_index_build(DarwinGpu* h, SeedIndex& ix, const DarwinSeedParams*
     // buckets = prefix sums of the histogram (seed_pos_table.cpp:66-101); hist was counted at [m + 1]
     size_t tmp_bytes = 0;
     CKS(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, ix.d_buckets, ix.d_buckets, (int64_t)(ix.n_buckets + 1), h->stream));
-    CKS(d_tmp.alloc(tmp_bytes));
+    CKS(d_tmp.alloc(tmp_bytes, h->stream));
     CKS(cub::DeviceScan::InclusiveSum(d_tmp.p, tmp_bytes, ix.d_buckets, ix.d_buckets, (int64_t)(ix.n_buckets + 1), h->stream));
     CKS(cudaMalloc(&ix.d_positions, sizeof(uint32_t) * std::max<uint64_t>(n_min, 1)));
-    CKS(d_fill.alloc(sizeof(uint32_t) * ix.n_buckets));
+    CKS(d_fill.alloc(sizeof(uint32_t) * ix.n_buckets, h->stream));
     CKS(cudaMemsetAsync(d_fill.p, 0, sizeof(uint32_t) * ix.n_buckets, h->stream));
     if (n_min) scatter_kernel<<<(unsigned)((n_min + 255) / 256), 256, 0, h->stream>>>(d_list.as<uint64_t>(), n_min, ix.d_buckets, d_fill.as<uint32_t>(), ix.d_positions);
     CKS(cudaGetLastError());
@@ -94,10 +97,9 @@ template <class T>
 static int exclusive_sum(DarwinGpu* h, const T* in, T* out, int64_t n) {
     size_t bytes = 0;
     CKS(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, h->stream));
-    DevBuf tmp; CKS(tmp.alloc(bytes));
+    DevBuf tmp; CKS(tmp.alloc(bytes, h->stream));
     CKS(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, in, out, n, h->stream));
-    CKS(cudaStreamSynchronize(h->stream));           // tmp is freed on return
-    return DARWIN_OK;
+    return DARWIN_OK;                                // tmp is released in stream order
 }
 
 __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, int n, uint32_t* __restrict__ dst) {
@@ -132,9 +134,9 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     }
     seed_base[ns] = slots;
     DevBuf d_jobs, d_base, d_seeds, d_nseeds, d_cnt, d_hoff, d_soff;
-    CKS(d_jobs.alloc(sizeof(MinJob) * ns)); CKS(d_base.alloc(sizeof(uint32_t) * (ns + 1))); CKS(d_seeds.alloc(sizeof(uint64_t) * slots));
-    CKS(d_nseeds.alloc(sizeof(uint32_t) * ns)); CKS(d_cnt.alloc(sizeof(uint32_t) * ((size_t)slots + 1))); CKS(d_hoff.alloc(sizeof(uint32_t) * ((size_t)slots + 1)));
-    CKS(d_soff.alloc(sizeof(uint32_t) * (ns + 1)));
+    CKS(d_jobs.alloc(sizeof(MinJob) * ns, h->stream)); CKS(d_base.alloc(sizeof(uint32_t) * (ns + 1), h->stream)); CKS(d_seeds.alloc(sizeof(uint64_t) * slots, h->stream));
+    CKS(d_nseeds.alloc(sizeof(uint32_t) * ns, h->stream)); CKS(d_cnt.alloc(sizeof(uint32_t) * ((size_t)slots + 1), h->stream)); CKS(d_hoff.alloc(sizeof(uint32_t) * ((size_t)slots + 1), h->stream));
+    CKS(d_soff.alloc(sizeof(uint32_t) * (ns + 1), h->stream));
     CKS(cudaMemcpyAsync(d_jobs.p, jobs.data(), sizeof(MinJob) * ns, cudaMemcpyHostToDevice, h->stream));
     CKS(cudaMemcpyAsync(d_base.p, seed_base.data(), sizeof(uint32_t) * (ns + 1), cudaMemcpyHostToDevice, h->stream));
     CKS(cudaMemsetAsync(d_cnt.p, 0, sizeof(uint32_t) * ((size_t)slots + 1), h->stream));
@@ -153,8 +155,8 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     CKS(cudaMemcpyAsync(&n_hits, d_hoff.as<uint32_t>() + slots, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CKS(cudaStreamSynchronize(h->stream));
     DevBuf d_k0, d_k1, d_v0, d_v1, d_tmp;
-    CKS(d_k0.alloc(sizeof(uint64_t) * n_hits)); CKS(d_k1.alloc(sizeof(uint64_t) * n_hits));
-    CKS(d_v0.alloc(sizeof(uint32_t) * n_hits)); CKS(d_v1.alloc(sizeof(uint32_t) * n_hits));
+    CKS(d_k0.alloc(sizeof(uint64_t) * n_hits, h->stream)); CKS(d_k1.alloc(sizeof(uint64_t) * n_hits, h->stream));
+    CKS(d_v0.alloc(sizeof(uint32_t) * n_hits, h->stream)); CKS(d_v1.alloc(sizeof(uint32_t) * n_hits, h->stream));
     hit_fill_kernel<<<gb, 256, 0, h->stream>>>(sc, ix.d_buckets, ix.d_positions, d_seeds.as<uint64_t>(), d_base.as<uint32_t>(), d_nseeds.as<uint32_t>(), ns, max_cap,
                                               d_hoff.as<uint32_t>(), d_k0.as<uint64_t>(), d_v0.as<uint32_t>());
     CKS(cudaGetLastError());
@@ -162,13 +164,13 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     size_t tmp_bytes = 0;
     CKS(cub::DeviceSegmentedSort::StableSortPairs(nullptr, tmp_bytes, d_k0.as<uint64_t>(), d_k1.as<uint64_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(),
                                                   (int64_t)n_hits, (int64_t)ns, d_soff.as<uint32_t>(), d_soff.as<uint32_t>() + 1, h->stream));
-    CKS(d_tmp.alloc(tmp_bytes));
+    CKS(d_tmp.alloc(tmp_bytes, h->stream));
     CKS(cub::DeviceSegmentedSort::StableSortPairs(d_tmp.p, tmp_bytes, d_k0.as<uint64_t>(), d_k1.as<uint64_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(),
                                                   (int64_t)n_hits, (int64_t)ns, d_soff.as<uint32_t>(), d_soff.as<uint32_t>() + 1, h->stream));
     const uint64_t* keys = d_k1.as<uint64_t>(); const uint32_t* vals = d_v1.as<uint32_t>();
     // candidate bins: count, scan, fill
     DevBuf d_ncand, d_coff;
-    CKS(d_ncand.alloc(sizeof(uint32_t) * (ns + 1))); CKS(d_coff.alloc(sizeof(uint32_t) * (ns + 1)));
+    CKS(d_ncand.alloc(sizeof(uint32_t) * (ns + 1), h->stream)); CKS(d_coff.alloc(sizeof(uint32_t) * (ns + 1), h->stream));
     CKS(cudaMemsetAsync(d_ncand.p, 0, sizeof(uint32_t) * (ns + 1), h->stream));
     candidate_kernel<false><<<(ns + 127) / 128, 128, 0, h->stream>>>(sc, keys, d_soff.as<uint32_t>(), ns, d_ncand.as<uint32_t>(), nullptr, nullptr);
     CKS(cudaGetLastError());
@@ -180,8 +182,8 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     h->stats.kernel_launches += 6;
     if (n_cands == 0) { *n_pool = 0; CKS(cudaEventRecord(h->ev1, h->stream)); CKS(cudaStreamSynchronize(h->stream)); CKS(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1)); return DARWIN_OK; }
     DevBuf d_cidx, d_cstr, d_wlo, d_wn, d_wn64, d_woff;
-    CKS(d_cidx.alloc(sizeof(uint32_t) * n_cands)); CKS(d_cstr.alloc(sizeof(uint32_t) * n_cands)); CKS(d_wlo.alloc(sizeof(uint32_t) * n_cands));
-    CKS(d_wn.alloc(sizeof(uint32_t) * ((size_t)n_cands + 1))); CKS(d_wn64.alloc(sizeof(uint64_t) * ((size_t)n_cands + 1))); CKS(d_woff.alloc(sizeof(uint64_t) * ((size_t)n_cands + 1)));
+    CKS(d_cidx.alloc(sizeof(uint32_t) * n_cands, h->stream)); CKS(d_cstr.alloc(sizeof(uint32_t) * n_cands, h->stream)); CKS(d_wlo.alloc(sizeof(uint32_t) * n_cands, h->stream));
+    CKS(d_wn.alloc(sizeof(uint32_t) * ((size_t)n_cands + 1), h->stream)); CKS(d_wn64.alloc(sizeof(uint64_t) * ((size_t)n_cands + 1), h->stream)); CKS(d_woff.alloc(sizeof(uint64_t) * ((size_t)n_cands + 1), h->stream));
     candidate_kernel<true><<<(ns + 127) / 128, 128, 0, h->stream>>>(sc, keys, d_soff.as<uint32_t>(), ns, nullptr, d_coff.as<uint32_t>(), d_cidx.as<uint32_t>());
     CKS(cudaGetLastError());
     CKS(cudaMemsetAsync(d_wn.p, 0, sizeof(uint32_t) * ((size_t)n_cands + 1), h->stream));
@@ -198,14 +200,14 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     *n_pool = need_pool;
     if (n_cands > anchors_cap || need_pool > pool_cap) { h->err = "seed output capacity: need " + std::to_string(n_cands) + " anchors, " + std::to_string(need_pool) + " pool entries"; return DARWIN_ERR_CAPACITY; }
     DevBuf d_w0, d_w1, d_pool, d_tanc, d_anc, d_tmp2;
-    CKS(d_w0.alloc(sizeof(uint64_t) * n_win)); CKS(d_w1.alloc(sizeof(uint64_t) * n_win)); CKS(d_pool.alloc(sizeof(uint64_t) * need_pool));
-    CKS(d_tanc.alloc(sizeof(DarwinSeedAnchor) * n_cands)); CKS(d_anc.alloc(sizeof(DarwinSeedAnchor) * n_cands));
+    CKS(d_w0.alloc(sizeof(uint64_t) * n_win, h->stream)); CKS(d_w1.alloc(sizeof(uint64_t) * n_win, h->stream)); CKS(d_pool.alloc(sizeof(uint64_t) * need_pool, h->stream));
+    CKS(d_tanc.alloc(sizeof(DarwinSeedAnchor) * n_cands, h->stream)); CKS(d_anc.alloc(sizeof(DarwinSeedAnchor) * n_cands, h->stream));
     window_copy_kernel<<<(unsigned)(((uint64_t)n_cands * 32 + 255) / 256), 256, 0, h->stream>>>(keys, vals, n_cands, d_wlo.as<uint32_t>(), d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w0.as<uint64_t>());
     CKS(cudaGetLastError());
     tmp_bytes = 0;
     CKS(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, d_w0.as<uint64_t>(), d_w1.as<uint64_t>(), (int64_t)n_win, (int64_t)n_cands,
                                            d_woff.as<uint64_t>(), d_woff.as<uint64_t>() + 1, h->stream));
-    CKS(d_tmp2.alloc(tmp_bytes));
+    CKS(d_tmp2.alloc(tmp_bytes, h->stream));
     CKS(cub::DeviceSegmentedSort::SortKeys(d_tmp2.p, tmp_bytes, d_w0.as<uint64_t>(), d_w1.as<uint64_t>(), (int64_t)n_win, (int64_t)n_cands,
                                            d_woff.as<uint64_t>(), d_woff.as<uint64_t>() + 1, h->stream));
     chain_kernel<<<(n_cands + 127) / 128, 128, 0, h->stream>>>(keys, vals, d_cidx.as<uint32_t>(), n_cands, d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w1.as<uint64_t>(),

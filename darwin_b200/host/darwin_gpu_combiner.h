@@ -13,6 +13,7 @@
 // Only include/darwin_gpu.h is needed here (no reference headers), so the merge / scatter logic is unit-tested on the
 // CPU with stand-in entry points (tests/cpp/test_combiner.cpp).
 #pragma once
+#include <algorithm>
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -32,18 +33,19 @@ struct GpuCalls {
     int (*extend)(DarwinGpu*, const DarwinExtendParams*, const DarwinAnchor*, int, const uint64_t*, uint64_t,
                   DarwinAlnRes*, uint8_t*, uint64_t);
     const char* (*last_error)(DarwinGpu*);
+    int (*seed)(DarwinGpu*, const DarwinSeedRead*, int, uint32_t*, DarwinSeedAnchor*, uint64_t, uint64_t*, uint64_t*, uint64_t, uint64_t*);
     static GpuCalls library() {
-        return GpuCalls{darwin_gpu_upload, darwin_gpu_tiles, darwin_gpu_filter, darwin_gpu_extend, darwin_gpu_last_error};
+        return GpuCalls{darwin_gpu_upload, darwin_gpu_tiles, darwin_gpu_filter, darwin_gpu_extend, darwin_gpu_last_error, darwin_gpu_seed};
     }
 };
 
 struct UploadSpan { uint64_t arena_addr; const char* ascii; uint64_t n; };
 
 struct CombinerStats {
-    uint64_t device_calls[3];   // [0] tiles, [1] filter, [2] extend: calls that reached the device
-    uint64_t requests[3];       // requests submitted by host threads
-    uint64_t items[3];          // tiles / candidates / anchors
-    uint64_t max_merged[3];     // largest number of requests served by one device call
+    uint64_t device_calls[4];   // [0] tiles, [1] filter, [2] extend, [3] seed: calls that reached the device
+    uint64_t requests[4];       // requests submitted by host threads
+    uint64_t items[4];          // tiles / candidates / anchors / reads
+    uint64_t max_merged[4];     // largest number of requests served by one device call
 };
 
 class GpuCombiner {
@@ -69,6 +71,13 @@ public:
         r.ares = res; r.ops = ops;
         return run(r, err);
     }
+    // == seeder_body for one caller's reads: anchors of read r, strand s are anchors[begin[2r+s] .. begin[2r+s+1]),
+    // their chained hits index into `pool`
+    int seed(const std::vector<UploadSpan>& up, const DarwinSeedRead* reads, int n, std::vector<uint32_t>* begin,
+             std::vector<DarwinSeedAnchor>* anchors, std::vector<uint64_t>* pool, std::string* err) {
+        Request r; r.kind = SEED; r.up = &up; r.sreads = reads; r.n = n; r.sbegin = begin; r.sanchors = anchors; r.spool = pool;
+        return run(r, err);
+    }
     // == g_InitializeReferenceMemory / g_InitializeReadMemory from any thread (rides along with the next tile batch)
     int upload(const std::vector<UploadSpan>& up, std::string* err) {
         Request r; r.kind = TILES; r.do_tb = 0; r.up = &up; r.n = 0;
@@ -78,7 +87,7 @@ public:
     DarwinGpu* handle() const { return h_; }
 
 private:
-    enum Kind { TILES = 0, FILTER = 1, EXTEND = 2 };
+    enum Kind { TILES = 0, FILTER = 1, EXTEND = 2, SEED = 3 };
     struct Request {
         Kind kind; int n = 0; bool done = false; int rc = 0; std::string err;
         const std::vector<UploadSpan>* up = nullptr;
@@ -89,12 +98,16 @@ private:
         // extend
         DarwinExtendParams ep{}; const DarwinAnchor* anchors = nullptr; const uint64_t* pool = nullptr; uint64_t n_pool = 0;
         DarwinAlnRes* ares = nullptr; std::vector<uint8_t>* ops = nullptr;
+        // seed
+        const DarwinSeedRead* sreads = nullptr; std::vector<uint32_t>* sbegin = nullptr;
+        std::vector<DarwinSeedAnchor>* sanchors = nullptr; std::vector<uint64_t>* spool = nullptr;
     };
 
     static bool mergeable(const Request& a, const Request& b) {
         if (a.kind != b.kind) return false;
         if (a.kind == TILES) return a.do_tb == b.do_tb;
         if (a.kind == FILTER) return memcmp(&a.fp, &b.fp, sizeof(a.fp)) == 0;
+        if (a.kind == SEED) return true;
         return memcmp(&a.ep, &b.ep, sizeof(a.ep)) == 0;
     }
 
@@ -178,6 +191,35 @@ private:
             if (rc) { fail_all(batch, rc, "darwin_gpu_filter"); return; }
             size_t at = 0;
             for (auto* b : batch) { if (b->n) memcpy(b->fres, res.data() + at, sizeof(DarwinFilterRes) * (size_t)b->n); at += (size_t)b->n; }
+        } else if (k == SEED) {
+            std::vector<DarwinSeedRead> reads; reads.reserve(total);
+            for (auto* b : batch) reads.insert(reads.end(), b->sreads, b->sreads + b->n);
+            std::vector<uint32_t> begin(2 * total + 1);
+            std::vector<DarwinSeedAnchor> anchors(std::max<size_t>(64, 16 * total));
+            std::vector<uint64_t> pool(std::max<size_t>(1 << 16, 8192 * total));
+            uint64_t na = 0, np = 0;
+            int rc = DARWIN_ERR_CAPACITY;
+            for (int attempt = 0; attempt < 3 && rc == DARWIN_ERR_CAPACITY; attempt++) {
+                rc = c_.seed(h_, reads.data(), (int)total, begin.data(), anchors.data(), anchors.size(), &na, pool.data(), pool.size(), &np);
+                if (rc == DARWIN_ERR_CAPACITY) { anchors.resize(std::max<size_t>(anchors.size(), na)); pool.resize(std::max<size_t>(pool.size(), np)); }
+            }
+            if (rc) { fail_all(batch, rc, "darwin_gpu_seed"); return; }
+            size_t at = 0;                                        // reads before this caller
+            for (auto* b : batch) {
+                const uint32_t a0 = begin[2 * at], a1 = begin[2 * (at + (size_t)b->n)];
+                uint64_t lo = UINT64_MAX, hi = 0;
+                for (uint32_t i = a0; i < a1; i++) {
+                    lo = std::min(lo, std::min(anchors[i].left_off, anchors[i].right_off));
+                    hi = std::max(hi, std::max(anchors[i].left_off + anchors[i].left_n, anchors[i].right_off + anchors[i].right_n));
+                }
+                if (lo == UINT64_MAX) { lo = 0; hi = 0; }
+                b->sbegin->resize(2 * (size_t)b->n + 1);
+                for (size_t i = 0; i <= 2 * (size_t)b->n; i++) (*b->sbegin)[i] = begin[2 * at + i] - a0;
+                b->sanchors->assign(anchors.begin() + a0, anchors.begin() + a1);
+                for (auto& a : *b->sanchors) { a.left_off -= lo; a.right_off -= lo; }
+                b->spool->assign(pool.begin() + lo, pool.begin() + hi);
+                at += (size_t)b->n;
+            }
         } else {
             // anchors of all callers back to back; their hit lists are rebased into one pool
             std::vector<DarwinAnchor> anchors; anchors.reserve(total);

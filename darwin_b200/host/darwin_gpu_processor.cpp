@@ -103,7 +103,7 @@ CombinerStats combiner_stats_total() {
     CombinerStats t; memset(&t, 0, sizeof(t));
     for (auto c : g_combiners) {
         const CombinerStats s = c->stats();
-        for (int k = 0; k < 3; k++) {
+        for (int k = 0; k < 4; k++) {
             t.device_calls[k] += s.device_calls[k]; t.requests[k] += s.requests[k]; t.items[k] += s.items[k];
             if (s.max_merged[k] > t.max_merged[k]) t.max_merged[k] = s.max_merged[k];
         }
@@ -261,6 +261,60 @@ void gpu_extender_body::operator()(extender_input input, extender_node::output_p
     get<0>(op).try_put(printer_input(printer_payload(reads, output), token));
 }
 
+// SeedPosTable construction on the GPUs (main.cpp:323-341 minimizer pass + :508): every GPU builds the table from its own
+// arena replica (the reference must have been uploaded); lanes share their GPU's table.
+void BuildSeedIndex() {
+    std::vector<DarwinChrom> chroms(Index::chr_id.size());
+    for (size_t c = 0; c < chroms.size(); c++) { chroms[c].start = Index::chr_coord[c]; chroms[c].len_unpadded = (uint32_t)Index::chr_len_unpadded[c]; }
+    DarwinSeedParams prm{cfg.seed_size, cfg.minimizer_window, (int32_t)cfg.bin_size, cfg.dsoft_threshold, cfg.num_seeds,
+                         cfg.seed_occurence_multiple, cfg.max_stride, cfg.do_overlap};
+    for (int d = 0; d < g_gpus; d++) {
+        int rc = darwin_gpu_seed_index(g_handles[d], &prm, chroms.data(), (int)chroms.size(), g_DRAM->referenceSize);
+        if (rc != DARWIN_OK) fail(g_handles[d], rc, "darwin_gpu_seed_index");
+        for (int l = 1; l < g_lanes; l++) {
+            rc = darwin_gpu_seed_index_share(g_handles[(size_t)l * g_gpus + d], g_handles[d]);
+            if (rc != DARWIN_OK) fail(g_handles[(size_t)l * g_gpus + d], rc, "darwin_gpu_seed_index_share");
+        }
+    }
+}
+
+// seeder_body::operator() (seeder.cpp:6-55): SeedPosTable::DSOFT for both strands of every read of the batch on the GPU;
+// the output has the reference's layout (anchors appended read by read, bucket boundaries per read).
+filter_input gpu_seeder_body::operator()(seeder_input input) {
+    reader_output& reads = get<0>(input);
+    size_t token = get<1>(input);
+    GpuCombiner& gc = combiner_for_token(token);
+    seeder_data output;
+    output.fwAnchorBuckets.push_back(0ull);
+    output.rcAnchorBuckets.push_back(0ull);
+    if (!reads.empty()) {
+        const std::vector<UploadSpan> spans = read_spans(reads);
+        std::vector<DarwinSeedRead> sr(reads.size());
+        for (size_t r = 0; r < reads.size(); r++) sr[r] = DarwinSeedRead{(uint64_t)(reads[r].seq.data() - g_DRAM->buffer), (uint32_t)reads[r].seq.size(), 0};
+        std::vector<uint32_t> begin; std::vector<DarwinSeedAnchor> anchors; std::vector<uint64_t> pool;
+        std::string err;
+        int rc = gc.seed(spans, sr.data(), (int)sr.size(), &begin, &anchors, &pool, &err);
+        if (rc != DARWIN_OK) fail_msg(rc, "gpu_seeder_body", err);
+        if (!spans.empty()) { t_resident_addr = spans[0].arena_addr; t_resident_end = spans.back().arena_addr + spans.back().n; }
+        for (size_t r = 0; r < reads.size(); r++)
+            for (int strand = 0; strand < 2; strand++) {
+                auto& dst = strand ? output.rcAnchors : output.fwAnchors;
+                auto& buckets = strand ? output.rcAnchorBuckets : output.fwAnchorBuckets;
+                for (uint32_t i = begin[2 * r + strand]; i < begin[2 * r + strand + 1]; i++) {
+                    const DarwinSeedAnchor& a = anchors[i];
+                    dst.emplace_back(a.hit_offset);
+                    Anchors& o = dst.back();
+                    o.left_chained_hits.assign(pool.begin() + a.left_off, pool.begin() + a.left_off + a.left_n);
+                    o.right_chained_hits.assign(pool.begin() + a.right_off, pool.begin() + a.right_off + a.right_n);
+                    o.num_chained_hits = (int)(a.left_n + a.right_n);
+                    o.anchor_score = 0;                                 // computed but never read downstream (seed_pos_table.cpp:453,:481)
+                }
+                buckets.push_back(dst.size());
+            }
+    } 
+    return filter_input(filter_payload(reads, output), token);
+}
+
 // filter_body::operator() (filter.cpp:8-225) with every first tile of the batch -- both strands, all reads -- in ONE
 // darwin_gpu_filter call instead of g_BatchAlignmentSIMD batches of 64 (filter.cpp:22, :75).  Request construction,
 // score and overlap tests run on the device; the ExtendLocations (chr_id / read_num lookups, chained hits) and the
@@ -297,7 +351,8 @@ extender_input gpu_filter_body::operator()(filter_input input) {
     }
     std::vector<DarwinFilterRes> res(cands.size());
     if (!cands.empty()) {
-        const std::vector<UploadSpan> spans = read_spans(reads);                       // the reads of this batch must be resident
+        std::vector<UploadSpan> spans = read_spans(reads);                             // the reads of this batch must be resident
+        if (!spans.empty() && t_resident_addr == spans[0].arena_addr && t_resident_end == spans.back().arena_addr + spans.back().n) spans.clear();
         DarwinFilterParams prm{cfg.first_tile_size, cfg.first_tile_score_threshold, cfg.min_overlap, 0};
         std::string err;
         int rc = gc.filter(prm, spans, cands.data(), (int)cands.size(), res.data(), &err);

@@ -37,6 +37,14 @@ struct gpu_extender_body {
     void operator()(extender_input input, extender_node::output_ports_type& op);
 };
 
+// == seeder_body (software/graph.h:200-203, seeder.cpp:6-55): D-SOFT of the whole batch on the GPU.  Needs the seed
+// position table: call BuildSeedIndex() once after the reference has been uploaded (it replaces
+// `sa = new SeedPosTable(...)`, main.cpp:508, and the minimizer pass over the reference, main.cpp:323-341).
+void BuildSeedIndex();
+struct gpu_seeder_body {
+    filter_input operator()(seeder_input input);
+};
+
 // == filter_body (software/graph.h:205-217, filter.cpp:8-225): same input/output tuples; the first tiles of the whole
 // batch (both strands) go to the GPU in one darwin_gpu_filter call; the slope filter is the reference's own.
 struct gpu_filter_body {

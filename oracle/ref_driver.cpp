@@ -651,7 +651,7 @@ int dref_pipeline(int first, int count, int use_gpu, char* out, uint64_t cap) {
         use_gpu &= 7;
         reader_output reads(g_reads.begin() + first, g_reads.begin() + first + count);
         seeder_input sin(reads, 0);
-        filter_input fin = seeder_body()(sin);
+        filter_input fin = (use_gpu >= 3) ? darwin_gpu_host::gpu_seeder_body()(sin) : seeder_body()(sin);
         extender_input ein = (use_gpu >= 2) ? darwin_gpu_host::gpu_filter_body()(fin) : filter_body()(fin);
         extender_node::output_ports_type ports;
         if (use_gpu) darwin_gpu_host::gpu_extender_body()(ein, ports);
@@ -704,7 +704,7 @@ int dref_pipeline(int first, int count, int use_gpu, char* out, uint64_t cap) {
 // ---- multi-threaded end-to-end run: `threads` host threads play the reference's tokens
 // (main.cpp:615-624); each pulls batches of `reads_per_batch` reads and runs seeder_body -> filter -> extender on them.
 // mode 0: the reference's CPU stages; mode 1: GPU extender only (filter tiles through g_BatchAlignmentSIMD);
-// mode 2: gpu_filter_body + gpu_extender_body.  With the GPU stages all threads share the per-GPU combiner
+// mode 2: gpu_filter_body + gpu_extender_body; mode 3: gpu_seeder_body as well (dref_gpu_seed_index first).  With the GPU stages all threads share the per-GPU combiner
 // (darwin_b200/host/darwin_gpu_combiner.h).  Output: canonical sorted lines like dref_pipeline (out may be NULL);
 // stats[0] = wall seconds, [1] = alignments, [2] = seconds inside seeder_body (summed over threads), [3] = filter stage,
 // [4] = extender stage, [5] = DP cells of the alignments' tile requests when dref_count_cells(1) was set (CPU modes).
@@ -731,7 +731,8 @@ int dref_pipeline_mt(int first, int count, int threads, int reads_per_batch, int
                     const int lo = first + b * reads_per_batch, hi = std::min(first + count, lo + reads_per_batch);
                     reader_output reads(g_reads.begin() + lo, g_reads.begin() + hi);
                     const auto a0 = now();
-                    filter_input fin = seeder_body()(seeder_input(reads, (size_t)t));
+                    filter_input fin = (mode >= 3) ? darwin_gpu_host::gpu_seeder_body()(seeder_input(reads, (size_t)t))
+                                                   : seeder_body()(seeder_input(reads, (size_t)t));
                     const auto a1 = now();
                     extender_input ein = (mode >= 2) ? darwin_gpu_host::gpu_filter_body()(fin) : filter_body()(fin);
                     const auto a2 = now();
@@ -781,6 +782,12 @@ int dref_pipeline_mt(int first, int count, int threads, int reads_per_batch, int
 void dref_combiner_stats(uint64_t* out) {
     darwin_gpu_host::CombinerStats s = darwin_gpu_host::combiner_stats_total();
     for (int k = 0; k < 3; k++) { out[k] = s.device_calls[k]; out[3 + k] = s.requests[k]; out[6 + k] = s.items[k]; out[9 + k] = s.max_merged[k]; }
+}
+
+// seed position table on the GPUs (after dref_gpu_init)
+int dref_gpu_seed_index(void) {
+    try { darwin_gpu_host::BuildSeedIndex(); } catch (const std::exception& e) { fprintf(stderr, "dref_gpu_seed_index: %s\n", e.what()); return -1; }
+    return 0;
 }
 
 // back to the software Processor (the reference's defaults, Processor.cpp:1063-1069)

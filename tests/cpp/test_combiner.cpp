@@ -10,10 +10,11 @@
 
 #include "../../darwin_b200/host/darwin_gpu_combiner.h"
 #include "../../oracle/gact_oracle.h"
+#include "../../oracle/dsoft_oracle.h"
 
 using namespace darwin_gpu_host;
 
-struct Fake { GactScoring sc; char* dram; uint64_t dram_bytes; std::atomic<int> device_calls; int fail_filter; };
+struct Fake { GactScoring sc; char* dram; uint64_t dram_bytes; std::atomic<int> device_calls; int fail_filter; DsoftIndex* ix; };
 static Fake* fake(DarwinGpu* h) { return reinterpret_cast<Fake*>(h); }
 static void device_latency() { std::this_thread::sleep_for(std::chrono::milliseconds(2)); }
 
@@ -38,7 +39,33 @@ static int f_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAncho
     memset(res, 0, sizeof(DarwinAlnRes) * (size_t)n);
     return gact_extend(&fake(h)->sc, fake(h)->dram, p, GACT_RULE_STREAM, a, n, pool, res, ops, cap);
 }
+static char rc_char(char c) { switch (c) { case 'A': return 'T'; case 'C': return 'G'; case 'G': return 'C'; case 'T': return 'A'; default: return 'N'; } }
+// darwin_gpu_seed stand-in: SeedPosTable::DSOFT of the oracle for both strands of every read, output in the C-ABI layout
+static int f_seed(DarwinGpu* h, const DarwinSeedRead* reads, int n, uint32_t* begin, DarwinSeedAnchor* anchors, uint64_t acap, uint64_t* na,
+                  uint64_t* pool, uint64_t pcap, uint64_t* np) {
+    fake(h)->device_calls++; device_latency();
+    uint64_t a = 0, p = 0;
+    for (int r = 0; r < n; r++)
+        for (int s = 0; s < 2; s++) {
+            begin[2 * r + s] = (uint32_t)a;
+            const uint32_t len = reads[r].read_len;
+            std::vector<char> seq(len + 160, 'N');
+            for (uint32_t q = 0; q < len; q++) seq[q] = s ? rc_char(fake(h)->dram[reads[r].read_addr + len - 1 - q]) : fake(h)->dram[reads[r].read_addr + q];
+            uint64_t used = 0;
+            const int got = dsoft_query(fake(h)->ix, seq.data(), len, 40, 20, 0, anchors + a, (int)(acap - a), pool + p, pcap - p, &used);
+            if (got < 0) return DARWIN_ERR_CAPACITY;
+            for (int i = 0; i < got; i++) { anchors[a + i].left_off += p; anchors[a + i].right_off += p; }
+            a += (uint64_t)got; p += used;
+        }
+    begin[2 * n] = (uint32_t)a; *na = a; *np = p;
+    return 0;
+}
 static const char* f_err(DarwinGpu*) { return "stand-in failure"; }
+
+static bool same_seed(const DarwinSeedAnchor& x, const uint64_t* px, const DarwinSeedAnchor& y, const uint64_t* py) {
+    return x.hit_offset == y.hit_offset && x.left_n == y.left_n && x.right_n == y.right_n &&
+           !memcmp(px + x.left_off, py + y.left_off, 8ull * x.left_n) && !memcmp(px + x.right_off, py + y.right_off, 8ull * x.right_n);
+}
 
 static bool same_aln(const DarwinAlnRes& a, const uint8_t* oa, const DarwinAlnRes& b, const uint8_t* ob) {
     if (a.n_ops != b.n_ops || a.cells != b.cells || a.reference_start_offset != b.reference_start_offset ||
@@ -56,11 +83,18 @@ extern "C" int combiner_selftest(const DarwinScoring* s, const char* dram, uint6
     std::vector<char> arena(dram_bytes, 'N');                         // the stand-in device starts empty: uploads must fill it
     fk.dram = arena.data(); fk.dram_bytes = dram_bytes; fk.device_calls = 0; fk.fail_filter = 0;
     DarwinGpu* h = reinterpret_cast<DarwinGpu*>(&fk);
-    GpuCalls calls{f_upload, f_tiles, f_filter, f_extend, f_err};
+    GpuCalls calls{f_upload, f_tiles, f_filter, f_extend, f_err, f_seed};
     GpuCombiner gc(h, calls);
+    // a small seed position table (k = 8) over the first chromosome named by the anchors, and the reads to seed
+    DsoftIndex ix;
+    const uint32_t chr_start = anchors[0].chr_start, chr_len = anchors[0].ref_len;
+    if (dsoft_index_build(&ix, dram, &chr_start, &chr_len, 1, chr_start + chr_len, 8, 3, 40, 64, 4)) return 4;
+    fk.ix = &ix;
+    std::vector<DarwinSeedRead> sreads(n_anchors);
+    for (int i = 0; i < n_anchors; i++) sreads[i] = DarwinSeedRead{anchors[i].read_addr, anchors[i].read_len, 0};
 
     // ground truth: one direct call each on the real arena
-    Fake truth; truth.sc = fk.sc; truth.dram = const_cast<char*>(dram); truth.dram_bytes = dram_bytes; truth.device_calls = 0; truth.fail_filter = 0;
+    Fake truth; truth.sc = fk.sc; truth.dram = const_cast<char*>(dram); truth.dram_bytes = dram_bytes; truth.device_calls = 0; truth.fail_filter = 0; truth.ix = &ix;
     DarwinGpu* ht = reinterpret_cast<DarwinGpu*>(&truth);
     const int words = 50;
     std::vector<DarwinTileRes> t_res(n_req); std::vector<uint64_t> t_tb((size_t)n_req * words);
@@ -73,6 +107,11 @@ extern "C" int combiner_selftest(const DarwinScoring* s, const char* dram, uint6
     for (int i = 0; i < n_anchors; i++) cap += 3ull * anchors[i].read_len;
     std::vector<uint8_t> a_ops(cap);
     if (f_extend(ht, &ep, anchors, n_anchors, pool, n_pool, a_res.data(), a_ops.data(), cap)) return 3;
+
+    std::vector<uint32_t> s_begin(2 * n_anchors + 1); std::vector<DarwinSeedAnchor> s_anc(1 << 14); std::vector<uint64_t> s_pool(1 << 22);
+    uint64_t s_na = 0, s_np = 0;
+    if (f_seed(ht, sreads.data(), n_anchors, s_begin.data(), s_anc.data(), s_anc.size(), &s_na, s_pool.data(), s_pool.size(), &s_np)) return 5;
+    if (s_na < (uint64_t)n_anchors) return 6;                    // the stand-in really finds the reads
 
     // the whole arena travels as upload spans attached to the FIRST request of every thread (in 3 pieces)
     std::atomic<int> bad(0);
@@ -96,6 +135,17 @@ extern "C" int combiner_selftest(const DarwinScoring* s, const char* dram, uint6
                     std::vector<DarwinAlnRes> r(hi - lo); std::vector<uint8_t> ops;
                     if (gc.extend(ep, none, anchors + lo, hi - lo, pool, n_pool, r.data(), &ops, &err)) bad |= 8;
                     else for (int i = lo; i < hi; i++) if (!same_aln(r[i - lo], ops.data(), a_res[i], a_ops.data())) bad |= 16; }
+                {   const int lo = (int)((int64_t)n_anchors * t / threads), hi = (int)((int64_t)n_anchors * (t + 1) / threads);
+                    std::vector<uint32_t> b; std::vector<DarwinSeedAnchor> a; std::vector<uint64_t> pl;
+                    if (gc.seed(none, sreads.data() + lo, hi - lo, &b, &a, &pl, &err)) bad |= 256;
+                    else {
+                        if (b.size() != 2 * (size_t)(hi - lo) + 1) bad |= 512;
+                        else for (int r = lo; r < hi; r++) for (int st = 0; st < 2; st++) {
+                            const uint32_t g0 = s_begin[2 * r + st], g1 = s_begin[2 * r + st + 1], m0 = b[2 * (r - lo) + st], m1 = b[2 * (r - lo) + st + 1];
+                            if (g1 - g0 != m1 - m0) { bad |= 512; continue; }
+                            for (uint32_t i = 0; i < g1 - g0; i++) if (!same_seed(a[m0 + i], pl.data(), s_anc[g0 + i], s_pool.data())) bad |= 1024;
+                        }
+                    } }
                 {   const int lo = (int)((int64_t)n_req * t / threads), hi = (int)((int64_t)n_req * (t + 1) / threads);
                     const int w = words - (t % 3);                      // callers may size their TB rows differently
                     std::vector<DarwinTileRes> r(hi - lo); std::vector<uint64_t> tb((size_t)(hi - lo) * w + 1);
@@ -111,6 +161,8 @@ extern "C" int combiner_selftest(const DarwinScoring* s, const char* dram, uint6
     for (auto& x : th) x.join();
     CombinerStats st = gc.stats();
     for (int k = 0; k < 3; k++) { stats_out[k] = st.device_calls[k]; stats_out[3 + k] = st.requests[k]; stats_out[6 + k] = st.max_merged[k]; }
+    stats_out[9] = st.device_calls[3]; stats_out[10] = st.requests[3]; stats_out[11] = st.max_merged[3];
+    dsoft_index_free(&ix);
     if (bad.load()) return 100 + bad.load();
     // errors reach every merged caller
     fk.fail_filter = 1;

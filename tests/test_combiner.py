@@ -39,13 +39,14 @@ def test_combiner_merges_and_scatters(selftest_lib, threads):
     cands["offset"] = np.maximum(anchors["query_pos"].astype(np.int64) - 40, 0)
     cands["strand"] = anchors["strand"]
     sc = abi.Scoring.from_values()
-    stats = np.zeros(9, np.uint64)
+    stats = np.zeros(12, np.uint64)
     rc = selftest_lib.combiner_selftest(C.byref(sc), abi.ptr(dram), C.c_uint64(len(dram)), abi.ptr(req), len(req),
                                         abi.ptr(cands), len(cands), abi.ptr(anchors), len(anchors), abi.ptr(hits),
                                         C.c_uint64(len(hits)), 320, 128, threads, abi.ptr(stats))
     assert rc == 0, rc
     calls, requests, merged = stats[0:3], stats[3:6], stats[6:9]
     assert list(requests) == [threads * 4, threads * 3, threads * 3]        # tiles: 3 rounds + the upload-only request
+    assert stats[10] == threads * 3 and (threads == 1 or (stats[9] < stats[10] and stats[11] >= 2))      # seeding requests
     if threads == 1:
         assert list(calls) == list(requests)
     else:
