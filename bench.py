@@ -247,27 +247,60 @@ def main():
     sampler.join(timeout=3)
 
     # ---- secondary: whole anchors through extender_body (in-kernel tile walking), stock params.cfg T=384/O=64 ----
+    # Every rank extends its own shard of reads against its own replica of the packed reference (no
+    # data-path collective); reads/s = all ranks' reads / slowest rank.
     extend_info = None
-    if args.extend_reads > 0 and rank == 0:
+    seed_info = None
+    if args.extend_reads > 0:
         from darwin_b200 import synth
-        ex_arena, ex_anchors, ex_hits = synth.anchor_batch(7, args.extend_reads, 10000, 4000000)
+        ref_len = 4000000
+        ex_arena, ex_anchors, ex_hits = synth.anchor_batch(7 + rank, args.extend_reads, 10000, ref_len)
         ex = darwin_b200.Processor(len(ex_arena), local)
         ex.InitializeScoringParameters(sc)
         ex.InitializeReferenceMemory(0, ex_arena)
-        ex.extender_body(ex_anchors[:64], ex_hits, 384, 64, 0)                     # warm-up
+        ex.extender_body(ex_anchors, ex_hits, 384, 64, 0)                          # warm-up at full size (buffers grown once)
         ex_out = (pinned((len(ex_anchors),), abi.ALN_RES), pinned((int(ex_anchors["read_len"].sum()) * 2,), np.uint8))
+        barrier()
         t0 = time.perf_counter()
         ex_res, ex_ops = ex.extender_body(ex_anchors, ex_hits, 384, 64, 0, out=ex_out)   # anchors + hits H2D, ops D2H
         ex_wall = time.perf_counter() - t0
         ex_st = ex.stats()
         ex_cells = float(ex_res["cells"].sum())
-        extend_info = {"workload": "extend_10kbp_T384_O64", "reads": int(args.extend_reads), "anchors": int(len(ex_anchors)),
-                       "aligned": int((ex_res["flags"] & 1).sum()), "tiles": int(ex_res["n_tiles"].sum()),
-                       "cells": ex_cells, "kernel_ms": ex_st.last_kernel_ms,
-                       "gcups_kernel": ex_cells / (ex_st.last_kernel_ms * 1e-3) / 1e9,
-                       "reads_per_s_kernel": args.extend_reads / (ex_st.last_kernel_ms * 1e-3),
-                       "reads_per_s_e2e": args.extend_reads / ex_wall,
-                       "note": "one anchor per read at its true locus, synthetic chained hits; host D-SOFT not included"}
+        # D-SOFT on the GPU for the same reads: seed position table build + seeding of both strands
+        chroms = np.zeros(1, abi.CHROM)
+        chroms["start"], chroms["len_unpadded"] = 128, ref_len
+        t0 = time.perf_counter()
+        ex.build_seed_index(abi.SeedParams.stock(), chroms, 128 + ref_len + ((-ref_len) % 128))
+        ix_s = time.perf_counter() - t0
+        sreads = np.zeros(len(ex_anchors), abi.SEED_READ)
+        sreads["read_addr"], sreads["read_len"] = ex_anchors["read_addr"], ex_anchors["read_len"]
+        ex.seeder_body(sreads)                                                     # warm-up at full size
+        barrier()
+        t0 = time.perf_counter()
+        sb, sa, sp = ex.seeder_body(sreads)
+        seed_wall = time.perf_counter() - t0
+        seed_ms = ex.stats().last_kernel_ms
+        agg = torch.tensor([ex_st.last_kernel_ms, ex_wall * 1e3, seed_ms, seed_wall * 1e3], dtype=torch.float64, device=dev)
+        tot = torch.tensor([ex_cells, float(int((ex_res["flags"] & 1).sum())), float(int(ex_res["n_tiles"].sum())), float(len(sa))],
+                           dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        k_ms, w_ms, sk_ms, sw_ms = [float(x) for x in agg]
+        cells_all, aligned_all, tiles_all, seed_anchors_all = [float(x) for x in tot]
+        reads_all = args.extend_reads * world
+        extend_info = {"workload": "extend_10kbp_T384_O64", "reads": int(reads_all), "reads_per_gpu": int(args.extend_reads),
+                       "aligned": int(aligned_all), "tiles": int(tiles_all), "cells": cells_all, "kernel_ms": k_ms,
+                       "gcups_kernel": cells_all / (k_ms * 1e-3) / 1e9,
+                       "reads_per_s_kernel": reads_all / (k_ms * 1e-3),
+                       "reads_per_s_e2e": reads_all / (w_ms * 1e-3),
+                       "note": "one anchor per read at its true locus, synthetic chained hits; every rank extends its own shard "
+                               "(max over ranks); D-SOFT not included"}
+        seed_info = {"workload": "dsoft_10kbp_k14_w3", "reads": int(reads_all), "index_build_s": ix_s, "reference_bp": ref_len,
+                     "kernel_ms": sk_ms, "reads_per_s_kernel": reads_all / (sk_ms * 1e-3), "reads_per_s_e2e": reads_all / (sw_ms * 1e-3),
+                     "anchors": int(seed_anchors_all),
+                     "note": "both strands of every read: minimizers, table look-ups, bin counting, candidates + chained hits "
+                             "(darwin_gpu_seed); e2e includes the D2H of all chained hits"}
         ex.close()
 
     # ---- secondary: first-tile filter (128x128 score-only, max-cell mode; filter.cpp:28-122) through darwin_gpu_filter ----
@@ -340,6 +373,8 @@ def main():
             line["extend"] = extend_info
         if filter_info:
             line["filter"] = filter_info
+        if seed_info:
+            line["seed"] = seed_info
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_leg(arena, req, args.cpu_seconds)
         print(json.dumps(line))
