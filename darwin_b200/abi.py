@@ -64,6 +64,15 @@ class SeedParams(C.Structure):
         return cls(14, 3, 64, 26, 1000, 40, 4, do_overlap)
 
 
+class AlignParams(C.Structure):
+    """What darwin_gpu_align_reads needs beyond the seeding parameters: params.cfg [GACT_first_tile], [GACT_extend]."""
+    _fields_ = [("filter", FilterParams), ("extend", ExtendParams), ("slope_threshold", C.c_float), ("reserved", C.c_int32)]
+
+    @classmethod
+    def stock(cls, tile_size=384, tile_overlap=64, do_overlap=0):
+        return cls(FilterParams(128, 60, 1000, 0), ExtendParams(tile_size, tile_overlap, do_overlap, 0), 0.05, 0)
+
+
 class GpuStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("tiles_fast", C.c_uint64), ("tiles_exact", C.c_uint64),
                 ("tiles_rerun", C.c_uint64), ("cells", C.c_uint64), ("cells_exact", C.c_uint64), ("tiles_xfast", C.c_uint64), ("last_kernel_ms", C.c_float), ("reserved", C.c_float),

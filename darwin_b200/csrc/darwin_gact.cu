@@ -10,6 +10,7 @@
 #include <vector>
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 
 #include "gact_common.cuh"
 #include "gact_exact.cuh"
@@ -994,7 +995,7 @@ int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, i
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 #define TMARK(name) do { if (tdbg) { double t_ = now_ms(); fprintf(stderr, "  [extend] %-18s %.2f ms\n", name, t_ - tlast); tlast = t_; } } while (0)
 
-static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n, uint64_t n_hits,
+static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n, const uint64_t* d_pool, uint64_t n_hits,
                         DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes, uint64_t* used_out, float* kernel_ms) {
     const bool tdbg = getenv("DARWIN_GPU_TIMING") != nullptr; double tlast = now_ms();
     // op slots: left part holds the (reversed) left extension, right part the right extension
@@ -1028,7 +1029,7 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
                                                            xfast_trace_bytes(p->tile_size, p->tile_size))))))) return rc;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * kCounters, h->stream));
     ExtendArgs ea;
-    ea.arena = h->d_arena; ea.anchors = (const DarwinAnchor*)h->d_buf[0]; ea.hit_pool = (const uint64_t*)h->d_buf[2];
+    ea.arena = h->d_arena; ea.anchors = (const DarwinAnchor*)h->d_buf[0]; ea.hit_pool = d_pool;
     ea.res = (DarwinAlnRes*)h->d_buf[1]; ea.ops = (uint8_t*)h->d_buf[3];
     ea.slot_base = (const uint64_t*)h->d_buf[4]; ea.slot_left = (const uint32_t*)h->d_buf[5]; ea.slot_size = (const uint32_t*)h->d_buf[6];
     ea.dbg = nullptr;
@@ -1088,23 +1089,13 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     return DARWIN_OK;
 }
 
-int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n,
-                      const uint64_t* hit_pool, uint64_t n_hits,
+// all anchors of a call, in chunks that bound the op-slot memory; d_pool = device-resident hit pool
+static int extend_all(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n, const uint64_t* d_pool, uint64_t n_hits,
                       DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes) {
-    if (!h || !p || n < 0 || (n && (!anchors || !res))) return DARWIN_ERR_INVALID;
-    if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
-    if (p->tile_size < 16 || p->tile_size > 1024 || p->tile_overlap < 0 || p->tile_overlap >= p->tile_size) {
-        h->err = "tile_size must be in [16,1024] and 0 <= tile_overlap < tile_size"; return DARWIN_ERR_INVALID;
-    }
-    if (n == 0) return DARWIN_OK;
-    CK(cudaSetDevice(h->device));
-    int rc;
-    if ((rc = grow_dev(h, 2, (size_t)std::max<uint64_t>(n_hits, 1) * 8))) return rc;
-    if (n_hits) CK(cudaMemcpyAsync(h->d_buf[2], hit_pool, n_hits * 8, cudaMemcpyHostToDevice, h->stream));
-    // Anchors go to the device in chunks so that the op slots (about 2 bytes per read base per anchor) stay bounded.
     const uint64_t kSlotBudget = 6ull << 30;
     uint64_t used_total = 0;
     float kernel_ms = 0.f;
+    int rc;
     for (int lo = 0; lo < n;) {
         int hi = lo; uint64_t bytes = 0;
         while (hi < n && hi - lo < (1 << 20)) {
@@ -1113,7 +1104,7 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
             bytes += sz; hi++;
         }
         uint64_t used = 0;
-        rc = extend_chunk(h, p, anchors + lo, hi - lo, n_hits, res + lo, ops_pool ? ops_pool + used_total : nullptr,
+        rc = extend_chunk(h, p, anchors + lo, hi - lo, d_pool, n_hits, res + lo, ops_pool ? ops_pool + used_total : nullptr,
                           ops_pool_bytes - used_total, &used, &kernel_ms);
         if (rc) return rc;
         for (int i = lo; i < hi; i++) res[i].ops_offset += used_total;
@@ -1122,6 +1113,113 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     }
     h->stats.last_kernel_ms = kernel_ms;
     return DARWIN_OK;
+}
+
+static int check_extend_params(DarwinGpu* h, const DarwinExtendParams* p) {
+    if (p->tile_size < 16 || p->tile_size > 1024 || p->tile_overlap < 0 || p->tile_overlap >= p->tile_size) {
+        h->err = "tile_size must be in [16,1024] and 0 <= tile_overlap < tile_size"; return DARWIN_ERR_INVALID;
+    }
+    return DARWIN_OK;
+}
+
+int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n,
+                      const uint64_t* hit_pool, uint64_t n_hits,
+                      DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes) {
+    if (!h || !p || n < 0 || (n && (!anchors || !res))) return DARWIN_ERR_INVALID;
+    if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
+    int rc;
+    if ((rc = check_extend_params(h, p))) return rc;
+    if (n == 0) return DARWIN_OK;
+    CK(cudaSetDevice(h->device));
+    if ((rc = grow_dev(h, 2, (size_t)std::max<uint64_t>(n_hits, 1) * 8))) return rc;
+    if (n_hits) CK(cudaMemcpyAsync(h->d_buf[2], hit_pool, n_hits * 8, cudaMemcpyHostToDevice, h->stream));
+    // Anchors go to the device in chunks so that the op slots (about 2 bytes per read base per anchor) stay bounded.
+    return extend_all(h, p, anchors, n, (const uint64_t*)h->d_buf[2], n_hits, res, ops_pool, ops_pool_bytes);
+}
+
+// The whole reference-guided pipeline for n resident reads in one call: D-SOFT (seeder.cpp / seed_pos_table.cpp:252-553),
+// first tiles + score / overlap tests (filter.cpp:28-223), slope filter (filter.cpp:227-289), extension
+// (extender.cpp:9-1065).  The chained hits never leave the device: the extension kernel reads them from the seeding
+// pool; only 32 bytes per candidate come up for the slope filter.  Output order == what extender_body is handed:
+// forward-strand locations (sorted by read, score desc, ...), then reverse-strand ones.
+int darwin_gpu_align_reads(DarwinGpu* h, const DarwinAlignParams* p, const DarwinSeedRead* reads, int n,
+                           DarwinAnchor* anchors_out, DarwinAlnRes* res, uint64_t cap, uint64_t* n_out,
+                           uint8_t* ops_pool, uint64_t ops_pool_bytes) {
+    if (!h || !p || n < 0 || !n_out || (n && !reads)) return DARWIN_ERR_INVALID;
+    if (!h->have_scoring || !h->seed_ix.ready) { h->err = "scoring / seed position table not initialised"; return DARWIN_ERR_NOT_READY; }
+    *n_out = 0;
+    int rc;
+    if ((rc = check_extend_params(h, &p->extend))) return rc;
+    if (n == 0) return DARWIN_OK;
+    CK(cudaSetDevice(h->device));
+    const SeedIndex& ix = h->seed_ix;
+    std::vector<uint32_t> begin(2 * (size_t)n + 1);
+    std::vector<DarwinSeedAnchor> sa;
+    DevBuf d_pool;
+    uint64_t n_sa = 0, n_pool = 0;
+    if ((rc = seed_query(h, ix, reads, n, begin.data(), nullptr, 0, &n_sa, nullptr, 0, &n_pool, &d_pool, &sa))) return rc;
+    const float seed_ms = h->stats.last_kernel_ms;
+    if (n_pool > 0xFFFFFFFFull) { h->err = "batch too large: more than 2^32 chained hits"; return DARWIN_ERR_INVALID; }
+    if (n_sa == 0) return DARWIN_OK;
+    // first tiles of every candidate (filter.cpp:44-56 look-ups)
+    std::vector<DarwinFilterCand> cands(n_sa);
+    std::vector<int> chr_of(n_sa);
+    for (int r = 0; r < n; r++)
+        for (int s = 0; s < 2; s++)
+            for (uint32_t i = begin[2 * r + s]; i < begin[2 * r + s + 1]; i++) {
+                const uint32_t hit = (uint32_t)(sa[i].hit_offset >> 32), offset = (uint32_t)sa[i].hit_offset;
+                const size_t c = std::upper_bound(ix.chr_start.begin(), ix.chr_start.end(), hit) - ix.chr_start.begin() - 1;
+                DarwinFilterCand& k = cands[i];
+                k = DarwinFilterCand{};
+                k.read_addr = reads[r].read_addr; k.hit = hit; k.offset = offset; k.chr_start = ix.chr_start[c]; k.chr_len = ix.chr_len[c];
+                k.read_len = reads[r].read_len; k.strand = (uint8_t)s;
+                chr_of[i] = (int)c;
+            }
+    std::vector<DarwinFilterRes> fres(n_sa);
+    if ((rc = darwin_gpu_filter(h, &p->filter, cands.data(), (int)n_sa, fres.data()))) return rc;
+    const float filter_ms = h->stats.last_kernel_ms;
+    // score + overlap tests, then the slope filter per strand (filter.cpp:87-124, :227-289; same sort, same float test)
+    struct Loc { int read_num, score; uint32_t rpos, qpos; uint32_t cand; };
+    std::vector<DarwinAnchor> anchors;
+    for (int s = 0; s < 2; s++) {
+        std::vector<Loc> locs;
+        for (int r = 0; r < n; r++)
+            for (uint32_t i = begin[2 * r + s]; i < begin[2 * r + s + 1]; i++)
+                if ((fres[i].flags & (DARWIN_FILTER_SCORE_OK | DARWIN_FILTER_OVERLAP_OK)) == (DARWIN_FILTER_SCORE_OK | DARWIN_FILTER_OVERLAP_OK))
+                    locs.push_back(Loc{r, fres[i].score, fres[i].reference_pos, fres[i].query_pos, i});
+        std::sort(locs.begin(), locs.end(), [](const Loc& a, const Loc& b) {
+            return ((a.read_num < b.read_num) || ((a.read_num == b.read_num) && (a.score > b.score)) ||
+                    ((a.read_num == b.read_num) && (a.score == b.score) && (a.rpos < b.rpos)) ||
+                    ((a.read_num == b.read_num) && (a.score == b.score) && (a.rpos == b.rpos) && (a.qpos < b.qpos)));
+        });
+        for (size_t a = 0; a < locs.size(); a++) {
+            if (locs[a].read_num == -1) continue;
+            const Loc& l = locs[a];
+            const DarwinSeedAnchor& sd = sa[l.cand];
+            DarwinAnchor an{};
+            an.read_addr = reads[l.read_num].read_addr; an.reference_pos = l.rpos; an.query_pos = l.qpos;
+            an.chr_start = cands[l.cand].chr_start; an.ref_len = cands[l.cand].chr_len; an.read_len = reads[l.read_num].read_len;
+            an.read_num = l.read_num; an.chr_id = chr_of[l.cand]; an.score = l.score;
+            an.left_hits_off = (uint32_t)sd.left_off; an.left_hits_n = sd.left_n;
+            an.right_hits_off = (uint32_t)sd.right_off; an.right_hits_n = sd.right_n;
+            an.strand = (uint8_t)s;
+            anchors.push_back(an);
+            for (size_t b = a + 1; b < locs.size(); b++) {
+                if (locs[b].read_num == -1) continue;
+                if (locs[b].read_num != l.read_num) break;
+                const float r1 = (float)l.rpos, q1 = (float)l.qpos, r2 = (float)locs[b].rpos, q2 = (float)locs[b].qpos;
+                if (std::abs((r1 - r2) / (q1 - q2) - 1) <= p->slope_threshold) locs[b].read_num = -1;
+            }
+        }
+    }
+    *n_out = anchors.size();
+    if (anchors.size() > cap) { h->err = "align output capacity: need " + std::to_string(anchors.size()); return DARWIN_ERR_CAPACITY; }
+    if (anchors.empty()) return DARWIN_OK;
+    if (!anchors_out || !res) return DARWIN_ERR_INVALID;
+    memcpy(anchors_out, anchors.data(), anchors.size() * sizeof(DarwinAnchor));
+    rc = extend_all(h, &p->extend, anchors.data(), (int)anchors.size(), d_pool.as<uint64_t>(), n_pool, res, ops_pool, ops_pool_bytes);
+    h->stats.last_kernel_ms += seed_ms + filter_ms;
+    return rc;
 }
 
 int darwin_gpu_seed_index(DarwinGpu* h, const DarwinSeedParams* p, const DarwinChrom* chroms, int n_chroms, uint64_t reference_size) {

@@ -15,6 +15,7 @@
 //   chain_kernel       one thread per candidate: greedy collinear chains to the left and right of the anchor
 //   order_kernel       one thread per strand: final order (chained hits descending, hit_offset ascending)
 #pragma once
+#include <vector>
 #include "gact_common.cuh"
 
 namespace dsoft {
@@ -409,4 +410,5 @@ struct SeedIndex {
     uint32_t* d_buckets = nullptr; uint64_t n_buckets = 0;
     uint32_t* d_positions = nullptr; uint64_t n_positions = 0;
     bool ready = false, owner = true;
+    std::vector<uint32_t> chr_start, chr_len;       // host copy: Index::chr_coord / Index::chr_len (padded)
 };

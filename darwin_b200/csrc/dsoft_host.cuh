@@ -89,6 +89,13 @@ static int seed_index_build(DarwinGpu* h, SeedIndex& ix, const DarwinSeedParams*
     CKS(cudaGetLastError());
     h->stats.kernel_launches += 2;
     CKS(cudaStreamSynchronize(h->stream));
+    // chromosome table for the resident pipeline: padded lengths = distance to the next chromosome (Index::chr_len)
+    ix.chr_start.resize(n_chroms); ix.chr_len.resize(n_chroms);
+    for (int c = 0; c < n_chroms; c++) {
+        ix.chr_start[c] = chroms[c].start;
+        const uint64_t next = (c + 1 < n_chroms) ? chroms[c + 1].start : reference_size;
+        ix.chr_len[c] = (uint32_t)(next > chroms[c].start ? next - chroms[c].start : chroms[c].len_unpadded);
+    }
     ix.ready = true;
     return DARWIN_OK;
 }
@@ -111,9 +118,12 @@ __global__ void widen_kernel(const uint32_t* __restrict__ src, uint32_t n, uint6
     if (i < n) dst[i] = src[i];
 }
 
+// keep_pool != nullptr: the chained-hit pool stays on the device (handed to *keep_pool) and the anchors go to *anchor_vec
+// (resized here) -- the resident pipeline (darwin_gpu_align_reads); otherwise everything is copied to the caller's buffers.
 static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* reads, int n, uint32_t* anchor_begin,
                       DarwinSeedAnchor* anchors, uint64_t anchors_cap, uint64_t* n_anchors,
-                      uint64_t* pool, uint64_t pool_cap, uint64_t* n_pool) {
+                      uint64_t* pool, uint64_t pool_cap, uint64_t* n_pool,
+                      DevBuf* keep_pool = nullptr, std::vector<DarwinSeedAnchor>* anchor_vec = nullptr) {
     using namespace dsoft;
     const SeedConst sc = ix.sc;
     const int ns = 2 * n;
@@ -198,7 +208,8 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     CKS(cudaStreamSynchronize(h->stream));
     const uint64_t need_pool = n_win + n_cands;
     *n_pool = need_pool;
-    if (n_cands > anchors_cap || need_pool > pool_cap) { h->err = "seed output capacity: need " + std::to_string(n_cands) + " anchors, " + std::to_string(need_pool) + " pool entries"; return DARWIN_ERR_CAPACITY; }
+    if (keep_pool) { anchor_vec->resize(n_cands); anchors = anchor_vec->data(); }
+    else if (n_cands > anchors_cap || need_pool > pool_cap) { h->err = "seed output capacity: need " + std::to_string(n_cands) + " anchors, " + std::to_string(need_pool) + " pool entries"; return DARWIN_ERR_CAPACITY; }
     DevBuf d_w0, d_w1, d_pool, d_tanc, d_anc, d_tmp2;
     CKS(d_w0.alloc(sizeof(uint64_t) * n_win, h->stream)); CKS(d_w1.alloc(sizeof(uint64_t) * n_win, h->stream)); CKS(d_pool.alloc(sizeof(uint64_t) * need_pool, h->stream));
     CKS(d_tanc.alloc(sizeof(DarwinSeedAnchor) * n_cands, h->stream)); CKS(d_anc.alloc(sizeof(DarwinSeedAnchor) * n_cands, h->stream));
@@ -218,7 +229,8 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     CKS(cudaEventRecord(h->ev1, h->stream));
     h->stats.kernel_launches += 7;
     CKS(cudaMemcpyAsync(anchors, d_anc.p, sizeof(DarwinSeedAnchor) * n_cands, cudaMemcpyDeviceToHost, h->stream));
-    CKS(cudaMemcpyAsync(pool, d_pool.p, sizeof(uint64_t) * need_pool, cudaMemcpyDeviceToHost, h->stream));
+    if (keep_pool) { keep_pool->p = d_pool.p; keep_pool->st = h->stream; d_pool.p = nullptr; }
+    else CKS(cudaMemcpyAsync(pool, d_pool.p, sizeof(uint64_t) * need_pool, cudaMemcpyDeviceToHost, h->stream));
     CKS(cudaStreamSynchronize(h->stream));
     CKS(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
     return DARWIN_OK;

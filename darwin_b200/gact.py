@@ -49,6 +49,8 @@ def load_library():
                                                  C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
         L.darwin_gpu_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64),
                                       C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.darwin_gpu_align_reads.argtypes = [C.c_void_p, C.POINTER(abi.AlignParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64]
         L.darwin_gpu_stats.argtypes = [C.c_void_p, C.POINTER(abi.GpuStats)]
         L.darwin_gpu_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _lib = L
@@ -57,7 +59,7 @@ def load_library():
 
 EXPORTS = ("darwin_gpu_create", "darwin_gpu_create_shared", "darwin_gpu_destroy", "darwin_gpu_set_scoring", "darwin_gpu_upload",
            "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_filter", "darwin_gpu_seed_index",
-           "darwin_gpu_seed_index_share", "darwin_gpu_seed_index_read", "darwin_gpu_seed", "darwin_gpu_stats", "darwin_gpu_int_peak",
+           "darwin_gpu_seed_index_share", "darwin_gpu_seed_index_read", "darwin_gpu_seed", "darwin_gpu_align_reads", "darwin_gpu_stats", "darwin_gpu_int_peak",
            "darwin_gpu_last_error", "darwin_gpu_version")
 
 
@@ -167,6 +169,34 @@ class Processor:
             self._check(rc)
             return begin, anchors[:na.value], pool[:npool.value]
         raise DarwinGpuError(abi.ERR_CAPACITY, "seed output capacity")
+
+    # seeder_body -> filter_body -> extender_body of main.cpp:590-624 in one resident call
+    def align_reads(self, reads, params=None, out=None):
+        """reads: SEED_READ array (resident).  Returns (anchors, DarwinAlnRes, ops): the locations handed to the extension
+        (anchors[i].read_num indexes `reads`; forward-strand locations first) and their alignments."""
+        rd = np.ascontiguousarray(reads, dtype=abi.SEED_READ)
+        prm = params or abi.AlignParams.stock()
+        n = len(rd)
+        cap = max(64, 8 * n)
+        ops_cap = int(rd["read_len"].astype(np.int64).sum()) * 6 + 65536
+        for _ in range(4):
+            if out is not None:
+                anchors, res, ops = out
+                cap, ops_cap = min(len(anchors), len(res)), len(ops)
+            else:
+                anchors, res, ops = np.empty(cap, abi.ANCHOR), np.empty(cap, abi.ALN_RES), np.empty(ops_cap, np.uint8)
+            n_out = C.c_uint64(0)
+            rc = self.lib.darwin_gpu_align_reads(self.h, C.byref(prm), abi.ptr(rd), n, abi.ptr(anchors), abi.ptr(res), C.c_uint64(cap),
+                                                 C.byref(n_out), abi.ptr(ops), C.c_uint64(ops_cap))
+            if rc == abi.ERR_CAPACITY and out is None:
+                if n_out.value > cap:
+                    cap = int(n_out.value)
+                else:
+                    ops_cap *= 2
+                continue
+            self._check(rc)
+            return anchors[:n_out.value], res[:n_out.value], ops
+        raise DarwinGpuError(abi.ERR_CAPACITY, "align output capacity")
 
     # the tile part of filter_body::operator() (filter.cpp:28-122, :131-223) for a batch of D-SOFT candidates
     def filter_body(self, cands, first_tile_size=128, first_tile_score_threshold=60, min_overlap=1000, out=None):

@@ -34,18 +34,21 @@ struct GpuCalls {
                   DarwinAlnRes*, uint8_t*, uint64_t);
     const char* (*last_error)(DarwinGpu*);
     int (*seed)(DarwinGpu*, const DarwinSeedRead*, int, uint32_t*, DarwinSeedAnchor*, uint64_t, uint64_t*, uint64_t*, uint64_t, uint64_t*);
+    int (*align)(DarwinGpu*, const DarwinAlignParams*, const DarwinSeedRead*, int, DarwinAnchor*, DarwinAlnRes*, uint64_t, uint64_t*,
+                 uint8_t*, uint64_t);
     static GpuCalls library() {
-        return GpuCalls{darwin_gpu_upload, darwin_gpu_tiles, darwin_gpu_filter, darwin_gpu_extend, darwin_gpu_last_error, darwin_gpu_seed};
+        return GpuCalls{darwin_gpu_upload, darwin_gpu_tiles, darwin_gpu_filter, darwin_gpu_extend, darwin_gpu_last_error, darwin_gpu_seed,
+                        darwin_gpu_align_reads};
     }
 };
 
 struct UploadSpan { uint64_t arena_addr; const char* ascii; uint64_t n; };
 
 struct CombinerStats {
-    uint64_t device_calls[4];   // [0] tiles, [1] filter, [2] extend, [3] seed: calls that reached the device
-    uint64_t requests[4];       // requests submitted by host threads
-    uint64_t items[4];          // tiles / candidates / anchors / reads
-    uint64_t max_merged[4];     // largest number of requests served by one device call
+    uint64_t device_calls[5];   // [0] tiles, [1] filter, [2] extend, [3] seed, [4] align: calls that reached the device
+    uint64_t requests[5];       // requests submitted by host threads
+    uint64_t items[5];          // tiles / candidates / anchors / reads / reads
+    uint64_t max_merged[5];     // largest number of requests served by one device call
 };
 
 class GpuCombiner {
@@ -78,6 +81,13 @@ public:
         Request r; r.kind = SEED; r.up = &up; r.sreads = reads; r.n = n; r.sbegin = begin; r.sanchors = anchors; r.spool = pool;
         return run(r, err);
     }
+    // == seeder_body + filter_body + extender_body for one caller's reads (darwin_gpu_align_reads); anchors[i].read_num
+    // indexes the caller's reads, res[i].ops_offset its `ops`
+    int align(const DarwinAlignParams& p, const std::vector<UploadSpan>& up, const DarwinSeedRead* reads, int n,
+              std::vector<DarwinAnchor>* anchors, std::vector<DarwinAlnRes>* res, std::vector<uint8_t>* ops, std::string* err) {
+        Request r; r.kind = ALIGN; r.ap = p; r.up = &up; r.sreads = reads; r.n = n; r.aanchors = anchors; r.ares_v = res; r.ops = ops;
+        return run(r, err);
+    }
     // == g_InitializeReferenceMemory / g_InitializeReadMemory from any thread (rides along with the next tile batch)
     int upload(const std::vector<UploadSpan>& up, std::string* err) {
         Request r; r.kind = TILES; r.do_tb = 0; r.up = &up; r.n = 0;
@@ -87,7 +97,7 @@ public:
     DarwinGpu* handle() const { return h_; }
 
 private:
-    enum Kind { TILES = 0, FILTER = 1, EXTEND = 2, SEED = 3 };
+    enum Kind { TILES = 0, FILTER = 1, EXTEND = 2, SEED = 3, ALIGN = 4 };
     struct Request {
         Kind kind; int n = 0; bool done = false; int rc = 0; std::string err;
         const std::vector<UploadSpan>* up = nullptr;
@@ -101,6 +111,8 @@ private:
         // seed
         const DarwinSeedRead* sreads = nullptr; std::vector<uint32_t>* sbegin = nullptr;
         std::vector<DarwinSeedAnchor>* sanchors = nullptr; std::vector<uint64_t>* spool = nullptr;
+        // align
+        DarwinAlignParams ap{}; std::vector<DarwinAnchor>* aanchors = nullptr; std::vector<DarwinAlnRes>* ares_v = nullptr;
     };
 
     static bool mergeable(const Request& a, const Request& b) {
@@ -108,6 +120,7 @@ private:
         if (a.kind == TILES) return a.do_tb == b.do_tb;
         if (a.kind == FILTER) return memcmp(&a.fp, &b.fp, sizeof(a.fp)) == 0;
         if (a.kind == SEED) return true;
+        if (a.kind == ALIGN) return memcmp(&a.ap, &b.ap, sizeof(a.ap)) == 0;
         return memcmp(&a.ep, &b.ep, sizeof(a.ep)) == 0;
     }
 
@@ -191,6 +204,36 @@ private:
             if (rc) { fail_all(batch, rc, "darwin_gpu_filter"); return; }
             size_t at = 0;
             for (auto* b : batch) { if (b->n) memcpy(b->fres, res.data() + at, sizeof(DarwinFilterRes) * (size_t)b->n); at += (size_t)b->n; }
+        } else if (k == ALIGN) {
+            std::vector<DarwinSeedRead> reads; reads.reserve(total);
+            uint64_t bases = 0;
+            for (auto* b : batch) { reads.insert(reads.end(), b->sreads, b->sreads + b->n); for (int i = 0; i < b->n; i++) bases += b->sreads[i].read_len; }
+            uint64_t cap = std::max<uint64_t>(64, 8 * total), ops_cap = 6 * bases + 65536, n_out = 0;
+            std::vector<DarwinAnchor> anchors; std::vector<DarwinAlnRes> res; std::vector<uint8_t> ops;
+            int rc = DARWIN_ERR_CAPACITY;
+            for (int attempt = 0; attempt < 4 && rc == DARWIN_ERR_CAPACITY; attempt++) {
+                anchors.resize(cap); res.resize(cap); ops.resize(ops_cap);
+                rc = c_.align(h_, &batch[0]->ap, reads.data(), (int)total, anchors.data(), res.data(), cap, &n_out, ops.data(), ops_cap);
+                if (rc == DARWIN_ERR_CAPACITY) { if (n_out > cap) cap = n_out; else ops_cap *= 2; }
+            }
+            if (rc) { fail_all(batch, rc, "darwin_gpu_align_reads"); return; }
+            // every caller's locations are contiguous inside the forward part and inside the reverse part (sorted by read)
+            size_t at = 0;
+            for (auto* b : batch) {
+                b->aanchors->clear(); b->ares_v->clear(); b->ops->clear();
+                for (uint64_t i = 0; i < n_out; i++) {
+                    const int rn = anchors[i].read_num;
+                    if (rn < (int)at || rn >= (int)(at + (size_t)b->n)) continue;
+                    DarwinAnchor a = anchors[i]; a.read_num = rn - (int)at;
+                    DarwinAlnRes r = res[i];
+                    const bool has = (r.flags & DARWIN_ALN_EMITTED) && !(r.flags & DARWIN_ALN_OPS_OVERFLOW) && r.n_ops;
+                    const uint64_t off = b->ops->size();
+                    if (has) b->ops->insert(b->ops->end(), ops.begin() + r.ops_offset, ops.begin() + r.ops_offset + r.n_ops);
+                    r.ops_offset = off;
+                    b->aanchors->push_back(a); b->ares_v->push_back(r);
+                }
+                at += (size_t)b->n;
+            }
         } else if (k == SEED) {
             std::vector<DarwinSeedRead> reads; reads.reserve(total);
             for (auto* b : batch) reads.insert(reads.end(), b->sreads, b->sreads + b->n);

@@ -103,7 +103,7 @@ CombinerStats combiner_stats_total() {
     CombinerStats t; memset(&t, 0, sizeof(t));
     for (auto c : g_combiners) {
         const CombinerStats s = c->stats();
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 5; k++) {
             t.device_calls[k] += s.device_calls[k]; t.requests[k] += s.requests[k]; t.items[k] += s.items[k];
             if (s.max_merged[k] > t.max_merged[k]) t.max_merged[k] = s.max_merged[k];
         }
@@ -188,6 +188,48 @@ static void to_anchor(const ExtendLocations& l, const Read& rd, int strand, std:
     a.strand = (uint8_t)strand;
 }
 
+// One extended anchor -> ExtendAlignments as extender_body would have pushed it (graph.h:97-121): offsets, strand,
+// AlignmentScore and the gapped strings rebuilt from the op string (extender.cpp:287-323 / :434-458).
+static void emit_alignment(const DarwinAnchor& a, const DarwinAlnRes& r, const std::vector<uint8_t>& ops, const std::vector<Read>& reads,
+                           extend_data& output) {
+    if (!(r.flags & DARWIN_ALN_EMITTED)) return;
+    if (r.flags & DARWIN_ALN_OPS_OVERFLOW) fail_msg(DARWIN_ERR_CAPACITY, "gpu_extender_body", "op string overflow");
+    const Read& rd = reads[a.read_num];
+    const char* qchars = a.strand ? rd.rc_seq.data() : rd.seq.data();        // extender.cpp:243 / :758
+    ExtendAlignments e;
+    e.read_num = a.read_num; e.chr_id = a.chr_id;
+    e.reference_start_offset = r.reference_start_offset; e.reference_end_offset = r.reference_end_offset;
+    e.query_start_offset = r.query_start_offset; e.query_end_offset = r.query_end_offset;
+    e.curr_reference_offset = r.reference_end_offset + 1; e.curr_query_offset = r.query_end_offset + 1;
+    e.reference_start_addr = a.chr_start; e.query_start_addr = (uint32_t)a.read_addr;
+    e.reference_length = a.ref_len; e.query_length = a.read_len;
+    e.left_extension_done = 1; e.right_extension_done = 1;
+    e.used_large_tile = false; e.do_print = true; e.strand = a.strand ? '-' : '+';
+    e.score = r.score; e.chain_score = 0;
+    e.aligned_reference_str.resize(r.n_ops); e.aligned_query_str.resize(r.n_ops);
+    const uint8_t* o = ops.data() + r.ops_offset;
+    uint32_t cr = a.reference_pos - a.chr_start, cq = a.query_pos;
+    for (int64_t p = (int64_t)r.n_left_ops - 1; p >= 0; p--) {
+        const uint8_t d = o[p];
+        e.aligned_reference_str[p] = (d == DARWIN_OP_I) ? '-' : g_DRAM->buffer[a.chr_start + cr];
+        e.aligned_query_str[p] = (d == DARWIN_OP_D) ? '-' : qchars[cq];
+        if (d != DARWIN_OP_I && cr > 0) cr--;
+        if (d != DARWIN_OP_D && cq > 0) cq--;
+    }
+    cr = a.reference_pos - a.chr_start + 1; cq = a.query_pos + 1;
+    for (uint32_t p = r.n_left_ops; p < r.n_ops; p++) {
+        const uint8_t d = o[p];
+        e.aligned_reference_str[p] = (d == DARWIN_OP_I) ? '-' : g_DRAM->buffer[a.chr_start + cr];
+        e.aligned_query_str[p] = (d == DARWIN_OP_D) ? '-' : qchars[cq];
+        if (d != DARWIN_OP_I && cr < a.ref_len) cr++;
+        if (d != DARWIN_OP_D && cq < a.read_len) cq++;
+    }
+    output.extend_alignments.push_back(e);
+    extender_body::num_extend_tiles += (int)r.n_tiles;
+    extender_body::num_active_tiles += (int)r.n_tiles;
+    extender_body::num_large_tiles += (int)r.n_large_tiles;
+}
+
 void gpu_extender_body::operator()(extender_input input, extender_node::output_ports_type& op) {
     auto& payload = get<0>(input);
     auto& reads = get<0>(payload);
@@ -215,47 +257,7 @@ void gpu_extender_body::operator()(extender_input input, extender_node::output_p
         std::string err;
         int rc = gc.extend(prm, spans, anchors.data(), n, pool.data(), pool.size(), res.data(), &ops, &err);
         if (rc != DARWIN_OK) fail_msg(rc, "gpu_extender_body", err);
-        for (int k = 0; k < n; k++) {
-            const DarwinAlnRes& r = res[k];
-            if (!(r.flags & DARWIN_ALN_EMITTED)) continue;
-            if (r.flags & DARWIN_ALN_OPS_OVERFLOW) fail_msg(DARWIN_ERR_CAPACITY, "gpu_extender_body", "op string overflow");
-            const DarwinAnchor& a = anchors[k];
-            const Read& rd = reads[a.read_num];
-            const char* qchars = a.strand ? rd.rc_seq.data() : rd.seq.data();        // extender.cpp:243 / :758
-            ExtendAlignments e;
-            e.read_num = a.read_num; e.chr_id = a.chr_id;
-            e.reference_start_offset = r.reference_start_offset; e.reference_end_offset = r.reference_end_offset;
-            e.query_start_offset = r.query_start_offset; e.query_end_offset = r.query_end_offset;
-            e.curr_reference_offset = r.reference_end_offset + 1; e.curr_query_offset = r.query_end_offset + 1;
-            e.reference_start_addr = a.chr_start; e.query_start_addr = (uint32_t)a.read_addr;
-            e.reference_length = a.ref_len; e.query_length = a.read_len;
-            e.left_extension_done = 1; e.right_extension_done = 1;
-            e.used_large_tile = false; e.do_print = true; e.strand = a.strand ? '-' : '+';
-            e.score = r.score; e.chain_score = 0;
-            // gapped strings from the op string (extender.cpp:287-323 / :434-458)
-            e.aligned_reference_str.resize(r.n_ops); e.aligned_query_str.resize(r.n_ops);
-            const uint8_t* o = ops.data() + r.ops_offset;
-            uint32_t cr = a.reference_pos - a.chr_start, cq = a.query_pos;
-            for (int64_t p = (int64_t)r.n_left_ops - 1; p >= 0; p--) {
-                const uint8_t d = o[p];
-                e.aligned_reference_str[p] = (d == DARWIN_OP_I) ? '-' : g_DRAM->buffer[a.chr_start + cr];
-                e.aligned_query_str[p] = (d == DARWIN_OP_D) ? '-' : qchars[cq];
-                if (d != DARWIN_OP_I && cr > 0) cr--;
-                if (d != DARWIN_OP_D && cq > 0) cq--;
-            }
-            cr = a.reference_pos - a.chr_start + 1; cq = a.query_pos + 1;
-            for (uint32_t p = r.n_left_ops; p < r.n_ops; p++) {
-                const uint8_t d = o[p];
-                e.aligned_reference_str[p] = (d == DARWIN_OP_I) ? '-' : g_DRAM->buffer[a.chr_start + cr];
-                e.aligned_query_str[p] = (d == DARWIN_OP_D) ? '-' : qchars[cq];
-                if (d != DARWIN_OP_I && cr < a.ref_len) cr++;
-                if (d != DARWIN_OP_D && cq < a.read_len) cq++;
-            }
-            output.extend_alignments.push_back(e);
-            extender_body::num_extend_tiles += (int)r.n_tiles;
-            extender_body::num_active_tiles += (int)r.n_tiles;
-            extender_body::num_large_tiles += (int)r.n_large_tiles;
-        }
+        for (int k = 0; k < n; k++) emit_alignment(anchors[k], res[k], ops, reads, output);
     }
     get<1>(op).try_put(token);                                                        // extender.cpp:1062-1063
     get<0>(op).try_put(printer_input(printer_payload(reads, output), token));
@@ -313,6 +315,32 @@ filter_input gpu_seeder_body::operator()(seeder_input input) {
             }
     } 
     return filter_input(filter_payload(reads, output), token);
+}
+
+// seeder_body + filter_body + extender_body of one batch in ONE device call (darwin_gpu_align_reads): the chained hits stay
+// in HBM between the stages, only the per-candidate first-tile results come up for the slope filter (restated inside the
+// library, filter.cpp:227-289).  Output == what gpu_seeder_body -> gpu_filter_body -> gpu_extender_body produce.
+void gpu_align_body::operator()(seeder_input input, extender_node::output_ports_type& op) {
+    reader_output& reads = get<0>(input);
+    size_t token = get<1>(input);
+    GpuCombiner& gc = combiner_for_token(token);
+    extend_data output;
+    if (!reads.empty()) {
+        const std::vector<UploadSpan> spans = read_spans(reads);
+        std::vector<DarwinSeedRead> sr(reads.size());
+        for (size_t r = 0; r < reads.size(); r++) sr[r] = DarwinSeedRead{(uint64_t)(reads[r].seq.data() - g_DRAM->buffer), (uint32_t)reads[r].seq.size(), 0};
+        DarwinAlignParams prm{};
+        prm.filter = DarwinFilterParams{cfg.first_tile_size, cfg.first_tile_score_threshold, cfg.min_overlap, 0};
+        prm.extend = DarwinExtendParams{cfg.tile_size, cfg.tile_overlap, cfg.do_overlap, 0};
+        prm.slope_threshold = cfg.slope_threshold;
+        std::vector<DarwinAnchor> anchors; std::vector<DarwinAlnRes> res; std::vector<uint8_t> ops;
+        std::string err;
+        int rc = gc.align(prm, spans, sr.data(), (int)sr.size(), &anchors, &res, &ops, &err);
+        if (rc != DARWIN_OK) fail_msg(rc, "gpu_align_body", err);
+        for (size_t k = 0; k < anchors.size(); k++) emit_alignment(anchors[k], res[k], ops, reads, output);
+    }
+    get<1>(op).try_put(token);
+    get<0>(op).try_put(printer_input(printer_payload(reads, output), token));
 }
 
 // filter_body::operator() (filter.cpp:8-225) with every first tile of the batch -- both strands, all reads -- in ONE

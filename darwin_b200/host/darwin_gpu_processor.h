@@ -45,6 +45,12 @@ struct gpu_seeder_body {
     filter_input operator()(seeder_input input);
 };
 
+// == the seeder -> filter -> extender chain of main.cpp:590-624 as ONE node body (needs BuildSeedIndex()): wire the reader's
+// gatekeeper output straight into it and its ports into the printer / ticketer like the extender's.
+struct gpu_align_body {
+    void operator()(seeder_input input, extender_node::output_ports_type& op);
+};
+
 // == filter_body (software/graph.h:205-217, filter.cpp:8-225): same input/output tuples; the first tiles of the whole
 // batch (both strands) go to the GPU in one darwin_gpu_filter call; the slope filter is the reference's own.
 struct gpu_filter_body {

@@ -204,6 +204,14 @@ typedef struct DarwinSeedAnchor {
     uint32_t right_n;
 } DarwinSeedAnchor;
 
+/* Everything darwin_gpu_align_reads needs beyond the seeding parameters fixed at darwin_gpu_seed_index time. */
+typedef struct DarwinAlignParams {
+    DarwinFilterParams filter;        /* params.cfg [GACT_first_tile] */
+    DarwinExtendParams extend;        /* params.cfg [GACT_extend] + do_overlap */
+    float   slope_threshold;          /* params.cfg slope_threshold (filter.cpp:271) */
+    int32_t reserved;
+} DarwinAlignParams;
+
 typedef struct DarwinGpuStats {
     uint64_t kernel_launches;   /* kernels of this library launched since create */
     uint64_t tiles_fast;        /* tiles finished by the packed fast path */
@@ -277,6 +285,15 @@ int darwin_gpu_seed_index_read(DarwinGpu* h, uint32_t* buckets, uint64_t buckets
 int darwin_gpu_seed(DarwinGpu* h, const DarwinSeedRead* reads, int n, uint32_t* anchor_begin /* 2n+1 */,
                     DarwinSeedAnchor* anchors, uint64_t anchors_cap, uint64_t* n_anchors,
                     uint64_t* pool, uint64_t pool_cap, uint64_t* n_pool);
+
+/* The reference-guided pipeline of one read batch in ONE call -- seeder_body, filter_body (incl. slopeFilter) and
+ * extender_body (main.cpp:590-624's seeder -> filter -> extender chain) -- with the chained hits kept in HBM between the
+ * stages.  Reads must be resident; darwin_gpu_seed_index must have been called.  anchors_out[i] / res[i] describe the
+ * i-th location handed to the extension (read_num = index into `reads`), forward-strand locations first, in the
+ * reference's order; *n_out = their number (also set on DARWIN_ERR_CAPACITY). */
+int darwin_gpu_align_reads(DarwinGpu* h, const DarwinAlignParams* p, const DarwinSeedRead* reads, int n,
+                           DarwinAnchor* anchors_out, DarwinAlnRes* res, uint64_t cap, uint64_t* n_out,
+                           uint8_t* ops_pool, uint64_t ops_pool_bytes);
 
 /* device-resident variants used by bench.py's `value` leg: same work, inputs and
  * outputs stay in HBM (pointers are device pointers of this handle's device). */

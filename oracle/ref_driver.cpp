@@ -704,7 +704,8 @@ int dref_pipeline(int first, int count, int use_gpu, char* out, uint64_t cap) {
 // ---- multi-threaded end-to-end run: `threads` host threads play the reference's tokens
 // (main.cpp:615-624); each pulls batches of `reads_per_batch` reads and runs seeder_body -> filter -> extender on them.
 // mode 0: the reference's CPU stages; mode 1: GPU extender only (filter tiles through g_BatchAlignmentSIMD);
-// mode 2: gpu_filter_body + gpu_extender_body; mode 3: gpu_seeder_body as well (dref_gpu_seed_index first).  With the GPU stages all threads share the per-GPU combiner
+// mode 2: gpu_filter_body + gpu_extender_body; mode 3: gpu_seeder_body as well (dref_gpu_seed_index first);
+// mode 4: gpu_align_body (one resident device call per merged batch).  With the GPU stages all threads share the per-GPU combiner
 // (darwin_b200/host/darwin_gpu_combiner.h).  Output: canonical sorted lines like dref_pipeline (out may be NULL);
 // stats[0] = wall seconds, [1] = alignments, [2] = seconds inside seeder_body (summed over threads), [3] = filter stage,
 // [4] = extender stage, [5] = DP cells of the alignments' tile requests when dref_count_cells(1) was set (CPU modes).
@@ -730,6 +731,25 @@ int dref_pipeline_mt(int first, int count, int threads, int reads_per_batch, int
                     if (b >= nbatches || failed.load()) break;
                     const int lo = first + b * reads_per_batch, hi = std::min(first + count, lo + reads_per_batch);
                     reader_output reads(g_reads.begin() + lo, g_reads.begin() + hi);
+                    if (mode >= 4) {                                   // all stages in one device call
+                        const auto b0 = now();
+                        extender_node::output_ports_type ports;
+                        darwin_gpu_host::gpu_align_body()(seeder_input(reads, (size_t)t), ports);
+                        t_extend[t] += secs(b0, now());
+                        auto& al = std::get<1>(std::get<0>(std::get<0>(ports).items[0])).extend_alignments;
+                        n_aln += al.size();
+                        if (out) {
+                            std::vector<std::string> mine;
+                            for (auto& e : al)
+                                mine.push_back(std::to_string(e.read_num + lo) + " " + std::to_string(e.chr_id) + " " + std::string(1, e.strand) + " " +
+                                               std::to_string(e.reference_start_offset) + " " + std::to_string(e.reference_end_offset) + " " +
+                                               std::to_string(e.query_start_offset) + " " + std::to_string(e.query_end_offset) + " " +
+                                               std::to_string(e.score) + " " + e.aligned_reference_str + " " + e.aligned_query_str);
+                            std::lock_guard<std::mutex> g(out_mutex);
+                            for (auto& l : mine) lines.push_back(std::move(l));
+                        }
+                        continue;
+                    }
                     const auto a0 = now();
                     filter_input fin = (mode >= 3) ? darwin_gpu_host::gpu_seeder_body()(seeder_input(reads, (size_t)t))
                                                    : seeder_body()(seeder_input(reads, (size_t)t));

@@ -65,7 +65,8 @@ def test_multithreaded_pipeline_matches_cpu_pipeline():
     try:
         assert L.dref_gpu_seed_index() == 0                      # seed position table on the GPU (for mode 3)
         # mode 1: GPU extender; 2: + GPU first-tile filter; 3: + GPU D-SOFT (no reference stage left but slopeFilter)
-        for mode, per_batch in ((2, 4), (1, 7), (2, 1), (3, 5), (3, 32)):
+        # mode 4: the resident pipeline call (darwin_gpu_align_reads) behind gpu_align_body
+        for mode, per_batch in ((2, 4), (1, 7), (2, 1), (3, 5), (3, 32), (4, 6), (4, 48)):
             n_gpu = L.dref_pipeline_mt(0, n_reads, threads, per_batch, mode, buf_gpu, C.c_uint64(cap), stats)
             assert n_gpu == n_cpu and buf_gpu.value == buf_cpu.value, (mode, per_batch, n_gpu, n_cpu)
         cs = (C.c_uint64 * 12)()
