@@ -56,3 +56,66 @@ def test_gpu_seeding_matches_reference(gpu, seed, overlap):
         p.close()
     finally:
         ref.set_extend(384, 64, 2, 0)
+
+
+def test_align_reads_equals_staged_calls(gpu):
+    """darwin_gpu_align_reads (resident pipeline) vs the same stages called one by one with the chained hits travelling
+    through the host: seeder_body -> filter_body -> slope filter (oracle restatement) -> extender_body."""
+    import darwin_b200
+    ref, n_reads = _case(13, 36, 0)
+    ref.seed(0, n_reads)
+    arena = ref.arena().copy()
+    sc = abi.Scoring.from_values()
+    p = gpu(len(arena), sc)
+    p.InitializeReferenceMemory(0, arena)
+    chroms = ref.chroms()
+    ref_size = int(ref.lib.dref_arena_reference_size())
+    p.build_seed_index(ref.seed_params(), chroms, ref_size)
+    reads = np.zeros(n_reads, abi.SEED_READ)
+    for r in range(n_reads):
+        reads[r]["read_addr"], reads[r]["read_len"] = ref.read_addr(r), ref.lib.dref_read_len(r)
+    # staged
+    begin, sanc, pool = p.seeder_body(reads)
+    cands = np.zeros(len(sanc), abi.FILTER_CAND)
+    rn = np.zeros(len(sanc), np.int32)
+    starts = chroms["start"].astype(np.int64)
+    padded = np.diff(np.concatenate([starts, [ref_size]]))
+    for r in range(n_reads):
+        for s in (0, 1):
+            for i in range(begin[2 * r + s], begin[2 * r + s + 1]):
+                hit, off = int(sanc[i]["hit_offset"]) >> 32, int(sanc[i]["hit_offset"]) & 0xFFFFFFFF
+                c = int(np.searchsorted(starts, hit, side="right")) - 1
+                cands[i] = (reads[r]["read_addr"], hit, off, starts[c], padded[c], reads[r]["read_len"], s, (0, 0, 0))
+                rn[i] = r
+    fres = p.filter_body(cands)
+    port = oracle.port(sc)
+    want_anchors, hp = [], []
+    for s in (0, 1):
+        m = np.nonzero((cands["strand"] == s) & ((fres["flags"] & 3) == 3))[0]
+        for i in m[port.slope_filter(rn[m], fres["score"][m], fres["reference_pos"][m], fres["query_pos"][m])]:
+            a = np.zeros(1, abi.ANCHOR)[0]
+            a["read_addr"], a["read_len"], a["read_num"], a["strand"] = cands[i]["read_addr"], cands[i]["read_len"], rn[i], s
+            a["reference_pos"], a["query_pos"], a["score"] = fres[i]["reference_pos"], fres[i]["query_pos"], fres[i]["score"]
+            a["chr_start"], a["ref_len"] = cands[i]["chr_start"], cands[i]["chr_len"]
+            a["chr_id"] = int(np.searchsorted(starts, int(cands[i]["hit"]), side="right")) - 1
+            for side in ("left", "right"):
+                lo, n = int(sanc[i][side + "_off"]), int(sanc[i][side + "_n"])
+                a[side + "_hits_off"], a[side + "_hits_n"] = sum(len(x) for x in hp), n
+                hp.append(pool[lo:lo + n])
+            want_anchors.append(a)
+    want_anchors = np.array(want_anchors, abi.ANCHOR)
+    wres, wops = p.extender_body(want_anchors, np.concatenate(hp), 384, 64, 0)
+    # resident
+    ganc, gres, gops = p.align_reads(reads)
+    assert len(ganc) == len(want_anchors) > n_reads // 2
+    for f in ("read_addr", "reference_pos", "query_pos", "chr_start", "ref_len", "read_len", "read_num", "chr_id", "score",
+              "left_hits_n", "right_hits_n", "strand"):
+        assert np.array_equal(ganc[f], want_anchors[f]), f
+    from conftest import alignments_equal, ALN_FIELDS_OURS
+    assert alignments_equal(wres, wops, gres, gops, ALN_FIELDS_OURS) == []
+    # caller-supplied buffers that are too small: the needed count comes back with DARWIN_ERR_CAPACITY
+    small = (np.empty(2, abi.ANCHOR), np.empty(2, abi.ALN_RES), np.empty(1 << 20, np.uint8))
+    with pytest.raises(darwin_b200.DarwinGpuError) as e:
+        p.align_reads(reads, out=small)
+    assert e.value.code == abi.ERR_CAPACITY
+    p.close()
