@@ -386,6 +386,7 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
         if (lane == 0) idx = atomicAdd(ea.counter, 1u);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx >= (unsigned)ea.n) break;
+        idx = ea.order[idx];
         const DarwinAnchor an = ea.anchors[idx];
         AnchorState a;
         a.cr = an.reference_pos - an.chr_start; a.cq = an.query_pos;           // extender.cpp:1083-1088
@@ -580,7 +581,7 @@ struct DarwinGpu {
     uint8_t* d_trace = nullptr; size_t trace_stride = 0; ChainRec* d_bound = nullptr;
     unsigned int* d_counter = nullptr;
     // growable device buffers
-    void* d_buf[10] = {nullptr}; size_t d_cap[10] = {0};
+    void* d_buf[12] = {nullptr}; size_t d_cap[12] = {0};
     void* h_buf[4] = {nullptr}; size_t h_cap[4] = {0};
     DarwinGpuStats stats{};
     std::string err;
@@ -738,7 +739,7 @@ int darwin_gpu_destroy(DarwinGpu* h) {
     if (!h) return DARWIN_ERR_INVALID;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < 10; i++) if (h->d_buf[i]) cudaFree(h->d_buf[i]);
+    for (int i = 0; i < 12; i++) if (h->d_buf[i]) cudaFree(h->d_buf[i]);
     for (int i = 0; i < 4; i++) if (h->h_buf[i]) cudaFreeHost(h->h_buf[i]);
     if (h->d_trace) cudaFree(h->d_trace);
     if (h->d_bound) cudaFree(h->d_bound);
@@ -1013,12 +1014,17 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
         size[i] = lcap[i] + 2u * (a.read_len - a.query_pos) + slack;
         base[i] = total; total += size[i];
     }
+    // queue order: longest reads first (their walks are the longest), so the tail of the launch is made of short ones
+    std::vector<uint32_t> order(n);
+    for (int i = 0; i < n; i++) order[i] = (uint32_t)i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return anchors[x].read_len > anchors[y].read_len; });
     TMARK("slots");
     int rc;
     const size_t an_b = (size_t)n * sizeof(DarwinAnchor), res_b = (size_t)n * sizeof(DarwinAlnRes);
     if ((rc = grow_dev(h, 0, an_b)) || (rc = grow_dev(h, 1, res_b)) ||
         (rc = grow_dev(h, 3, total + 16)) || (rc = grow_dev(h, 4, (size_t)n * 8)) || (rc = grow_dev(h, 5, (size_t)n * 4)) ||
-        (rc = grow_dev(h, 6, (size_t)n * 4)) || (rc = grow_dev(h, 7, (size_t)n * 8))) return rc;
+        (rc = grow_dev(h, 6, (size_t)n * 4)) || (rc = grow_dev(h, 7, (size_t)n * 8)) || (rc = grow_dev(h, 10, (size_t)n * 4))) return rc;
+    CK(cudaMemcpyAsync(h->d_buf[10], order.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[0], anchors, an_b, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[4], base.data(), (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[5], lcap.data(), (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
@@ -1032,6 +1038,7 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     ea.arena = h->d_arena; ea.anchors = (const DarwinAnchor*)h->d_buf[0]; ea.hit_pool = d_pool;
     ea.res = (DarwinAlnRes*)h->d_buf[1]; ea.ops = (uint8_t*)h->d_buf[3];
     ea.slot_base = (const uint64_t*)h->d_buf[4]; ea.slot_left = (const uint32_t*)h->d_buf[5]; ea.slot_size = (const uint32_t*)h->d_buf[6];
+    ea.order = (const uint32_t*)h->d_buf[10];
     ea.dbg = nullptr;
     if (getenv("DARWIN_GPU_DEBUG")) { CK(cudaMalloc(&ea.dbg, (size_t)n * 128 * 8 * 4)); CK(cudaMemset(ea.dbg, 0, (size_t)n * 128 * 8 * 4)); }
     ea.n = n; ea.T = p->tile_size; ea.O = p->tile_overlap; ea.do_overlap = p->do_overlap; ea.counter = h->d_counter;
@@ -1298,6 +1305,13 @@ int darwin_gpu_int_peak(DarwinGpu* h, double out[10]) {
     cudaFree(d);
     return DARWIN_OK;
 }
+
+void* darwin_gpu_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 16) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void darwin_gpu_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int darwin_gpu_stats(DarwinGpu* h, DarwinGpuStats* out) {
     if (!h || !out) return DARWIN_ERR_INVALID;

@@ -59,7 +59,7 @@ def load_library():
 
 EXPORTS = ("darwin_gpu_create", "darwin_gpu_create_shared", "darwin_gpu_destroy", "darwin_gpu_set_scoring", "darwin_gpu_upload",
            "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_filter", "darwin_gpu_seed_index",
-           "darwin_gpu_seed_index_share", "darwin_gpu_seed_index_read", "darwin_gpu_seed", "darwin_gpu_align_reads", "darwin_gpu_stats", "darwin_gpu_int_peak",
+           "darwin_gpu_seed_index_share", "darwin_gpu_seed_index_read", "darwin_gpu_seed", "darwin_gpu_align_reads", "darwin_gpu_host_alloc", "darwin_gpu_host_free", "darwin_gpu_stats", "darwin_gpu_int_peak",
            "darwin_gpu_last_error", "darwin_gpu_version")
 
 

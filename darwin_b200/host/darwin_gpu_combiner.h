@@ -15,6 +15,7 @@
 #pragma once
 #include <algorithm>
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -36,9 +37,11 @@ struct GpuCalls {
     int (*seed)(DarwinGpu*, const DarwinSeedRead*, int, uint32_t*, DarwinSeedAnchor*, uint64_t, uint64_t*, uint64_t*, uint64_t, uint64_t*);
     int (*align)(DarwinGpu*, const DarwinAlignParams*, const DarwinSeedRead*, int, DarwinAnchor*, DarwinAlnRes*, uint64_t, uint64_t*,
                  uint8_t*, uint64_t);
+    void* (*host_alloc)(uint64_t);    // page-locked buffers for the merged op strings (nullptr: plain malloc)
+    void (*host_free)(void*);
     static GpuCalls library() {
         return GpuCalls{darwin_gpu_upload, darwin_gpu_tiles, darwin_gpu_filter, darwin_gpu_extend, darwin_gpu_last_error, darwin_gpu_seed,
-                        darwin_gpu_align_reads};
+                        darwin_gpu_align_reads, darwin_gpu_host_alloc, darwin_gpu_host_free};
     }
 };
 
@@ -54,6 +57,9 @@ struct CombinerStats {
 class GpuCombiner {
 public:
     GpuCombiner(DarwinGpu* h, const GpuCalls& calls) : h_(h), c_(calls) { memset(&st_, 0, sizeof(st_)); }
+    ~GpuCombiner() { if (ops_buf_) { if (c_.host_free) c_.host_free(ops_buf_); else free(ops_buf_); } }
+    GpuCombiner(const GpuCombiner&) = delete;
+    GpuCombiner& operator=(const GpuCombiner&) = delete;
 
     // == g_BatchAlignmentSIMD for one caller; merged with other callers using the same do_traceback
     int tiles(int do_traceback, const DarwinTileReq* req, int n, DarwinTileRes* res, uint64_t* tb_words, int tb_words_per_req,
@@ -151,6 +157,17 @@ private:
         return r.rc;
     }
 
+    // Reused landing buffer of the merged op strings (only the combining thread touches it): page-locked when the library
+    // provides it, grown geometrically, never zero-filled.
+    uint8_t* ops_buffer(uint64_t bytes) {
+        if (bytes <= ops_cap_) return ops_buf_;
+        if (ops_buf_) { if (c_.host_free) c_.host_free(ops_buf_); else free(ops_buf_); ops_buf_ = nullptr; ops_cap_ = 0; }
+        const uint64_t want = bytes + bytes / 2;
+        ops_buf_ = (uint8_t*)(c_.host_alloc ? c_.host_alloc(want) : malloc(want));
+        if (ops_buf_) ops_cap_ = want;
+        return ops_buf_;
+    }
+
     void fail_all(std::vector<Request*>& batch, int rc, const char* what) {
         const std::string msg = std::string(what) + ": " + (c_.last_error ? c_.last_error(h_) : "");
         for (auto* b : batch) { b->rc = rc; b->err = msg; }
@@ -208,12 +225,15 @@ private:
             std::vector<DarwinSeedRead> reads; reads.reserve(total);
             uint64_t bases = 0;
             for (auto* b : batch) { reads.insert(reads.end(), b->sreads, b->sreads + b->n); for (int i = 0; i < b->n; i++) bases += b->sreads[i].read_len; }
-            uint64_t cap = std::max<uint64_t>(64, 8 * total), ops_cap = 6 * bases + 65536, n_out = 0;
-            std::vector<DarwinAnchor> anchors; std::vector<DarwinAlnRes> res; std::vector<uint8_t> ops;
+            uint64_t cap = std::max<uint64_t>(64, 8 * total), ops_cap = std::max<uint64_t>(ops_cap_, 6 * bases + 65536), n_out = 0;
+            std::vector<DarwinAnchor> anchors; std::vector<DarwinAlnRes> res;
+            uint8_t* ops = nullptr;
             int rc = DARWIN_ERR_CAPACITY;
             for (int attempt = 0; attempt < 4 && rc == DARWIN_ERR_CAPACITY; attempt++) {
-                anchors.resize(cap); res.resize(cap); ops.resize(ops_cap);
-                rc = c_.align(h_, &batch[0]->ap, reads.data(), (int)total, anchors.data(), res.data(), cap, &n_out, ops.data(), ops_cap);
+                anchors.resize(cap); res.resize(cap);
+                ops = ops_buffer(ops_cap);
+                if (!ops) { fail_all(batch, DARWIN_ERR_CAPACITY, "host buffer for the op strings"); return; }
+                rc = c_.align(h_, &batch[0]->ap, reads.data(), (int)total, anchors.data(), res.data(), cap, &n_out, ops, ops_cap);
                 if (rc == DARWIN_ERR_CAPACITY) { if (n_out > cap) cap = n_out; else ops_cap *= 2; }
             }
             if (rc) { fail_all(batch, rc, "darwin_gpu_align_reads"); return; }
@@ -228,7 +248,7 @@ private:
                     DarwinAlnRes r = res[i];
                     const bool has = (r.flags & DARWIN_ALN_EMITTED) && !(r.flags & DARWIN_ALN_OPS_OVERFLOW) && r.n_ops;
                     const uint64_t off = b->ops->size();
-                    if (has) b->ops->insert(b->ops->end(), ops.begin() + r.ops_offset, ops.begin() + r.ops_offset + r.n_ops);
+                    if (has) b->ops->insert(b->ops->end(), ops + r.ops_offset, ops + r.ops_offset + r.n_ops);
                     r.ops_offset = off;
                     b->aanchors->push_back(a); b->ares_v->push_back(r);
                 }
@@ -279,9 +299,10 @@ private:
                 }
             }
             std::vector<DarwinAlnRes> res(total);
-            std::vector<uint8_t> ops(cap);
+            uint8_t* ops = ops_buffer(cap);
+            if (!ops) { fail_all(batch, DARWIN_ERR_CAPACITY, "host buffer for the op strings"); return; }
             const int rc = c_.extend(h_, &batch[0]->ep, anchors.data(), (int)total, pool.empty() ? nullptr : pool.data(), pool.size(),
-                                     res.data(), ops.data(), cap);
+                                     res.data(), ops, cap);
             if (rc) { fail_all(batch, rc, "darwin_gpu_extend"); return; }
             // op strings are dense and in anchor order: each caller owns one contiguous slice of the pool
             size_t at = 0;
@@ -294,7 +315,7 @@ private:
                     if (r.ops_offset + r.n_ops > hi) hi = r.ops_offset + r.n_ops;
                 }
                 if (lo == UINT64_MAX) { lo = 0; hi = 0; }
-                if (b->ops) b->ops->assign(ops.begin() + lo, ops.begin() + hi);
+                if (b->ops) b->ops->assign(ops + lo, ops + hi);
                 for (int i = 0; i < b->n; i++) {
                     b->ares[i] = res[at + i];
                     b->ares[i].ops_offset = (res[at + i].ops_offset >= lo) ? res[at + i].ops_offset - lo : 0;
@@ -311,6 +332,7 @@ private:
     std::deque<Request*> q_;
     bool busy_ = false;
     CombinerStats st_;
+    uint8_t* ops_buf_ = nullptr; uint64_t ops_cap_ = 0;
 };
 
 } // namespace darwin_gpu_host

@@ -224,7 +224,7 @@ static void emit_alignment(const DarwinAnchor& a, const DarwinAlnRes& r, const s
         if (d != DARWIN_OP_I && cr < a.ref_len) cr++;
         if (d != DARWIN_OP_D && cq < a.read_len) cq++;
     }
-    output.extend_alignments.push_back(e);
+    output.extend_alignments.push_back(std::move(e));
     extender_body::num_extend_tiles += (int)r.n_tiles;
     extender_body::num_active_tiles += (int)r.n_tiles;
     extender_body::num_large_tiles += (int)r.n_large_tiles;
@@ -340,7 +340,7 @@ void gpu_align_body::operator()(seeder_input input, extender_node::output_ports_
         for (size_t k = 0; k < anchors.size(); k++) emit_alignment(anchors[k], res[k], ops, reads, output);
     }
     get<1>(op).try_put(token);
-    get<0>(op).try_put(printer_input(printer_payload(reads, output), token));
+    get<0>(op).try_put(printer_input(printer_payload(reads, std::move(output)), token));
 }
 
 // filter_body::operator() (filter.cpp:8-225) with every first tile of the batch -- both strands, all reads -- in ONE

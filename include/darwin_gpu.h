@@ -301,6 +301,11 @@ int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, i
                             void* d_res, void* d_tb_words, int tb_words_per_req,
                             int max_ref_size, int max_query_size);
 
+/* Page-locked host memory for request / result buffers: DMA goes straight to it (no staging copy, full PCIe rate).
+ * Any buffer handed to the calls above may come from here; plain malloc'ed memory works too, slower. */
+void* darwin_gpu_host_alloc(uint64_t bytes);
+void  darwin_gpu_host_free(void* p);
+
 int darwin_gpu_stats(DarwinGpu* h, DarwinGpuStats* out);
 
 /* Roofline denominator: measured issue rate, in 1e9 32-bit lane-ops per second, of packed-int16 /
