@@ -119,3 +119,43 @@ def test_align_reads_equals_staged_calls(gpu):
         p.align_reads(reads, out=small)
     assert e.value.code == abi.ERR_CAPACITY
     p.close()
+
+
+def test_gpu_seeding_long_reads_and_many_reads(gpu):
+    """ONT-like 30-50 kbp reads (tens of minimizer chunks per strand, the stride-4 tail of the seed list) and reads shorter
+    than one chunk, against the reference's seeder_body."""
+    rng = np.random.default_rng(3)
+    ref = oracle.reference("patched")
+    ref.set_scoring(abi.Scoring.from_values())
+    ref.set_dsoft_defaults()
+    ref.set_extend(384, 64, 2, 0)
+    ref.reset_arena()
+    genome = synth.random_seq(rng, 400000)
+    genome[250000:253000] = genome[50000:53000]                       # an exact repeat: multi-hit buckets
+    ref.add_chr("chrL", genome.tobytes(), True)
+    ref.build_index()
+    lens = [50000, 41234, 30001, 2047, 2048, 2049, 300, 129, 100, 65 + 14]
+    for k, L in enumerate(lens):
+        p = int(rng.integers(0, len(genome) - L))
+        r = synth.mutate_fast(rng, genome[p:p + L], 0.04, 0.03, 0.05)
+        if k % 2:
+            r = synth.revcomp(r)
+        ref.add_read("r%d" % k, np.ascontiguousarray(r).tobytes())
+    n_reads = ref.lib.dref_num_reads()
+    ref.seed(0, n_reads)
+    begin, anchors, pool = ref.seed_anchors()
+    arena = ref.arena().copy()
+    p = gpu(len(arena), abi.Scoring.from_values())
+    p.InitializeReferenceMemory(0, arena)
+    p.build_seed_index(ref.seed_params(), ref.chroms(), int(ref.lib.dref_arena_reference_size()))
+    reads = np.zeros(n_reads, abi.SEED_READ)
+    for r in range(n_reads):
+        reads[r]["read_addr"], reads[r]["read_len"] = ref.read_addr(r), ref.lib.dref_read_len(r)
+    gbeg, ganc, gpool = p.seeder_body(reads)
+    assert np.array_equal(gbeg, begin)
+    want, got = strand_views(begin, anchors, n_reads), strand_views(gbeg, ganc, n_reads)
+    for r in range(n_reads):
+        for s in (0, 1):
+            assert same_seed_output(got[r][s], gpool, want[r][s], pool), (r, s, lens[r] if r < len(lens) else None)
+    assert len(anchors) >= 6 and int(anchors["left_n"].max()) > 1000
+    p.close()
