@@ -143,6 +143,11 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
         max_cap = std::max(max_cap, cap);
     }
     seed_base[ns] = slots;
+    // 32-bit offsets index the seed slots, the hits and the candidates of one call: keep a call below ~1.5 G read bases
+    // (about 150 k reads of 10 kbp); larger batches are the caller's to split
+    uint64_t bases = 0, slots64 = 0;
+    for (int r = 0; r < n; r++) { bases += reads[r].read_len; slots64 += 2ull * (seed_base[2 * r + 1] - seed_base[2 * r]); }
+    if (bases > 1500000000ull || slots64 != slots) { h->err = "seeding batch too large (more than 1.5 G read bases in one call)"; return DARWIN_ERR_INVALID; }
     DevBuf d_jobs, d_base, d_seeds, d_nseeds, d_cnt, d_hoff, d_soff;
     CKS(d_jobs.alloc(sizeof(MinJob) * ns, h->stream)); CKS(d_base.alloc(sizeof(uint32_t) * (ns + 1), h->stream)); CKS(d_seeds.alloc(sizeof(uint64_t) * slots, h->stream));
     CKS(d_nseeds.alloc(sizeof(uint32_t) * ns, h->stream)); CKS(d_cnt.alloc(sizeof(uint32_t) * ((size_t)slots + 1), h->stream)); CKS(d_hoff.alloc(sizeof(uint32_t) * ((size_t)slots + 1), h->stream));
