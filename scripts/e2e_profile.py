@@ -11,7 +11,8 @@ mode = int(sys.argv[4]) if len(sys.argv) > 4 else 2          # 2: host D-SOFT + 
 ref, L = load_driver()
 load_case(ref, 9, 10_000_000, n_reads, 13333)
 stats = (C.c_double * 8)()
-assert L.dref_gpu_init(1) == 0
+gpus = int(os.environ.get('E2E_GPUS', '1'))
+assert L.dref_gpu_init(gpus) == 0
 if mode >= 3:
     import time as _t
     t0 = _t.time(); assert L.dref_gpu_seed_index() == 0; print("seed position table on the GPU: %.2f s" % (_t.time() - t0))
@@ -19,8 +20,8 @@ for rep in range(3):
     n = L.dref_pipeline_mt(0, n_reads, threads, per_batch, mode, None, C.c_uint64(0), stats)
     g = list(stats)
     nb = (n_reads + per_batch - 1) // per_batch
-    print("mode %d threads %d, %d reads, %d per batch: wall %.3f s (%.0f reads/s) | seed %.3f filter %.3f extend %.3f thread-s | per batch: seed %.2f ms filter %.2f ms extend %.2f ms" % (
-        mode, threads, n_reads, per_batch, g[0], n_reads / g[0], g[2], g[3], g[4], g[2] / nb * 1e3, g[3] / nb * 1e3, g[4] / nb * 1e3))
+    print("gpus %d mode %d threads %d, %d reads, %d per batch: wall %.3f s (%.0f reads/s) | seed %.3f filter %.3f extend %.3f thread-s | per batch: seed %.2f ms filter %.2f ms extend %.2f ms" % (
+        gpus, mode, threads, n_reads, per_batch, g[0], n_reads / g[0], g[2], g[3], g[4], g[2] / nb * 1e3, g[3] / nb * 1e3, g[4] / nb * 1e3))
 if os.environ.get("DARWIN_GPU_TIMING"):
     pass
 L.dref_use_cpu_table(); L.dref_gpu_shutdown()

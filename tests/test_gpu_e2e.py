@@ -76,3 +76,29 @@ def test_multithreaded_pipeline_matches_cpu_pipeline():
     finally:
         L.dref_use_cpu_table()
         L.dref_gpu_shutdown()
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libdarwin_ref_gpu.so not built (needs /root/reference at build time)")
+def test_pipeline_across_all_visible_gpus():
+    """Tokens spread over every visible GPU (each with its own arena replica and seed position table, reads sharded by
+    token, no data-path collective): same bytes as the CPU pipeline.  On a one-GPU box this repeats the single-GPU case."""
+    import torch
+    gpus = max(1, torch.cuda.device_count())
+    ref, L = load_driver()
+    n_reads = 64
+    load_case(ref, 6, 500000, n_reads, 5000)
+    cap = 256 << 20
+    buf_cpu, buf_gpu = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    stats = (C.c_double * 8)()
+    threads = min(8, os.cpu_count() or 1)
+    n_cpu = L.dref_pipeline_mt(0, n_reads, threads, 4, 0, buf_cpu, C.c_uint64(cap), stats)
+    assert n_cpu > n_reads // 2
+    assert L.dref_gpu_init(gpus) == 0
+    try:
+        assert L.dref_gpu_seed_index() == 0
+        for mode, per_batch in ((4, 3), (2, 5)):
+            n_gpu = L.dref_pipeline_mt(0, n_reads, threads, per_batch, mode, buf_gpu, C.c_uint64(cap), stats)
+            assert n_gpu == n_cpu and buf_gpu.value == buf_cpu.value, (gpus, mode)
+    finally:
+        L.dref_use_cpu_table()
+        L.dref_gpu_shutdown()
