@@ -25,11 +25,11 @@ def load_driver():
     return ref, L
 
 
-def load_case(ref, seed, genome_len, n_reads, read_len, err=(0.015, 0.09, 0.045)):
+def load_case(ref, seed, genome_len, n_reads, read_len, err=(0.015, 0.09, 0.045), do_overlap=0, tile=(384, 64)):
     rng = np.random.default_rng(seed)
     ref.set_scoring(abi.Scoring.from_values())
     ref.set_dsoft_defaults()
-    ref.set_extend(384, 64, 2, 0)
+    ref.set_extend(tile[0], tile[1], 2, do_overlap)
     ref.reset_arena()
     genome = synth.random_seq(rng, genome_len)
     for _ in range(max(2, genome_len // 500000)):
@@ -102,3 +102,30 @@ def test_pipeline_across_all_visible_gpus():
     finally:
         L.dref_use_cpu_table()
         L.dref_gpu_shutdown()
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libdarwin_ref_gpu.so not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("do_overlap,tile", [(1, (384, 64)), (0, (320, 128)), (1, (256, 64))])
+def test_pipeline_other_modes(do_overlap, tile):
+    """De novo overlap mode (argv[3] = 1: D-SOFT stops after N+1 seeds, SV window of one bin, large tiles keep T) and other
+    tile geometries through the staged and the resident GPU pipeline."""
+    ref, L = load_driver()
+    n_reads = 48
+    try:
+        load_case(ref, 8 + do_overlap, 400000, n_reads, 5000, do_overlap=do_overlap, tile=tile)
+        cap = 256 << 20
+        buf_cpu, buf_gpu = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        stats = (C.c_double * 8)()
+        n_cpu = L.dref_pipeline_mt(0, n_reads, 4, 4, 0, buf_cpu, C.c_uint64(cap), stats)
+        assert n_cpu > n_reads // 2
+        assert L.dref_gpu_init(1) == 0
+        try:
+            assert L.dref_gpu_seed_index() == 0
+            for mode, per_batch in ((3, 6), (4, 6), (4, 48)):
+                n_gpu = L.dref_pipeline_mt(0, n_reads, 4, per_batch, mode, buf_gpu, C.c_uint64(cap), stats)
+                assert n_gpu == n_cpu and buf_gpu.value == buf_cpu.value, (do_overlap, tile, mode)
+        finally:
+            L.dref_use_cpu_table()
+            L.dref_gpu_shutdown()
+    finally:
+        ref.set_extend(384, 64, 2, 0)
