@@ -412,10 +412,11 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
             int crt = T, cqt = T;
             if (a.large && ea.do_overlap == 0) { crt = rt; cqt = qt; }           // extender.cpp:261 / :408
             // lane 0 walks the traceback and records the ops in shared memory; the warp then consumes them together
-            uint8_t* opbuf = cx.wsmem + KernelGeom<K>::kOpsOff;             // behind the tile's own shared memory
-            SmemOpSink sink{opbuf, 0, kOpsSmemBytes, 0};
+            uint32_t* opbuf = reinterpret_cast<uint32_t*>(cx.wsmem + KernelGeom<K>::kOpsOff);   // behind the tile's own shared memory
+            SmemOpSink sink{opbuf, 0, kOpsSmemBytes * 4, 0, 0u};
             TileOut out{};
             process_tile<K>(cx, ks, t, true, out, sink);
+            if (lane == 0) sink.finish();
             const int len = __shfl_sync(0xffffffffu, out.total, 0);
             const uint32_t tfl = __shfl_sync(0xffffffffu, out.tflags | ((uint32_t)sink.overflow << 8), 0);
             __syncwarp();

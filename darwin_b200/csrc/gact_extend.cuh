@@ -39,13 +39,19 @@ struct AnchorState {
     uint64_t cells;
 };
 
-// The traceback (one lane) only records the tile's ops, one byte each, in shared memory ...
+// The traceback (one lane) only records the tile's ops, 2 bits each (16 per 32-bit word, the reference's TB-word packing,
+// Processor.cpp:568-582), in shared memory ...
 struct SmemOpSink {
-    uint8_t* buf; int n; int cap; int overflow;
-    __device__ __forceinline__ void operator()(uint32_t d) { if (n < cap) buf[n] = (uint8_t)d; else overflow = 1; n++; }
+    uint32_t* words; int n; int cap; int overflow; uint32_t cur;
+    __device__ __forceinline__ void operator()(uint32_t d) {
+        cur |= d << (2 * (n & 15));
+        n++;
+        if ((n & 15) == 0) { if (n <= cap) words[(n >> 4) - 1] = cur; else overflow = 1; cur = 0; }
+    }
     __device__ __forceinline__ int count() const { return n; }
+    __device__ __forceinline__ void finish() { if (n & 15) { if (n <= cap) words[n >> 4] = cur; else overflow = 1; } }
 };
-constexpr int kOpsSmemBytes = 4096;                 // >= 4 * tile_size ops of one traceback (i_steps + j_steps <= 2 * max_tb_steps)
+constexpr int kOpsSmemBytes = 1024;                 // 4096 ops >= i_steps + j_steps of the largest tile (1984 + 960)
 
 // ... and the whole warp consumes them (extender.cpp:280-331 / :427-466 and the rc twins): one 32-op TB word per
 // iteration, one lane per op.  The reference's `break` leaves only the 32-op loop, so inside word w the ops up to and
@@ -53,7 +59,7 @@ constexpr int kOpsSmemBytes = 4096;                 // >= 4 * tile_size ops of o
 // reference / query bases consumed, and the taken ops are stored with one coalesced store per word.
 struct ConsumeResult { uint32_t consumed, ref_steps, qry_steps; };
 
-__device__ __forceinline__ ConsumeResult consume_ops_warp(const uint8_t* ops, int total, int S, bool left,
+__device__ __forceinline__ ConsumeResult consume_ops_warp(const uint32_t* ops, int total, int S, bool left,
                                                           uint8_t* slot, uint32_t lcap, uint32_t rcap,
                                                           uint32_t nleft, uint32_t nright, uint32_t& overflow) {
     const int lane = lane_id();
@@ -62,7 +68,7 @@ __device__ __forceinline__ ConsumeResult consume_ops_warp(const uint8_t* ops, in
     for (int w0 = 0; w0 < total; w0 += 32) {
         const int k = w0 + lane;
         const bool valid = k < total;
-        const uint32_t d = valid ? ops[k] : 0u;
+        const uint32_t d = valid ? ((ops[k >> 4] >> (2 * (k & 15))) & 3u) : 0u;
         const int np = min(32, total - w0);
         const uint32_t mM = __ballot_sync(0xffffffffu, valid && d == DARWIN_OP_M);
         const int thr = S - steps - 1;                              // first position p with steps + p + 1 >= S

@@ -173,6 +173,17 @@ void InstallProcessorTable() {
 
 // arena range this thread's last gpu_filter_body call made resident (lets gpu_extender_body skip the same upload)
 static thread_local uint64_t t_resident_addr = ~0ull, t_resident_end = 0;
+static thread_local int t_resident_gpu = -1;         // the marker is only valid for the GPU (arena replica) it was sent to
+
+static int gpu_of_token(size_t token) { return g_gpus > 0 ? (int)(token % (size_t)g_gpus) : 0; }
+static bool already_resident(size_t token, const std::vector<UploadSpan>& spans) {
+    return !spans.empty() && t_resident_gpu == gpu_of_token(token) && t_resident_addr == spans[0].arena_addr &&
+           t_resident_end == spans.back().arena_addr + spans.back().n;
+}
+static void mark_resident(size_t token, const std::vector<UploadSpan>& spans) {
+    if (spans.empty()) return;
+    t_resident_gpu = gpu_of_token(token); t_resident_addr = spans[0].arena_addr; t_resident_end = spans.back().arena_addr + spans.back().n;
+}
 
 // ExtendLocations (graph.h:83-91) -> DarwinAnchor (what makeForward/BackwardAlignment look up, extender.cpp:1067-1159)
 static void to_anchor(const ExtendLocations& l, const Read& rd, int strand, std::vector<uint64_t>& pool, DarwinAnchor& a) {
@@ -250,7 +261,7 @@ void gpu_extender_body::operator()(extender_input input, extender_node::output_p
         // the reads of this batch must be resident (the software reference reads g_DRAM directly); gpu_filter_body has
         // normally sent them already when it ran on this thread
         std::vector<UploadSpan> spans = read_spans(reads);
-        if (!spans.empty() && t_resident_addr == spans[0].arena_addr && t_resident_end == spans.back().arena_addr + spans.back().n) spans.clear();
+        if (already_resident(token, spans)) spans.clear();
         DarwinExtendParams prm{cfg.tile_size, cfg.tile_overlap, cfg.do_overlap, 0};
         std::vector<DarwinAlnRes> res(n);
         std::vector<uint8_t> ops;
@@ -297,7 +308,7 @@ filter_input gpu_seeder_body::operator()(seeder_input input) {
         std::string err;
         int rc = gc.seed(spans, sr.data(), (int)sr.size(), &begin, &anchors, &pool, &err);
         if (rc != DARWIN_OK) fail_msg(rc, "gpu_seeder_body", err);
-        if (!spans.empty()) { t_resident_addr = spans[0].arena_addr; t_resident_end = spans.back().arena_addr + spans.back().n; }
+        mark_resident(token, spans);
         for (size_t r = 0; r < reads.size(); r++)
             for (int strand = 0; strand < 2; strand++) {
                 auto& dst = strand ? output.rcAnchors : output.fwAnchors;
@@ -380,12 +391,12 @@ extender_input gpu_filter_body::operator()(filter_input input) {
     std::vector<DarwinFilterRes> res(cands.size());
     if (!cands.empty()) {
         std::vector<UploadSpan> spans = read_spans(reads);                             // the reads of this batch must be resident
-        if (!spans.empty() && t_resident_addr == spans[0].arena_addr && t_resident_end == spans.back().arena_addr + spans.back().n) spans.clear();
+        if (already_resident(token, spans)) spans.clear();
         DarwinFilterParams prm{cfg.first_tile_size, cfg.first_tile_score_threshold, cfg.min_overlap, 0};
         std::string err;
         int rc = gc.filter(prm, spans, cands.data(), (int)cands.size(), res.data(), &err);
         if (rc != DARWIN_OK) fail_msg(rc, "gpu_filter_body", err);
-        if (!spans.empty()) { t_resident_addr = spans[0].arena_addr; t_resident_end = spans.back().arena_addr + spans.back().n; }
+        mark_resident(token, spans);
     }
     for (int strand = 0; strand < 2; strand++) {
         const auto& anchors = strand ? data.rcAnchors : data.fwAnchors;
