@@ -53,23 +53,23 @@ __global__ void pack_arena_kernel(uint8_t* __restrict__ arena, const char* __res
 }
 
 struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568-582 (32 ops per u64; written as 2 x u32)
-    uint32_t* words; int cap32; int n; uint32_t cur; int shift; int overflow;
-    __device__ TbWordSink(uint64_t* w, int cap64) : words(reinterpret_cast<uint32_t*>(w)), cap32(2 * cap64), n(0), cur(0), shift(0), overflow(0) {}
+    uint32_t* wptr; uint32_t* wend; uint32_t* wbeg; int n; uint32_t cur; int shift; int overflow;
+    __device__ TbWordSink(uint64_t* w, int cap64)
+        : wptr(reinterpret_cast<uint32_t*>(w)), wend(reinterpret_cast<uint32_t*>(w) + 2 * cap64), wbeg(reinterpret_cast<uint32_t*>(w)),
+          n(0), cur(0), shift(0), overflow(0) {}
     __device__ __forceinline__ void operator()(uint32_t d) {
         cur |= d << shift;
         shift += 2; n++;
         if (shift == 32) {
-            const int w = (n >> 4) - 1;
-            if (w < cap32) words[w] = cur; else overflow = 1;
-            cur = 0; shift = 0;
+            if (wptr < wend) *wptr = cur; else overflow = 1;
+            wptr++; cur = 0; shift = 0;
         }
     }
     __device__ __forceinline__ int count() const { return n; }
     __device__ __forceinline__ void finish() {
         if (n == 0) return;
-        int w = n >> 4;                                       // next 32-bit word to write
-        if (shift) { if (w < cap32) words[w] = cur; else overflow = 1; w++; }
-        if (w & 1) { if (w < cap32) words[w] = 0; else overflow = 1; }     // zero the upper half of the last u64
+        if (shift) { if (wptr < wend) *wptr = cur; else overflow = 1; wptr++; }
+        if ((wptr - wbeg) & 1) { if (wptr < wend) *wptr = 0; else overflow = 1; }     // zero the upper half of the last u64
     }
 };
 
@@ -413,7 +413,7 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
             if (a.large && ea.do_overlap == 0) { crt = rt; cqt = qt; }           // extender.cpp:261 / :408
             // lane 0 walks the traceback and records the ops in shared memory; the warp then consumes them together
             uint32_t* opbuf = reinterpret_cast<uint32_t*>(cx.wsmem + KernelGeom<K>::kOpsOff);   // behind the tile's own shared memory
-            SmemOpSink sink{opbuf, 0, kOpsSmemBytes * 4, 0, 0u};
+            SmemOpSink sink{opbuf, 0, kOpsSmemBytes * 4, 0, 0u, 0};
             TileOut out{};
             process_tile<K>(cx, ks, t, true, out, sink);
             if (lane == 0) sink.finish();

@@ -42,14 +42,14 @@ struct AnchorState {
 // The traceback (one lane) only records the tile's ops, 2 bits each (16 per 32-bit word, the reference's TB-word packing,
 // Processor.cpp:568-582), in shared memory ...
 struct SmemOpSink {
-    uint32_t* words; int n; int cap; int overflow; uint32_t cur;
+    uint32_t* wptr; int n; int cap; int overflow; uint32_t cur; int shift;
     __device__ __forceinline__ void operator()(uint32_t d) {
-        cur |= d << (2 * (n & 15));
-        n++;
-        if ((n & 15) == 0) { if (n <= cap) words[(n >> 4) - 1] = cur; else overflow = 1; cur = 0; }
+        cur |= d << shift;
+        shift += 2; n++;
+        if (shift == 32) { if (n <= cap) *wptr = cur; else overflow = 1; wptr++; cur = 0; shift = 0; }
     }
     __device__ __forceinline__ int count() const { return n; }
-    __device__ __forceinline__ void finish() { if (n & 15) { if (n <= cap) words[n >> 4] = cur; else overflow = 1; } }
+    __device__ __forceinline__ void finish() { if (shift) { if (n <= cap) *wptr = cur; else overflow = 1; } }
 };
 constexpr int kOpsSmemBytes = 1024;                 // 4096 ops >= i_steps + j_steps of the largest tile (1984 + 960)
 

@@ -347,37 +347,44 @@ __device__ int fast_traceback(const uint32_t* band, int Q, int R, int max_tb, Ti
     using G = FastGeom<K, BH>;
     const BandMap<K, BH> bm(Q, R);
     const int i0 = Q - 1, j0 = R - 1;
-    int v = i0 / K, r = i0 - v * K;
+    const int v = i0 / K;
+    int r = i0 - v * K;                           // row inside the virtual lane
     int t = bm.t_of(j0, v);                       // position inside virtual lane v's window
     const uint32_t* wp = band + (size_t)v * G::kLp + t;
-    int sh = (r < 3) ? 5 * r : 16 + 5 * (r - 3);  // bit position of row r inside the word
+    // bit position of row r inside a band word (rows 0-2 in bits 0-14, rows 3-5 in bits 16-30): one 5-bit entry per row,
+    // indexed by r5 = 5 * r
+    constexpr uint32_t kShTab = 0u | (5u << 5) | (10u << 10) | (16u << 15) | (21u << 20) | (26u << 25);
+    int r5 = 5 * r;
     // i = i0 - is, j = j0 - js: the loop of Processor.cpp:613-618 runs while is < min(Q, max_tb) and js < min(R, max_tb)
     const int lim_i = min(Q, max_tb), lim_j = min(R, max_tb);
-    int is = 0, js = 0;
-    uint32_t where = FT_DIAG;
-    int rc = FAST_OK;
-    while (is < lim_i && js < lim_j) {
-        if ((unsigned)t >= (unsigned)G::kL) { rc = FAST_BAND; break; }
+    int left_i = lim_i, left_j = lim_j;           // steps still allowed in each direction
+    uint32_t where = FT_DIAG, st = FT_DIAG;
+    // The walk is one dependent chain on ONE lane, so its cost is the number of instructions per op: arithmetic on small
+    // look-up words, two exits, nothing to set up on the way out.
+    for (;;) {
+        if (min(left_i, left_j) <= 0 || (unsigned)t >= (unsigned)G::kL) break;
         const uint32_t w = GLOBAL ? __ldcg(wp) : *wp;
-        const uint32_t code = (w >> sh) & 31u;
-        const uint32_t T = code >> 2;
+        const uint32_t code = (w >> ((kShTab >> r5) & 31u)) & 31u;
         // a DIAG-state cell whose pointer is DEL/INS switches state and is re-read by the reference (:628-633):
         // nothing moves in between, so the gap step is taken right away
-        const uint32_t st = (where == FT_DIAG) ? T : where;
-        if (st >= FT_ZERO) { if (st == FT_L) rc = FAST_LFLAG; break; }          // ZERO: path ends (:640-642)
-        const bool up = (st != FT_DEL), left = (st != FT_INS);
-        sink(st == FT_DIAG ? DARWIN_OP_M : (st == FT_DEL ? DARWIN_OP_D : DARWIN_OP_I));
-        // next state: gaps stay open while their "extended" bit is set (:648-653, :662-667)
-        where = (st == FT_DEL && (code & 1u)) ? FT_DEL : (st == FT_INS && (code & 2u)) ? FT_INS : FT_DIAG;
-        if (left) { js++; t--; wp--; }
-        if (up) {
-            is++;
-            if (r == 0) { r = K - 1; sh = (K - 1 < 3) ? 5 * (K - 1) : 16 + 5 * (K - 1 - 3); t += K; wp -= (G::kLp - K); }
-            else { r--; sh = (r == 2) ? 10 : sh - 5; }
-        }
+        st = (where == FT_DIAG) ? (code >> 2) : where;
+        if (st >= FT_ZERO) break;                                                // ZERO: path ends (:640-642); L: exact rerun
+        sink((0x36u >> (2 * st)) & 3u);                                          // DEL -> D (2), INS -> I (1), DIAG -> M (3)
+        // next state: gaps stay open while their "extended" bit is set (:648-653, :662-667): bit 0 for DEL, bit 1 for INS
+        where = ((code >> st) & (st < FT_DIAG ? 1u : 0u)) ? st : FT_DIAG;
+        const int mv_left = (st != FT_INS), mv_up = (st != FT_DEL);
+        left_j -= mv_left; t -= mv_left; wp -= mv_left;
+        left_i -= mv_up; r5 -= 5 * mv_up;
+        const int wrap = r5 < 0;                                                 // row above belongs to the previous virtual lane
+        r5 += wrap * (5 * K); t += wrap * K; wp -= wrap * (G::kLp - K);
+    }
+    int rc = FAST_OK;
+    if (min(left_i, left_j) > 0) {                                               // not the regular end of the walk
+        if ((unsigned)t >= (unsigned)G::kL) rc = FAST_BAND;                      // path left the stored band
+        else if (st == FT_L) rc = FAST_LFLAG;                                    // long-gap candidate met in DIAG state
     }
     if (rc != FAST_OK) return rc;
-    out.query_offset = is; out.ref_offset = js; out.total = sink.count(); out.tflags = 0;
+    out.query_offset = lim_i - left_i; out.ref_offset = lim_j - left_j; out.total = sink.count(); out.tflags = 0;
     return FAST_OK;
 }
 
