@@ -53,20 +53,30 @@ __global__ void pack_arena_kernel(uint8_t* __restrict__ arena, const char* __res
 }
 
 struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568-582 (32 ops per u64; written as 2 x u32)
-    uint32_t* wptr; uint32_t* wend; uint32_t* wbeg; int n; uint32_t cur; int shift; int overflow;
-    __device__ TbWordSink(uint64_t* w, int cap64)
+    uint32_t* wptr; uint32_t* wend; uint32_t* wbeg; int n; uint32_t cur; int shift; int overflow; bool wr;
+    // every lane may run the sink with identical state (warp-uniform traceback); only the writer lane stores
+    __device__ TbWordSink(uint64_t* w, int cap64, bool writer)
         : wptr(reinterpret_cast<uint32_t*>(w)), wend(reinterpret_cast<uint32_t*>(w) + 2 * cap64), wbeg(reinterpret_cast<uint32_t*>(w)),
-          n(0), cur(0), shift(0), overflow(0) {}
+          n(0), cur(0), shift(0), overflow(0), wr(writer) {}
+    __device__ __forceinline__ void flush_word() {
+        if (wptr < wend) { if (wr) *wptr = cur; } else overflow = 1;
+        wptr++; cur = 0; shift = 0;
+    }
     __device__ __forceinline__ void operator()(uint32_t d) {
         cur |= d << shift;
         shift += 2; n++;
-        if (shift == 32) {
-            if (wptr < wend) *wptr = cur; else overflow = 1;
-            wptr++; cur = 0; shift = 0;
+        if (shift == 32) flush_word();
+    }
+    __device__ __forceinline__ void run_m(int count) {          // `count` times M (0b11)
+        while (count > 0) {
+            const int take = min((32 - shift) >> 1, count);
+            cur |= (0xFFFFFFFFu >> (32 - 2 * take)) << shift;
+            shift += 2 * take; n += take; count -= take;
+            if (shift == 32) flush_word();
         }
     }
     __device__ __forceinline__ int count() const { return n; }
-    __device__ __forceinline__ void finish() {
+    __device__ __forceinline__ void finish() {                  // writer lane only
         if (n == 0) return;
         if (shift) { if (wptr < wend) *wptr = cur; else overflow = 1; wptr++; }
         if ((wptr - wbeg) & 1) { if (wptr < wend) *wptr = 0; else overflow = 1; }     // zero the upper half of the last u64
@@ -154,17 +164,14 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
                     const int score = single ? fast_forward<KK>(fc, v, t.Q, t.R)
                                     : !wide ? fast_forward_multi<KK, 5, kBandHalf>(fc, mv, gband, t.Q, t.R)
                                             : fast_forward_multi<KK, 4, kBandHalfWide>(ks.fcw, mv, gband, t.Q, t.R);
-                    int rc = FAST_OK;
-                    if (lane == 0) {
-                        Sink trial = sink;
-                        TileOut o2{};
-                        rc = single ? fast_traceback<KK, false>(v.band, t.Q, t.R, t.max_tb, o2, trial)
-                                    : !wide ? fast_traceback<KK, true>(gband, t.Q, t.R, t.max_tb, o2, trial)
-                                            : fast_traceback<KK, true, Sink, kBandHalfWide>(gband, t.Q, t.R, t.max_tb, o2, trial);
-                        if (rc == FAST_OK) { sink = trial; out = o2; }
-                    }
-                    rc = __shfl_sync(0xffffffffu, rc, 0);
+                    // warp-uniform traceback on a copy of the sink: committed only when the clean rule holds
+                    Sink trial = sink;
+                    TileOut o2{};
+                    const int rc = single ? fast_traceback<KK, false>(v.band, t.Q, t.R, t.max_tb, o2, trial)
+                                 : !wide ? fast_traceback<KK, true>(gband, t.Q, t.R, t.max_tb, o2, trial)
+                                         : fast_traceback<KK, true, Sink, kBandHalfWide>(gband, t.Q, t.R, t.max_tb, o2, trial);
                     if (rc == FAST_OK) {
+                        sink = trial; out = o2;
                         out.score = score; out.ref_max_pos = t.R - 1; out.query_max_pos = t.Q - 1;
                         cx.n_fast++;
                         return;
@@ -257,7 +264,7 @@ tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelSc
                   rq.align_fields, (int)rq.max_tb_steps};
         TileOut out{};
         const bool too_big = t.Q > kMaxTile || t.R > kMaxTile;
-        TbWordSink sink(tb_words + (size_t)idx * tb_words_per_req, tb_words_per_req);
+        TbWordSink sink(tb_words + (size_t)idx * tb_words_per_req, tb_words_per_req, lane == 0);
         if (!too_big) process_tile<K>(cx, ks, t, do_traceback != 0, out, sink);
         if (lane == 0) {
             if (do_traceback) sink.finish();
@@ -413,7 +420,7 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
             if (a.large && ea.do_overlap == 0) { crt = rt; cqt = qt; }           // extender.cpp:261 / :408
             // lane 0 walks the traceback and records the ops in shared memory; the warp then consumes them together
             uint32_t* opbuf = reinterpret_cast<uint32_t*>(cx.wsmem + KernelGeom<K>::kOpsOff);   // behind the tile's own shared memory
-            SmemOpSink sink{opbuf, 0, kOpsSmemBytes * 4, 0, 0u, 0};
+            SmemOpSink sink{opbuf, 0, kOpsSmemBytes * 4, 0, 0u, 0, lane == 0};
             TileOut out{};
             process_tile<K>(cx, ks, t, true, out, sink);
             if (lane == 0) sink.finish();

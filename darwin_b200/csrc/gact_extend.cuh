@@ -42,11 +42,23 @@ struct AnchorState {
 // The traceback (one lane) only records the tile's ops, 2 bits each (16 per 32-bit word, the reference's TB-word packing,
 // Processor.cpp:568-582), in shared memory ...
 struct SmemOpSink {
-    uint32_t* wptr; int n; int cap; int overflow; uint32_t cur; int shift;
+    uint32_t* wptr; int n; int cap; int overflow; uint32_t cur; int shift; bool wr;     // wr: this lane stores (lane 0)
+    __device__ __forceinline__ void flush_word() {
+        if (n <= cap) { if (wr) *wptr = cur; } else overflow = 1;
+        wptr++; cur = 0; shift = 0;
+    }
     __device__ __forceinline__ void operator()(uint32_t d) {
         cur |= d << shift;
         shift += 2; n++;
-        if (shift == 32) { if (n <= cap) *wptr = cur; else overflow = 1; wptr++; cur = 0; shift = 0; }
+        if (shift == 32) flush_word();
+    }
+    __device__ __forceinline__ void run_m(int count) {          // `count` times M (0b11)
+        while (count > 0) {
+            const int take = min((32 - shift) >> 1, count);
+            cur |= (0xFFFFFFFFu >> (32 - 2 * take)) << shift;
+            shift += 2 * take; n += take; count -= take;
+            if (shift == 32) flush_word();
+        }
     }
     __device__ __forceinline__ int count() const { return n; }
     __device__ __forceinline__ void finish() { if (shift) { if (n <= cap) *wptr = cur; else overflow = 1; } }
