@@ -184,7 +184,7 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
                 if (xok) {
                     const int score = xfast_forward(ks.xc, xv, gband, reinterpret_cast<uint4*>(cx.ws.bound), t.Q, t.R);
                     __syncwarp();
-                    if (lane == 0) xfast_traceback(gband, t.Q, t.R, t.max_tb, out, sink);
+                    xfast_traceback(gband, t.Q, t.R, t.max_tb, out, sink);          // warp-uniform
                     out.score = score; out.ref_max_pos = t.R - 1; out.query_max_pos = t.Q - 1;
                     cx.n_xfast++;
                     return;

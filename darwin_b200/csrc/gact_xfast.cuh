@@ -207,16 +207,38 @@ __device__ int xfast_forward(const XConst& xc, const XSmemView& v, uint32_t* tra
     return (int)(cw >> 5) - xc.bias;
 }
 
-// Traceback over the full trace (Processor.cpp:585-716), ONE lane.
+// Traceback over the full trace (Processor.cpp:585-716), executed by the whole warp with identical state in every lane
+// (see fast_traceback): in the DIAG state lane k probes cell (i-k, j-k), a ballot gives the length of the run of DIAG
+// pointers, which is emitted and skipped at once -- on the 1984x960 tiles that replaces thousands of dependent global
+// loads on one lane by a few dozen warp-wide ones.  Every other cell goes through the generic step.
 template <class Sink>
 __device__ void xfast_traceback(const uint32_t* trace, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
     constexpr int K = XK;
+    const int lane = lane_id();
     const int steps = R + 63;
     int i = Q - 1, j = R - 1;
     const int lim_i = min(Q, max_tb), lim_j = min(R, max_tb);
-    int is = 0, js = 0;
+    int left_i = lim_i, left_j = lim_j;
     uint32_t where = X_DIAG, tfl = 0;
-    while (is < lim_i && js < lim_j) {
+    for (;;) {
+        const int lim = min(left_i, left_j);
+        if (lim <= 0) break;
+        if (where == X_DIAG) {
+            const bool ok = lane < lim;                                          // implies i - lane >= 0 and j - lane >= 0
+            const int ii = ok ? i - lane : 0, jj = ok ? j - lane : 0;
+            const int vg = ii / K, r = ii - vg * K;
+            const int strip = vg >> 6, vl = vg & 63;
+            uint32_t w = 0;
+            if (ok) w = __ldcg(trace + ((size_t)strip * steps + (size_t)(jj + vl)) * 64 + vl);
+            const uint32_t code = (w >> ((r & 1) * 7 + (r >> 1) * 16)) & 127u;
+            const uint32_t is_m = __ballot_sync(0xffffffffu, ok && (code >> 4) == X_DIAG);
+            const int run = (is_m == 0xffffffffu) ? 32 : __ffs(~is_m) - 1;
+            if (run > 0) {
+                sink.run_m(run);
+                i -= run; j -= run; left_i -= run; left_j -= run;
+                continue;
+            }
+        }
         const int vg = i / K, r = i - vg * K;
         const int strip = vg >> 6, vl = vg & 63;
         const uint32_t w = __ldcg(trace + ((size_t)strip * steps + (size_t)(j + vl)) * 64 + vl);
@@ -234,10 +256,10 @@ __device__ void xfast_traceback(const uint32_t* trace, int Q, int R, int max_tb,
         else if (st == X_INS)  { sink(DARWIN_OP_I); up = true; left = false; where = (code & 2u) ? X_INS : X_DIAG; }
         else if (st == X_DELL) { sink(DARWIN_OP_D); up = false; left = true; where = (code & 4u) ? X_DELL : X_DIAG; }
         else                   { sink(DARWIN_OP_I); up = true; left = false; where = (code & 8u) ? X_INSL : X_DIAG; }
-        if (left) { j--; js++; }
-        if (up) { i--; is++; }
+        if (left) { j--; left_j--; }
+        if (up) { i--; left_i--; }
     }
-    out.query_offset = is; out.ref_offset = js; out.total = sink.count(); out.tflags = tfl;
+    out.query_offset = lim_i - left_i; out.ref_offset = lim_j - left_j; out.total = sink.count(); out.tflags = tfl;
 }
 
 } // namespace gact
