@@ -97,7 +97,9 @@ template <int K> struct KernelGeom {
     static constexpr size_t kFast = (K == 0) ? 0 : FastGeom<(K == 0 ? 4 : K)>::kSmemBytes;
     static constexpr size_t kNeed = (K == 0) ? sizeof(ExactSmem) : (kFast > MultiSmemView::kBytes ? kFast : MultiSmemView::kBytes);
     static_assert(XSmemView::kBytes <= MultiSmemView::kBytes, "xfast view must fit");
-    static constexpr size_t kTileBytes = ((kNeed > sizeof(ExactSmem) ? kNeed : sizeof(ExactSmem)) + 15) & ~(size_t)15;
+    static constexpr size_t kNeed2 = kNeed > sizeof(ExactSmem) ? kNeed : sizeof(ExactSmem);
+    static constexpr size_t kBigEnd = (K == 0) ? 0 : 16000 + 2 * (size_t)kRawBig;      // big raw windows live at offset 16000
+    static constexpr size_t kTileBytes = ((kNeed2 > kBigEnd ? kNeed2 : kBigEnd) + 15) & ~(size_t)15;
     // raw packed windows for the TMA staging: single-strip fast tiles use a small pair behind the tile region; bigger
     // tiles (multi-strip / packed exact / unpacked exact) use the spare space of the tile region (K > 0) or a big pair (K = 0)
     static constexpr int kRawSmallStride = (K == 0) ? kRawBig : ((32 * K + 32 + 15) & ~15);
