@@ -190,9 +190,10 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
     const FastRegs kr(fc);                                               // scoring constants in registers
     uint32_t sendH = fc.hm_init, sendF = fc.f_top, sendFL = fc.fl_top;   // state below my last row (previous step)
     uint32_t diag_in = fc.hm_init;                                       // Hm(row above, previous column)
-    uint32_t corner = 0;
     const int src = (lane + 31) & 31;
-    const int steps = R + 63;
+    // the corner cell (Q-1, R-1) is the last valid cell of the wavefront (step R-1+vc): nothing after it is ever read,
+    // so the loop ends there and the corner score is simply what its owner holds afterwards
+    const int steps = sc_step + 1;
     uint32_t rq_next = v.P[32 - lane];                                   // step 0: j = -lane (dummy unless lane 0)
     // band window of my two virtual lanes: t = s - (K+1)*v + c1 (t(i,j) with j = s - v)
     int t_lo = -(K + 1) * lane + bm.c1;                                  // at s = 0
@@ -219,10 +220,6 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
             const uint32_t code = fast_cell(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
             if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
         }
-        if (s == sc_step) {                                              // warp-uniform, taken once per tile
-#pragma unroll
-            for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - kr.diaga;
-        }
         diag_in = inH;
         sendH = Hm[K - 1]; sendF = F; sendFL = FL;
         // band store: one word per (virtual lane, step): rows 0-2 in bits 0-14, rows 3-5 in bits 16-30
@@ -231,6 +228,9 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
         t_lo++; bp++;
     }
     __syncwarp();
+    uint32_t corner = 0;
+#pragma unroll
+    for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - kr.diaga;
     // corner owner: virtual lane vc -> physical lane vc & 31, half vc >> 5
     uint32_t cw = __shfl_sync(0xffffffffu, corner, vc & 31);
     cw = (vc >= 32) ? (cw >> 16) : (cw & 0xFFFFu);
