@@ -292,7 +292,9 @@ __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, u
         uint32_t* bp = gband + (size_t)vg * G::kLp + t_lo;
         uint32_t rlo = (lane == 0 && R > 0) ? v.sref[0] : 5u, rhi = 5u;  // reference bases of step 0
 
-        for (int s = 0; s < steps; s++) {
+        // the corner is the last valid cell of the last strip: its loop ends there (nothing later is ever read)
+        const int strip_steps = (strip == nstrips - 1) ? sc_step + 1 : steps;
+        for (int s = 0; s < strip_steps; s++) {
             uint32_t inH = __shfl_sync(0xffffffffu, sendH, src);
             uint32_t F   = __shfl_sync(0xffffffffu, sendF, src);
             uint32_t FL  = __shfl_sync(0xffffffffu, sendFL, src);
@@ -315,10 +317,6 @@ __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, u
                 const uint32_t code = fast_cell<S>(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
                 if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
             }
-            if (strip == nstrips - 1 && s == sc_step) {
-#pragma unroll
-                for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - kr.diaga;
-            }
             diag_in = inH;
             sendH = Hm[K - 1]; sendF = F; sendFL = FL;
             if (lane == 31 && strip + 1 < nstrips && (unsigned)(s - 63) < (unsigned)R) {   // bottom row of the strip
@@ -330,6 +328,10 @@ __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, u
             t_lo++; bp++;
         }
         __syncwarp();
+        if (strip == nstrips - 1) {
+#pragma unroll
+            for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - kr.diaga;
+        }
     }
     const int vl = vc & 63;
     uint32_t cw = __shfl_sync(0xffffffffu, corner, vl & 31);

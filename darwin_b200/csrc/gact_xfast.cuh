@@ -110,7 +110,9 @@ __device__ int xfast_forward(const XConst& xc, const XSmemView& v, uint32_t* tra
         uint32_t* tr = trace + (size_t)strip * steps * 64 + lane;
         uint32_t rlo = (lane == 0 && R > 0) ? v.sref[0] : 5u, rhi = 5u;
 
-        for (int s = 0; s < steps; s++) {
+        // the corner is the last valid cell of the last strip: its loop ends there (nothing later is ever read)
+        const int strip_steps = (strip == nstrips - 1) ? sc_step + 1 : steps;
+        for (int s = 0; s < strip_steps; s++) {
             if (strip > 0 && (s & 31) == 0) {                                // next 32 boundary records -> shared memory
                 const int jj = s + lane;
                 if (jj < R) v.rec[((s >> 5) & 1) * 32 + lane] = __ldcg(bound + jj);
@@ -183,10 +185,6 @@ __device__ int xfast_forward(const XConst& xc, const XSmemView& v, uint32_t* tra
                 FL     = __viaddmax_u16x2(FL | 0x00080008u, lgeh, HoL);
                 if (r < 2) acc0 += code << (7 * r); else acc1 += code << (7 * (r - 2));
             }
-            if (strip == nstrips - 1 && s == sc_step) {
-#pragma unroll
-                for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - diaga;
-            }
             diag_in = inH;
             sH = Hm[K - 1]; sF = F; sFL = FL; sf0 = f0; sfl0 = fl0; sfc = fc; sflc = flc;
             if (lane == 31 && strip + 1 < nstrips && (unsigned)(s - 63) < (unsigned)R) {       // bottom row of the strip
@@ -200,6 +198,10 @@ __device__ int xfast_forward(const XConst& xc, const XSmemView& v, uint32_t* tra
             tr += 64;
         }
         __syncwarp();
+        if (strip == nstrips - 1) {
+#pragma unroll
+            for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - diaga;
+        }
     }
     const int vl = vc & 63;
     uint32_t cw = __shfl_sync(0xffffffffu, corner, vl & 31);

@@ -172,17 +172,29 @@ void InstallProcessorTable() {
 }
 
 // arena range this thread's last gpu_filter_body call made resident (lets gpu_extender_body skip the same upload)
-static thread_local uint64_t t_resident_addr = ~0ull, t_resident_end = 0;
+static thread_local uint64_t t_resident_addr = ~0ull, t_resident_end = 0, t_resident_print = 0;
 static thread_local int t_resident_gpu = -1;         // the marker is only valid for the GPU (arena replica) it was sent to
 
 static int gpu_of_token(size_t token) { return g_gpus > 0 ? (int)(token % (size_t)g_gpus) : 0; }
+// cheap fingerprint of what the spans hold (the arena is reused after a wrap, main.cpp:652-655: same addresses, new reads)
+static uint64_t span_fingerprint(const std::vector<UploadSpan>& spans) {
+    uint64_t f = 1469598103934665603ull;
+    for (const auto& s : spans) {
+        const uint64_t n = s.n, step = n > 256 ? n / 32 : 1;
+        for (uint64_t k = 0; k < n; k += step) { f ^= (unsigned char)s.ascii[k]; f *= 1099511628211ull; }
+        if (n) { f ^= (unsigned char)s.ascii[n - 1]; f *= 1099511628211ull; }
+        f ^= n; f *= 1099511628211ull;
+    }
+    return f;
+}
 static bool already_resident(size_t token, const std::vector<UploadSpan>& spans) {
     return !spans.empty() && t_resident_gpu == gpu_of_token(token) && t_resident_addr == spans[0].arena_addr &&
-           t_resident_end == spans.back().arena_addr + spans.back().n;
+           t_resident_end == spans.back().arena_addr + spans.back().n && t_resident_print == span_fingerprint(spans);
 }
 static void mark_resident(size_t token, const std::vector<UploadSpan>& spans) {
     if (spans.empty()) return;
     t_resident_gpu = gpu_of_token(token); t_resident_addr = spans[0].arena_addr; t_resident_end = spans.back().arena_addr + spans.back().n;
+    t_resident_print = span_fingerprint(spans);
 }
 
 // ExtendLocations (graph.h:83-91) -> DarwinAnchor (what makeForward/BackwardAlignment look up, extender.cpp:1067-1159)
