@@ -14,6 +14,17 @@ pytestmark = pytest.mark.gpu
 LIB = os.path.join(os.path.dirname(os.path.abspath(oracle.__file__)), "_ref", "libdarwin_ref_gpu.so")
 
 
+def first_difference(mode, per_batch, n_gpu, n_cpu, buf_gpu, buf_cpu):
+    """Failure message: which canonical alignment line differs first (read, chromosome, strand, offsets, score)."""
+    g, c = buf_gpu.value.split(b"\n"), buf_cpu.value.split(b"\n")
+    for k, (a, b) in enumerate(zip(g, c)):
+        if a != b:
+            return "mode %d, %d reads per batch: %d vs %d alignments; line %d differs: GPU %r | CPU %r" % (
+                mode, per_batch, n_gpu, n_cpu, k, a[:80], b[:80])
+    return "mode %d, %d reads per batch: %d vs %d alignments; common prefix identical (%d vs %d lines)" % (
+        mode, per_batch, n_gpu, n_cpu, len(g), len(c))
+
+
 def load_driver():
     ref = oracle.Reference.__new__(oracle.Reference)
     ref.lib = C.CDLL(LIB)
@@ -68,7 +79,7 @@ def test_multithreaded_pipeline_matches_cpu_pipeline():
         # mode 4: the resident pipeline call (darwin_gpu_align_reads) behind gpu_align_body
         for mode, per_batch in ((2, 4), (1, 7), (2, 1), (3, 5), (3, 32), (4, 6), (4, 48)):
             n_gpu = L.dref_pipeline_mt(0, n_reads, threads, per_batch, mode, buf_gpu, C.c_uint64(cap), stats)
-            assert n_gpu == n_cpu and buf_gpu.value == buf_cpu.value, (mode, per_batch, n_gpu, n_cpu)
+            assert n_gpu == n_cpu and buf_gpu.value == buf_cpu.value, first_difference(mode, per_batch, n_gpu, n_cpu, buf_gpu, buf_cpu)
         cs = (C.c_uint64 * 12)()
         L.dref_combiner_stats(cs)
         # requests of different host threads really shared device calls
