@@ -11,7 +11,7 @@ load_case(ref, 21, genome, n_reads, 13333)
 cap = 1 << 30
 buf_cpu, buf_gpu = C.create_string_buffer(cap), C.create_string_buffer(cap)
 stats = (C.c_double * 8)()
-threads = os.cpu_count() or 1
+threads = int(os.environ.get("E2E_THREADS", os.cpu_count() or 1))
 t0 = time.time()
 n_cpu = L.dref_pipeline_mt(0, n_reads, threads, 1, 0, buf_cpu, C.c_uint64(cap), stats)
 cpu_text = buf_cpu.value
