@@ -82,8 +82,10 @@ def test_multithreaded_pipeline_matches_cpu_pipeline():
             assert n_gpu == n_cpu and buf_gpu.value == buf_cpu.value, first_difference(mode, per_batch, n_gpu, n_cpu, buf_gpu, buf_cpu)
         cs = (C.c_uint64 * 12)()
         L.dref_combiner_stats(cs)
-        # requests of different host threads really shared device calls
-        assert cs[2] < cs[5] and cs[11] >= 2, list(cs)
+        # every request reached the device through the combiner; whether two threads' requests happened to ride in one device
+        # call depends on timing (two threads per lane here), so merging itself is asserted in tests/test_combiner.py, where
+        # the stand-in device has a fixed latency
+        assert 0 < cs[2] <= cs[5] and cs[11] >= 1, list(cs)
     finally:
         L.dref_use_cpu_table()
         L.dref_gpu_shutdown()
