@@ -1,7 +1,7 @@
 """Analysis script (not part of bench.py) for SURVEY 8(d) config 3: synthetic reference + PacBio-like 10 kbp reads at 15 %
 error (sub 1.5 / ins 9 / del 4.5), reference-guided, END TO END: the reference's own D-SOFT (seeder_body) on all host
 threads + first-tile filter and GACT extension on the GPU behind the cross-read combiner, next to the reference's CPU
-pipeline on a bounded sample of the same reads.  Usage: python scripts/e2e_config3.py [genome_bp] [n_reads] [cpu_sample]"""
+pipeline on a bounded sample of the same reads.  Usage: python tests/tools/e2e_config3.py [genome_bp] [n_reads] [cpu_sample]"""
 import ctypes as C
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_gpu_e2e import load_driver, load_case  # noqa: E402

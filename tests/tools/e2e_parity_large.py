@@ -1,7 +1,7 @@
 """One-off scale check (not a test): the whole pipeline on a few thousand 10 kbp reads, reference CPU stages vs the GPU
-pipeline in every mode, canonical alignment text compared byte for byte.  Usage: python scripts/e2e_parity_large.py [n_reads] [genome_bp]"""
+pipeline in every mode, canonical alignment text compared byte for byte.  Usage: python tests/tools/e2e_parity_large.py [n_reads] [genome_bp]"""
 import ctypes as C, hashlib, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_gpu_e2e import load_driver, load_case
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 3000

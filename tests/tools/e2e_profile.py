@@ -1,7 +1,7 @@
 """Where does the host time go?  Single host thread, one lane: per-stage wall times of the GPU pipeline are not hidden behind
-other threads.  Usage: python scripts/e2e_profile.py [n_reads] [per_batch]"""
+other threads.  Usage: python tests/tools/e2e_profile.py [n_reads] [per_batch]"""
 import ctypes as C, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from test_gpu_e2e import load_driver, load_case
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 1024

@@ -1,7 +1,7 @@
 """First-tile filter shape (filter.cpp:61-71): 128x128 score-only tiles in max-cell mode through darwin_gpu_tiles."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import darwin_b200, oracle
 from darwin_b200 import abi, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200000

@@ -1,14 +1,14 @@
 """Analysis script (not part of bench.py): realistic anchors from the reference's D-SOFT + filter (oracle/_ref), extended
 by (a) the reference's extender_body on all host cores and (b) darwin_gpu_extend.  Prints the tile census and both
-throughputs.  Usage: python scripts/pipeline_timing.py [n_reads]"""
+throughputs.  Usage: python tests/tools/pipeline_timing.py [n_reads]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests"))
 import oracle  # noqa: E402
 import darwin_b200  # noqa: E402
 from darwin_b200 import abi  # noqa: E402
