@@ -592,7 +592,6 @@ struct DarwinGpu {
     unsigned int* d_counter = nullptr;
     // growable device buffers
     void* d_buf[12] = {nullptr}; size_t d_cap[12] = {0};
-    void* h_buf[4] = {nullptr}; size_t h_cap[4] = {0};
     DarwinGpuStats stats{};
     std::string err;
     SeedIndex seed_ix;                          // D-SOFT seed position table (dsoft_host.cuh); lanes share the parent's
@@ -609,16 +608,6 @@ static int grow_dev(DarwinGpu* h, int slot, size_t bytes) {
     h->d_cap[slot] = want;
     return DARWIN_OK;
 }
-static int grow_host(DarwinGpu* h, int slot, size_t bytes) {
-    if (bytes <= h->h_cap[slot]) return DARWIN_OK;
-    if (h->h_buf[slot]) cudaFreeHost(h->h_buf[slot]);
-    h->h_buf[slot] = nullptr; h->h_cap[slot] = 0;
-    size_t want = bytes + bytes / 4 + 256;
-    CK(cudaMallocHost(&h->h_buf[slot], want));
-    h->h_cap[slot] = want;
-    return DARWIN_OK;
-}
-
 #include "dsoft_host.cuh"
 
 // per-warp exact-path scratch sized for the largest tile of the call
@@ -750,7 +739,6 @@ int darwin_gpu_destroy(DarwinGpu* h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < 12; i++) if (h->d_buf[i]) cudaFree(h->d_buf[i]);
-    for (int i = 0; i < 4; i++) if (h->h_buf[i]) cudaFreeHost(h->h_buf[i]);
     if (h->d_trace) cudaFree(h->d_trace);
     if (h->d_bound) cudaFree(h->d_bound);
     if (h->d_counter) cudaFree(h->d_counter);
@@ -1074,11 +1062,10 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     { float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1)); *kernel_ms += ms; }
     TMARK("kernel+res D2H");
     std::vector<uint64_t> dense(n);
-    uint64_t used = 0; int overflow = 0;
+    uint64_t used = 0;
     for (int i = 0; i < n; i++) {
         dense[i] = used;
-        if (res[i].flags & DARWIN_ALN_OPS_OVERFLOW) overflow = 1;
-        else if (res[i].flags & DARWIN_ALN_EMITTED) used += res[i].n_ops;
+        if ((res[i].flags & DARWIN_ALN_EMITTED) && !(res[i].flags & DARWIN_ALN_OPS_OVERFLOW)) used += res[i].n_ops;
         h->stats.cells += res[i].cells;
     }
     if (used > ops_pool_bytes) { h->err = "ops_pool too small: need " + std::to_string(used); return DARWIN_ERR_CAPACITY; }
@@ -1095,7 +1082,6 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     if (used && ops_pool) CK(cudaMemcpyAsync(ops_pool, d_dense, used, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     TMARK("compact+D2H");
-    (void)overflow;
     *used_out = used;
     if (ea.dbg) {
         std::vector<uint32_t> hd((size_t)n * 128 * 8);
