@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=1000000, help="tiles per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--extend-reads", type=int, default=8000,
+    ap.add_argument("--extend-reads", type=int, default=16000,
                     help="secondary measurement: reads of 10 kbp through the in-kernel anchor walker (0 = skip)")
     ap.add_argument("--filter-tiles", type=int, default=400000,
                     help="secondary measurement: first-tile filter candidates through darwin_gpu_filter (0 = skip)")
