@@ -2,6 +2,8 @@
 #include "darwin_gpu_processor.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdlib>
 #include <deque>
 #include <mutex>
@@ -59,6 +61,12 @@ static std::vector<UploadSpan> read_spans(const std::vector<Read>& reads) {
 
 // Layout of g_handles / g_combiners: lane-major, g_handles[lane * g_gpus + gpu]; lane 0 of every GPU owns the arena replica.
 static int g_gpus = 0, g_lanes = 0;
+
+// where the host threads' time goes in gpu_align_body (nanoseconds, summed over threads): [0] building the request,
+// [1] blocked in the combiner (device call + waiting for it), [2] rebuilding ExtendAlignments (gapped strings)
+static std::atomic<uint64_t> g_prof_ns[3];
+static inline uint64_t now_ns() { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+void host_profile(double out_seconds[3]) { for (int k = 0; k < 3; k++) out_seconds[k] = (double)g_prof_ns[k].exchange(0) * 1e-9; }
 
 size_t InitializeProcessor(int threads, int gpus, std::string /*chip_ids*/) {
     if (gpus < 1) gpus = 1;
@@ -349,6 +357,7 @@ void gpu_align_body::operator()(seeder_input input, extender_node::output_ports_
     GpuCombiner& gc = combiner_for_token(token);
     extend_data output;
     if (!reads.empty()) {
+        const uint64_t t0 = now_ns();
         const std::vector<UploadSpan> spans = read_spans(reads);
         std::vector<DarwinSeedRead> sr(reads.size());
         for (size_t r = 0; r < reads.size(); r++) sr[r] = DarwinSeedRead{(uint64_t)(reads[r].seq.data() - g_DRAM->buffer), (uint32_t)reads[r].seq.size(), 0};
@@ -358,9 +367,13 @@ void gpu_align_body::operator()(seeder_input input, extender_node::output_ports_
         prm.slope_threshold = cfg.slope_threshold;
         std::vector<DarwinAnchor> anchors; std::vector<DarwinAlnRes> res; std::vector<uint8_t> ops;
         std::string err;
+        const uint64_t t1 = now_ns();
         int rc = gc.align(prm, spans, sr.data(), (int)sr.size(), &anchors, &res, &ops, &err);
         if (rc != DARWIN_OK) fail_msg(rc, "gpu_align_body", err);
+        const uint64_t t2 = now_ns();
         for (size_t k = 0; k < anchors.size(); k++) emit_alignment(anchors[k], res[k], ops, reads, output);
+        const uint64_t t3 = now_ns();
+        g_prof_ns[0] += t1 - t0; g_prof_ns[1] += t2 - t1; g_prof_ns[2] += t3 - t2;
     }
     get<1>(op).try_put(token);
     get<0>(op).try_put(printer_input(printer_payload(reads, std::move(output)), token));

@@ -64,6 +64,7 @@ DarwinGpu* handle_for_token(size_t token);
 GpuCombiner& combiner_for_token(size_t token);       // the per-GPU batcher all stage bodies go through
 CombinerStats combiner_stats(size_t token);
 CombinerStats combiner_stats_total();              // summed over all GPUs and lanes
+void host_profile(double out_seconds[3]);          // gpu_align_body: request building / blocked in the combiner / rebuilding ExtendAlignments (thread-seconds since the last call)
 const char* last_error();
 
 } // namespace darwin_gpu_host

@@ -804,6 +804,8 @@ void dref_combiner_stats(uint64_t* out) {
     for (int k = 0; k < 3; k++) { out[k] = s.device_calls[k]; out[3 + k] = s.requests[k]; out[6 + k] = s.items[k]; out[9 + k] = s.max_merged[k]; }
 }
 
+void dref_host_profile(double* out3) { darwin_gpu_host::host_profile(out3); }
+
 // seed position table on the GPUs (after dref_gpu_init)
 int dref_gpu_seed_index(void) {
     try { darwin_gpu_host::BuildSeedIndex(); } catch (const std::exception& e) { fprintf(stderr, "dref_gpu_seed_index: %s\n", e.what()); return -1; }

@@ -22,6 +22,8 @@ for rep in range(3):
     nb = (n_reads + per_batch - 1) // per_batch
     print("gpus %d mode %d threads %d, %d reads, %d per batch: wall %.3f s (%.0f reads/s) | seed %.3f filter %.3f extend %.3f thread-s | per batch: seed %.2f ms filter %.2f ms extend %.2f ms" % (
         gpus, mode, threads, n_reads, per_batch, g[0], n_reads / g[0], g[2], g[3], g[4], g[2] / nb * 1e3, g[3] / nb * 1e3, g[4] / nb * 1e3))
-if os.environ.get("DARWIN_GPU_TIMING"):
-    pass
+if mode >= 4:
+    hp = (C.c_double * 3)()
+    L.dref_host_profile(hp)
+    print("gpu_align_body thread-seconds over the 3 repetitions: building requests %.2f, blocked in the combiner %.2f, rebuilding ExtendAlignments %.2f" % tuple(hp))
 L.dref_use_cpu_table(); L.dref_gpu_shutdown()
