@@ -824,6 +824,52 @@ int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint
     return DARWIN_OK;
 }
 
+int darwin_gpu_upload_spans(DarwinGpu* h, const DarwinSpan* spans, int n_spans) {
+    if (!h || n_spans < 0 || (n_spans && !spans)) return DARWIN_ERR_INVALID;
+    for (int k = 0; k < n_spans; k++) {
+        if (!spans[k].ascii && spans[k].n) return DARWIN_ERR_INVALID;
+        if (spans[k].arena_addr + spans[k].n > h->arena_bytes) { h->err = "upload beyond arena"; return DARWIN_ERR_INVALID; }
+    }
+    CK(cudaSetDevice(h->device));
+    int b = 0, flushes = 0;
+    uint64_t fill = 0;
+    int first = 0;                                   // first span of the staging buffer being filled
+    auto flush = [&](int upto) -> int {              // spans [first, upto) sit back to back in h_stage[b]
+        if (fill == 0) return DARWIN_OK;
+        CK(cudaMemcpyAsync(h->d_stage[b], h->h_stage[b], fill, cudaMemcpyHostToDevice, h->stream));
+        uint64_t at = 0;
+        for (int k = first; k < upto; k++) {
+            const uint64_t a = spans[k].arena_addr, n = spans[k].n;
+            if (n == 0) continue;
+            const uint64_t nbytes = ((a + n - 1) >> 1) - (a >> 1) + 1;
+            pack_arena_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(h->d_arena, h->d_stage[b] + at, a, n);
+            CK(cudaGetLastError());
+            h->stats.kernel_launches++;
+            at += n;
+        }
+        CK(cudaEventRecord(h->ev_stage[b], h->stream));
+        b ^= 1; fill = 0; first = upto; flushes++;
+        if (flushes >= 2) CK(cudaEventSynchronize(h->ev_stage[b]));          // the buffer we are about to refill is free again
+        return DARWIN_OK;
+    };
+    int rc;
+    for (int k = 0; k < n_spans; k++) {
+        const uint64_t n = spans[k].n;
+        if (n > h->stage_bytes) {                    // a span larger than the staging buffers goes the chunked way
+            if ((rc = flush(k))) return rc;
+            if ((rc = darwin_gpu_upload(h, spans[k].arena_addr, spans[k].ascii, n))) return rc;
+            first = k + 1;
+            continue;
+        }
+        if (fill + n > h->stage_bytes && (rc = flush(k))) return rc;
+        memcpy(h->h_stage[b] + fill, spans[k].ascii, n);
+        fill += n;
+    }
+    if ((rc = flush(n_spans))) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    return DARWIN_OK;
+}
+
 static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_req, int n,
                         DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR,
                         const unsigned int* idx_list = nullptr, const unsigned int* idx_count = nullptr);

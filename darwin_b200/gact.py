@@ -38,6 +38,7 @@ def load_library():
         L.darwin_gpu_destroy.argtypes = [C.c_void_p]
         L.darwin_gpu_set_scoring.argtypes = [C.c_void_p, C.POINTER(abi.Scoring)]
         L.darwin_gpu_upload.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+        L.darwin_gpu_upload_spans.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.darwin_gpu_tiles.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.darwin_gpu_tiles_device.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.darwin_gpu_extend.argtypes = [C.c_void_p, C.POINTER(abi.ExtendParams), C.c_void_p, C.c_int, C.c_void_p,
@@ -59,7 +60,7 @@ def load_library():
 
 EXPORTS = ("darwin_gpu_create", "darwin_gpu_create_shared", "darwin_gpu_destroy", "darwin_gpu_set_scoring", "darwin_gpu_upload",
            "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_filter", "darwin_gpu_seed_index",
-           "darwin_gpu_seed_index_share", "darwin_gpu_seed_index_read", "darwin_gpu_seed", "darwin_gpu_align_reads", "darwin_gpu_host_alloc", "darwin_gpu_host_free", "darwin_gpu_stats", "darwin_gpu_int_peak",
+           "darwin_gpu_seed_index_share", "darwin_gpu_seed_index_read", "darwin_gpu_seed", "darwin_gpu_align_reads", "darwin_gpu_host_alloc", "darwin_gpu_host_free", "darwin_gpu_upload_spans", "darwin_gpu_stats", "darwin_gpu_int_peak",
            "darwin_gpu_last_error", "darwin_gpu_version")
 
 
@@ -108,6 +109,14 @@ class Processor:
         self._check(self.lib.darwin_gpu_upload(self.h, C.c_uint64(int(arena_addr)), abi.ptr(a), C.c_uint64(a.size)))
 
     InitializeReadMemory = InitializeReferenceMemory
+
+    def upload_spans(self, spans):
+        """Several uploads in one call: `spans` = [(arena_addr, uint8 array), ...] (darwin_gpu_upload_spans)."""
+        keep = [np.ascontiguousarray(a if isinstance(a, np.ndarray) else np.frombuffer(a, np.uint8)) for _, a in spans]
+        rec = np.zeros(len(spans), np.dtype([("arena_addr", "<u8"), ("ascii", "<u8"), ("n", "<u8")]))
+        for k, ((addr, _), a) in enumerate(zip(spans, keep)):
+            rec[k] = (int(addr), a.ctypes.data, a.size)
+        self._check(self.lib.darwin_gpu_upload_spans(self.h, abi.ptr(rec), len(rec)))
 
     # g_BatchAlignmentSIMD (Processor.cpp:718-762)
     def BatchAlignmentSIMD(self, requests, do_traceback=1, tb_words_per_req=None, out=None):

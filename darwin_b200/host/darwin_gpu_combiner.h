@@ -39,9 +39,10 @@ struct GpuCalls {
                  uint8_t*, uint64_t);
     void* (*host_alloc)(uint64_t);    // page-locked buffers for the merged op strings (nullptr: plain malloc)
     void (*host_free)(void*);
+    int (*upload_spans)(DarwinGpu*, const DarwinSpan*, int);   // all uploads of a merged call at once (nullptr: one by one)
     static GpuCalls library() {
         return GpuCalls{darwin_gpu_upload, darwin_gpu_tiles, darwin_gpu_filter, darwin_gpu_extend, darwin_gpu_last_error, darwin_gpu_seed,
-                        darwin_gpu_align_reads, darwin_gpu_host_alloc, darwin_gpu_host_free};
+                        darwin_gpu_align_reads, darwin_gpu_host_alloc, darwin_gpu_host_free, darwin_gpu_upload_spans};
     }
 };
 
@@ -174,12 +175,22 @@ private:
     }
 
     void execute(std::vector<Request*>& batch) {
-        for (auto* b : batch)
-            if (b->up)
-                for (const auto& s : *b->up) {
-                    const int rc = c_.upload(h_, s.arena_addr, s.ascii, s.n);
-                    if (rc) { fail_all(batch, rc, "darwin_gpu_upload"); return; }
-                }
+        if (c_.upload_spans) {
+            std::vector<DarwinSpan> all;
+            for (auto* b : batch)
+                if (b->up) for (const auto& s : *b->up) all.push_back(DarwinSpan{s.arena_addr, s.ascii, s.n});
+            if (!all.empty()) {
+                const int rc = c_.upload_spans(h_, all.data(), (int)all.size());
+                if (rc) { fail_all(batch, rc, "darwin_gpu_upload_spans"); return; }
+            }
+        } else {
+            for (auto* b : batch)
+                if (b->up)
+                    for (const auto& s : *b->up) {
+                        const int rc = c_.upload(h_, s.arena_addr, s.ascii, s.n);
+                        if (rc) { fail_all(batch, rc, "darwin_gpu_upload"); return; }
+                    }
+        }
         size_t total = 0;
         for (auto* b : batch) total += (size_t)b->n;
         const Kind k = batch[0]->kind;

@@ -245,6 +245,12 @@ int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s);
  * sender.cpp:4-97): copy n ASCII bases to arena offset arena_addr (any alignment). */
 int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint64_t n);
 
+/* Several uploads in one call (the reads of many host batches ahead of one merged device call): same effect as calling
+ * darwin_gpu_upload once per span, but the spans share the staging buffers, the copies are queued back to back and the
+ * call synchronises once. */
+typedef struct DarwinSpan { uint64_t arena_addr; const char* ascii; uint64_t n; } DarwinSpan;
+int darwin_gpu_upload_spans(DarwinGpu* h, const DarwinSpan* spans, int n_spans);
+
 /* replaces g_BatchAlignmentSIMD (Processor.cpp:718-762): n independent tiles.
  * tb_words may be NULL when do_traceback == 0. */
 int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, int n,

@@ -115,3 +115,32 @@ def test_extend_random_vs_oracle(gpu):
         assert alignments_equal(pres, pops, res, ops, ALN_FIELDS_OURS) == []
         assert (res["flags"] & 1).sum() > 0
     p.close()
+
+
+def test_upload_spans_equals_single_upload(gpu):
+    """darwin_gpu_upload_spans (many spans, shared staging buffers, odd boundaries, one span larger than a staging buffer)
+    leaves the arena exactly as one darwin_gpu_upload of the whole range does."""
+    sc = abi.Scoring.from_values()
+    arena, req = synth.tile_batch_fast(23, 3000, 320)
+    big = np.concatenate([arena, synth.random_seq(np.random.default_rng(1), 40 << 20)])      # + a 40 MB tail (> 32 MB staging)
+    p1 = gpu(len(big), sc)
+    p1.InitializeReferenceMemory(0, big)
+    p2 = gpu(len(big), sc)
+    rng = np.random.default_rng(2)
+    cuts = sorted(set([0, len(arena)] + [int(x) for x in rng.integers(1, len(arena), 200)]))
+    spans = [(a, big[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    rng.shuffle(spans)
+    spans.append((len(arena), big[len(arena):]))                                             # the oversized span
+    p2.upload_spans(spans)
+    r1, t1 = p1.BatchAlignmentSIMD(req, 1)
+    r2, t2 = p2.BatchAlignmentSIMD(req, 1)
+    assert tiles_equal(r1, t1, r2, t2) == []
+    tail = np.zeros(64, abi.TILE_REQ)
+    tail["ref_bases_start_addr"] = len(arena) + np.arange(64) * 600000 + 1
+    tail["query_bases_start_addr"] = tail["ref_bases_start_addr"] + 7
+    tail["ref_size"], tail["query_size"], tail["max_tb_steps"], tail["align_fields"] = 300, 300, 600, 1
+    a1, b1 = p1.BatchAlignmentSIMD(tail, 1)
+    a2, b2 = p2.BatchAlignmentSIMD(tail, 1)
+    assert tiles_equal(a1, b1, a2, b2) == []
+    p1.close()
+    p2.close()
