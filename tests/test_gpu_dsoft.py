@@ -159,3 +159,28 @@ def test_gpu_seeding_long_reads_and_many_reads(gpu):
             assert same_seed_output(got[r][s], gpool, want[r][s], pool), (r, s, lens[r] if r < len(lens) else None)
     assert len(anchors) >= 6 and int(anchors["left_n"].max()) > 1000
     p.close()
+
+
+@pytest.mark.parametrize("k,w,stride", [(12, 5, 4), (13, 9, 2)])
+def test_gpu_seeding_other_seed_shapes(gpu, k, w, stride):
+    from test_oracle_dsoft import small_case
+    ref, n_reads = small_case(k, w, stride)
+    try:
+        ref.seed(0, n_reads)
+        begin, anchors, pool = ref.seed_anchors()
+        arena = ref.arena().copy()
+        p = gpu(len(arena), abi.Scoring.from_values())
+        p.InitializeReferenceMemory(0, arena)
+        p.build_seed_index(ref.seed_params(), ref.chroms(), int(ref.lib.dref_arena_reference_size()))
+        reads = np.zeros(n_reads, abi.SEED_READ)
+        for r in range(n_reads):
+            reads[r]["read_addr"], reads[r]["read_len"] = ref.read_addr(r), ref.lib.dref_read_len(r)
+        gbeg, ganc, gpool = p.seeder_body(reads)
+        assert np.array_equal(gbeg, begin)
+        want, got = strand_views(begin, anchors, n_reads), strand_views(gbeg, ganc, n_reads)
+        for r in range(n_reads):
+            for s in (0, 1):
+                assert same_seed_output(got[r][s], gpool, want[r][s], pool), (k, w, r, s)
+        p.close()
+    finally:
+        ref.set_dsoft_defaults()

@@ -77,3 +77,49 @@ def test_minimizer_rule():
             want.append((p << 32) | m)
             last_m, last_p = m, p
     assert list(out[:n]) == want and n > 300
+
+
+def small_case(k, w, stride, n_reads=12, seed=None):
+    """A reference driver loaded with a 200 kbp genome and a few reads, D-SOFT parameters (k, w, max_stride) set."""
+    import ctypes as C
+    rng = np.random.default_rng(seed if seed is not None else k)
+    ref = oracle.reference("patched")
+    ref.set_scoring(abi.Scoring.from_values())
+    ref.lib.dref_set_dsoft(k, w, 64, 26, 300, 40, 1000, stride, 128, 60, 64, 1000, C.c_float(0.05))
+    ref.set_extend(384, 64, 2, 0)
+    ref.reset_arena()
+    genome = synth.random_seq(rng, 200000)
+    ref.add_chr("c", genome.tobytes(), True)
+    ref.build_index()
+    for r in range(n_reads):
+        L = int(rng.integers(2000, 7000))
+        p = int(rng.integers(0, len(genome) - L))
+        s = synth.mutate_fast(rng, genome[p:p + L], 0.04, 0.04, 0.04)
+        if r % 2:
+            s = synth.revcomp(s)
+        ref.add_read("r%d" % r, np.ascontiguousarray(s).tobytes())
+    return ref, n_reads
+
+
+@pytest.mark.skipif(not oracle.have_reference(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("k,w,stride", [(12, 5, 4), (13, 9, 2), (15, 4, 1)])
+def test_dsoft_port_other_seed_shapes(k, w, stride):
+    """w = 5 and w = 9 take the reference's AVX2 specialisations (seed_pos_table.h:374-522), other w the generic loop; all
+    follow the same emission rule, which is what the port restates."""
+    ref, n_reads = small_case(k, w, stride)
+    try:
+        ref.seed(0, n_reads)
+        begin, anchors, pool = ref.seed_anchors()
+        arena = np.concatenate([ref.arena().copy(), np.full(256, ord("N"), np.uint8)])
+        dp = oracle.DsoftPort(arena, ref.chroms(), int(ref.lib.dref_arena_reference_size()), ref.seed_params())
+        views = strand_views(begin, anchors, n_reads)
+        for r in range(n_reads):
+            L, addr = ref.lib.dref_read_len(r), ref.read_addr(r)
+            fwd = arena[addr:addr + L]
+            for s in (0, 1):
+                a, p = dp.query(np.ascontiguousarray(synth.revcomp(fwd) if s else fwd))
+                assert same_seed_output(a, p, views[r][s], pool), (k, w, r, s)
+        assert len(anchors) >= n_reads
+        dp.close()
+    finally:
+        ref.set_dsoft_defaults()
