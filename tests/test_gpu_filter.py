@@ -40,6 +40,12 @@ def test_filter_body_custom_candidates(gpu):
     res = p.filter_body(g["custom_cands"], 128, 60, 1000)
     want = oracle.port(sc).filter(g["arena"], g["custom_cands"], 128, 60, 1000)
     assert np.array_equal(res, want) and 0 < int((res["flags"] & 1).sum()) < len(res) and (res["flags"] & 2).any() and not (res["flags"] & 2).all()
+    # a first_tile_size beyond the packed path's 128: every tile is handed over to the exact path inside the same call
+    st0 = p.stats()
+    res = p.filter_body(g["custom_cands"], 200, 60, 1000)
+    st1 = p.stats()
+    assert np.array_equal(res, oracle.port(sc).filter(g["arena"], g["custom_cands"], 200, 60, 1000))
+    assert st1.tiles_exact - st0.tiles_exact > len(res) // 2
     p.close()
 
 
