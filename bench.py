@@ -251,6 +251,7 @@ def main():
     # data-path collective); reads/s = all ranks' reads / slowest rank.
     extend_info = None
     seed_info = None
+    align_info = None
     if args.extend_reads > 0:
         from darwin_b200 import synth
         ref_len = 4000000
@@ -280,14 +281,26 @@ def main():
         sb, sa, sp = ex.seeder_body(sreads)
         seed_wall = time.perf_counter() - t0
         seed_ms = ex.stats().last_kernel_ms
-        agg = torch.tensor([ex_st.last_kernel_ms, ex_wall * 1e3, seed_ms, seed_wall * 1e3], dtype=torch.float64, device=dev)
-        tot = torch.tensor([ex_cells, float(int((ex_res["flags"] & 1).sum())), float(int(ex_res["n_tiles"].sum())), float(len(sa))],
-                           dtype=torch.float64, device=dev)
+        # the whole reference-guided pipeline in one resident call (darwin_gpu_align_reads): D-SOFT, first tiles, slope filter,
+        # extension of every surviving location -- reads in, alignments (coordinates, score, op strings) out
+        al_out = (pinned((len(ex_anchors) * 8,), abi.ANCHOR), pinned((len(ex_anchors) * 8,), abi.ALN_RES),
+                  pinned((int(ex_anchors["read_len"].sum()) * 6,), np.uint8))
+        ex.align_reads(sreads, out=al_out)                                         # warm-up at full size
+        barrier()
+        t0 = time.perf_counter()
+        al_anchors, al_res, _ = ex.align_reads(sreads, out=al_out)
+        al_wall = time.perf_counter() - t0
+        al_ms = ex.stats().last_kernel_ms
+        al_n = float(int((al_res["flags"] & 1).sum()))
+        al_cells = float(al_res["cells"].sum())
+        agg = torch.tensor([ex_st.last_kernel_ms, ex_wall * 1e3, seed_ms, seed_wall * 1e3, al_ms, al_wall * 1e3], dtype=torch.float64, device=dev)
+        tot = torch.tensor([ex_cells, float(int((ex_res["flags"] & 1).sum())), float(int(ex_res["n_tiles"].sum())), float(len(sa)),
+                            al_n, al_cells], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(agg, op=dist.ReduceOp.MAX)
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        k_ms, w_ms, sk_ms, sw_ms = [float(x) for x in agg]
-        cells_all, aligned_all, tiles_all, seed_anchors_all = [float(x) for x in tot]
+        k_ms, w_ms, sk_ms, sw_ms, ak_ms, aw_ms = [float(x) for x in agg]
+        cells_all, aligned_all, tiles_all, seed_anchors_all, al_n_all, al_cells_all = [float(x) for x in tot]
         reads_all = args.extend_reads * world
         extend_info = {"workload": "extend_10kbp_T384_O64", "reads": int(reads_all), "reads_per_gpu": int(args.extend_reads),
                        "aligned": int(aligned_all), "tiles": int(tiles_all), "cells": cells_all, "kernel_ms": k_ms,
@@ -301,6 +314,11 @@ def main():
                      "anchors": int(seed_anchors_all),
                      "note": "both strands of every read: minimizers, table look-ups, bin counting, candidates + chained hits "
                              "(darwin_gpu_seed); e2e includes the D2H of all chained hits"}
+        align_info = {"workload": "align_reads_10kbp_stock_params", "reads": int(reads_all), "alignments": int(al_n_all),
+                      "cells": al_cells_all, "kernel_ms": ak_ms, "reads_per_s_kernel": reads_all / (ak_ms * 1e-3),
+                      "reads_per_s_e2e": reads_all / (aw_ms * 1e-3), "gcups_e2e": al_cells_all / (aw_ms * 1e-3) / 1e9,
+                      "note": "resident reads in, alignments out through ONE call per rank: D-SOFT + first-tile filter + slope "
+                              "filter + GACT extension on the GPU (darwin_gpu_align_reads); e2e includes the D2H of all op strings"}
         ex.close()
 
     # ---- secondary: first-tile filter (128x128 score-only, max-cell mode; filter.cpp:28-122) through darwin_gpu_filter ----
@@ -376,6 +394,8 @@ def main():
             line["filter"] = filter_info
         if seed_info:
             line["seed"] = seed_info
+        if align_info:
+            line["align"] = align_info
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_leg(arena, req, args.cpu_seconds)
         print(json.dumps(line))
