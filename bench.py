@@ -284,7 +284,7 @@ def main():
         # the whole reference-guided pipeline in one resident call (darwin_gpu_align_reads): D-SOFT, first tiles, slope filter,
         # extension of every surviving location -- reads in, alignments (coordinates, score, op strings) out
         al_out = (pinned((len(ex_anchors) * 8,), abi.ANCHOR), pinned((len(ex_anchors) * 8,), abi.ALN_RES),
-                  pinned((int(ex_anchors["read_len"].sum()) * 6,), np.uint8))
+                  pinned((int(ex_anchors["read_len"].sum()) * 3,), np.uint8))
         ex.align_reads(sreads, out=al_out)                                         # warm-up at full size
         barrier()
         t0 = time.perf_counter()
