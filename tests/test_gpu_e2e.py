@@ -142,3 +142,52 @@ def test_pipeline_other_modes(do_overlap, tile):
             L.dref_gpu_shutdown()
     finally:
         ref.set_extend(384, 64, 2, 0)
+
+
+@pytest.mark.skipif(not os.path.exists(LIB), reason="oracle/_ref/libdarwin_ref_gpu.so not built (needs /root/reference at build time)")
+def test_de_novo_all_vs_all_overlap():
+    """argv[3] = 1: the read set is its own reference -- every read is a chromosome of the seed position table
+    (hundreds of short chromosomes: chromosome look-ups, tiles clamped at chromosome ends, extension running off both
+    ends) and is aligned against all of them.  Staged and resident GPU pipelines vs the reference's CPU stages."""
+    ref, L = load_driver()
+    rng = np.random.default_rng(31)
+    genome = synth.random_seq(rng, 150000)
+    reads = []
+    for k in range(90):                                            # ~2.5x coverage: neighbouring reads overlap
+        Lr = int(rng.integers(2500, 6000))
+        p = int(rng.integers(0, len(genome) - Lr))
+        r = synth.mutate_fast(rng, genome[p:p + Lr], 0.03, 0.03, 0.03)
+        reads.append(np.ascontiguousarray(synth.revcomp(r) if k % 3 == 0 else r))
+    try:
+        ref.set_scoring(abi.Scoring.from_values())
+        ref.set_dsoft_defaults()
+        ref.set_extend(384, 64, 2, 1)
+        ref.reset_arena()
+        for k, r in enumerate(reads):
+            ref.add_chr("read%d" % k, r.tobytes(), True)
+        ref.build_index()
+        for k, r in enumerate(reads):
+            ref.add_read("read%d" % k, r.tobytes())
+        n_reads = len(reads)
+        cap = 256 << 20
+        buf_cpu, buf_gpu = C.create_string_buffer(cap), C.create_string_buffer(cap)
+        stats = (C.c_double * 8)()
+        n_cpu = L.dref_pipeline_mt(0, n_reads, 4, 5, 0, buf_cpu, C.c_uint64(cap), stats)
+        assert n_cpu > n_reads                                     # every read finds itself and its neighbours
+        assert L.dref_gpu_init(1) == 0
+        try:
+            assert L.dref_gpu_seed_index() == 0
+            for mode, per_batch in ((2, 5), (3, 7), (4, 4), (4, 90)):
+                n_gpu = L.dref_pipeline_mt(0, n_reads, 4, per_batch, mode, buf_gpu, C.c_uint64(cap), stats)
+                assert n_gpu == n_cpu and buf_gpu.value == buf_cpu.value, first_difference(mode, per_batch, n_gpu, n_cpu, buf_gpu, buf_cpu)
+            # the reference's MHAP printer (printer.cpp:100-180) on top of the GPU stages
+            sam_cpu, sam_gpu = C.create_string_buffer(cap), C.create_string_buffer(cap)
+            n2 = L.dref_pipeline(0, n_reads, 8 | 3, sam_gpu, C.c_uint64(cap))
+            L.dref_use_cpu_table()
+            n1 = L.dref_pipeline(0, n_reads, 8, sam_cpu, C.c_uint64(cap))
+            assert n1 > 0 and n1 == n2 and sam_cpu.value == sam_gpu.value
+        finally:
+            L.dref_use_cpu_table()
+            L.dref_gpu_shutdown()
+    finally:
+        ref.set_extend(384, 64, 2, 0)
