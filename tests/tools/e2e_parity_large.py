@@ -7,7 +7,10 @@ from test_gpu_e2e import load_driver, load_case
 n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
 genome = int(sys.argv[2]) if len(sys.argv) > 2 else 5_000_000
 ref, L = load_driver()
-load_case(ref, 21, genome, n_reads, 13333)
+read_len = int(os.environ.get('E2E_READ_LEN', '13333'))
+err = tuple(float(x) for x in os.environ.get('E2E_ERR', '0.015,0.09,0.045').split(','))      # sub, ins, del
+tile = tuple(int(x) for x in os.environ.get('E2E_TILE', '384,64').split(','))
+load_case(ref, 21, genome, n_reads, read_len, err=err, tile=tile)
 cap = 1 << 30
 buf_cpu, buf_gpu = C.create_string_buffer(cap), C.create_string_buffer(cap)
 stats = (C.c_double * 8)()
