@@ -18,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <exception>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -145,7 +146,10 @@ private:
                 if (mergeable(*batch[0], **it)) { batch.push_back(*it); it = q_.erase(it); } else ++it;
             }
             lk.unlock();
-            execute(batch);
+            try { execute(batch); }
+            catch (const std::exception& e) {                    // e.g. bad_alloc while merging: every caller of the batch fails, nobody hangs
+                for (auto* b : batch) { b->rc = DARWIN_ERR_CAPACITY; b->err = std::string("combiner: ") + e.what(); }
+            }
             lk.lock();
             const Kind k = batch[0]->kind;
             st_.device_calls[k]++;
