@@ -8,7 +8,9 @@ max_tb_steps 640.  One "step" = one pass of the hot path over the whole batch (d
 
   value : GCUPS with the packed arena, requests and outputs resident in HBM (CUDA events on the library's stream)
   e2e   : GCUPS through the public call `Processor.BatchAlignmentSIMD` with HOST buffers: ASCII upload of the
-          batch's sequences + request H2D + result/TB-word D2H inside the timed region
+          batch's sequences + request H2D + result/TB-word D2H inside the timed region, every step; the steps are
+          issued from two host threads (one handle each, one shared arena replica: the reference's token model), so
+          one step's copies overlap the other lane's kernels.  e2e.single_lane_value = the same from one thread
   roofline: integer-pipe cell-update roofline of SURVEY 8(d): achieved = cells/s * 32 int-ops, peak = measured
           packed-int16 ALU issue rate of this GPU (darwin_gpu_int_peak microbenchmark, run live)
   cpu_baseline: the reference's own BatchAlignmentSIMD (oracle/_ref, compiled from the unmodified sources) on a
@@ -149,6 +151,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extend-reads", type=int, default=16000,
                     help="secondary measurement: reads of 10 kbp through the in-kernel anchor walker (0 = skip)")
+    ap.add_argument("--e2e-lanes", type=int, default=4,
+                    help="host threads (handles sharing one arena replica) issuing the end-to-end steps")
     ap.add_argument("--filter-tiles", type=int, default=400000,
                     help="secondary measurement: first-tile filter candidates through darwin_gpu_filter (0 = skip)")
     args = ap.parse_args()
@@ -242,7 +246,67 @@ def main():
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_single = world * cells * e2e_steps / (float(t[0]) * 1e-3) / 1e9
+
+    # The same calls from two host threads, one lane (handle) each over one shared arena replica -- the reference's own
+    # concurrency model (TBB tokens, main.cpp:615-624): the H2D + packing of one step overlaps the kernels
+    # of the other lane's step, and so do the D2H tails.  Every step still moves all of its inputs and outputs.
+    proc.close()
+    L = max(1, args.e2e_lanes)
+    lane_procs = [darwin_b200.Processor(L * len(arena), local)]
+    lane_procs[0].InitializeScoringParameters(sc)
+    lanes = [(lane_procs[0], 0, h_req, h_res, h_tb)]
+    for k in range(1, L):
+        lane_procs.append(darwin_b200.Processor(0, local, parent=lane_procs[0]))
+        r = pinned(req.shape, abi.TILE_REQ); r[:] = req
+        r["ref_bases_start_addr"] += k * len(arena); r["query_bases_start_addr"] += k * len(arena)
+        lanes.append((lane_procs[k], k * len(arena), r, pinned((n,), abi.TILE_RES), pinned((n, tbw), np.uint64)))
+    lane_err = []
+
+    def lane_steps(p, off, hreq, hres, htb, k, wait_for, uploaded):
+        try:
+            if wait_for is not None:
+                wait_for.wait()                                  # out of lockstep: this lane's copies meet the other's kernels
+            for _ in range(k):
+                p.InitializeReferenceMemory(off, h_arena)
+                uploaded.set()
+                p.BatchAlignmentSIMD(hreq, 1, tbw, out=(hres, htb))
+        except Exception as e:                                   # a failed lane fails the bench, loudly
+            lane_err.append(e)
+            uploaded.set()
+
+    def run_lanes(k_each):
+        ev = [threading.Event() for _ in range(L)]              # lane k starts once lane k-1 has uploaded its first step
+        th = [threading.Thread(target=lane_steps, args=(*lanes[k], k_each, ev[k - 1] if k else None, ev[k])) for k in range(L)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        if lane_err:
+            raise lane_err[0]
+
+    ref_res, ref_tb = h_res.copy(), h_tb.copy()
+    run_lanes(1)                                                 # warm both lanes; both must reproduce the serial results
+    used = (ref_res["total_TB_pointers"].astype(np.int64) + 31) // 32
+    mask = np.arange(tbw)[None, :] < used[:, None]
+    for _, _, _, hres, htb in lanes:
+        if not (np.array_equal(hres, ref_res) and np.array_equal(htb[mask], ref_tb[mask])):
+            raise SystemExit("bench: a lane's results differ from the single-lane results")
+    k_each = max(3, args.steps)                                  # per lane; a step is ~0.08 s
+    e2e_steps = L * k_each
+    barrier()
+    t0 = time.perf_counter()
+    run_lanes(k_each)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * cells * e2e_steps / (float(t[0]) * 1e-3) / 1e9
+    for lp in reversed(lane_procs):
+        lp.close()
+    proc = darwin_b200.Processor(len(arena), local)
+    proc.InitializeScoringParameters(sc)
     sampler.stop_flag = True
     sampler.join(timeout=3)
 
@@ -384,7 +448,9 @@ def main():
                 "wall_ms_per_step": wall_ms_max / args.steps,
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps},
+                        "steps": e2e_steps, "lanes": L, "single_lane_value": e2e_single,
+                        "note": "one host thread per lane, one handle each over one arena replica (the reference's token model); "
+                                "every step uploads its sequences and requests and reads all results + TB words back"},
                 "gpu_launches": int(launches), "roofline": roof,
                 "tiles": {"fast": int(st_end.tiles_fast - st0.tiles_fast), "exact": int(st_end.tiles_exact - st0.tiles_exact),
                           "rerun": int(st_end.tiles_rerun - st0.tiles_rerun)}}

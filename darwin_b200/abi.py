@@ -23,7 +23,7 @@ ALN_OPS_OVERFLOW = 1 << 1
 ALN_EXACT_RERUN = 1 << 2
 ALN_LONG_INS_PATH = 1 << 3
 
-OK, ERR_NO_DEVICE, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOT_READY = 0, -1, -2, -3, -4, -5
+OK, ERR_NO_DEVICE, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOT_READY, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 
 
 class Scoring(C.Structure):

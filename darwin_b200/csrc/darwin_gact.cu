@@ -599,6 +599,14 @@ struct DarwinGpu {
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DARWIN_ERR_CUDA; } } while (0)
 
+// No C++ exception crosses the C boundary: host allocations that fail become a status.
+static int on_exception(DarwinGpu* h, const std::exception& e) {
+    const bool oom = dynamic_cast<const std::bad_alloc*>(&e) != nullptr;
+    if (h) h->err = std::string(oom ? "host out of memory: " : "internal error: ") + e.what();
+    return oom ? DARWIN_ERR_NOMEM : DARWIN_ERR_INVALID;
+}
+#define GUARDED_END catch (const std::exception& e_) { return on_exception(h, e_); }
+
 static int grow_dev(DarwinGpu* h, int slot, size_t bytes) {
     if (bytes <= h->d_cap[slot]) return DARWIN_OK;
     if (h->d_buf[slot]) cudaFree(h->d_buf[slot]);
@@ -681,11 +689,23 @@ const char* darwin_gpu_version(void) { return "darwin-gact-b200 0.1 (sm_100a)"; 
 
 static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, DarwinGpu* parent);
 
-int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) { return create_handle(out, device, arena_bytes, nullptr); }
+int darwin_gpu_destroy(DarwinGpu* h);
+static thread_local std::string t_create_err = "null handle";
+
+// A create that fails half-way frees what it took and leaves *out = NULL; darwin_gpu_last_error(NULL) has the reason.
+static int create_checked(DarwinGpu** out, int device, uint64_t arena_bytes, DarwinGpu* parent) {
+    int rc;
+    try { rc = create_handle(out, device, arena_bytes, parent); }
+    catch (const std::exception& e) { rc = on_exception(out ? *out : nullptr, e); if (out && !*out) t_create_err = e.what(); }
+    if (rc != DARWIN_OK && out && *out) { t_create_err = (*out)->err; darwin_gpu_destroy(*out); *out = nullptr; cudaGetLastError(); }
+    return rc;
+}
+
+int darwin_gpu_create(DarwinGpu** out, int device, uint64_t arena_bytes) { return create_checked(out, device, arena_bytes, nullptr); }
 
 int darwin_gpu_create_shared(DarwinGpu** out, DarwinGpu* parent) {
     if (!parent) return DARWIN_ERR_INVALID;
-    return create_handle(out, parent->device, parent->arena_bytes, parent);
+    return create_checked(out, parent->device, parent->arena_bytes, parent);
 }
 
 static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, DarwinGpu* parent) {
@@ -759,7 +779,7 @@ int darwin_gpu_destroy(DarwinGpu* h) {
     return DARWIN_OK;
 }
 
-const char* darwin_gpu_last_error(DarwinGpu* h) { return h ? h->err.c_str() : "null handle"; }
+const char* darwin_gpu_last_error(DarwinGpu* h) { return h ? h->err.c_str() : t_create_err.c_str(); }
 
 int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s) {
     if (!h || !s) return DARWIN_ERR_INVALID;
@@ -824,7 +844,7 @@ int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint
     return DARWIN_OK;
 }
 
-int darwin_gpu_upload_spans(DarwinGpu* h, const DarwinSpan* spans, int n_spans) {
+int darwin_gpu_upload_spans(DarwinGpu* h, const DarwinSpan* spans, int n_spans) try {
     if (!h || n_spans < 0 || (n_spans && !spans)) return DARWIN_ERR_INVALID;
     for (int k = 0; k < n_spans; k++) {
         if (!spans[k].ascii && spans[k].n) return DARWIN_ERR_INVALID;
@@ -868,7 +888,7 @@ int darwin_gpu_upload_spans(DarwinGpu* h, const DarwinSpan* spans, int n_spans) 
     if ((rc = flush(n_spans))) return rc;
     CK(cudaStreamSynchronize(h->stream));
     return DARWIN_OK;
-}
+} GUARDED_END
 
 static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_req, int n,
                         DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR,
@@ -917,7 +937,7 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
 }
 
 int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, int n,
-                     DarwinTileRes* res, uint64_t* tb_words, int tb_words_per_req) {
+                     DarwinTileRes* res, uint64_t* tb_words, int tb_words_per_req) try {
     if (!h || n < 0 || (n && (!req || !res))) return DARWIN_ERR_INVALID;
     if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
     if (do_traceback && (!tb_words || tb_words_per_req <= 0)) return DARWIN_ERR_INVALID;
@@ -941,7 +961,8 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
     // caller buffers receive the DMA directly; pageable ones go through the two pinned staging buffers.
     const bool pin_res = is_pinned(res), pin_tb = !do_traceback || is_pinned(tb_words);
     const size_t per_tile = sizeof(DarwinTileRes) + tb_row;
-    int chunk = (pin_res && pin_tb) ? 131072 : (int)std::max<size_t>(1024, h->stage_bytes / per_tile);
+    if (!(pin_res && pin_tb) && per_tile > h->stage_bytes) { h->err = "tb_words_per_req too large for pageable output buffers"; return DARWIN_ERR_INVALID; }
+    int chunk = (pin_res && pin_tb) ? 131072 : (int)std::max<size_t>(1, h->stage_bytes / per_tile);
     chunk = std::min(chunk, n);
     const int nchunks = (n + chunk - 1) / chunk;
     CK(cudaEventRecord(h->ev0, h->stream));
@@ -977,9 +998,9 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
     h->stats.cells += cells;
     for (int i = 0; i < n; i++) if (res[i].status == 2) { h->err = "tb_words_per_req too small"; return DARWIN_ERR_CAPACITY; }
     return DARWIN_OK;
-}
+} GUARDED_END
 
-int darwin_gpu_filter(DarwinGpu* h, const DarwinFilterParams* p, const DarwinFilterCand* cands, int n, DarwinFilterRes* res) {
+int darwin_gpu_filter(DarwinGpu* h, const DarwinFilterParams* p, const DarwinFilterCand* cands, int n, DarwinFilterRes* res) try {
     if (!h || !p || n < 0 || (n && (!cands || !res))) return DARWIN_ERR_INVALID;
     if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
     if (p->first_tile_size < 1 || p->first_tile_size > kMaxTile) { h->err = "first_tile_size must be in [1,1984]"; return DARWIN_ERR_INVALID; }
@@ -1017,7 +1038,7 @@ int darwin_gpu_filter(DarwinGpu* h, const DarwinFilterParams* p, const DarwinFil
     CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
     h->stats.cells += (uint64_t)n * std::min<uint32_t>(fts, kMaxTile) * std::min<uint32_t>(fts, kMaxTile);
     return DARWIN_OK;
-}
+} GUARDED_END
 
 int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, int n,
                             void* d_res, void* d_tb_words, int tb_words_per_req, int max_ref_size, int max_query_size) {
@@ -1173,7 +1194,7 @@ static int check_extend_params(DarwinGpu* h, const DarwinExtendParams* p) {
 
 int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n,
                       const uint64_t* hit_pool, uint64_t n_hits,
-                      DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes) {
+                      DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes) try {
     if (!h || !p || n < 0 || (n && (!anchors || !res))) return DARWIN_ERR_INVALID;
     if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
     int rc;
@@ -1184,7 +1205,7 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
     if (n_hits) CK(cudaMemcpyAsync(h->d_buf[2], hit_pool, n_hits * 8, cudaMemcpyHostToDevice, h->stream));
     // Anchors go to the device in chunks so that the op slots (about 2 bytes per read base per anchor) stay bounded.
     return extend_all(h, p, anchors, n, (const uint64_t*)h->d_buf[2], n_hits, res, ops_pool, ops_pool_bytes);
-}
+} GUARDED_END
 
 // The whole reference-guided pipeline for n resident reads in one call: D-SOFT (seeder.cpp / seed_pos_table.cpp:252-553),
 // first tiles + score / overlap tests (filter.cpp:28-223), slope filter (filter.cpp:227-289), extension
@@ -1193,7 +1214,7 @@ int darwin_gpu_extend(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnc
 // forward-strand locations (sorted by read, score desc, ...), then reverse-strand ones.
 int darwin_gpu_align_reads(DarwinGpu* h, const DarwinAlignParams* p, const DarwinSeedRead* reads, int n,
                            DarwinAnchor* anchors_out, DarwinAlnRes* res, uint64_t cap, uint64_t* n_out,
-                           uint8_t* ops_pool, uint64_t ops_pool_bytes) {
+                           uint8_t* ops_pool, uint64_t ops_pool_bytes) try {
     if (!h || !p || n < 0 || !n_out || (n && !reads)) return DARWIN_ERR_INVALID;
     if (!h->have_scoring || !h->seed_ix.ready) { h->err = "scoring / seed position table not initialised"; return DARWIN_ERR_NOT_READY; }
     *n_out = 0;
@@ -1269,14 +1290,14 @@ int darwin_gpu_align_reads(DarwinGpu* h, const DarwinAlignParams* p, const Darwi
     rc = extend_all(h, &p->extend, anchors.data(), (int)anchors.size(), d_pool.as<uint64_t>(), n_pool, res, ops_pool, ops_pool_bytes);
     h->stats.last_kernel_ms += seed_ms + filter_ms;
     return rc;
-}
+} GUARDED_END
 
-int darwin_gpu_seed_index(DarwinGpu* h, const DarwinSeedParams* p, const DarwinChrom* chroms, int n_chroms, uint64_t reference_size) {
+int darwin_gpu_seed_index(DarwinGpu* h, const DarwinSeedParams* p, const DarwinChrom* chroms, int n_chroms, uint64_t reference_size) try {
     if (!h || !p || n_chroms < 0 || (n_chroms && !chroms)) return DARWIN_ERR_INVALID;
     if (!h->seed_ix.owner && h->seed_ix.ready) { h->err = "the seed position table belongs to the parent handle"; return DARWIN_ERR_INVALID; }
     CK(cudaSetDevice(h->device));
     return seed_index_build(h, h->seed_ix, p, chroms, n_chroms, reference_size);
-}
+} GUARDED_END
 
 int darwin_gpu_seed_index_share(DarwinGpu* h, DarwinGpu* parent) {
     if (!h || !parent || !parent->seed_ix.ready) return DARWIN_ERR_INVALID;
@@ -1287,7 +1308,7 @@ int darwin_gpu_seed_index_share(DarwinGpu* h, DarwinGpu* parent) {
 
 int darwin_gpu_seed(DarwinGpu* h, const DarwinSeedRead* reads, int n, uint32_t* anchor_begin,
                     DarwinSeedAnchor* anchors, uint64_t anchors_cap, uint64_t* n_anchors,
-                    uint64_t* pool, uint64_t pool_cap, uint64_t* n_pool) {
+                    uint64_t* pool, uint64_t pool_cap, uint64_t* n_pool) try {
     if (!h || n < 0 || !anchor_begin || !n_anchors || !n_pool || (n && !reads)) return DARWIN_ERR_INVALID;
     if (!h->seed_ix.ready) { h->err = "darwin_gpu_seed_index was not called"; return DARWIN_ERR_NOT_READY; }
     *n_anchors = 0; *n_pool = 0; anchor_begin[0] = 0;
@@ -1295,7 +1316,7 @@ int darwin_gpu_seed(DarwinGpu* h, const DarwinSeedRead* reads, int n, uint32_t* 
     if ((anchors_cap && !anchors) || (pool_cap && !pool)) return DARWIN_ERR_INVALID;
     CK(cudaSetDevice(h->device));
     return seed_query(h, h->seed_ix, reads, n, anchor_begin, anchors, anchors_cap, n_anchors, pool, pool_cap, n_pool);
-}
+} GUARDED_END
 
 /* test / diagnostics: copy the table back (buckets: n_buckets + 1 entries) */
 int darwin_gpu_seed_index_read(DarwinGpu* h, uint32_t* buckets, uint64_t buckets_cap, uint32_t* positions, uint64_t positions_cap,

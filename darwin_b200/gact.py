@@ -77,7 +77,8 @@ class Processor:
         else:
             rc = self.lib.darwin_gpu_create(C.byref(self.h), int(device), C.c_uint64(int(arena_bytes)))
         if rc:
-            msg = self.lib.darwin_gpu_last_error(self.h).decode() if self.h else "no usable CUDA device"
+            msg = "no usable CUDA device" if rc == abi.ERR_NO_DEVICE else self.lib.darwin_gpu_last_error(None).decode()
+            self.h = None                          # a failed create leaves no handle behind
             raise DarwinGpuError(rc, msg)
         self.arena_bytes = int(arena_bytes)
         self.device = device

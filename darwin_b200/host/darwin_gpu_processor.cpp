@@ -20,7 +20,7 @@ static std::mutex g_error_mutex;
 static uint64_t g_arena_bytes = 4ull * 1024ull * 1024ull * 1024ull;       // DRAM.cpp:8
 
 static void fail(DarwinGpu* h, int rc, const char* what) {
-    std::string msg = std::string(what) + ": " + (h ? darwin_gpu_last_error(h) : "no handle") + " (" + std::to_string(rc) + ")";
+    std::string msg = std::string(what) + ": " + darwin_gpu_last_error(h) + " (" + std::to_string(rc) + ")";
     { std::lock_guard<std::mutex> g(g_error_mutex); g_error = msg; }
     throw std::runtime_error(msg);                                       // no silent CPU fallback
 }

@@ -37,7 +37,8 @@ typedef enum DarwinStatus {
     DARWIN_ERR_INVALID     = -2,  /* bad argument (== Darwin::Status::InvalidData, Darwin.bond:36-40) */
     DARWIN_ERR_CUDA        = -3,  /* a CUDA call failed; see darwin_gpu_last_error */
     DARWIN_ERR_CAPACITY    = -4,  /* caller-provided output buffer too small */
-    DARWIN_ERR_NOT_READY   = -5   /* scoring / arena not initialised */
+    DARWIN_ERR_NOT_READY   = -5,  /* scoring / arena not initialised */
+    DARWIN_ERR_NOMEM       = -6   /* host allocation failed inside the library (no C++ exception crosses this boundary) */
 } DarwinStatus;
 
 /* align_fields bits (software/graph.h:22-26, Darwin.bond:97) */
@@ -230,7 +231,7 @@ typedef struct DarwinGpu DarwinGpu;   /* opaque */
 /* replaces InitializeProcessor (Processor.h:50): one handle per device/host thread.
  * arena_bytes = size of the byte-addressed sequence arena this handle mirrors
  * (the reference's g_DRAM, DRAM.cpp:8); the device keeps it 4-bit packed. */
-int darwin_gpu_create(DarwinGpu** h, int device, uint64_t arena_bytes);
+int darwin_gpu_create(DarwinGpu** h, int device, uint64_t arena_bytes);   /* on failure *h = NULL, nothing leaks, and darwin_gpu_last_error(NULL) has the reason */
 /* A further handle ("lane") on the parent's device that SHARES the parent's arena replica: own stream, own scratch,
  * own result buffers.  Lets several host threads keep kernels of independent batches in flight on one GPU (the
  * reference's tokens, main.cpp:615-624) without one arena copy per thread.  Uploads through any lane are visible to

@@ -172,3 +172,30 @@ def test_wide_score_multistrip_T1024(gpu, vals):
     assert fast + exact == len(req)
     if vals[0] * 1024 > 2047:
         assert fast >= 20                    # beyond the 11-bit layout, yet mostly on the fast path
+
+
+def test_failed_create_leaves_no_handle_and_names_the_reason(gpu):
+    import darwin_b200
+    with pytest.raises(darwin_b200.DarwinGpuError) as e:
+        darwin_b200.Processor(1 << 46)                       # 32 TiB of packed arena: cudaMalloc must refuse
+    assert e.value.code == abi.ERR_CUDA and "cudaMalloc" in str(e.value)
+    p = gpu(1 << 16, abi.Scoring.from_values())   # the device is still usable afterwards
+    p.InitializeReferenceMemory(0, b"ACGT" * 64)
+    req = np.zeros(1, abi.TILE_REQ)
+    req["ref_size"] = req["query_size"] = 64
+    req["query_bases_start_addr"] = 64
+    req["max_tb_steps"] = 128
+    res, _ = p.BatchAlignmentSIMD(req)
+    assert int(res["total_TB_pointers"][0]) > 0
+
+
+def test_oversized_tb_row_with_pageable_buffers_is_rejected(gpu):
+    import darwin_b200
+    p = gpu(1 << 16, abi.Scoring.from_values())
+    p.InitializeReferenceMemory(0, b"ACGT" * 64)
+    req = np.zeros(2, abi.TILE_REQ)
+    req["ref_size"] = req["query_size"] = 64
+    req["max_tb_steps"] = 128
+    with pytest.raises(darwin_b200.DarwinGpuError) as e:
+        p.BatchAlignmentSIMD(req, tb_words_per_req=(40 << 20) // 8)   # one TB row larger than the pinned staging buffer
+    assert e.value.code == abi.ERR_INVALID
