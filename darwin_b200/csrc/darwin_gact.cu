@@ -607,6 +607,11 @@ static int on_exception(DarwinGpu* h, const std::exception& e) {
 }
 #define GUARDED_END catch (const std::exception& e_) { return on_exception(h, e_); }
 
+struct DevFree {                                 // frees a raw device allocation on every exit path
+    void* p = nullptr;
+    ~DevFree() { if (p) cudaFree(p); }
+};
+
 static int grow_dev(DarwinGpu* h, int slot, size_t bytes) {
     if (bytes <= h->d_cap[slot]) return DARWIN_OK;
     if (h->d_buf[slot]) cudaFree(h->d_buf[slot]);
@@ -1105,7 +1110,8 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     ea.slot_base = (const uint64_t*)h->d_buf[4]; ea.slot_left = (const uint32_t*)h->d_buf[5]; ea.slot_size = (const uint32_t*)h->d_buf[6];
     ea.order = (const uint32_t*)h->d_buf[10];
     ea.dbg = nullptr;
-    if (getenv("DARWIN_GPU_DEBUG")) { CK(cudaMalloc(&ea.dbg, (size_t)n * 128 * 8 * 4)); CK(cudaMemset(ea.dbg, 0, (size_t)n * 128 * 8 * 4)); }
+    DevFree dbg_guard;
+    if (getenv("DARWIN_GPU_DEBUG")) { CK(cudaMalloc(&ea.dbg, (size_t)n * 128 * 8 * 4)); dbg_guard.p = ea.dbg; CK(cudaMemset(ea.dbg, 0, (size_t)n * 128 * 8 * 4)); }
     ea.n = n; ea.T = p->tile_size; ea.O = p->tile_overlap; ea.do_overlap = p->do_overlap; ea.counter = h->d_counter;
     CK(cudaEventRecord(h->ev0, h->stream));
     const int K = pick_k(h, p->tile_size, 1);
@@ -1154,7 +1160,6 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
         std::vector<uint32_t> hd((size_t)n * 128 * 8);
         CK(cudaMemcpy(hd.data(), ea.dbg, hd.size() * 4, cudaMemcpyDeviceToHost));
         FILE* f = fopen(getenv("DARWIN_GPU_DEBUG"), "wb"); if (f) { fwrite(hd.data(), 4, hd.size(), f); fclose(f); }
-        cudaFree(ea.dbg);
     }
     return DARWIN_OK;
 }
@@ -1338,6 +1343,7 @@ int darwin_gpu_int_peak(DarwinGpu* h, double out[10]) {
     for (int i = 0; i < 16; i++) host_in[i] = 0x00030001u * (i + 3);
     uint32_t* d = nullptr;
     CK(cudaMalloc(&d, 64 * sizeof(uint32_t)));
+    DevFree d_guard; d_guard.p = d;
     CK(cudaMemcpy(d, host_in, sizeof(host_in), cudaMemcpyHostToDevice));
     const int iters = 4096, blocks = h->sm_count * 8, threads = 256;
     for (int kind = 0; kind < 10; kind++) {
@@ -1365,7 +1371,6 @@ int darwin_gpu_int_peak(DarwinGpu* h, double out[10]) {
         }
         out[kind] = (double)blocks * threads * iters * 16.0 / (best * 1e-3) / 1e9;
     }
-    cudaFree(d);
     return DARWIN_OK;
 }
 

@@ -85,7 +85,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kMinThreads)
 minimizer_kernel(const uint8_t* __restrict__ arena, const SeedConst sc, const MinJob* __restrict__ jobs,
                  uint64_t* __restrict__ seeds, uint32_t* __restrict__ n_seeds,
-                 int* __restrict__ carry, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ hist) {
+                 int* __restrict__ carry, unsigned long long* __restrict__ cursor, uint32_t* __restrict__ hist,
+                 uint32_t chunks_per_job) {            // MODE 1/2: 1-D grid of jobs x chunks_per_job blocks (no 65535 limit on either)
     constexpr int IPT = kChunk / kMinThreads;                    // 8 positions per thread
     __shared__ uint8_t codes[kChunk + 64];
     __shared__ uint32_t hs[kChunk + 32];                         // hashes of positions base-w .. base+kChunk-1 (w <= 32)
@@ -94,7 +95,8 @@ minimizer_kernel(const uint8_t* __restrict__ arena, const SeedConst sc, const Mi
     __shared__ int incl_s[kMinThreads];
     __shared__ int tot_s, last_s;
     const int k = sc.k, w = sc.w, lead = w - 1;
-    const MinJob job = jobs[MODE == 0 ? blockIdx.x : blockIdx.y];
+    const uint32_t jb = MODE == 0 ? blockIdx.x : blockIdx.x / chunks_per_job;
+    const MinJob job = jobs[jb];
     const int strand = MODE == 0 ? (int)(blockIdx.x & 1) : 0;
     const uint32_t len = job.len;
     const uint32_t centinel = (~0x0fu & (len + 15u)) - (uint32_t)k;
@@ -102,9 +104,9 @@ minimizer_kernel(const uint8_t* __restrict__ arena, const SeedConst sc, const Mi
     int carry_start = 0;                                         // run start carried into the chunk (last_p = 0 initially)
     int emitted = 0;                                             // minimizers emitted so far (MODE 0)
     const uint32_t n_chunks = (end + kChunk - 1) / kChunk;
-    uint32_t chunk = MODE == 0 ? 0u : blockIdx.x;
+    uint32_t chunk = MODE == 0 ? 0u : blockIdx.x % chunks_per_job;
     if (MODE != 0 && chunk >= n_chunks) return;
-    if (MODE == 1) carry_start = carry[(size_t)blockIdx.y * gridDim.x + chunk];
+    if (MODE == 1) carry_start = carry[(size_t)jb * chunks_per_job + chunk];
     for (; chunk < n_chunks; chunk++) {
         const uint32_t base = chunk * kChunk;
         // codes of positions base-w .. base+kChunk+k-2
@@ -145,7 +147,7 @@ minimizer_kernel(const uint8_t* __restrict__ arena, const SeedConst sc, const Mi
         incl_s[threadIdx.x] = incl;
         __syncthreads();
         if (MODE == 2) {
-            if (threadIdx.x == kMinThreads - 1) carry[(size_t)blockIdx.y * gridDim.x + chunk] = incl;
+            if (threadIdx.x == kMinThreads - 1) carry[(size_t)jb * chunks_per_job + chunk] = incl;
             return;
         }
         const int excl = threadIdx.x ? incl_s[threadIdx.x - 1] : INT_MIN;

@@ -38,6 +38,7 @@ static void free_index(SeedIndex& ix) {
 
 static int seed_index_build(DarwinGpu* h, SeedIndex& ix, const DarwinSeedParams* p, const DarwinChrom* chroms, int n_chroms, uint64_t reference_size) {
     using namespace dsoft;
+    if (n_chroms == 0) { h->err = "seed position table needs at least one chromosome"; return DARWIN_ERR_INVALID; }
     free_index(ix);
     int rc = seed_const_from(p, reference_size, ix.sc, h->err);
     if (rc) return rc;
@@ -59,15 +60,16 @@ static int seed_index_build(DarwinGpu* h, SeedIndex& ix, const DarwinSeedParams*
     CKS(d_carry.alloc(sizeof(int) * (size_t)n_chroms * max_chunks, h->stream)); CKS(d_cursor.alloc(sizeof(unsigned long long), h->stream));
     CKS(cudaMemcpyAsync(d_jobs.p, jobs.data(), sizeof(MinJob) * n_chroms, cudaMemcpyHostToDevice, h->stream));
     CKS(cudaMemsetAsync(d_cursor.p, 0, sizeof(unsigned long long), h->stream));
-    const dim3 grid(max_chunks, n_chroms);
-    minimizer_kernel<2><<<grid, kMinThreads, 0, h->stream>>>(h->d_arena, sc, d_jobs.as<MinJob>(), nullptr, nullptr, d_carry.as<int>(), nullptr, nullptr);
+    if ((uint64_t)max_chunks * (uint64_t)n_chroms > 0x7FFFFFFFull) { h->err = "reference too fragmented: chromosomes x chunks exceeds 2^31 blocks"; return DARWIN_ERR_INVALID; }
+    const unsigned grid = (unsigned)((uint64_t)max_chunks * (uint64_t)n_chroms);
+    minimizer_kernel<2><<<grid, kMinThreads, 0, h->stream>>>(h->d_arena, sc, d_jobs.as<MinJob>(), nullptr, nullptr, d_carry.as<int>(), nullptr, nullptr, max_chunks);
     CKS(cudaGetLastError());
     // pass A left the position of the last change of every chunk; turn it into the run start carried INTO every chunk
     // (entries of chunks beyond a chromosome's end are never read)
     carry_kernel<<<(n_chroms + 127) / 128, 128, 0, h->stream>>>(d_carry.as<int>(), n_chroms, (int)max_chunks);
     CKS(cudaGetLastError());
     minimizer_kernel<1><<<grid, kMinThreads, 0, h->stream>>>(h->d_arena, sc, d_jobs.as<MinJob>(), d_list.as<uint64_t>(), nullptr, d_carry.as<int>(),
-                                                            d_cursor.as<unsigned long long>(), ix.d_buckets);
+                                                            d_cursor.as<unsigned long long>(), ix.d_buckets, max_chunks);
     CKS(cudaGetLastError());
     h->stats.kernel_launches += 3;
     unsigned long long n_min = 0;
@@ -156,7 +158,7 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     CKS(cudaMemcpyAsync(d_base.p, seed_base.data(), sizeof(uint32_t) * (ns + 1), cudaMemcpyHostToDevice, h->stream));
     CKS(cudaMemsetAsync(d_cnt.p, 0, sizeof(uint32_t) * ((size_t)slots + 1), h->stream));
     CKS(cudaEventRecord(h->ev0, h->stream));
-    minimizer_kernel<0><<<ns, kMinThreads, 0, h->stream>>>(h->d_arena, sc, d_jobs.as<MinJob>(), d_seeds.as<uint64_t>(), d_nseeds.as<uint32_t>(), nullptr, nullptr, nullptr);
+    minimizer_kernel<0><<<ns, kMinThreads, 0, h->stream>>>(h->d_arena, sc, d_jobs.as<MinJob>(), d_seeds.as<uint64_t>(), d_nseeds.as<uint32_t>(), nullptr, nullptr, nullptr, 0u);
     CKS(cudaGetLastError());
     const uint64_t grid_threads = (uint64_t)ns * max_cap;
     const unsigned gb = (unsigned)((grid_threads + 255) / 256);

@@ -184,3 +184,36 @@ def test_gpu_seeding_other_seed_shapes(gpu, k, w, stride):
         p.close()
     finally:
         ref.set_dsoft_defaults()
+
+
+def test_seed_index_over_many_short_chromosomes(gpu):
+    """De novo sized chromosome lists (more entries than a CUDA grid's y/z extent, 65 535): the table equals the CPU
+    restatement's.  An empty list is refused."""
+    import darwin_b200
+    rng = np.random.default_rng(11)
+    n_chr = 70001
+    lens = rng.integers(40, 121, n_chr).astype(np.int64)
+    lens[123] = 5000                                                    # one chromosome spans several chunks
+    padded = (lens + 127) // 128 * 128
+    starts = 128 + np.concatenate([[0], np.cumsum(padded)[:-1]])
+    ref_size = int(starts[-1] + padded[-1])
+    arena = np.full(ref_size, ord("N"), np.uint8)
+    for s, L in zip(starts, lens):
+        arena[s:s + L] = synth.random_seq(rng, int(L))
+    chroms = np.zeros(n_chr, abi.CHROM)
+    chroms["start"], chroms["len_unpadded"] = starts, lens
+    prm = abi.SeedParams.stock()
+    p = gpu(len(arena), abi.Scoring.from_values())
+    p.InitializeReferenceMemory(0, arena)
+    p.build_seed_index(prm, chroms, ref_size)
+    dp = oracle.DsoftPort(np.concatenate([arena, np.full(256, ord("N"), np.uint8)]), chroms, ref_size, prm)
+    wb, wp = dp.index_arrays()
+    gb, gp, max_occ = p.seed_index_arrays()
+    assert max_occ == dp.ix.kmer_max_occurence and np.array_equal(gb, wb) and len(gp) == len(wp)
+    small = np.nonzero((np.diff(wb.astype(np.int64)) > 0) & (np.diff(wb.astype(np.int64)) <= max_occ))[0]
+    for b in small[:: max(1, len(small) // 20000)]:
+        assert np.array_equal(gp[wb[b]:wb[b + 1]], wp[wb[b]:wb[b + 1]])
+    dp.close()
+    with pytest.raises(darwin_b200.DarwinGpuError) as e:
+        p.build_seed_index(prm, chroms[:0], ref_size)
+    assert e.value.code == abi.ERR_INVALID
