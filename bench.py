@@ -111,7 +111,7 @@ def cpu_reference_leg(arena, req, seconds_target, threads=None):
             "sample": "%d of the workload's %dx%d tiles, %.1f s wall, %s" % (
                 n, TILE, TILE, secs, "oracle/_ref BatchAlignmentSIMD (AVX2), std::thread x cores" if kind == "reference"
                 else "oracle/gact_oracle.c scalar port"),
-            "tiles_per_s": n / secs}
+            "tiles_per_s": n / secs, "sample_tiles": n, "sample_ms": secs * 1e3}
 
 
 def run_reference(args):
@@ -120,19 +120,21 @@ def run_reference(args):
         return 0
     arena, req = make_workload(min(args.tiles, 200000), 1)
     per_step = max(4.0, min(30.0, 150.0 / max(1, args.steps + args.warmup)))
-    vals = []
+    vals, ms = [], []
     cb = None
     for s in range(args.warmup + args.steps):
         cb = cpu_reference_leg(arena, req, per_step)
         if s >= args.warmup:
             vals.append(cb["value"])
+            ms.append(cb["sample_ms"])
     v = float(np.mean(vals))
     cb["value"] = v
     line = {"impl": "reference", "metric": "gact_gcups", "value": v, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int16", "data": "synthetic",
             "config": {"workload": "gact_tiles_T%d_O%d" % (TILE, OVERLAP), "tile_size": TILE, "tile_overlap": OVERLAP,
-                       "error_rate": 0.15, "note": "bounded sample of the same tile batch per step"},
+                       "error_rate": 0.15, "tiles_per_step": cb["sample_tiles"],
+                       "note": "bounded sample of the same tile batch per step (ms_per_step is the sample's)"},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "reads_per_s_equiv": cb["tiles_per_s"] * (TILE - OVERLAP) / 2.0 / 10000.0}
