@@ -294,7 +294,7 @@ def main():
     for _, _, _, hres, htb in lanes:
         if not (np.array_equal(hres, ref_res) and np.array_equal(htb[mask], ref_tb[mask])):
             raise SystemExit("bench: a lane's results differ from the single-lane results")
-    k_each = max(3, args.steps)                                  # per lane; a step is ~0.08 s
+    k_each = max(4, 2 * args.steps)                              # per lane; a step is ~0.08 s, the ramp and drain of the lanes ~0.05 s
     e2e_steps = L * k_each
     barrier()
     t0 = time.perf_counter()

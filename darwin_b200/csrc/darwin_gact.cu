@@ -27,29 +27,54 @@ using namespace gact;
 // =====================================================================================================
 
 // ASCII -> 4-bit arena codes (Nt2Int, Processor.cpp:21-46: ACGT either case -> 0..3, everything else -> N).
-// One thread per output byte (two bases); bytes only half covered by [addr, addr+n) are read-modify-written.
-__global__ void pack_arena_kernel(uint8_t* __restrict__ arena, const char* __restrict__ ascii, uint64_t addr, uint64_t n) {
-    const uint64_t first = addr >> 1, last = (addr + n - 1) >> 1;
-    const uint64_t b = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b > last) return;
-    uint32_t out = arena[b];
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const uint64_t a = 2 * b + h;
-        if (a >= addr && a < addr + n) {
-            const char c = ascii[a - addr];
-            uint32_t code;
-            switch (c) {
-                case 'a': case 'A': code = 0; break;
-                case 'c': case 'C': code = 1; break;
-                case 'g': case 'G': code = 2; break;
-                case 't': case 'T': code = 3; break;
-                default: code = 4; break;
-            }
-            out = (out & ~(0xFu << (4 * h))) | (code << (4 * h));
-        }
+__device__ __forceinline__ uint32_t nt_code(char c) {
+    switch (c) {
+        case 'a': case 'A': return 0;
+        case 'c': case 'C': return 1;
+        case 'g': case 'G': return 2;
+        case 't': case 'T': return 3;
+        default: return 4;
     }
-    arena[b] = (uint8_t)out;
+}
+
+// Two characters -> one arena byte, as a 64 KB table (the hot entries, pairs of ACGT, stay in L1): the packing kernel
+// shares the SMs with the tile kernels of the other lanes, which are ALU-bound, so it spends loads instead of ALU work.
+__device__ uint8_t g_pair_lut[65536];
+__global__ void pair_lut_kernel() {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;              // low byte = character at the even address
+    g_pair_lut[i] = (uint8_t)(nt_code((char)(i & 0xFF)) | (nt_code((char)(i >> 8)) << 4));
+}
+
+// One thread per 8 arena bytes (16 bases).  Groups inside [addr, addr + n) take one 16-byte load, eight table look-ups
+// and one 8-byte store when the staging pointer is congruent to addr modulo 16 (the upload paths arrange that); the two
+// edge groups -- and every group otherwise -- go byte by byte, read-modify-writing bytes only half covered.
+__global__ void __launch_bounds__(128) pack_arena_kernel(uint8_t* __restrict__ arena, const char* __restrict__ ascii, uint64_t addr, uint64_t n) {
+    const uint64_t first = addr >> 1, last = (addr + n - 1) >> 1;
+    const uint64_t b0 = (first & ~7ull) + 8ull * ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (b0 > last) return;
+    const bool congruent = (((uint64_t)(uintptr_t)ascii - addr) & 15ull) == 0;
+    if (congruent && 2 * b0 >= addr && 2 * b0 + 16 <= addr + n) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(ascii + (2 * b0 - addr)));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const uint32_t p0 = __ldg(&g_pair_lut[w[2 * k] & 0xFFFFu]), p1 = __ldg(&g_pair_lut[w[2 * k] >> 16]);
+            const uint32_t p2 = __ldg(&g_pair_lut[w[2 * k + 1] & 0xFFFFu]), p3 = __ldg(&g_pair_lut[w[2 * k + 1] >> 16]);
+            o[k] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+        }
+        *reinterpret_cast<uint2*>(arena + b0) = make_uint2(o[0], o[1]);
+        return;
+    }
+    for (uint64_t b = b0 < first ? first : b0; b < b0 + 8 && b <= last; b++) {
+        uint32_t out = arena[b];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint64_t a = 2 * b + h;
+            if (a >= addr && a < addr + n) out = (out & ~(0xFu << (4 * h))) | (nt_code(ascii[a - addr]) << (4 * h));
+        }
+        arena[b] = (uint8_t)out;
+    }
 }
 
 struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568-582 (32 ops per u64; written as 2 x u32)
@@ -751,6 +776,8 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
         CK(cudaEventCreateWithFlags(&h->ev_chunk[b], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
     }
+    pair_lut_kernel<<<256, 256, 0, h->stream>>>();                             // per device; idempotent
+    CK(cudaGetLastError());
     CK(cudaMalloc(&h->d_counter, sizeof(unsigned int) * kCounters));
     h->max_warps = h->sm_count * 16;                                           // scratch is sized for this many resident warps
     int rc = configure_kernels(h);
@@ -823,6 +850,13 @@ static bool is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost;
 }
 
+// staging pointer `src` must be congruent to `a` modulo 16 for the vector path (any pointer is correct)
+static void launch_pack(DarwinGpu* h, const char* src, uint64_t a, uint64_t n) {
+    const uint64_t groups = ((a + n - 1) >> 4) - (a >> 4) + 1;                 // 8 arena bytes = 16 bases per thread
+    pack_arena_kernel<<<(unsigned)((groups + 127) / 128), 128, 0, h->stream>>>(h->d_arena, src, a, n);   // small CTAs fit into the registers the resident tile kernels leave free
+    h->stats.kernel_launches++;
+}
+
 int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint64_t n) {
     if (!h || (!ascii && n)) return DARWIN_ERR_INVALID;
     if (arena_addr + n > h->arena_bytes) { h->err = "upload beyond arena"; return DARWIN_ERR_INVALID; }
@@ -832,17 +866,16 @@ int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint
     uint64_t done = 0;
     for (int c = 0; done < n; c++) {
         const int b = c & 1;
-        const uint64_t chunk = std::min<uint64_t>(n - done, h->stage_bytes);
+        const uint64_t chunk = std::min<uint64_t>(n - done, h->stage_bytes - 16);
         const char* src = ascii + done;
+        const uint64_t a = arena_addr + done;
+        char* dst = h->d_stage[b] + (a & 15);                        // device staging congruent to the arena address (mod 16)
         if (c >= 2) CK(cudaEventSynchronize(h->ev_stage[b]));       // staging buffer b is free again
         if (!pinned) { memcpy(h->h_stage[b], src, chunk); src = h->h_stage[b]; }   // overlaps the previous chunk's DMA
-        CK(cudaMemcpyAsync(h->d_stage[b], src, chunk, cudaMemcpyHostToDevice, h->stream));
-        const uint64_t a = arena_addr + done;
-        const uint64_t nbytes = ((a + chunk - 1) >> 1) - (a >> 1) + 1;
-        pack_arena_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(h->d_arena, h->d_stage[b], a, chunk);
+        CK(cudaMemcpyAsync(dst, src, chunk, cudaMemcpyHostToDevice, h->stream));
+        launch_pack(h, dst, a, chunk);
         CK(cudaGetLastError());
         CK(cudaEventRecord(h->ev_stage[b], h->stream));
-        h->stats.kernel_launches++;
         done += chunk;
     }
     CK(cudaStreamSynchronize(h->stream));                            // synchronous like the reference's memcpy into g_DRAM
@@ -856,6 +889,8 @@ int darwin_gpu_upload_spans(DarwinGpu* h, const DarwinSpan* spans, int n_spans) 
         if (spans[k].arena_addr + spans[k].n > h->arena_bytes) { h->err = "upload beyond arena"; return DARWIN_ERR_INVALID; }
     }
     CK(cudaSetDevice(h->device));
+    // every span sits in the staging buffer at an offset congruent to its arena address modulo 16
+    auto span_offset = [](uint64_t fill_, uint64_t a) { return ((fill_ + 15) & ~15ull) + (a & 15); };
     int b = 0, flushes = 0;
     uint64_t fill = 0;
     int first = 0;                                   // first span of the staging buffer being filled
@@ -866,10 +901,9 @@ int darwin_gpu_upload_spans(DarwinGpu* h, const DarwinSpan* spans, int n_spans) 
         for (int k = first; k < upto; k++) {
             const uint64_t a = spans[k].arena_addr, n = spans[k].n;
             if (n == 0) continue;
-            const uint64_t nbytes = ((a + n - 1) >> 1) - (a >> 1) + 1;
-            pack_arena_kernel<<<(unsigned)((nbytes + 255) / 256), 256, 0, h->stream>>>(h->d_arena, h->d_stage[b] + at, a, n);
+            at = span_offset(at, a);
+            launch_pack(h, h->d_stage[b] + at, a, n);
             CK(cudaGetLastError());
-            h->stats.kernel_launches++;
             at += n;
         }
         CK(cudaEventRecord(h->ev_stage[b], h->stream));
@@ -880,15 +914,17 @@ int darwin_gpu_upload_spans(DarwinGpu* h, const DarwinSpan* spans, int n_spans) 
     int rc;
     for (int k = 0; k < n_spans; k++) {
         const uint64_t n = spans[k].n;
-        if (n > h->stage_bytes) {                    // a span larger than the staging buffers goes the chunked way
+        if (n == 0) continue;
+        if (n + 32 > h->stage_bytes) {               // a span larger than the staging buffers goes the chunked way
             if ((rc = flush(k))) return rc;
             if ((rc = darwin_gpu_upload(h, spans[k].arena_addr, spans[k].ascii, n))) return rc;
             first = k + 1;
             continue;
         }
-        if (fill + n > h->stage_bytes && (rc = flush(k))) return rc;
-        memcpy(h->h_stage[b] + fill, spans[k].ascii, n);
-        fill += n;
+        if (span_offset(fill, spans[k].arena_addr) + n > h->stage_bytes && (rc = flush(k))) return rc;
+        const uint64_t off = span_offset(fill, spans[k].arena_addr);
+        memcpy(h->h_stage[b] + off, spans[k].ascii, n);
+        fill = off + n;
     }
     if ((rc = flush(n_spans))) return rc;
     CK(cudaStreamSynchronize(h->stream));

@@ -144,3 +144,38 @@ def test_upload_spans_equals_single_upload(gpu):
     assert tiles_equal(a1, b1, a2, b2) == []
     p1.close()
     p2.close()
+
+
+def test_upload_mixed_case_and_non_acgt_at_every_alignment(gpu):
+    """Nt2Int semantics of the packing kernel (Processor.cpp:21-46): lower case counts, everything else is N -- on the
+    vector path, on the byte-wise edges and for spans shorter than one 16-base group, at all 16 address alignments."""
+    sc = abi.Scoring.from_values()
+    arena, req = synth.tile_batch_fast(31, 400, 96)
+    rng = np.random.default_rng(32)
+    lower = rng.random(len(arena)) < 0.3
+    arena[lower] = np.frombuffer(arena[lower].tobytes().lower(), np.uint8)
+    odd = rng.random(len(arena)) < 0.03
+    arena[odd] = rng.choice(np.frombuffer(b"NnRYKMSWxX-*.\x00\xff@[`{", np.uint8), int(odd.sum()))
+    want = oracle.port(sc).tiles(arena, req, 1, oracle.Port.STREAM, tb_words_per_req=14)[:2]
+    p1 = gpu(len(arena) + 64, sc)
+    p1.InitializeReferenceMemory(0, arena)
+    r1, t1 = p1.BatchAlignmentSIMD(req, 1, 14)
+    assert tiles_equal(want[0], want[1], r1, t1) == []
+    # the same bytes shifted to every alignment, uploaded as ragged spans (1..40 bases) and through the chunked call
+    for shift in range(1, 17):
+        p2 = gpu(len(arena) + 64, sc)
+        cuts = [0]
+        while cuts[-1] < len(arena):
+            cuts.append(min(len(arena), cuts[-1] + int(rng.integers(1, 41 if shift % 2 else 5000))))
+        spans = [(shift + a, arena[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+        if shift % 4 == 0:
+            p2.InitializeReadMemory(shift, arena)
+        else:
+            p2.upload_spans(spans)
+        rq = req.copy()
+        rq["ref_bases_start_addr"] += shift
+        rq["query_bases_start_addr"] += shift
+        r2, t2 = p2.BatchAlignmentSIMD(rq, 1, 14)
+        assert tiles_equal(want[0], want[1], r2, t2) == [], shift
+        p2.close()
+    p1.close()
