@@ -429,10 +429,10 @@ def main():
         per_gpu_gcups = value / world
         roof = {"bound": "int_alu", "achieved": per_gpu_gcups * OPS_PER_CELL, "peak": int_peak,
                 "unit": "Gint-op/s", "frac": (per_gpu_gcups * OPS_PER_CELL / int_peak) if int_peak else None,
-                # dram__bytes_read+write of tiles_kernel<5> from the committed ncu capture (profiles/r1_s3_tiles_kernel5_*:
-                # 76.8 MB read + 15.3 MB written per 200k-tile launch = 460 B per tile), scaled to this launch's tile count;
+                # dram__bytes_read+write of tiles_kernel<5> from the committed ncu capture (profiles/r1_s4_tiles_kernel5_*:
+                # 76.6 MB read + 12.6 MB written per 200k-tile launch = 446 B per tile), scaled to this launch's tile count;
                 # algorithmic bytes: ~460 B per tile (320 B packed bases + 32 B request + 16 B result + the used TB words)
-                "traffic": 460.2 * n,
+                "traffic": 446.0 * n,
                 "peak_detail_glaneops": dict(zip(["vimnmx_u16x2", "viaddmnmx_u16x2", "vimnmx3_u16x2", "iadd3", "lop3_3reg", "imad", "lop3_2reg", "lop3_imm", "prmt", "shfl_idx"], int_detail)) if int_detail else None,
                 "note": "SURVEY 8(d) integer-pipe roofline: 32 algorithmic int-ops per cell; peak = measured packed "
                         "s16x2 DPX/ALU issue rate (2 cells per lane-op) of this GPU; HBM is not the bound "
