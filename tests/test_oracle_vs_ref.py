@@ -94,3 +94,54 @@ def test_config1_sample_reference_plumbing():
     for rule in (oracle.Port.STREAM, oracle.Port.CLEAN):
         got, gops = port.extend(ref.arena(), abi.ExtendParams(384, 64, 0, 0), anchors, hits, rule)
         assert alignments_equal(want, wops, got, gops, ALN_FIELDS) == []
+
+
+@pytest.mark.parametrize("seed,scheme,T,O,ovl", [(41, (2, -6, -1, -4, -2, -25, -1), 128, 32, 0),
+                                                 (42, (2, -3, -1, -3, -2, -8, -1), 512, 64, 0),
+                                                 (43, (2, -6, -1, -4, -2, -25, -1), 200, 150, 1),
+                                                 (44, (1, -1, 0, -2, -1, -4, 0), 384, 64, 0)])
+def test_extend_live_port_equals_reference(seed, scheme, T, O, ovl):
+    """extender_body of the compiled reference on fresh reads (structural insertions / deletions that force large tiles,
+    both strands, reads hanging over the chromosome ends) with anchors from its own D-SOFT + filter, against the
+    restatement: tile sizes and scoring schemes the committed fixtures do not hold."""
+    from conftest import alignments_equal
+    rng = np.random.default_rng(seed)
+    genome = synth.random_seq(rng, 60000)
+    sc = abi.Scoring.from_values(*scheme)
+    ref = oracle.reference("patched")
+    ref.set_scoring(sc)
+    ref.set_dsoft_defaults()
+    ref.set_extend(T, O, 2, ovl)
+    ref.reset_arena()
+    ref.add_chr("chrL", genome.tobytes(), True)
+    ref.build_index()
+    n_reads = 6
+    for k in range(n_reads):
+        L = int(rng.integers(2500, 4500))
+        p = int(rng.integers(0, len(genome) - L)) if k < 4 else (0 if k == 4 else len(genome) - L)
+        src = genome[p:p + L]
+        if k % 3 == 1:
+            src = np.concatenate([src[:L // 2], synth.random_seq(rng, 400), src[L // 2:]])
+        elif k % 3 == 2:
+            src = np.concatenate([src[:L // 3], src[L // 3 + 500:]])
+        r = synth.mutate(rng, src, 0.04, 0.04, 0.04, indel_run=(3, 40) if k % 2 else None)
+        if k >= 4:                                                       # overhang beyond the chromosome end
+            r = np.concatenate([synth.random_seq(rng, 300), r]) if k == 4 else np.concatenate([r, synth.random_seq(rng, 300)])
+        if k % 2 == 0:
+            r = synth.revcomp(r)
+        ref.add_read("r%d" % k, np.ascontiguousarray(r).tobytes())
+    A, H, hb = [], [], 0
+    for k in range(n_reads):
+        a, h = ref.seed_filter(k, 1)
+        a = a.copy()
+        a["left_hits_off"] += hb
+        a["right_hits_off"] += hb
+        hb += len(h)
+        A.append(a)
+        H.append(h)
+    anchors, hits = np.concatenate(A), np.concatenate(H)
+    assert len(anchors) >= n_reads - 1
+    want, want_ops = ref.extend(anchors, hits)
+    got, got_ops = oracle.port(sc).extend(ref.arena().copy(), abi.ExtendParams(T, O, ovl, 0), anchors, hits, oracle.Port.STREAM)
+    assert alignments_equal(want, want_ops, got, got_ops) == []
+    assert int((want["flags"] & 1).sum()) >= 1
