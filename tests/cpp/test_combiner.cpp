@@ -30,6 +30,7 @@ static int f_tiles(DarwinGpu* h, int tb, const DarwinTileReq* req, int n, Darwin
 }
 static int f_filter(DarwinGpu* h, const DarwinFilterParams* p, const DarwinFilterCand* c, int n, DarwinFilterRes* res) {
     fake(h)->device_calls++; device_latency();
+    if (fake(h)->fail_filter == 2) throw std::bad_alloc();
     if (fake(h)->fail_filter) return DARWIN_ERR_CUDA;
     return gact_filter(&fake(h)->sc, fake(h)->dram, p, c, n, res);
 }
@@ -173,5 +174,22 @@ extern "C" int combiner_selftest(const DarwinScoring* s, const char* dram, uint6
         if (gc.filter(fp, none, cands, n_cands, r.data(), &err) == DARWIN_ERR_CUDA && err.find("stand-in failure") != std::string::npos) errs++;
     });
     for (auto& x : th2) x.join();
-    return errs.load() == threads ? 0 : 50;
+    if (errs.load() != threads) return 50;
+    // an exception inside the combining thread (host allocation failure while merging) fails the batch's callers and
+    // leaves the combiner usable: nobody waits forever on a lane that stayed busy
+    fk.fail_filter = 2;
+    std::atomic<int> thrown(0);
+    std::vector<std::thread> th3;
+    for (int t = 0; t < threads; t++) th3.emplace_back([&] {
+        std::string err; std::vector<DarwinFilterRes> r(n_cands); const std::vector<UploadSpan> none;
+        const int rc = gc.filter(fp, none, cands, n_cands, r.data(), &err);
+        if (rc == DARWIN_ERR_CAPACITY && err.find("combiner:") != std::string::npos) thrown++;
+    });
+    for (auto& x : th3) x.join();
+    if (thrown.load() != threads) return 51;
+    fk.fail_filter = 0;
+    {   std::string err; std::vector<DarwinFilterRes> r(n_cands); const std::vector<UploadSpan> none;
+        if (gc.filter(fp, none, cands, n_cands, r.data(), &err)) return 52;
+        if (n_cands && memcmp(r.data(), f_res.data(), sizeof(DarwinFilterRes) * n_cands)) return 53; }
+    return 0;
 }
