@@ -1,0 +1,35 @@
+"""CPU: the reference arm of bench.py (`--impl reference`) prints the contract's JSON line from the compiled reference
+(or the port when oracle/_ref is absent) on a bounded sample, and ranks other than 0 exit silently."""
+import json
+import os
+import subprocess
+import sys
+
+from conftest import ROOT
+
+
+def _run(extra_env=None):
+    env = dict(os.environ)
+    env.update(extra_env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "1",
+                           "--warmup", "0", "--tiles", "1500"], capture_output=True, text=True, env=env, timeout=600)
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = _run()
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "gact_gcups" and d["unit"] == "GCUPS" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 0 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"] == "gact_tiles_T320_O128" and d["config"]["tiles_per_step"] == 1500
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "1500 of" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["vs_baseline"] is None and d["dtype"] == "int16" and d["data"] == "synthetic"
+
+
+def test_reference_arm_other_ranks_do_no_work():
+    r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
