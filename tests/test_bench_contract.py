@@ -33,3 +33,13 @@ def test_reference_arm_prints_the_contract_line():
 def test_reference_arm_other_ranks_do_no_work():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_own_arm_fails_loudly_without_a_gpu():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1", "--tiles", "100"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout) and not r.stdout.strip().startswith("{")
