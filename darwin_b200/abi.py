@@ -22,6 +22,7 @@ ALN_EMITTED = 1 << 0
 ALN_OPS_OVERFLOW = 1 << 1
 ALN_EXACT_RERUN = 1 << 2
 ALN_LONG_INS_PATH = 1 << 3
+TILE_LONG_INS_PATH = 0x10          # DarwinTileRes.status bit (include/darwin_gpu.h)
 
 OK, ERR_NO_DEVICE, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NOT_READY, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
 

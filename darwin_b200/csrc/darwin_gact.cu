@@ -299,7 +299,7 @@ tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelSc
             r.score = out.score; r.ref_offset = (uint16_t)out.ref_offset; r.query_offset = (uint16_t)out.query_offset;
             r.ref_max_pos = (uint16_t)out.ref_max_pos; r.query_max_pos = (uint16_t)out.query_max_pos;
             r.total_TB_pointers = (uint16_t)out.total; r.index = (uint8_t)rq.index;
-            r.status = too_big ? 1 : (sink.overflow ? 2 : 0);
+            r.status = (uint8_t)((too_big ? 1 : (sink.overflow ? 2 : 0)) | ((out.tflags & 1u) ? DARWIN_TILE_LONG_INS_PATH : 0));
             res[idx] = r;
         }
         __syncwarp();
@@ -1037,7 +1037,7 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
     if ((rc = read_counters(h))) return rc;
     CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
     h->stats.cells += cells;
-    for (int i = 0; i < n; i++) if (res[i].status == 2) { h->err = "tb_words_per_req too small"; return DARWIN_ERR_CAPACITY; }
+    for (int i = 0; i < n; i++) if ((res[i].status & 0x0F) == 2) { h->err = "tb_words_per_req too small"; return DARWIN_ERR_CAPACITY; }
     return DARWIN_OK;
 } GUARDED_END
 

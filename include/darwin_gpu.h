@@ -92,8 +92,14 @@ typedef struct DarwinTileRes {
     uint16_t query_max_pos;
     uint16_t total_TB_pointers;
     uint8_t  index;                   /* uint8 in the reference too (BatchSize) */
-    uint8_t  status;                  /* 0 = OK */
+    uint8_t  status;                  /* low nibble: 0 = OK, 1 = tile larger than DARWIN_MAX_TILE, 2 = tb_words_per_req too small;
+                                       * bit 4: DARWIN_TILE_LONG_INS_PATH */
 } DarwinTileRes;
+
+/* DarwinTileRes.status bit: the traceback of this tile entered the long-insertion state.  The reference reads
+ * uninitialised vectors there (software/Processor.cpp:259-260, used :405-408, :444), so its answer for such a tile
+ * depends on the build; tiles WITHOUT this bit are identical under every build of the reference. */
+#define DARWIN_TILE_LONG_INS_PATH 0x10u
 
 /* One anchor == ExtendLocations (software/graph.h:83-91) plus what
  * makeForwardAlignment / makeBackwardAlignment look up (extender.cpp:1067-1159). */

@@ -11,6 +11,9 @@ Fixtures (all seeded; inputs are synthetic, expected outputs come from the refer
   filter_v1.npz  3 chromosomes (one 5 kbp) + 48 reads (some hanging over chromosome ends): the candidates of the reference's
                  seeder_body, the first-tile results of its BatchAlignmentSIMD on filter_body's requests, and the
                  ExtendLocations its filter_body (tiles + slope filter) returns
+  config1_v1.npz BASELINE.json configs[0]: the reference's own sample reference (software/data/sample_ref.fa, sacCer3 chrI)
+                 with 40 simulated reads (the reads file is missing from the reference tree), stock params.cfg read through
+                 the reference's ConfigFile: arena, anchors of its seeder + filter, extender_body results (patched; `asis_same`)
   rtl_kat.npz    the RTL testbench's 10 known-answer pairs (RTL/GACT/test_data/{ref,query}_320.txt) and
                  their "Total score" lines (test_align.txt) -- score-level vectors only
 """
@@ -102,6 +105,19 @@ def gen_tiles():
     np.savez_compressed(os.path.join(OUT, "tiles_v1.npz"), **out)
 
 
+ALN_CMP = ("flags", "n_ops", "reference_start_offset", "reference_end_offset", "query_start_offset", "query_end_offset",
+           "n_tiles", "n_large_tiles", "score", "cells")
+
+
+def same_alignments(rp, opsp, ra, opsa):
+    """Per anchor: do the two flavours agree on every reported field and on the op string?  (`ops_offset` is a position in
+    the flavour's own pool and is not compared.)"""
+    return np.array([all(rp[k][f] == ra[k][f] for f in ALN_CMP) and
+                     np.array_equal(opsp[rp[k]["ops_offset"]:rp[k]["ops_offset"] + rp[k]["n_ops"]],
+                                    opsa[ra[k]["ops_offset"]:ra[k]["ops_offset"] + ra[k]["n_ops"]])
+                     for k in range(len(rp))])
+
+
 def gen_extend():
     rng = np.random.default_rng(7)
     genome = synth.random_seq(rng, 150000)
@@ -146,9 +162,7 @@ def gen_extend():
             res[fl] = (anchors, hits, r_, ops[:used].copy(), ref.arena().copy())
         (anchors, hits, rp, opsp, arena) = res["patched"]
         (_, _, ra, opsa, _) = res["as-is"]
-        same = np.array([rp[k] == ra[k] and np.array_equal(opsp[rp[k]["ops_offset"]:rp[k]["ops_offset"] + rp[k]["n_ops"]],
-                                                          opsa[ra[k]["ops_offset"]:ra[k]["ops_offset"] + ra[k]["n_ops"]])
-                         for k in range(len(anchors))])
+        same = same_alignments(rp, opsp, ra, opsa)
         tag = "T%d_O%d_ovl%d" % (T, O, ovl)
         out[tag + "_anchors"] = anchors
         out[tag + "_hits"] = hits
@@ -238,6 +252,54 @@ def gen_filter():
           "| custom", len(cands2), "locations", len(all_loc), len(all_loc96), "score<60:", int((all_loc["score"] < 60).sum()))
 
 
+def gen_config1(n_reads=40):
+    """configs[0]: software/data/sample_ref.fa + software/params.cfg, reference-guided.  The arena (chromosome + reads as the
+    reference's reader lays them out) is committed, so the GPU test needs neither /root/reference nor the read simulator."""
+    seq = b"".join(l.strip() for l in open(os.path.join(REF, "software", "data", "sample_ref.fa"), "rb") if not l.startswith(b">"))
+    g = np.char.upper(np.frombuffer(seq, np.uint8).view("S1")).view(np.uint8)
+    res = {}
+    for fl in ("patched", "as-is"):
+        rng = np.random.default_rng(1)
+        ref = oracle.reference(fl)
+        ref.load_cfg(os.path.join(REF, "software", "params.cfg"), 0)
+        ref.reset_arena()
+        ref.add_chr("sacCer3.chrI", seq, True)
+        ref.build_index()
+        addrs, lens = [], []
+        for k in range(n_reads):
+            L = int(rng.integers(8000, 12000))
+            p = int(rng.integers(0, len(g) - L))
+            r = synth.mutate_fast(rng, g[p:p + L], 0.05, 0.05, 0.05)
+            if rng.random() < 0.5:
+                r = synth.revcomp(r)
+            r = np.ascontiguousarray(r)
+            _, addr = ref.add_read("r%d" % k, r.tobytes())
+            addrs.append(addr)
+            lens.append(len(r))
+        A, H, hb = [], [], 0
+        for k in range(n_reads):
+            a, h = ref.seed_filter(k, 1)
+            a = a.copy()
+            a["left_hits_off"] += hb
+            a["right_hits_off"] += hb
+            hb += len(h)
+            A.append(a)
+            H.append(h)
+        anchors, hits = np.concatenate(A), np.concatenate(H)
+        r_, ops = ref.extend(anchors, hits)
+        used = int((r_["ops_offset"] + r_["n_ops"]).max())
+        res[fl] = (anchors, hits, r_, ops[:used].copy(), ref.arena().copy(), np.array(addrs, np.uint64), np.array(lens, np.uint32), ref.chroms())
+    anchors, hits, rp, opsp, arena, addrs, lens, chroms = res["patched"]
+    _, _, ra, opsa, _, _, _, _ = res["as-is"]
+    same = same_alignments(rp, opsp, ra, opsa)
+    # 2 bits per base where possible keeps the fixture small: the arena is stored as is (deflate does the rest)
+    np.savez_compressed(os.path.join(OUT, "config1_v1.npz"), arena=arena, read_addr=addrs, read_len=lens, chroms=chroms,
+                        anchors=anchors, hits=hits, res=rp, ops=opsp, asis_same=same, scoring=np.array(SCHEMES["stock"], np.int32),
+                        extend=np.array([384, 64, 0], np.int32))
+    print("config1: reads", n_reads, "anchors", len(anchors), "emitted", int((rp["flags"] & 1).sum()), "tiles", int(rp["n_tiles"].sum()),
+          "large", int(rp["n_large_tiles"].sum()), "as-is identical", int(same.sum()))
+
+
 def gen_rtl():
     d = os.path.join(REF, "RTL", "GACT", "test_data")
     refs = open(os.path.join(d, "ref_320.txt")).read().split()
@@ -254,4 +316,5 @@ if __name__ == "__main__":
     gen_tiles()
     gen_extend()
     gen_filter()
+    gen_config1()
     gen_rtl()

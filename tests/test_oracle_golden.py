@@ -77,3 +77,30 @@ def test_rtl_known_answer_scores():
     for rule in (oracle.Port.STRIPED, oracle.Port.STREAM, oracle.Port.CLEAN):
         res, _, _ = port.tiles(arena, req, 1, rule)
         assert res["score"].tolist() == g["scores"].tolist()
+
+
+# ---- the as-is half of the parity report on the CPU: restatement vs fixtures ----------------
+@pytest.mark.parametrize("scheme", SCHEMES)
+def test_tiles_asis_rule_on_fixture(golden_tiles, scheme):
+    """Tiles on which the two builds of the reference disagree all walk through the long-insertion state."""
+    import parity_cases as pc
+    g = golden_tiles
+    port = oracle.port(abi.Scoring.from_values(*g[scheme + "_scoring"].tolist()))
+    _, _, flags = port.tiles(g[scheme + "_arena"], g[scheme + "_req"], 1, oracle.Port.STREAM, tb_words_per_req=260)
+    c = pc.check_asis_rule((flags & 2) != 0, g[scheme + "_asis_same"], scheme)
+    assert c["flagged"] < c["n"]
+
+
+def test_config1_fixture_matches_restatement():
+    """BASELINE.json configs[0] (sample reference, stock params.cfg): the committed fixture vs the restatement, and the
+    as-is rule on its anchors."""
+    import os
+    import parity_cases as pc
+    from conftest import GOLDEN, ALN_FIELDS
+    g = np.load(os.path.join(GOLDEN, "config1_v1.npz"))
+    port = oracle.port(abi.Scoring.from_values(*g["scoring"].tolist()))
+    T, O, ovl = [int(x) for x in g["extend"]]
+    res, ops = port.extend(g["arena"], abi.ExtendParams(T, O, ovl, 0), g["anchors"], g["hits"], oracle.Port.STREAM)
+    assert alignments_equal(g["res"], g["ops"], res, ops, ALN_FIELDS) == []
+    c = pc.check_asis_rule((res["flags"] & abi.ALN_LONG_INS_PATH) != 0, g["asis_same"], "config1")
+    assert c["n"] == len(g["anchors"]) and 0 < c["asis_differs"] <= c["flagged"] < c["n"]
