@@ -70,7 +70,7 @@ def test_tiles_live_both_flavours(gpu, scheme):
     assert tiles_equal(want, wtb, res, tb) == []
     c = pc.check_asis_rule((res["status"] & abi.TILE_LONG_INS_PATH) != 0, same, "live tiles/" + scheme)
     print("parity report, tiles, %s: %d tiles, %d differ between the reference's builds, %d flagged" % (scheme, c["n"], c["asis_differs"], c["flagged"]))
-    assert c["flagged"] > 0 and c["flagged"] < c["n"] // 2
+    assert c["flagged"] > 0 and (scheme != "stock" or c["flagged"] < c["n"] // 2)
     p.close()
 
 
