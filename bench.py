@@ -35,36 +35,69 @@ sys.path.insert(0, ROOT)
 
 TILE, OVERLAP = 320, 128
 OPS_PER_CELL = 32          # algorithmic integer ops per DP cell
+# ALU-pipe utilisation of the dominant kernel in the committed `ncu --set full` capture (profiles/, sm__inst_executed_pipe_alu
+# .avg.pct_of_peak_sustained_active); the honest ceiling figure next to roofline.frac, which the tagged-score formulation
+# pushes above 1 (it needs fewer than the 32 nominal ops per cell)
+NCU_ALU_PIPE_BUSY = {"value": 80.2, "source": "profiles/r1_s4_tiles_kernel5_ncu_summary.txt"}
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons of one GPU during the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons of one GPU during the timed regions (B200_PROFILING.md), in-process through
+    NVML (no fork per sample: eight ranks forking nvidia-smi at 10 Hz cost the round-1 end-to-end legs host time)."""
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.25):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.index, self.period, self.samples, self.reasons, self.max_mhz, self.stop_flag = index, period, [], set(), None, False
+        self.nvml, self.handle, self.how = None, None, "nvml"
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            # torchrun leaves CUDA_VISIBLE_DEVICES alone on this box: CUDA ordinal == NVML index; honour a mask if there is one
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [x for x in vis.split(",") if x.strip() != ""]
+                if index < len(ids) and ids[index].strip().isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml, self.how = None, "nvidia-smi"
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        self.samples.append(float(f[0]))
+        self.max_mhz = float(f[1])
+        for (n, _), v in zip(self.REASONS, f[2:6]):
+            if v.lower().startswith("active"):
+                self.reasons.add(n)
 
     def run(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                self.samples.append(float(f[0]))
-                self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
+                if self.nvml is None:
+                    self._sample_smi()
+                else:
+                    nv = self.nvml
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                    bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    for n, attr in self.REASONS:
+                        if bits & int(getattr(nv, attr)):
+                            self.reasons.add(n)
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(self.period if self.nvml is not None else 1.0)
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "how": self.how}
 
 
 def make_workload(n_tiles, seed):
@@ -109,7 +142,7 @@ def cpu_reference_leg(arena, req, seconds_target, threads=None):
     gcups = n * cells_per_tile / secs / 1e9
     return {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind,
             "sample": "%d of the workload's %dx%d tiles, %.1f s wall, %s" % (
-                n, TILE, TILE, secs, "oracle/_ref BatchAlignmentSIMD (AVX2), std::thread x cores" if kind == "reference"
+                n, TILE, TILE, secs, "oracle/_ref BatchAlignmentSIMD (AVX2), std::thread x cores, posix_memalign in place of tbbmalloc" if kind == "reference"
                 else "oracle/gact_oracle.c scalar port"),
             "tiles_per_s": n / secs, "sample_tiles": n, "sample_ms": secs * 1e3}
 
@@ -142,6 +175,231 @@ def run_reference(args):
     return 0
 
 
+# =====================================================================================================================
+# Read-level legs: BASELINE.json configs[2] (10 Mbp + 10 k PacBio-like reads, 1 GPU), configs[3] (250 Mbp + a FIXED set of
+# 200 k reads, strong-sharded over the ranks, reference replicated), configs[4] (50 kbp ONT-like reads, tile_size sweep,
+# de novo overlap mode).  Every timed pass starts from page-locked HOST reads: read upload (ASCII H2D + packing), D-SOFT,
+# first tiles, slope filter, extension and the D2H of locations / results / op strings are all inside the timer.
+# =====================================================================================================================
+PACBIO = (0.015, 0.09, 0.045)      # sub / ins / del, 15 %
+ONT = (0.04, 0.03, 0.05)           # 12 %
+
+
+def _pinned(shape, dtype):
+    import torch
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    t = torch.empty(max(nbytes, 16), dtype=torch.uint8, pin_memory=True)
+    return t.numpy()[:nbytes].view(dtype).reshape(shape)
+
+
+class ReadLeg:
+    """One reference replica + this rank's reads, two lanes (host threads, one handle each over the shared arena replica
+    and seed position table) that take chunks of reads alternately: the upload and the host part of one chunk overlap the
+    kernels of the other lane's chunk."""
+
+    def __init__(self, local, sc, genome_len, n_total, lo, hi, read_len, err, seed, chunk_reads, lanes=2, self_reference=False):
+        import torch
+        import darwin_b200
+        from darwin_b200 import abi, workloads
+        self.abi = abi
+        dev = torch.device("cuda", local)
+        self.case = c = workloads.ReadSetCase(dev, genome_len, n_total, lo, hi, read_len, err, seed)
+        self.chunk = max(1, min(chunk_reads, c.n))
+        self.n = c.n
+        self.self_reference = self_reference
+        if self_reference:
+            # de novo mode (software/README.md:26): the reads file is its own reference -- every read is a chromosome of the
+            # table AND a read; arena = [128 N][reads as chromosomes][reads]
+            self.ref_end = abi_ref_end = 128 + c.n * c.stride
+            self.arena_bytes = abi_ref_end + c.n * c.stride + 128
+            chroms = np.zeros(c.n, abi.CHROM)
+            chroms["start"] = 128 + np.arange(c.n, dtype=np.uint64) * c.stride
+            chroms["len_unpadded"] = read_len
+            self.chroms = chroms
+            self.seed_reads = c.seed_reads.copy()
+            self.seed_reads["read_addr"] = abi_ref_end + np.arange(c.n, dtype=np.uint64) * np.uint64(c.stride)
+        else:
+            self.ref_end, self.arena_bytes, self.chroms, self.seed_reads = c.ref_end, c.arena_bytes, c.chroms, c.seed_reads
+        self.procs = [darwin_b200.Processor(self.arena_bytes, local)]
+        self.procs[0].InitializeScoringParameters(sc)
+        t0 = time.perf_counter()
+        if self_reference:
+            self.procs[0].InitializeReferenceMemory(0, np.full(128, ord("N"), np.uint8))
+            self.procs[0].InitializeReferenceMemory(128, c.reads_numpy(0, c.n))
+        else:
+            self.procs[0].InitializeReferenceMemory(0, c.ref_numpy())
+        self.ref_upload_s = time.perf_counter() - t0
+        for _ in range(1, max(1, lanes)):
+            self.procs.append(darwin_b200.Processor(0, local, parent=self.procs[0]))
+        self.index_s = None
+        self.out = []
+        per_read = 3 if not self_reference else 24                    # locations per read the output buffers are sized for
+        for _ in self.procs:
+            cap = self.chunk * per_read + 64
+            self.out.append((_pinned((cap,), abi.ANCHOR), _pinned((cap,), abi.ALN_RES),
+                             _pinned((int(self.chunk * (per_read if self_reference else 2.6) * read_len * 1.1) + 65536,), np.uint8)))
+
+    def build_index(self, do_overlap=0):
+        t0 = time.perf_counter()
+        ref_size = self.ref_end
+        self.procs[0].build_seed_index(self.abi.SeedParams.stock(do_overlap), self.chroms, ref_size)
+        self.index_s = time.perf_counter() - t0
+
+    def one_pass(self, params, n_reads=None):
+        """All reads of the shard (or the first n_reads) through upload + darwin_gpu_align_reads, chunk by chunk.
+        Returns dict(wall_s, kernel_ms, seed_ms, filter_ms, extend_ms, alignments, locations, cells, ops, h2d, d2h)."""
+        n = self.n if n_reads is None else min(self.n, n_reads)
+        chunks = [(a, min(n, a + self.chunk)) for a in range(0, n, self.chunk)]
+        tot = {"kernel_ms": 0.0, "seed_ms": 0.0, "filter_ms": 0.0, "extend_ms": 0.0, "alignments": 0, "locations": 0, "cells": 0.0,
+               "ops": 0, "h2d": 0, "d2h": 0, "score_sum": 0}
+        lock = threading.Lock()
+        errs = []
+        nxt = [0]
+
+        def lane(k):
+            p, (o_an, o_res, o_ops) = self.procs[k], self.out[k]
+            try:
+                while True:
+                    with lock:
+                        i = nxt[0]
+                        nxt[0] += 1
+                    if i >= len(chunks):
+                        return
+                    a, b = chunks[i]
+                    ascii_ = self.case.reads_numpy(a, b)
+                    p.InitializeReadMemory(int(self.seed_reads["read_addr"][a]), ascii_)          # H2D + packing
+                    an, res, _ = p.align_reads(self.seed_reads[a:b], params, out=(o_an, o_res, o_ops))
+                    st = p.stats()
+                    em = (res["flags"] & 1) != 0
+                    nops = int(res["n_ops"][em].sum())
+                    with lock:
+                        tot["kernel_ms"] += st.last_kernel_ms; tot["seed_ms"] += st.last_seed_ms
+                        tot["filter_ms"] += st.last_filter_ms; tot["extend_ms"] += st.last_extend_ms
+                        tot["alignments"] += int(em.sum()); tot["locations"] += len(res)
+                        tot["cells"] += float(res["cells"].sum()); tot["ops"] += nops
+                        tot["score_sum"] += int(res["score"][em].sum())
+                        tot["h2d"] += ascii_.nbytes + (b - a) * 16
+                        tot["d2h"] += len(res) * (64 + 56) + nops
+            except Exception as e:
+                errs.append(e)
+
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=lane, args=(k,)) for k in range(len(self.procs))]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+        tot["wall_s"] = time.perf_counter() - t0
+        if errs:
+            raise errs[0]
+        tot["reads"] = n
+        return tot
+
+    def close(self):
+        for p in reversed(self.procs):
+            p.close()
+        self.procs = []
+
+
+def _agg(dist, dev, world, tot, keys_max, keys_sum):
+    import torch
+    a = torch.tensor([tot[k] for k in keys_max], dtype=torch.float64, device=dev)
+    b = torch.tensor([float(tot[k]) for k in keys_sum], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+    out = {k: float(v) for k, v in zip(keys_max, a)}
+    out.update({k: float(v) for k, v in zip(keys_sum, b)})
+    return out
+
+
+def run_read_leg(name, note, local, rank, world, dist, barrier, sc, int_peak, genome_len, n_total, strong, read_len, err, seed,
+                 chunk_reads, tiles, passes=1, lanes=2, self_reference=False, do_overlap=0):
+    """tiles: list of (tile_size, tile_overlap) run on the same resident case; returns {name or name_T<T>: info}."""
+    import torch
+    from darwin_b200 import abi, workloads
+    dev = torch.device("cuda", local)
+    if strong:
+        per = -(-n_total // world)
+        per += (-per) % workloads.BLOCK
+        lo, hi = min(n_total, rank * per), min(n_total, (rank + 1) * per)
+    else:
+        lo, hi = 0, n_total
+        seed = seed + 1000 * rank                                       # weak scaling: every rank owns its own read set
+    leg = ReadLeg(local, sc, genome_len, n_total, lo, hi, read_len, err, seed, chunk_reads, lanes, self_reference)
+    leg.build_index(do_overlap)
+    out = {}
+    for (T, O) in tiles:
+        prm = abi.AlignParams.stock(T, O, do_overlap)
+        leg.one_pass(prm, n_reads=min(leg.n, 2 * leg.chunk * len(leg.procs)))       # warm-up: buffers grown, pools filled
+        acc = None
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            t = leg.one_pass(prm)
+            acc = t if acc is None else {k: (acc[k] + t[k]) for k in acc}
+        barrier()
+        acc["wall_s"] = time.perf_counter() - t0
+        a = _agg(dist, dev, world, acc, ["wall_s", "kernel_ms", "extend_ms", "seed_ms", "filter_ms"],
+                 ["reads", "alignments", "locations", "cells", "ops", "h2d", "d2h", "score_sum"])
+        lanes_n = len(leg.procs)
+        # kernel times are summed over the lanes' calls, which overlap on the device: the device-time rate uses the per-lane
+        # share as a lower bound of the busy time, the end-to-end rate uses the wall clock
+        gcups_ext = a["cells"] / world / (a["extend_ms"] * 1e-3) / 1e9 if a["extend_ms"] else None
+        info = {"workload": name, "reference_bp": genome_len, "reads": int(a["reads"] / passes), "read_len": read_len,
+                "error_profile_sub_ins_del": list(err), "tile_size": T, "tile_overlap": O, "do_overlap": do_overlap,
+                "scaling": "strong" if strong else "weak", "passes": passes, "lanes": lanes_n, "chunk_reads": leg.chunk,
+                "locations": int(a["locations"] / passes), "alignments": int(a["alignments"] / passes), "cells": a["cells"] / passes,
+                "reads_per_s_e2e": a["reads"] / a["wall_s"], "gcups_e2e": a["cells"] / a["wall_s"] / 1e9,
+                "wall_ms": a["wall_s"] * 1e3 / passes,
+                "extend_kernel_ms_slowest_rank": a["extend_ms"] / passes, "seed_kernel_ms": a["seed_ms"] / passes,
+                "filter_kernel_ms": a["filter_ms"] / passes,
+                "gcups_extend_kernel_per_gpu": gcups_ext,
+                "roofline_frac_extend_kernel": (gcups_ext * OPS_PER_CELL / int_peak) if (gcups_ext and int_peak) else None,
+                "h2d_bytes": int(a["h2d"] / passes), "d2h_bytes": int(a["d2h"] / passes),
+                "index_build_s": leg.index_s, "reference_upload_s": leg.ref_upload_s, "score_checksum": int(a["score_sum"] / passes),
+                "note": note}
+        out[name if len(tiles) == 1 else "%s_T%d" % (name, T)] = info
+    leg.close()
+    del leg
+    torch.cuda.empty_cache()
+    return out
+
+
+def cpu_reads_leg(genome_len, read_len, err, seed, T, O, n_sample, threads=None):
+    """The reference's own per-read chain (seeder_body -> filter_body -> extender_body, one read per batch as main.cpp feeds
+    them) on a bounded sample of the same read set, all host cores (oracle/_ref, as-is flavour)."""
+    import torch
+    import ctypes as C
+    import oracle
+    from darwin_b200 import abi, workloads
+    if not oracle.have_reference():
+        return None
+    cores = threads or os.cpu_count() or 1
+    cpu = torch.device("cpu")
+    genome = workloads.genome_codes(genome_len, seed, torch.device("cuda") if torch.cuda.is_available() else cpu)
+    blk = workloads.simulate_block(genome, 0, seed, read_len, err, n=min(n_sample, workloads.BLOCK)).cpu().numpy()
+    ga = np.frombuffer(b"ACGT", np.uint8)[genome.cpu().numpy()]
+    ref = oracle.reference("as-is")
+    ref.set_scoring(abi.Scoring.from_values())
+    ref.set_dsoft_defaults()
+    ref.set_extend(T, O, 2, 0)
+    ref.reset_arena()
+    t0 = time.perf_counter()
+    ref.add_chr("chrS", ga.tobytes(), True)
+    ref.build_index()
+    index_s = time.perf_counter() - t0
+    n = len(blk)
+    for k in range(n):
+        ref.add_read("r%d" % k, np.ascontiguousarray(blk[k, :read_len]).tobytes())
+    st = (C.c_double * 8)()
+    alns = ref.lib.dref_pipeline_cpu_mt(0, n, cores, st)
+    return {"kind": "reference", "cores": cores, "sample": "%d reads of the same set, seeder_body -> filter_body -> extender_body per read, "
+            "std::thread x %d, %.1f s wall (index build %.1f s not counted)" % (n, cores, st[0], index_s),
+            "reads_per_s": n / st[0], "gcups": st[5] / st[0] / 1e9, "alignments": int(alns),
+            "stage_thread_seconds_seed_filter_extend": [st[2], st[3], st[4]], "unit": "reads/s", "value": n / st[0]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -157,6 +415,14 @@ def main():
                     help="host threads (handles sharing one arena replica) issuing the end-to-end steps")
     ap.add_argument("--filter-tiles", type=int, default=400000,
                     help="secondary measurement: first-tile filter candidates through darwin_gpu_filter (0 = skip)")
+    ap.add_argument("--config3-reads", type=int, default=10000,
+                    help="configs[2]: 10 Mbp reference, this many PacBio-like 10 kbp reads per GPU, reads in -> alignments out (0 = skip)")
+    ap.add_argument("--config4-reads", type=int, default=200000,
+                    help="configs[3]: 250 Mbp replicated reference, a FIXED set of this many 10 kbp reads strong-sharded over the ranks (0 = skip)")
+    ap.add_argument("--config4-genome", type=int, default=250000000)
+    ap.add_argument("--config5-reads", type=int, default=1000,
+                    help="configs[4]: ONT-like 50 kbp reads per GPU, tile_size 256/512/1024 + de novo overlap mode (0 = skip)")
+    ap.add_argument("--read-lanes", type=int, default=2, help="host threads (lanes) feeding the read-level legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -309,15 +575,12 @@ def main():
         lp.close()
     proc = darwin_b200.Processor(len(arena), local)
     proc.InitializeScoringParameters(sc)
-    sampler.stop_flag = True
-    sampler.join(timeout=3)
 
     # ---- secondary: whole anchors through extender_body (in-kernel tile walking), stock params.cfg T=384/O=64 ----
     # Every rank extends its own shard of reads against its own replica of the packed reference (no
     # data-path collective); reads/s = all ranks' reads / slowest rank.
     extend_info = None
     seed_info = None
-    align_info = None
     if args.extend_reads > 0:
         from darwin_b200 import synth
         ref_len = 4000000
@@ -327,8 +590,11 @@ def main():
         ex.InitializeReferenceMemory(0, ex_arena)
         ex.extender_body(ex_anchors, ex_hits, 384, 64, 0)                          # warm-up at full size (buffers grown once)
         ex_out = (pinned((len(ex_anchors),), abi.ALN_RES), pinned((int(ex_anchors["read_len"].sum()) * 2,), np.uint8))
+        reads_at = int(ex_anchors["read_addr"].min())                              # the reads follow the chromosome in the arena
+        h_reads = pinned((len(ex_arena) - reads_at,), np.uint8); h_reads[:] = ex_arena[reads_at:]
         barrier()
         t0 = time.perf_counter()
+        ex.InitializeReadMemory(reads_at, h_reads)                                 # the reads' ASCII H2D + packing is part of the step
         ex_res, ex_ops = ex.extender_body(ex_anchors, ex_hits, 384, 64, 0, out=ex_out)   # anchors + hits H2D, ops D2H
         ex_wall = time.perf_counter() - t0
         ex_st = ex.stats()
@@ -347,26 +613,14 @@ def main():
         sb, sa, sp = ex.seeder_body(sreads)
         seed_wall = time.perf_counter() - t0
         seed_ms = ex.stats().last_kernel_ms
-        # the whole reference-guided pipeline in one resident call (darwin_gpu_align_reads): D-SOFT, first tiles, slope filter,
-        # extension of every surviving location -- reads in, alignments (coordinates, score, op strings) out
-        al_out = (pinned((len(ex_anchors) * 8,), abi.ANCHOR), pinned((len(ex_anchors) * 8,), abi.ALN_RES),
-                  pinned((int(ex_anchors["read_len"].sum()) * 3,), np.uint8))
-        ex.align_reads(sreads, out=al_out)                                         # warm-up at full size
-        barrier()
-        t0 = time.perf_counter()
-        al_anchors, al_res, _ = ex.align_reads(sreads, out=al_out)
-        al_wall = time.perf_counter() - t0
-        al_ms = ex.stats().last_kernel_ms
-        al_n = float(int((al_res["flags"] & 1).sum()))
-        al_cells = float(al_res["cells"].sum())
-        agg = torch.tensor([ex_st.last_kernel_ms, ex_wall * 1e3, seed_ms, seed_wall * 1e3, al_ms, al_wall * 1e3], dtype=torch.float64, device=dev)
-        tot = torch.tensor([ex_cells, float(int((ex_res["flags"] & 1).sum())), float(int(ex_res["n_tiles"].sum())), float(len(sa)),
-                            al_n, al_cells], dtype=torch.float64, device=dev)
+        agg = torch.tensor([ex_st.last_kernel_ms, ex_wall * 1e3, seed_ms, seed_wall * 1e3], dtype=torch.float64, device=dev)
+        tot = torch.tensor([ex_cells, float(int((ex_res["flags"] & 1).sum())), float(int(ex_res["n_tiles"].sum())), float(len(sa))],
+                           dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(agg, op=dist.ReduceOp.MAX)
             dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        k_ms, w_ms, sk_ms, sw_ms, ak_ms, aw_ms = [float(x) for x in agg]
-        cells_all, aligned_all, tiles_all, seed_anchors_all, al_n_all, al_cells_all = [float(x) for x in tot]
+        k_ms, w_ms, sk_ms, sw_ms = [float(x) for x in agg]
+        cells_all, aligned_all, tiles_all, seed_anchors_all = [float(x) for x in tot]
         reads_all = args.extend_reads * world
         extend_info = {"workload": "extend_10kbp_T384_O64", "reads": int(reads_all), "reads_per_gpu": int(args.extend_reads),
                        "aligned": int(aligned_all), "tiles": int(tiles_all), "cells": cells_all, "kernel_ms": k_ms,
@@ -374,17 +628,12 @@ def main():
                        "reads_per_s_kernel": reads_all / (k_ms * 1e-3),
                        "reads_per_s_e2e": reads_all / (w_ms * 1e-3),
                        "note": "one anchor per read at its true locus, synthetic chained hits; every rank extends its own shard "
-                               "(max over ranks); D-SOFT not included"}
+                               "(max over ranks); e2e = read upload (ASCII H2D + packing) + anchors/hits H2D + kernels + op D2H; D-SOFT not included"}
         seed_info = {"workload": "dsoft_10kbp_k14_w3", "reads": int(reads_all), "index_build_s": ix_s, "reference_bp": ref_len,
                      "kernel_ms": sk_ms, "reads_per_s_kernel": reads_all / (sk_ms * 1e-3), "reads_per_s_e2e": reads_all / (sw_ms * 1e-3),
                      "anchors": int(seed_anchors_all),
                      "note": "both strands of every read: minimizers, table look-ups, bin counting, candidates + chained hits "
                              "(darwin_gpu_seed); e2e includes the D2H of all chained hits"}
-        align_info = {"workload": "align_reads_10kbp_stock_params", "reads": int(reads_all), "alignments": int(al_n_all),
-                      "cells": al_cells_all, "kernel_ms": ak_ms, "reads_per_s_kernel": reads_all / (ak_ms * 1e-3),
-                      "reads_per_s_e2e": reads_all / (aw_ms * 1e-3), "gcups_e2e": al_cells_all / (aw_ms * 1e-3) / 1e9,
-                      "note": "resident reads in, alignments out through ONE call per rank: D-SOFT + first-tile filter + slope "
-                              "filter + GACT extension on the GPU (darwin_gpu_align_reads); e2e includes the D2H of all op strings"}
         ex.close()
 
     # ---- secondary: first-tile filter (128x128 score-only, max-cell mode; filter.cpp:28-122) through darwin_gpu_filter ----
@@ -411,6 +660,49 @@ def main():
                        "packed_tiles": int(fp.stats().tiles_filter)}
         fp.close()
 
+    # ---- read-level legs: BASELINE.json configs[2], [3], [4] (reads in -> alignments out, host buffers, upload timed) ----
+    int_peak, int_detail = None, None
+    try:
+        int_detail = proc.int_peak()
+        int_peak = 2.0 * max(int_detail[:3])      # packed s16x2 ops only (alu pipe); IADD3/LOP3/IMAD are reported
+    except Exception:
+        pass
+    read_legs = {}
+    if args.config3_reads > 0:
+        read_legs.update(run_read_leg(
+            "config3", "BASELINE.json configs[2]: synthetic 10 Mbp reference + PacBio-like 10 kbp reads (15 %: sub 1.5 / ins 9 / del 4.5), "
+            "stock params.cfg, reference-guided; every rank runs its own read set against its own replica",
+            local, rank, world, dist, barrier, sc, int_peak, 10000000, args.config3_reads, False, 10000, PACBIO, 31,
+            5000, [(384, 64)], passes=2, lanes=args.read_lanes))
+    if args.config4_reads > 0:
+        read_legs.update(run_read_leg(
+            "config4", "BASELINE.json configs[3]: synthetic chr1-scale reference replicated per GPU + ONE fixed set of 10 kbp reads at 15 % "
+            "(5/5/5) sharded contiguously over the ranks (strong scaling); reads/s = set size / slowest rank",
+            local, rank, world, dist, barrier, sc, int_peak, args.config4_genome, args.config4_reads, True, 10000, (0.05, 0.05, 0.05), 41,
+            12500, [(384, 64)], passes=1, lanes=args.read_lanes))
+    if args.config5_reads > 0:
+        read_legs.update(run_read_leg(
+            "config5", "BASELINE.json configs[4]: ONT-like 50 kbp reads at 12 % (sub 4 / ins 3 / del 5) against a 20 Mbp reference, tile_overlap 64",
+            local, rank, world, dist, barrier, sc, int_peak, 20000000, args.config5_reads, False, 50000, ONT, 51,
+            500, [(256, 64), (512, 64), (1024, 64)], passes=1, lanes=args.read_lanes))
+        read_legs.update(run_read_leg(
+            "config5_denovo", "BASELINE.json configs[4], de novo mode (argv[3] = 1): the read set is its own reference, all-vs-all, "
+            "50 kbp ONT-like reads at ~5x coverage of a 10 Mbp genome, tile_size 256",
+            local, rank, world, dist, barrier, sc, int_peak, 10000000, max(200, args.config5_reads), False, 50000, ONT, 52,
+            250, [(256, 64)], passes=1, lanes=args.read_lanes, self_reference=True, do_overlap=1))
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the reference's CPU chain on bounded samples of the same read sets (reported baseline, N = 1 only)
+        try:
+            if "config3" in read_legs:
+                read_legs["config3"]["cpu_baseline"] = cpu_reads_leg(10000000, 10000, PACBIO, 31, 384, 64, 512)
+            if "config5_T512" in read_legs:
+                read_legs["config5_T512"]["cpu_baseline"] = cpu_reads_leg(20000000, 50000, ONT, 51, 512, 64, 64)
+        except Exception as e:                                     # the baseline is a report, never a reason to lose the bench line
+            read_legs["cpu_baseline_error"] = repr(e)
+
+    sampler.stop_flag = True                                       # clocks were sampled over every timed region above
+    sampler.join(timeout=3)
+
     # checksum of the last step (guards against "fast because wrong"): every tile must have produced a path
     assert int((res["total_TB_pointers"] > 0).sum()) > 0.99 * n, "tiles without traceback"
 
@@ -420,19 +712,14 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        int_peak, int_detail = None, None
-        try:
-            int_detail = proc.int_peak()
-            int_peak = 2.0 * max(int_detail[:3])      # packed s16x2 ops only (alu pipe); IADD3/LOP3/IMAD are reported
-        except Exception:
-            pass
         per_gpu_gcups = value / world
         roof = {"bound": "int_alu", "achieved": per_gpu_gcups * OPS_PER_CELL, "peak": int_peak,
                 "unit": "Gint-op/s", "frac": (per_gpu_gcups * OPS_PER_CELL / int_peak) if int_peak else None,
                 # dram__bytes_read+write of tiles_kernel<5> from the committed ncu capture (profiles/r1_s4_tiles_kernel5_*:
                 # 76.6 MB read + 12.6 MB written per 200k-tile launch = 446 B per tile), scaled to this launch's tile count;
                 # algorithmic bytes: ~460 B per tile (320 B packed bases + 32 B request + 16 B result + the used TB words)
-                "traffic": 446.0 * n,
+                "traffic": 446.0 * n, "traffic_source": "constant_from_ncu (profiles/: dram__bytes_read+write per tile of the committed capture x tiles; not a live counter)",
+                "alu_pipe_busy_ncu_pct": NCU_ALU_PIPE_BUSY,
                 "peak_detail_glaneops": dict(zip(["vimnmx_u16x2", "viaddmnmx_u16x2", "vimnmx3_u16x2", "iadd3", "lop3_3reg", "imad", "lop3_2reg", "lop3_imm", "prmt", "shfl_idx"], int_detail)) if int_detail else None,
                 "note": "SURVEY 8(d) integer-pipe roofline: 32 algorithmic int-ops per cell; peak = measured packed "
                         "s16x2 DPX/ALU issue rate (2 cells per lane-op) of this GPU; HBM is not the bound "
@@ -462,8 +749,7 @@ def main():
             line["filter"] = filter_info
         if seed_info:
             line["seed"] = seed_info
-        if align_info:
-            line["align"] = align_info
+        line.update(read_legs)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_leg(arena, req, args.cpu_seconds)
         print(json.dumps(line))

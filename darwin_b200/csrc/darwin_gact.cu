@@ -10,6 +10,7 @@
 #include <vector>
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <cmath>
 
 #include "gact_common.cuh"
@@ -466,10 +467,6 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
             }
             if (tfl & 1) a.flags |= DARWIN_ALN_LONG_INS_PATH;
             if (tfl & 0x100) overflow = 1;
-            if (ea.dbg && lane == 0 && a.n_tiles <= 128) {
-                uint32_t* d = ea.dbg + ((size_t)idx * 128 + (a.n_tiles - 1)) * 8;
-                d[0] = t.R; d[1] = t.Q; d[2] = len; d[3] = a.cr; d[4] = a.cq; d[5] = a.rso; d[6] = a.qso; d[7] = a.large | (left << 1);
-            }
             after_tile(a, len);
         }
         if (cx.n_rerun != rerun0) a.flags |= DARWIN_ALN_EXACT_RERUN;
@@ -620,7 +617,11 @@ struct DarwinGpu {
     DarwinGpuStats stats{};
     std::string err;
     SeedIndex seed_ix;                          // D-SOFT seed position table (dsoft_host.cuh); lanes share the parent's
+    bool timing_dbg = false;                    // DARWIN_GPU_TIMING=1: per-phase host timings of darwin_gpu_extend on stderr
+    DarwinGpu* parent = nullptr;                // lanes: the handle that owns the arena replica and the seed position table
+    std::vector<DarwinGpu*> lanes;              // parent: live lanes (guarded by g_lane_mutex)
 };
+static std::mutex g_lane_mutex;
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DARWIN_ERR_CUDA; } } while (0)
 
@@ -745,6 +746,7 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return DARWIN_ERR_NO_DEVICE;
     DarwinGpu* h = new DarwinGpu();
     h->device = device;
+    h->timing_dbg = getenv("DARWIN_GPU_TIMING") != nullptr;
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
@@ -759,6 +761,7 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     }
     h->arena_bytes = arena_bytes;
     if (parent) {                                                              // another lane of the same device: one arena replica
+        { std::lock_guard<std::mutex> g(g_lane_mutex); parent->lanes.push_back(h); h->parent = parent; }
         h->d_arena = parent->d_arena; h->owns_arena = false;
         if (parent->have_scoring) { h->ks = parent->ks; h->filt = parent->filt; h->have_scoring = true; }
         h->seed_ix = parent->seed_ix; h->seed_ix.owner = false;                // and one seed position table
@@ -788,6 +791,11 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
 
 int darwin_gpu_destroy(DarwinGpu* h) {
     if (!h) return DARWIN_ERR_INVALID;
+    {   // lanes point into the parent's arena replica and seed position table: the parent goes last
+        std::lock_guard<std::mutex> g(g_lane_mutex);
+        if (!h->lanes.empty()) { h->err = "darwin_gpu_destroy: " + std::to_string(h->lanes.size()) + " lane(s) of this handle are still alive"; return DARWIN_ERR_INVALID; }
+        if (h->parent) { auto& v = h->parent->lanes; v.erase(std::remove(v.begin(), v.end(), h), v.end()); h->parent = nullptr; }
+    }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (int i = 0; i < 12; i++) if (h->d_buf[i]) cudaFree(h->d_buf[i]);
@@ -840,6 +848,10 @@ int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s) {
     h->ks.xc = make_xconst(d, h->ks.fc);
     h->filt = make_filter_const(d);
     h->have_scoring = true;
+    {   // lanes created before this call follow their parent (a lane may still set its own scoring afterwards)
+        std::lock_guard<std::mutex> g(g_lane_mutex);
+        for (DarwinGpu* l : h->lanes) { l->ks = h->ks; l->filt = h->filt; l->have_scoring = true; }
+    }
     return DARWIN_OK;
 }
 
@@ -1104,7 +1116,7 @@ static double now_ms() { return std::chrono::duration<double, std::milli>(std::c
 
 static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinAnchor* anchors, int n, const uint64_t* d_pool, uint64_t n_hits,
                         DarwinAlnRes* res, uint8_t* ops_pool, uint64_t ops_pool_bytes, uint64_t* used_out, float* kernel_ms) {
-    const bool tdbg = getenv("DARWIN_GPU_TIMING") != nullptr; double tlast = now_ms();
+    const bool tdbg = h->timing_dbg; double tlast = now_ms();          // DARWIN_GPU_TIMING, read once in create_handle
     // op slots: left part holds the (reversed) left extension, right part the right extension
     std::vector<uint64_t> base(n); std::vector<uint32_t> lcap(n), size(n);
     uint64_t total = 0;
@@ -1145,9 +1157,6 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     ea.res = (DarwinAlnRes*)h->d_buf[1]; ea.ops = (uint8_t*)h->d_buf[3];
     ea.slot_base = (const uint64_t*)h->d_buf[4]; ea.slot_left = (const uint32_t*)h->d_buf[5]; ea.slot_size = (const uint32_t*)h->d_buf[6];
     ea.order = (const uint32_t*)h->d_buf[10];
-    ea.dbg = nullptr;
-    DevFree dbg_guard;
-    if (getenv("DARWIN_GPU_DEBUG")) { CK(cudaMalloc(&ea.dbg, (size_t)n * 128 * 8 * 4)); dbg_guard.p = ea.dbg; CK(cudaMemset(ea.dbg, 0, (size_t)n * 128 * 8 * 4)); }
     ea.n = n; ea.T = p->tile_size; ea.O = p->tile_overlap; ea.do_overlap = p->do_overlap; ea.counter = h->d_counter;
     CK(cudaEventRecord(h->ev0, h->stream));
     const int K = pick_k(h, p->tile_size, 1);
@@ -1192,11 +1201,6 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     CK(cudaStreamSynchronize(h->stream));
     TMARK("compact+D2H");
     *used_out = used;
-    if (ea.dbg) {
-        std::vector<uint32_t> hd((size_t)n * 128 * 8);
-        CK(cudaMemcpy(hd.data(), ea.dbg, hd.size() * 4, cudaMemcpyDeviceToHost));
-        FILE* f = fopen(getenv("DARWIN_GPU_DEBUG"), "wb"); if (f) { fwrite(hd.data(), 4, hd.size(), f); fclose(f); }
-    }
     return DARWIN_OK;
 }
 
@@ -1329,6 +1333,7 @@ int darwin_gpu_align_reads(DarwinGpu* h, const DarwinAlignParams* p, const Darwi
     if (!anchors_out || !res) return DARWIN_ERR_INVALID;
     memcpy(anchors_out, anchors.data(), anchors.size() * sizeof(DarwinAnchor));
     rc = extend_all(h, &p->extend, anchors.data(), (int)anchors.size(), d_pool.as<uint64_t>(), n_pool, res, ops_pool, ops_pool_bytes);
+    h->stats.last_seed_ms = seed_ms; h->stats.last_filter_ms = filter_ms; h->stats.last_extend_ms = h->stats.last_kernel_ms;
     h->stats.last_kernel_ms += seed_ms + filter_ms;
     return rc;
 } GUARDED_END
@@ -1337,7 +1342,16 @@ int darwin_gpu_seed_index(DarwinGpu* h, const DarwinSeedParams* p, const DarwinC
     if (!h || !p || n_chroms < 0 || (n_chroms && !chroms)) return DARWIN_ERR_INVALID;
     if (!h->seed_ix.owner && h->seed_ix.ready) { h->err = "the seed position table belongs to the parent handle"; return DARWIN_ERR_INVALID; }
     CK(cudaSetDevice(h->device));
-    return seed_index_build(h, h->seed_ix, p, chroms, n_chroms, reference_size);
+    {   // rebuilding frees the table the lanes are reading
+        std::lock_guard<std::mutex> g(g_lane_mutex);
+        if (h->seed_ix.ready && !h->lanes.empty()) { h->err = "darwin_gpu_seed_index: cannot rebuild the table while lanes share it"; return DARWIN_ERR_INVALID; }
+    }
+    const int rc = seed_index_build(h, h->seed_ix, p, chroms, n_chroms, reference_size);
+    if (rc == DARWIN_OK) {                           // lanes created before the first build adopt the table
+        std::lock_guard<std::mutex> g(g_lane_mutex);
+        for (DarwinGpu* l : h->lanes) { l->seed_ix = h->seed_ix; l->seed_ix.owner = false; }
+    }
+    return rc;
 } GUARDED_END
 
 int darwin_gpu_seed_index_share(DarwinGpu* h, DarwinGpu* parent) {

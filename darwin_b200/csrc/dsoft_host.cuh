@@ -2,6 +2,7 @@
 // DarwinGpu handle is defined.  Kernels: dsoft.cuh.  CUB supplies the scans and the segmented sorts.
 #pragma once
 #include <cub/cub.cuh>
+#include <thrust/iterator/transform_iterator.h>
 #include "dsoft.cuh"
 
 #define CKS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DARWIN_ERR_CUDA; } } while (0)
@@ -111,6 +112,20 @@ static int exclusive_sum(DarwinGpu* h, const T* in, T* out, int64_t n) {
     return DARWIN_OK;                                // tmp is released in stream order
 }
 
+// 64-bit sum of a 32-bit array (synchronises the stream)
+struct WidenU32 { __host__ __device__ uint64_t operator()(uint32_t x) const { return (uint64_t)x; } };
+static int sum_u64(DarwinGpu* h, const uint32_t* in, int64_t n, uint64_t* out) {
+    thrust::transform_iterator<WidenU32, const uint32_t*, uint64_t> it(in, WidenU32());
+    DevBuf d_out, tmp; size_t bytes = 0;
+    CKS(d_out.alloc(sizeof(uint64_t), h->stream));
+    CKS(cub::DeviceReduce::Sum(nullptr, bytes, it, d_out.as<uint64_t>(), n, h->stream));
+    CKS(tmp.alloc(bytes, h->stream));
+    CKS(cub::DeviceReduce::Sum(tmp.p, bytes, it, d_out.as<uint64_t>(), n, h->stream));
+    CKS(cudaMemcpyAsync(out, d_out.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CKS(cudaStreamSynchronize(h->stream));
+    return DARWIN_OK;
+}
+
 __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, int n, uint32_t* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];
@@ -145,8 +160,8 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
         max_cap = std::max(max_cap, cap);
     }
     seed_base[ns] = slots;
-    // 32-bit offsets index the seed slots, the hits and the candidates of one call: keep a call below ~1.5 G read bases
-    // (about 150 k reads of 10 kbp); larger batches are the caller's to split
+    // 32-bit offsets index the seed slots of one call: keep a call below ~1.5 G read bases (about 150 k reads of 10 kbp);
+    // the hits get their own 64-bit check below; larger batches are the caller's to split
     uint64_t bases = 0, slots64 = 0;
     for (int r = 0; r < n; r++) { bases += reads[r].read_len; slots64 += 2ull * (seed_base[2 * r + 1] - seed_base[2 * r]); }
     if (bases > 1500000000ull || slots64 != slots) { h->err = "seeding batch too large (more than 1.5 G read bases in one call)"; return DARWIN_ERR_INVALID; }
@@ -165,6 +180,14 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     hit_count_kernel<<<gb, 256, 0, h->stream>>>(sc, ix.d_buckets, ix.d_positions, d_seeds.as<uint64_t>(), d_base.as<uint32_t>(), d_nseeds.as<uint32_t>(), ns, max_cap, d_cnt.as<uint32_t>());
     CKS(cudaGetLastError());
     int rc;
+    // The hit offsets are 32-bit: the total (slots x up to max_occ hits each -- NOT bounded by the base count above) is
+    // summed in 64 bits first, and a batch beyond 2^32 - 1 hits is refused instead of wrapping the prefix sums.
+    uint64_t hits64 = 0;
+    if ((rc = sum_u64(h, d_cnt.as<uint32_t>(), (int64_t)slots + 1, &hits64))) return rc;
+    if (hits64 > 0xFFFFFFFFull) {
+        h->err = "seeding batch too large: " + std::to_string(hits64) + " seed hits exceed 2^32 - 1; split the reads over several calls";
+        return DARWIN_ERR_CAPACITY;
+    }
     if ((rc = exclusive_sum(h, d_cnt.as<uint32_t>(), d_hoff.as<uint32_t>(), (int64_t)slots + 1))) return rc;
     gather_u32_kernel<<<(ns + 1 + 255) / 256, 256, 0, h->stream>>>(d_hoff.as<uint32_t>(), d_base.as<uint32_t>(), ns + 1, d_soff.as<uint32_t>());
     CKS(cudaGetLastError());

@@ -24,7 +24,6 @@ struct ExtendArgs {
     int T, O, do_overlap;
     const uint32_t* order;        // work queue order: longest expected anchor first (LPT), so the last wave is short
     unsigned int* counter;        // work queue head
-    uint32_t* dbg;                // optional: per anchor 128 tiles x 8 words (R, Q, len, cr, cq, rso, qso, large)
 };
 
 // Anchor registers shared by the whole warp (all lanes hold identical copies).

@@ -106,6 +106,8 @@ public:
 
 private:
     enum Kind { TILES = 0, FILTER = 1, EXTEND = 2, SEED = 3, ALIGN = 4 };
+    // merged items per device call: tiles, candidates, anchors, reads (seeding), reads (resident pipeline)
+    static constexpr uint64_t kMaxMergedItems[5] = {1u << 22, 1u << 22, 1u << 18, 1u << 15, 1u << 15};
     struct Request {
         Kind kind; int n = 0; bool done = false; int rc = 0; std::string err;
         const std::vector<UploadSpan>* up = nullptr;
@@ -142,8 +144,13 @@ private:
             busy_ = true;
             std::vector<Request*> batch;
             batch.push_back(q_.front()); q_.pop_front();
+            // ... up to a bounded number of items per device call: the library indexes the seed hits of one call with
+            // 32 bits (dsoft_host.cuh), and a call that large gains nothing from growing further
+            uint64_t items = (uint64_t)batch[0]->n;
             for (auto it = q_.begin(); it != q_.end();) {
-                if (mergeable(*batch[0], **it)) { batch.push_back(*it); it = q_.erase(it); } else ++it;
+                if (mergeable(*batch[0], **it) && items + (uint64_t)(*it)->n <= kMaxMergedItems[batch[0]->kind]) {
+                    items += (uint64_t)(*it)->n; batch.push_back(*it); it = q_.erase(it);
+                } else ++it;
             }
             lk.unlock();
             try { execute(batch); }
@@ -214,11 +221,19 @@ private:
             std::vector<uint64_t> tbw(tb ? total * (size_t)words : 1);
             const int rc = total ? c_.tiles(h_, tb, req.data(), (int)total, res.data(), tb ? tbw.data() : nullptr, words) : 0;
             if (rc) { fail_all(batch, rc, "darwin_gpu_tiles"); return; }
+            // the merged call ran with the widest TB row of the batch: a caller whose own row is narrower than one of its
+            // tiles' tracebacks gets what the unmerged call would have given it (status 2, DARWIN_ERR_CAPACITY)
             size_t at = 0;
             for (auto* b : batch) {
                 for (int i = 0; i < b->n; i++) {
                     b->tres[i] = res[at + i];
-                    if (tb) memcpy(b->tb + (size_t)i * b->words, tbw.data() + (at + i) * (size_t)words, sizeof(uint64_t) * (size_t)b->words);
+                    if (tb) {
+                        memcpy(b->tb + (size_t)i * b->words, tbw.data() + (at + i) * (size_t)words, sizeof(uint64_t) * (size_t)b->words);
+                        if (((size_t)res[at + i].total_TB_pointers + 31) / 32 > (size_t)b->words) {
+                            b->tres[i].status = (uint8_t)((b->tres[i].status & 0xF0) | 2);
+                            b->rc = DARWIN_ERR_CAPACITY; b->err = "darwin_gpu_tiles: tb_words_per_req too small";
+                        }
+                    }
                 }
                 at += (size_t)b->n;
             }
@@ -314,10 +329,15 @@ private:
                 }
             }
             std::vector<DarwinAlnRes> res(total);
-            uint8_t* ops = ops_buffer(cap);
-            if (!ops) { fail_all(batch, DARWIN_ERR_CAPACITY, "host buffer for the op strings"); return; }
-            const int rc = c_.extend(h_, &batch[0]->ep, anchors.data(), (int)total, pool.empty() ? nullptr : pool.data(), pool.size(),
-                                     res.data(), ops, cap);
+            uint8_t* ops = nullptr;
+            int rc = DARWIN_ERR_CAPACITY;
+            for (int attempt = 0; attempt < 4 && rc == DARWIN_ERR_CAPACITY; attempt++) {     // like ALIGN: grow the op pool and retry
+                ops = ops_buffer(cap);
+                if (!ops) { fail_all(batch, DARWIN_ERR_CAPACITY, "host buffer for the op strings"); return; }
+                rc = c_.extend(h_, &batch[0]->ep, anchors.data(), (int)total, pool.empty() ? nullptr : pool.data(), pool.size(),
+                               res.data(), ops, cap);
+                if (rc == DARWIN_ERR_CAPACITY) cap *= 2;
+            }
             if (rc) { fail_all(batch, rc, "darwin_gpu_extend"); return; }
             // op strings are dense and in anchor order: each caller owns one contiguous slice of the pool
             size_t at = 0;

@@ -30,15 +30,20 @@ static void fail_msg(int rc, const char* what, const std::string& detail) {
     throw std::runtime_error(msg);
 }
 
-const char* last_error() { return g_error.c_str(); }
+// a thread-local copy: the pointer stays valid while other host threads record their own errors
+const char* last_error() {
+    static thread_local std::string copy;
+    { std::lock_guard<std::mutex> g(g_error_mutex); copy = g_error; }
+    return copy.c_str();
+}
 
 DarwinGpu* handle_for_token(size_t token) {
-    if (g_handles.empty()) { g_error = "InitializeProcessor was not called"; throw std::runtime_error(g_error); }
+    if (g_handles.empty()) fail_msg(DARWIN_ERR_NOT_READY, "handle_for_token", "InitializeProcessor was not called");
     return g_handles[token % g_handles.size()];
 }
 
 GpuCombiner& combiner_for_token(size_t token) {
-    if (g_combiners.empty()) { g_error = "InitializeProcessor was not called"; throw std::runtime_error(g_error); }
+    if (g_combiners.empty()) fail_msg(DARWIN_ERR_NOT_READY, "combiner_for_token", "InitializeProcessor was not called");
     return *g_combiners[token % g_combiners.size()];
 }
 

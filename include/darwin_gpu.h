@@ -230,6 +230,11 @@ typedef struct DarwinGpuStats {
     float    last_kernel_ms;    /* CUDA-event time of the last tiles/extend/filter kernel(s) */
     float    reserved;
     uint64_t tiles_filter;      /* score-only tiles finished by the packed filter path (two tiles per warp) */
+    float    last_seed_ms;      /* darwin_gpu_align_reads: CUDA-event time of the D-SOFT kernels of the last call */
+    float    last_filter_ms;    /*   ... of the first-tile filter kernels */
+    float    last_extend_ms;    /*   ... of the extension kernels (anchor walking + score / compaction) */
+    float    reserved2;
+    uint64_t tiles_scoreonly;   /* large tiles settled by the score-only pre-pass (corner ZERO: no traceback needed) */
 } DarwinGpuStats;
 
 typedef struct DarwinGpu DarwinGpu;   /* opaque */
@@ -241,7 +246,9 @@ int darwin_gpu_create(DarwinGpu** h, int device, uint64_t arena_bytes);   /* on 
 /* A further handle ("lane") on the parent's device that SHARES the parent's arena replica: own stream, own scratch,
  * own result buffers.  Lets several host threads keep kernels of independent batches in flight on one GPU (the
  * reference's tokens, main.cpp:615-624) without one arena copy per thread.  Uploads through any lane are visible to
- * all of them once darwin_gpu_upload returns.  The parent must be destroyed last. */
+ * all of them once darwin_gpu_upload returns.  Ordering rules (enforced): darwin_gpu_destroy(parent) fails with
+ * DARWIN_ERR_INVALID while lanes are alive; darwin_gpu_set_scoring on the parent also reaches its lanes; the first
+ * darwin_gpu_seed_index on the parent is adopted by existing lanes, a REbuild is refused while lanes share the table. */
 int darwin_gpu_create_shared(DarwinGpu** h, DarwinGpu* parent);
 int darwin_gpu_destroy(DarwinGpu* h);
 

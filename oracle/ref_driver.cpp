@@ -567,6 +567,48 @@ double dref_extend_mt(const DarwinAnchor* anchors, int n, const uint64_t* hit_po
     return s;
 }
 
+// Timing leg for reads/s: the reference's whole per-read chain -- seeder_body -> filter_body -> extender_body, one read per
+// batch exactly as main.cpp:590-702 feeds them (readBufferLimit = 64 bytes) -- on `nthreads` std::threads playing the
+// reference's tokens.  stats[0] = wall seconds, [1] = alignments, [2..4] = seconds inside the three stages (summed over
+// threads), [5] = DP cells of the extension's tile requests.  Returns the number of alignments.
+int dref_pipeline_cpu_mt(int first, int count, int nthreads, double* stats) {
+    if (nthreads < 1) nthreads = 1;
+    std::atomic<int> next(0); std::atomic<uint64_t> alns(0);
+    std::vector<double> ts(nthreads, 0.0), tf(nthreads, 0.0), te(nthreads, 0.0);
+    g_cells = 0; g_tiles = 0; g_count_cells = 1;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t0 = now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) {
+        th.emplace_back([&, t]() {
+            for (;;) {
+                const int k = next.fetch_add(1);
+                if (k >= count) break;
+                reader_output reads(1, g_reads[first + k]);
+                const auto a0 = now();
+                filter_input fin = seeder_body()(seeder_input(reads, (size_t)t));
+                const auto a1 = now();
+                extender_input ein = filter_body()(fin);
+                const auto a2 = now();
+                extender_node::output_ports_type ports;
+                extender_body()(ein, ports);
+                const auto a3 = now();
+                ts[t] += secs(a0, a1); tf[t] += secs(a1, a2); te[t] += secs(a2, a3);
+                alns += std::get<1>(std::get<0>(std::get<0>(ports).items[0])).extend_alignments.size();
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    if (stats) {
+        stats[0] = secs(t0, now()); stats[1] = (double)alns.load(); stats[2] = stats[3] = stats[4] = 0;
+        for (int t = 0; t < nthreads; t++) { stats[2] += ts[t]; stats[3] += tf[t]; stats[4] += te[t]; }
+        stats[5] = (double)g_cells.load();
+    }
+    g_count_cells = 0;
+    return (int)alns.load();
+}
+
 int dref_num_reads(void) { return (int)g_reads.size(); }
 int dref_read_len(int k) { return (k >= 0 && k < (int)g_reads.size()) ? (int)g_reads[k].seq.size() : -1; }
 uint64_t dref_read_addr(int k) { return (k >= 0 && k < (int)g_reads.size()) ? (uint64_t)(g_reads[k].seq.data() - g_DRAM->buffer) : 0; }
