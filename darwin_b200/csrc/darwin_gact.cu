@@ -17,6 +17,7 @@
 #include "gact_exact.cuh"
 #include "gact_fast.cuh"
 #include "gact_xfast.cuh"
+#include "gact_score.cuh"
 #include "gact_extend.cuh"
 #include "gact_filter.cuh"
 #include "dsoft.cuh"
@@ -109,7 +110,7 @@ struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568
     }
 };
 
-struct KernelScoring { DevScoring sc; FastConst fc; XConst xc; FastConst fcw; };   // fcw: wide-score layout (4 tag bits)
+struct KernelScoring { DevScoring sc; FastConst fc; XConst xc; FastConst fcw; ScoreConst sf; };   // fcw: wide-score layout (4 tag bits); sf: score-only pre-pass
 
 
 __device__ __forceinline__ void load_scoring(const DevScoring& sc, int* ssub) {
@@ -146,7 +147,7 @@ struct WarpCtx {
     unsigned char* wsmem;         // this warp's dynamic shared memory (fast view and ExactSmem alias each other)
     TmaStage ts_small, ts_big;    // TMA staging windows (small: single-strip fast tiles; big: everything else)
     WarpScratch ws;
-    uint32_t n_fast, n_exact, n_rerun, n_xfast;
+    uint32_t n_fast, n_exact, n_rerun, n_xfast, n_scoreonly;
     unsigned long long cells_exact;
 };
 
@@ -185,6 +186,12 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
             XSmemView xv(cx.wsmem);
             bool has_n = single ? stage_tile(cx, t, v.sref, v.sqry, true) : stage_tile(cx, t, mv.sref, mv.sqry, false);
             if (!has_n) {
+                // large tiles: score-only pre-pass first -- a corner that is provably ZERO ends the tile without any trace
+                if (large && ks.sf.eligible && score_only_corner_is_zero(ks.sf, mv, t.Q, t.R)) {
+                    out.score = 0; out.ref_max_pos = t.R - 1; out.query_max_pos = t.Q - 1;      // H(corner) = 0, no pointers
+                    cx.n_scoreonly++;
+                    return;
+                }
                 uint32_t* gband = reinterpret_cast<uint32_t*>(cx.ws.trace);
                 // large tiles bridge long gaps by construction: the clean rule would almost always be refused, so
                 // shapes the packed exact path accepts go there directly
@@ -251,7 +258,7 @@ __device__ __forceinline__ WarpCtx make_ctx(const uint8_t* arena, const int* ssu
     cx.ts_big = TmaStage{cx.wsmem + KernelGeom<K>::kBigRawOff, kRawBig, mbar, 0u};
     tma_stage_init(mbar);
     cx.ws = WarpScratch{trace_base + (size_t)gw * trace_stride, bound_base + (size_t)gw * kMaxTile};
-    cx.n_fast = cx.n_exact = cx.n_rerun = cx.n_xfast = 0; cx.cells_exact = 0;
+    cx.n_fast = cx.n_exact = cx.n_rerun = cx.n_xfast = cx.n_scoreonly = 0; cx.cells_exact = 0;
     return cx;
 }
 
@@ -262,6 +269,7 @@ __device__ __forceinline__ void flush_counters(const WarpCtx& cx, unsigned int* 
         if (cx.n_rerun) atomicAdd(counter + 3, cx.n_rerun);
         if (cx.cells_exact) atomicAdd(reinterpret_cast<unsigned long long*>(counter + 4), cx.cells_exact);
         if (cx.n_xfast) atomicAdd(counter + 6, cx.n_xfast);
+        if (cx.n_scoreonly) atomicAdd(counter + 7, cx.n_scoreonly);
     }
 }
 
@@ -595,7 +603,7 @@ __global__ void int_peak_kernel(uint32_t* out, const uint32_t* in, int iters) {
 // =====================================================================================================
 // Host side: handle + C-ABI
 // =====================================================================================================
-constexpr int kCounters = 16;    // [0] queue head, [1] fast, [2] exact, [3] rerun, [4,5] cells_exact, [6] xfast, [8] filter hand-over count, [9] filter tiles
+constexpr int kCounters = 16;    // [0] queue head, [1] fast, [2] exact, [3] rerun, [4,5] cells_exact, [6] xfast, [7] score-only large tiles, [8] filter hand-over count, [9] filter tiles
 
 struct DarwinGpu {
     int device = 0;
@@ -710,6 +718,7 @@ static int read_counters(DarwinGpu* h) {
     h->stats.tiles_fast += c[1]; h->stats.tiles_exact += c[2]; h->stats.tiles_rerun += c[3];
     h->stats.cells_exact += ((uint64_t)c[5] << 32) | c[4];
     h->stats.tiles_xfast += c[6];
+    h->stats.tiles_scoreonly += c[7];
     h->stats.tiles_filter += c[9];
     return DARWIN_OK;
 }
@@ -846,6 +855,7 @@ int darwin_gpu_set_scoring(DarwinGpu* h, const DarwinScoring* s) {
     h->ks.fc = make_fast_const(d);
     h->ks.fcw = make_fast_const(d, 4);
     h->ks.xc = make_xconst(d, h->ks.fc);
+    h->ks.sf = make_score_const(d, h->ks.fc);
     h->filt = make_filter_const(d);
     h->have_scoring = true;
     {   // lanes created before this call follow their parent (a lane may still set its own scoring afterwards)

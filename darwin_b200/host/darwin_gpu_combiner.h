@@ -107,7 +107,7 @@ public:
 private:
     enum Kind { TILES = 0, FILTER = 1, EXTEND = 2, SEED = 3, ALIGN = 4 };
     // merged items per device call: tiles, candidates, anchors, reads (seeding), reads (resident pipeline)
-    static constexpr uint64_t kMaxMergedItems[5] = {1u << 22, 1u << 22, 1u << 18, 1u << 15, 1u << 15};
+    static uint64_t max_merged_items(int kind) { return kind <= 1 ? (1u << 22) : kind == 2 ? (1u << 18) : (1u << 15); }
     struct Request {
         Kind kind; int n = 0; bool done = false; int rc = 0; std::string err;
         const std::vector<UploadSpan>* up = nullptr;
@@ -148,7 +148,7 @@ private:
             // 32 bits (dsoft_host.cuh), and a call that large gains nothing from growing further
             uint64_t items = (uint64_t)batch[0]->n;
             for (auto it = q_.begin(); it != q_.end();) {
-                if (mergeable(*batch[0], **it) && items + (uint64_t)(*it)->n <= kMaxMergedItems[batch[0]->kind]) {
+                if (mergeable(*batch[0], **it) && items + (uint64_t)(*it)->n <= max_merged_items(batch[0]->kind)) {
                     items += (uint64_t)(*it)->n; batch.push_back(*it); it = q_.erase(it);
                 } else ++it;
             }

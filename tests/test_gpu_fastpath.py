@@ -199,3 +199,55 @@ def test_oversized_tb_row_with_pageable_buffers_is_rejected(gpu):
     with pytest.raises(darwin_b200.DarwinGpuError) as e:
         p.BatchAlignmentSIMD(req, tb_words_per_req=(40 << 20) // 8)   # one TB row larger than the pinned staging buffer
     assert e.value.code == abi.ERR_INVALID
+
+
+def _large_tiles(seed, n, related_every=3):
+    """1984x960 / 960x1984 corner-traceback tiles as the extender requests them after a stall (extender.cpp:61-78): mostly
+    UNRELATED sequences (spurious anchors: the corner is ZERO, no pointers), some true continuations, some with the corner
+    sitting right after a long gap, some clipped at a sequence end."""
+    rng = np.random.default_rng(seed)
+    parts, pos = [np.full(64, ord("N"), np.uint8)], 64
+    req = np.zeros(n, abi.TILE_REQ)
+    for k in range(n):
+        R, Q = (1984, 960) if k % 2 else (960, 1984)
+        if k % 7 == 5:
+            R -= int(rng.integers(1, 300))                       # clipped at a chromosome / read end
+        r = synth.random_seq(rng, R)
+        if k % related_every == 0:
+            q = synth.mutate(rng, r, 0.05, 0.05, 0.05, indel_run=(2, 60))
+            q = np.concatenate([q, synth.random_seq(rng, max(0, Q - len(q)))])[:Q]
+        elif k % related_every == 1 and k % 4 == 1:
+            # related, but the end of the query is a 30-base insertion: the corner sits inside / right after a long gap
+            q = synth.mutate(rng, r[:Q - 30] if Q - 30 <= R else r, 0.03, 0.02, 0.02)
+            q = np.concatenate([q, synth.random_seq(rng, max(0, Q - len(q)))])[:Q]
+        else:
+            q = synth.random_seq(rng, Q)
+        fl = [1, 21, 7, 19][k % 4]
+        req[k]["ref_bases_start_addr"], req[k]["ref_size"] = pos, len(r)
+        pos += len(r)
+        req[k]["query_bases_start_addr"], req[k]["query_size"] = pos, len(q)
+        pos += len(q)
+        parts += [r, q]
+        req[k]["max_tb_steps"], req[k]["align_fields"], req[k]["index"] = 768, fl, k % 250
+    return np.concatenate(parts + [np.full(64, ord("N"), np.uint8)]), req
+
+
+@pytest.mark.parametrize("vals", [(2, -6, -1, -4, -2, -25, -1), (2, -3, -1, -3, -2, -8, -1), (1, -1, 0, -2, -1, -4, 0)])
+def test_large_tiles_score_only_prepass(gpu, vals):
+    """The score-only pre-pass (gact_score.cuh) settles large tiles whose corner is provably ZERO and hands every other one
+    to the traced paths; results are the reference's either way, and the pre-pass really is what ran for the zero ones."""
+    sc = abi.Scoring.from_values(*vals)
+    arena, req = _large_tiles(900 + vals[1], 48)
+    p = gpu(len(arena), sc)
+    p.InitializeReferenceMemory(0, arena)
+    st0 = p.stats()
+    res, tb = p.BatchAlignmentSIMD(req, 1, tb_words_per_req=50)
+    st1 = p.stats()
+    pres, ptb, _ = oracle.port(sc).tiles(arena, req, 1, oracle.Port.STREAM, tb_words_per_req=50)
+    assert tiles_equal(pres, ptb, res, tb) == []
+    zero = int((pres["total_TB_pointers"] == 0).sum())
+    settled = st1.tiles_scoreonly - st0.tiles_scoreonly
+    assert zero > 10 and 0 < settled <= zero                     # never claims a tile that has pointers ...
+    assert settled >= zero - 3                                   # ... and misses at most the rare "long chain exactly 0" corners
+    assert int((pres["total_TB_pointers"] > 0).sum()) > 10
+    p.close()

@@ -64,6 +64,7 @@ def test_dsoft_anchors_extend_identically(gpu, T, O, ovl):
     assert alignments_equal(want_res, want_ops, res, ops, ALN_FIELDS) == []
     assert len(anchors) >= 60 and int((res["flags"] & 1).sum()) >= 50
     if T == 384:
-        assert int(res["n_large_tiles"].sum()) > 0            # the large-tile fallback was exercised
+        assert int(res["n_large_tiles"].sum()) > 0            # the large-tile fallback was exercised ...
+        assert st1.tiles_scoreonly - st0.tiles_scoreonly > 0  # ... and some of those tiles ended in the score-only pre-pass
     assert st1.tiles_fast - st0.tiles_fast > 0
     p.close()
