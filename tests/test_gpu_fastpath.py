@@ -247,7 +247,9 @@ def test_large_tiles_score_only_prepass(gpu, vals):
     assert tiles_equal(pres, ptb, res, tb) == []
     zero = int((pres["total_TB_pointers"] == 0).sum())
     settled = st1.tiles_scoreonly - st0.tiles_scoreonly
-    assert zero > 10 and 0 < settled <= zero                     # never claims a tile that has pointers ...
+    assert 0 <= settled <= zero                                  # never claims a tile that has pointers ...
     assert settled >= zero - 3                                   # ... and misses at most the rare "long chain exactly 0" corners
+    if vals[0] == 2:
+        assert zero > 10                                         # (+1/-1 scoring never reaches a zero corner on random sequences)
     assert int((pres["total_TB_pointers"] > 0).sum()) > 10
     p.close()
