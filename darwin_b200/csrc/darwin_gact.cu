@@ -185,9 +185,12 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
             MultiSmemView mv(cx.wsmem);
             XSmemView xv(cx.wsmem);
             bool has_n = single ? stage_tile(cx, t, v.sref, v.sqry, true) : stage_tile(cx, t, mv.sref, mv.sqry, false);
-            if (!has_n) {
+            // tiles with N stay on the packed path when the scoring allows it (fast_cell<S, true>); their exact reruns use
+            // the unpacked path
+            const bool n_fast = has_n && (wide ? ks.fcw.n_ok : fc.n_ok);
+            if (!has_n || n_fast) {
                 // large tiles: score-only pre-pass first -- a corner that is provably ZERO ends the tile without any trace
-                if (large && ks.sf.eligible && score_only_corner_is_zero(ks.sf, mv, t.Q, t.R)) {
+                if (!has_n && large && ks.sf.eligible && score_only_corner_is_zero(ks.sf, mv, t.Q, t.R)) {
                     out.score = 0; out.ref_max_pos = t.R - 1; out.query_max_pos = t.Q - 1;      // H(corner) = 0, no pointers
                     cx.n_scoreonly++;
                     return;
@@ -195,10 +198,14 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
                 uint32_t* gband = reinterpret_cast<uint32_t*>(cx.ws.trace);
                 // large tiles bridge long gaps by construction: the clean rule would almost always be refused, so
                 // shapes the packed exact path accepts go there directly
-                if (single || !xok || !large) {
-                    const int score = single ? fast_forward<KK>(fc, v, t.Q, t.R)
-                                    : !wide ? fast_forward_multi<KK, 5, kBandHalf>(fc, mv, gband, t.Q, t.R)
-                                            : fast_forward_multi<KK, 4, kBandHalfWide>(ks.fcw, mv, gband, t.Q, t.R);
+                if (single || !xok || !large || has_n) {
+                    int score;
+                    if (!has_n) score = single ? fast_forward<KK>(fc, v, t.Q, t.R)
+                                      : !wide ? fast_forward_multi<KK, 5, kBandHalf>(fc, mv, gband, t.Q, t.R)
+                                              : fast_forward_multi<KK, 4, kBandHalfWide>(ks.fcw, mv, gband, t.Q, t.R);
+                    else        score = single ? fast_forward<KK, true>(fc, v, t.Q, t.R)
+                                      : !wide ? fast_forward_multi<KK, 5, kBandHalf, true>(fc, mv, gband, t.Q, t.R)
+                                              : fast_forward_multi<KK, 4, kBandHalfWide, true>(ks.fcw, mv, gband, t.Q, t.R);
                     // warp-uniform traceback on a copy of the sink: committed only when the clean rule holds
                     Sink trial = sink;
                     TileOut o2{};
@@ -213,10 +220,10 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
                     }
                     cx.n_rerun++;
                     __syncwarp();
-                    if (xok && single) stage_tile(cx, t, xv.sref, xv.sqry, false);        // the fast view kept them elsewhere
+                    if (xok && single && !has_n) stage_tile(cx, t, xv.sref, xv.sqry, false);        // the fast view kept them elsewhere
                     // (multi-strip tiles: MultiSmemView and XSmemView keep the sequences at the same offsets)
                 }
-                if (xok) {
+                if (xok && !has_n) {
                     const int score = xfast_forward(ks.xc, xv, gband, reinterpret_cast<uint4*>(cx.ws.bound), t.Q, t.R);
                     __syncwarp();
                     xfast_traceback(gband, t.Q, t.R, t.max_tb, out, sink);          // warp-uniform

@@ -20,7 +20,8 @@
 //
 // Fast-path preconditions (checked on the host / per tile, otherwise the exact path runs):
 //   uniform match/mismatch matrix, match > 0 > mismatch, gap_open <= gap_extend < 0, long gaps <= 0,
-//   (match * min(Q,R) + bias) < 2048, no N in the tile, Q <= 64*K, R <= 64*K, corner traceback.
+//   (match * min(Q,R) + bias) < 2048, Q <= 64*K, R <= 64*K, corner traceback.  Tiles containing N run the HASN
+//   instantiation (one extra ALU-pipe and one FMA-pipe instruction per cell pair) when mismatch <= sub_N <= 0.
 #pragma once
 #include "gact_common.cuh"
 
@@ -60,6 +61,8 @@ struct FastConst {                                  // packed constants derived 
     int32_t  max_score;   // largest corner score representable: 2047 - B
     int32_t  eligible;    // scoring admits the fast path
     int32_t  match;
+    uint32_t nmul;        // (sub_N - mismatch) * U / 4: multiplier of the packed "N involved" flags (value 4 per half)
+    int32_t  n_ok;        // tiles containing N may stay on the packed path (mismatch <= sub_N <= 0)
     uint32_t one[4];      // all 1, opaque to the compiler: `x * one[k] + c` stays an IMAD (fma pipe) instead of an ALU add
 };
 
@@ -92,6 +95,9 @@ __host__ inline FastConst make_fast_const(const DevScoring& sc, int S = 5) {
     f.gea = (ge * U) * 65537;
     f.lgoa = (lgo * U + (int)(FT_L << ts)) * 65537; f.lgea = (lge * U) * 65537;
     f.geh = pk(ge * U); f.lgeh = pk(lge * U);
+    // N bases (Nt2Int code 4, Processor.cpp:21-46; sub_N for N against anything, :50-74): see fast_cell<S, true>
+    f.n_ok = f.eligible && sc.subn <= 0 && sc.subn >= mm;
+    f.nmul = (uint32_t)((sc.subn - mm) * U / 4);
     return f;
 }
 
@@ -122,23 +128,28 @@ template <int K, int BH = kBandHalf> struct BandMap {
 
 // Scoring constants of one tile in registers.
 struct FastRegs {
-    uint32_t zeroc, pkc32, negc32, diaga, goa, gofa, lgoa, geh, lgeh, one0, one1, one2, one3;
+    uint32_t zeroc, pkc32, negc32, diaga, goa, gofa, lgoa, geh, lgeh, one0, one1, one2, one3, nmul;
     __device__ explicit FastRegs(const FastConst& fc)
         : zeroc(fc.zeroc), pkc32(fc.pkc32), negc32((uint32_t)fc.negc32), diaga((uint32_t)fc.diaga), goa((uint32_t)fc.goa),
           gofa((uint32_t)fc.gofa), lgoa((uint32_t)fc.lgoa), geh(fc.geh), lgeh(fc.lgeh),
-          one0(fc.one[0]), one1(fc.one[1]), one2(fc.one[2]), one3(fc.one[3]) {}
+          one0(fc.one[0]), one1(fc.one[1]), one2(fc.one[2]), one3(fc.one[3]), nmul(fc.nmul) {}
 };
 
 // One packed cell pair (two int16 cells): recurrence of Processor.cpp:293-366 on tagged scores.
 // d = Hm of the row above at the previous column (in), Hm of this row at the previous column (out).
 // S = 5: the layout described above.  S = 4 (wide scores): source in bits 3:1, one shared "extended" bit 0; the 5-bit
 // trace code (same as S = 5) is assembled from Hk's source, E's bit 0 and F's bit 0 (one more ALU op per cell pair).
-template <int S = 5>
+//
+// HASN: the tile contains N.  Reference N is code 4, query N is remapped to 12 when the rows are loaded, so an N on either
+// side always counts as a "mismatch" (x != 0, also N against N) and bit 2 of (rq | qq) says "N involved"; the substitution
+// score then becomes sub_N: sb + 4 * nmul = (sub_N - mismatch) * U on top of the mismatch already folded into d.
+template <int S = 5, bool HASN = false>
 __device__ __forceinline__ uint32_t fast_cell(const FastRegs& k, uint32_t rq, uint32_t qq, uint32_t& d, uint32_t& Hm,
                                               uint32_t& E, uint32_t& EL, uint32_t& F, uint32_t& FL) {
     const uint32_t x  = rq ^ qq;
     const uint32_t t  = __vminu2(x, 0x00010001u);                // 1 = mismatch, per half
-    const uint32_t sb = t * k.negc32 + k.pkc32;                  // IMAD: (match-mismatch)*32 or 0
+    uint32_t sb = t * k.negc32 + k.pkc32;                        // IMAD: (match-mismatch)*32 or 0
+    if (HASN) sb = ((rq | qq) & 0x00040004u) * k.nmul + sb;      // LOP3 + IMAD: N involved -> sub_N
     const uint32_t hd = __viaddmax_u16x2(d, sb, k.zeroc);        // max(Hdiag + s, 0)          :298-299
     const uint32_t h1 = __vimax3_u16x2(hd, E, F);
     const uint32_t Hk = __vimax3_u16x2(h1, EL, FL);              // H with the winner's tag      :300-303
@@ -166,22 +177,27 @@ __device__ __forceinline__ uint32_t fast_cell(const FastRegs& k, uint32_t rq, ui
 
 // Forward pass of one tile.  Sequences must already be staged (codes 0..3) in v.sref / v.sqry.
 // Returns the corner score H(Q-1, R-1) in all lanes.
-template <int K>
+// dummy bases outside the tile: they mismatch everything and (HASN) carry no "N involved" bit
+constexpr uint32_t kDummyRef = 16u, kDummyQry = 32u;
+// query base as the cell update wants it: N (4) becomes 12 in tiles that contain N (see fast_cell)
+template <bool HASN> __device__ __forceinline__ uint32_t qry_code(uint32_t c) { return HASN ? (c | ((c & 4u) << 1)) : c; }
+
+template <int K, bool HASN = false>
 __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q, int R) {
     using G = FastGeom<K>;
     const int lane = lane_id();
-    // packed reference pairs: P[32 + j] = r[j] | r[j-32] << 16, dummy base 5 outside [0,R)
+    // packed reference pairs: P[32 + j] = r[j] | r[j-32] << 16, dummy base outside [0,R)
     for (int k = lane; k < G::kPWords; k += 32) {
         const int j = k - 32;
-        const uint32_t lo = (j >= 0 && j < R) ? v.sref[j] : 5u;
-        const uint32_t hi = (j - 32 >= 0 && j - 32 < R) ? v.sref[j - 32] : 5u;
+        const uint32_t lo = (j >= 0 && j < R) ? v.sref[j] : kDummyRef;
+        const uint32_t hi = (j - 32 >= 0 && j - 32 < R) ? v.sref[j - 32] : kDummyRef;
         v.P[k] = lo | (hi << 16);
     }
     uint32_t qq[K], Hm[K], E[K], EL[K];
 #pragma unroll
     for (int r = 0; r < K; r++) {
         const int ilo = K * lane + r, ihi = K * (lane + 32) + r;
-        qq[r] = (ilo < Q ? (uint32_t)v.sqry[ilo] : 6u) | ((ihi < Q ? (uint32_t)v.sqry[ihi] : 6u) << 16);
+        qq[r] = (ilo < Q ? qry_code<HASN>(v.sqry[ilo]) : kDummyQry) | ((ihi < Q ? qry_code<HASN>(v.sqry[ihi]) : kDummyQry) << 16);
         Hm[r] = fc.hm_init; E[r] = fc.e_init; EL[r] = fc.el_init;
     }
     __syncwarp();
@@ -217,7 +233,7 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
         uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
         for (int r = 0; r < K; r++) {
-            const uint32_t code = fast_cell(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
+            const uint32_t code = fast_cell<5, HASN>(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
             if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
         }
         diag_in = inH;
@@ -258,7 +274,7 @@ template <int K, int BH = kBandHalf> __host__ __device__ inline size_t multi_ban
     return (size_t)((Q + K - 1) / K + 64) * FastGeom<K, BH>::kLp * 4;
 }
 
-template <int K, int S = 5, int BH = kBandHalf>
+template <int K, int S = 5, int BH = kBandHalf, bool HASN = false>
 __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, uint32_t* gband, int Q, int R) {
     using G = FastGeom<K, BH>;
     const int lane = lane_id();
@@ -278,7 +294,7 @@ __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, u
 #pragma unroll
         for (int r = 0; r < K; r++) {
             const int ilo = row0 + K * lane + r, ihi = row0 + K * (lane + 32) + r;
-            qq[r] = (ilo < Q ? (uint32_t)v.sqry[ilo] : 6u) | ((ihi < Q ? (uint32_t)v.sqry[ihi] : 6u) << 16);
+            qq[r] = (ilo < Q ? qry_code<HASN>(v.sqry[ilo]) : kDummyQry) | ((ihi < Q ? qry_code<HASN>(v.sqry[ihi]) : kDummyQry) << 16);
             Hm[r] = fc.hm_init; E[r] = fc.e_init; EL[r] = fc.el_init;
         }
         uint32_t sendH = fc.hm_init, sendF = fc.f_top, sendFL = fc.fl_top;
@@ -290,7 +306,7 @@ __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, u
         const int vg = strip * 64 + lane;                                // my low-half global virtual lane
         int t_lo = -lane - K * vg + bm.c1;                               // t(i,j) at s = 0 (j = -lane)
         uint32_t* bp = gband + (size_t)vg * G::kLp + t_lo;
-        uint32_t rlo = (lane == 0 && R > 0) ? v.sref[0] : 5u, rhi = 5u;  // reference bases of step 0
+        uint32_t rlo = (lane == 0 && R > 0) ? v.sref[0] : kDummyRef, rhi = kDummyRef;  // reference bases of step 0
 
         // the corner is the last valid cell of the last strip: its loop ends there (nothing later is ever read)
         const int strip_steps = (strip == nstrips - 1) ? sc_step + 1 : steps;
@@ -307,14 +323,14 @@ __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, u
             const uint32_t rq = rlo | (rhi << 16);
             {   // prefetch the reference bases of step s+1: columns s+1-lane and s+1-lane-32
                 const int jl = s + 1 - lane, jh = jl - 32;
-                rlo = ((unsigned)jl < (unsigned)R) ? v.sref[jl] : 5u;
-                rhi = ((unsigned)jh < (unsigned)R) ? v.sref[jh] : 5u;
+                rlo = ((unsigned)jl < (unsigned)R) ? v.sref[jl] : kDummyRef;
+                rhi = ((unsigned)jh < (unsigned)R) ? v.sref[jh] : kDummyRef;
             }
             uint32_t d = diag_in;
             uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
             for (int r = 0; r < K; r++) {
-                const uint32_t code = fast_cell<S>(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
+                const uint32_t code = fast_cell<S, HASN>(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
                 if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
             }
             diag_in = inH;

@@ -67,9 +67,37 @@ def test_band_exit_falls_back_to_exact(gpu):
     assert rerun > 0 and fast > 0
 
 
-def test_tiles_with_n_use_exact_path(gpu):
-    fast, exact, rerun = _run(gpu, abi.Scoring.from_values(), *_ragged_batch(6, 400, 320, n_rate=0.004))
-    assert exact > 0 and fast > 0
+def _tiles_with_n(arena, req):
+    return sum(1 for r in req if (arena[int(r["ref_bases_start_addr"]):int(r["ref_bases_start_addr"]) + int(r["ref_size"])] == ord("N")).any()
+               or (arena[int(r["query_bases_start_addr"]):int(r["query_bases_start_addr"]) + int(r["query_size"])] == ord("N")).any())
+
+
+@pytest.mark.parametrize("vals", [(2, -6, -1, -4, -2, -25, -1), (2, -3, -3, -3, -2, -8, -1), (2, -6, 0, -4, -2, -25, -1)])
+@pytest.mark.parametrize("tmax,n_rate", [(320, 0.004), (384, 0.02), (512, 0.004)])
+def test_tiles_with_n_stay_on_packed_path(gpu, vals, tmax, n_rate):
+    """N bases (Nt2Int -> 4, scored sub_N against anything, Processor.cpp:21-46, :50-74) no longer force the unpacked exact
+    path: single N, N runs, N against N, on both sequences, single-strip and multi-strip geometries, sub_N = mismatch and 0."""
+    arena, req = _ragged_batch(6 + tmax, 400, tmax, n_rate=n_rate)
+    rng = np.random.default_rng(tmax)
+    for k in range(0, len(req), 9):                            # N runs and N-vs-N columns on top of the sprinkled ones
+        a, b = int(req[k]["ref_bases_start_addr"]), int(req[k]["query_bases_start_addr"])
+        L = min(int(req[k]["ref_size"]), int(req[k]["query_size"]))
+        if L > 40:
+            p0 = int(rng.integers(0, L - 30))
+            arena[a + p0:a + p0 + 12] = ord("N")
+            arena[b + p0:b + p0 + 20] = ord("n") if k % 2 else ord("N")
+    with_n = _tiles_with_n(arena, req)
+    fast, exact, rerun = _run(gpu, abi.Scoring.from_values(*vals), arena, req)
+    assert with_n > 100 and fast + exact == len(req)
+    assert exact <= rerun                                      # only reruns (long-gap ties, band exits) leave the packed path
+    assert fast >= len(req) - rerun
+
+
+def test_tiles_with_n_unpackable_scoring_use_exact_path(gpu):
+    """sub_N below the mismatch score cannot be expressed as a non-negative packed correction: such tiles keep the exact path."""
+    arena, req = _ragged_batch(6, 300, 320, n_rate=0.004)
+    fast, exact, rerun = _run(gpu, abi.Scoring.from_values(2, -6, -9, -4, -2, -25, -1), arena, req)
+    assert exact >= _tiles_with_n(arena, req) > 0 and fast > 0
 
 
 def test_truncated_traceback(gpu):
