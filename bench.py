@@ -420,7 +420,7 @@ def main():
     ap.add_argument("--config4-reads", type=int, default=200000,
                     help="configs[3]: 250 Mbp replicated reference, a FIXED set of this many 10 kbp reads strong-sharded over the ranks (0 = skip)")
     ap.add_argument("--config4-genome", type=int, default=250000000)
-    ap.add_argument("--config5-reads", type=int, default=1000,
+    ap.add_argument("--config5-reads", type=int, default=2000,
                     help="configs[4]: ONT-like 50 kbp reads per GPU, tile_size 256/512/1024 + de novo overlap mode (0 = skip)")
     ap.add_argument("--read-lanes", type=int, default=2, help="host threads (lanes) feeding the read-level legs")
     args = ap.parse_args()
@@ -684,12 +684,12 @@ def main():
         read_legs.update(run_read_leg(
             "config5", "BASELINE.json configs[4]: ONT-like 50 kbp reads at 12 % (sub 4 / ins 3 / del 5) against a 20 Mbp reference, tile_overlap 64",
             local, rank, world, dist, barrier, sc, int_peak, 20000000, args.config5_reads, False, 50000, ONT, 51,
-            500, [(256, 64), (512, 64), (1024, 64)], passes=1, lanes=args.read_lanes))
+            1000, [(256, 64), (512, 64), (1024, 64)], passes=1, lanes=args.read_lanes))
         read_legs.update(run_read_leg(
             "config5_denovo", "BASELINE.json configs[4], de novo mode (argv[3] = 1): the read set is its own reference, all-vs-all, "
             "50 kbp ONT-like reads at ~5x coverage of a 10 Mbp genome, tile_size 256",
-            local, rank, world, dist, barrier, sc, int_peak, 10000000, max(200, args.config5_reads), False, 50000, ONT, 52,
-            250, [(256, 64)], passes=1, lanes=args.read_lanes, self_reference=True, do_overlap=1))
+            local, rank, world, dist, barrier, sc, int_peak, 10000000, max(200, args.config5_reads // 2), False, 50000, ONT, 52,
+            500, [(256, 64)], passes=1, lanes=args.read_lanes, self_reference=True, do_overlap=1))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # the reference's CPU chain on bounded samples of the same read sets (reported baseline, N = 1 only)
         try:

@@ -53,6 +53,8 @@ def load_library():
         L.darwin_gpu_align_reads.argtypes = [C.c_void_p, C.POINTER(abi.AlignParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64]
         L.darwin_gpu_stats.argtypes = [C.c_void_p, C.POINTER(abi.GpuStats)]
+        L.darwin_gpu_cigar.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.darwin_gpu_sam_select.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.darwin_gpu_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _lib = L
     return _lib
@@ -61,7 +63,7 @@ def load_library():
 EXPORTS = ("darwin_gpu_create", "darwin_gpu_create_shared", "darwin_gpu_destroy", "darwin_gpu_set_scoring", "darwin_gpu_upload",
            "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_filter", "darwin_gpu_seed_index",
            "darwin_gpu_seed_index_share", "darwin_gpu_seed_index_read", "darwin_gpu_seed", "darwin_gpu_align_reads", "darwin_gpu_host_alloc", "darwin_gpu_host_free", "darwin_gpu_upload_spans", "darwin_gpu_stats", "darwin_gpu_int_peak",
-           "darwin_gpu_last_error", "darwin_gpu_version")
+           "darwin_gpu_last_error", "darwin_gpu_version", "darwin_gpu_cigar", "darwin_gpu_sam_select")
 
 
 class Processor:
@@ -258,6 +260,34 @@ class Processor:
         s = abi.GpuStats()
         self._check(self.lib.darwin_gpu_stats(self.h, C.byref(s)))
         return s
+
+
+def cigar(res_row, ops_pool, query_length):
+    """CIGAR of one alignment (printer_body::AlignmentToSam, printer.cpp:236-301) from its op string (darwin_gpu_cigar)."""
+    lib = load_library()
+    r = np.ascontiguousarray(np.asarray(res_row, dtype=abi.ALN_RES).reshape(1))
+    ops = np.ascontiguousarray(ops_pool, dtype=np.uint8)
+    cap = 16 * (int(r["n_ops"][0]) + 4)
+    out = np.empty(cap, np.uint8)
+    n = C.c_uint64(0)
+    rc = lib.darwin_gpu_cigar(abi.ptr(r), abi.ptr(ops), int(query_length), abi.ptr(out), C.c_uint64(cap), C.byref(n))
+    if rc:
+        raise DarwinGpuError(rc, "darwin_gpu_cigar")
+    return out[:n.value].tobytes().decode()
+
+
+def sam_select(anchors, res):
+    """Print order and overlap suppression of printer_body::sam_printer (printer.cpp:15-47): (order, keep)."""
+    lib = load_library()
+    an = np.ascontiguousarray(anchors, dtype=abi.ANCHOR)
+    rs = np.ascontiguousarray(res, dtype=abi.ALN_RES)
+    order = np.zeros(max(len(rs), 1), np.uint32)
+    keep = np.zeros(max(len(rs), 1), np.uint8)
+    n = C.c_uint64(0)
+    rc = lib.darwin_gpu_sam_select(abi.ptr(an), abi.ptr(rs), C.c_uint64(len(rs)), abi.ptr(order), abi.ptr(keep), C.byref(n))
+    if rc:
+        raise DarwinGpuError(rc, "darwin_gpu_sam_select")
+    return order[:n.value], keep[:n.value].astype(bool)
 
 
 def read_params_cfg(path):

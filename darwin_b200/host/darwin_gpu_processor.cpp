@@ -384,6 +384,69 @@ void gpu_align_body::operator()(seeder_input input, extender_node::output_ports_
     get<0>(op).try_put(printer_input(printer_payload(reads, std::move(output)), token));
 }
 
+// Reads in, SAM out (see the header).  Field by field what printer_body::sam_printer / AlignmentToSam print (printer.cpp:49-78,
+// :206-306).
+std::string gpu_sam_body::operator()(seeder_input input) {
+    reader_output& reads = get<0>(input);
+    size_t token = get<1>(input);
+    GpuCombiner& gc = combiner_for_token(token);
+    std::string out;
+    if (reads.empty()) return out;
+    const std::vector<UploadSpan> spans = read_spans(reads);
+    std::vector<DarwinSeedRead> sr(reads.size());
+    for (size_t r = 0; r < reads.size(); r++) sr[r] = DarwinSeedRead{(uint64_t)(reads[r].seq.data() - g_DRAM->buffer), (uint32_t)reads[r].seq.size(), 0};
+    DarwinAlignParams prm{};
+    prm.filter = DarwinFilterParams{cfg.first_tile_size, cfg.first_tile_score_threshold, cfg.min_overlap, 0};
+    prm.extend = DarwinExtendParams{cfg.tile_size, cfg.tile_overlap, cfg.do_overlap, 0};
+    prm.slope_threshold = cfg.slope_threshold;
+    std::vector<DarwinAnchor> anchors; std::vector<DarwinAlnRes> res; std::vector<uint8_t> ops;
+    std::string err;
+    int rc = gc.align(prm, spans, sr.data(), (int)sr.size(), &anchors, &res, &ops, &err);
+    if (rc != DARWIN_OK) fail_msg(rc, "gpu_sam_body", err);
+    const size_t n = anchors.size();
+    std::vector<uint32_t> order(n ? n : 1); std::vector<uint8_t> keep(n ? n : 1);
+    uint64_t m = 0;
+    rc = darwin_gpu_sam_select(anchors.data(), res.data(), n, order.data(), keep.data(), &m);
+    if (rc != DARWIN_OK) fail_msg(rc, "gpu_sam_body", "darwin_gpu_sam_select");
+    std::vector<char> cigar;
+    for (uint64_t k = 0; k < m; k++) {
+        if (!keep[k]) continue;
+        const DarwinAnchor& a = anchors[order[k]];
+        const DarwinAlnRes& r = res[order[k]];
+        if (r.flags & DARWIN_ALN_OPS_OVERFLOW) fail_msg(DARWIN_ERR_CAPACITY, "gpu_sam_body", "op string overflow");
+        extender_body::num_extend_tiles += (int)r.n_tiles;
+        extender_body::num_active_tiles += (int)r.n_tiles;
+        extender_body::num_large_tiles += (int)r.n_large_tiles;
+        const Read& rd = reads[a.read_num];
+        if (printer_body::done_header == 0) {                                // printer.cpp:55-62 (checked again under the lock)
+            std::lock_guard<std::mutex> g(::io_lock);                   // software/printer.cpp:3, declared in graph.h:190
+            if (printer_body::done_header == 0) {
+                out += "@HD\tVN:1.6\tSO:coordinate\n";
+                for (size_t c = 0; c < Index::chr_id.size(); c++)
+                    out += "@SQ\tSN:" + Index::chr_id[c] + "\tLN:" + std::to_string(Index::chr_len_unpadded[c]) + "\n";
+                printer_body::done_header = 1;
+            }
+        }
+        uint64_t len = 0;
+        cigar.resize(16 * ((size_t)r.n_ops + 4));
+        rc = darwin_gpu_cigar(&r, ops.data(), a.read_len, cigar.data(), cigar.size(), &len);
+        if (rc != DARWIN_OK) fail_msg(rc, "gpu_sam_body", "darwin_gpu_cigar");
+        const bool minus = a.strand != 0;
+        out += std::string(rd.description.c_str());                          // QNAME (:209)
+        out += '\t'; out += std::to_string((minus ? 16 : 0) + 64);           // FLAG (:210-224)
+        out += '\t'; out += std::string(Index::chr_id[a.chr_id].c_str());    // RNAME (:226)
+        out += '\t'; out += std::to_string(1 + r.reference_start_offset);    // POS (:227)
+        out += "\t60\t";                                                    // MAPQ (:230)
+        out.append(cigar.data(), (size_t)len);
+        out += "\t*\t0\t0\t";                                               // RNEXT, PNEXT, TLEN (:314-316)
+        if (minus) out.append(rd.rc_seq.data(), rd.rc_seq.size()); else out.append(rd.seq.data(), rd.seq.size());   // SEQ (:212-222)
+        out += "\t*\tAS:i:"; out += std::to_string(r.score);                // QUAL, AS (:317-318)
+        out += "\tZS:i:"; out += std::to_string(r.score);                   // CHAIN_SCORE = score (:320)
+        out += '\n';
+    }
+    return out;
+}
+
 // filter_body::operator() (filter.cpp:8-225) with every first tile of the batch -- both strands, all reads -- in ONE
 // darwin_gpu_filter call instead of g_BatchAlignmentSIMD batches of 64 (filter.cpp:22, :75).  Request construction,
 // score and overlap tests run on the device; the ExtendLocations (chr_id / read_num lookups, chained hits) and the

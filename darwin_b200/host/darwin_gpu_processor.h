@@ -51,6 +51,16 @@ struct gpu_align_body {
     void operator()(seeder_input input, extender_node::output_ports_type& op);
 };
 
+// == the whole align graph of main.cpp:590-624 INCLUDING the output stage (printer_body::sam_printer, printer.cpp:7-98) for the
+// reference-guided mode: reads in, SAM text out.  The alignments never become ExtendAlignments: print order and overlap
+// suppression come from darwin_gpu_sam_select, the CIGAR from darwin_gpu_cigar -- straight from the op strings, no gapped
+// strings are rebuilt (that rebuild was what bounded gpu_align_body + printer_body).  The text is byte-identical to what
+// printer_body prints for the same batch (header included, once per process, under the reference's io_lock / done_header).
+// De novo mode (cfg.do_overlap = 1) prints the gapped strings themselves and keeps using gpu_align_body + printer_body.
+struct gpu_sam_body {
+    std::string operator()(seeder_input input);
+};
+
 // == filter_body (software/graph.h:205-217, filter.cpp:8-225): same input/output tuples; the first tiles of the whole
 // batch (both strands) go to the GPU in one darwin_gpu_filter call; the slope filter is the reference's own.
 struct gpu_filter_body {

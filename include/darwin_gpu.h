@@ -315,6 +315,21 @@ int darwin_gpu_align_reads(DarwinGpu* h, const DarwinAlignParams* p, const Darwi
                            DarwinAnchor* anchors_out, DarwinAlnRes* res, uint64_t cap, uint64_t* n_out,
                            uint8_t* ops_pool, uint64_t ops_pool_bytes);
 
+/* Output stage (host functions, no device work): what printer_body needs from an alignment, straight from the op string.
+ *
+ * replaces the CIGAR construction of printer_body::AlignmentToSam (software/printer.cpp:236-301): leading soft clip
+ * (query_start_offset), one run per maximal run of equal ops (I: '-' in the reference string, D: '-' in the query string,
+ * M otherwise), trailing soft clip (query_length - query_end_offset - 1); "*" when empty.  Writes *len characters (no
+ * terminator); DARWIN_ERR_CAPACITY reports the needed size in *len. */
+int darwin_gpu_cigar(const DarwinAlnRes* r, const uint8_t* ops_pool, uint32_t query_length, char* out, uint64_t cap, uint64_t* len);
+
+/* replaces the ordering and overlap suppression of printer_body::sam_printer (printer.cpp:15-47) for the alignments of any
+ * number of reads: order[k] = index (into anchors / res) of the k-th EMITTED alignment in print order -- stable sort by
+ * (read_num, score descending) -- and keep[k] = 1 when it is printed, 0 when more than half of its query span is covered by
+ * a better alignment of the same read.  order and keep need room for n entries; *n_order = number of emitted alignments. */
+int darwin_gpu_sam_select(const DarwinAnchor* anchors, const DarwinAlnRes* res, uint64_t n, uint32_t* order, uint8_t* keep,
+                          uint64_t* n_order);
+
 /* device-resident variants used by bench.py's `value` leg: same work, inputs and
  * outputs stay in HBM (pointers are device pointers of this handle's device). */
 int darwin_gpu_tiles_device(DarwinGpu* h, int do_traceback, const void* d_req, int n,

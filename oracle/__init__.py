@@ -339,7 +339,13 @@ def port(scoring):
 
 
 def reference(flavour="patched"):
-    return Reference(flavour)
+    """A driver handle in a DEFINED state.  The configuration of the compiled reference is process-global (`cfg`, like the
+    reference's own main.cpp), so a test that left tile_size = 1024 / do_overlap = 1 behind would silently change how the
+    next test seeds its reads: every new handle starts from the stock params.cfg values."""
+    r = Reference(flavour)
+    r.set_dsoft_defaults()
+    r.set_extend(384, 64, 2, 0)
+    return r
 
 
 def have_reference():

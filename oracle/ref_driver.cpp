@@ -693,6 +693,15 @@ int dref_pipeline(int first, int count, int use_gpu, char* out, uint64_t cap) {
         use_gpu &= 7;
         reader_output reads(g_reads.begin() + first, g_reads.begin() + first + count);
         seeder_input sin(reads, 0);
+        if (sam && use_gpu == 5) {                             // native output stage: reads in, SAM text out (gpu_sam_body)
+            printer_body::done_header = 0;
+            const std::string text = darwin_gpu_host::gpu_sam_body()(sin);
+            if (text.size() + 1 > cap) return -2;
+            memcpy(out, text.data(), text.size()); out[text.size()] = 0;
+            int lines = 0;
+            for (char c : text) lines += c == '\n';
+            return lines;
+        }
         filter_input fin = (use_gpu >= 3) ? darwin_gpu_host::gpu_seeder_body()(sin) : seeder_body()(sin);
         extender_input ein = (use_gpu >= 2) ? darwin_gpu_host::gpu_filter_body()(fin) : filter_body()(fin);
         extender_node::output_ports_type ports;
@@ -773,6 +782,16 @@ int dref_pipeline_mt(int first, int count, int threads, int reads_per_batch, int
                     if (b >= nbatches || failed.load()) break;
                     const int lo = first + b * reads_per_batch, hi = std::min(first + count, lo + reads_per_batch);
                     reader_output reads(g_reads.begin() + lo, g_reads.begin() + hi);
+                    if (mode == 5) {                                   // all stages + the native SAM output stage
+                        const auto b0 = now();
+                        const std::string text = darwin_gpu_host::gpu_sam_body()(seeder_input(reads, (size_t)t));
+                        t_extend[t] += secs(b0, now());
+                        uint64_t nl = 0;
+                        for (char c : text) nl += c == '\n';
+                        n_aln += nl;
+                        if (out) { std::lock_guard<std::mutex> g(out_mutex); lines.push_back(text); }
+                        continue;
+                    }
                     if (mode >= 4) {                                   // all stages in one device call
                         const auto b0 = now();
                         extender_node::output_ports_type ports;
@@ -832,7 +851,8 @@ int dref_pipeline_mt(int first, int count, int threads, int reads_per_batch, int
         uint64_t pos = 0;
         for (auto& l : lines) {
             if (pos + l.size() + 2 > cap) return -2;
-            memcpy(out + pos, l.data(), l.size()); pos += l.size(); out[pos++] = '\n';
+            memcpy(out + pos, l.data(), l.size()); pos += l.size();
+            if (mode != 5) out[pos++] = '\n';                   // mode 5 chunks are whole SAM blocks (sorted by their first line)
         }
         out[pos] = 0;
     }
