@@ -366,13 +366,36 @@ enum : int { FAST_OK = 0, FAST_LFLAG = 1, FAST_BAND = 2 };
 // M (gap steps, the end of the path, band exits) are handled one at a time by the generic step below, which every lane
 // executes redundantly.  Only lane 0's sink writes.
 // Returns FAST_OK, or the reason the tile must be recomputed by the exact path (warp-uniform).
+// Geometry of a stored band as the traceback sees it: K rows per virtual lane, window of 2*BH+1 steps per virtual lane with
+// lane stride LP (in steps), W words per (virtual lane, step) -- rows 0-5 in word 0, rows 6-11 in word 1.
+template <int K_, int BH_, int LP_, int W_ = 1> struct TraceGeo {
+    static constexpr int K = K_, BH = BH_, kL = 2 * BH_ + 1, kLp = LP_, W = W_;
+};
+
+template <class GEO, bool GLOBAL, class Sink>
+__device__ int fast_traceback_g(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink);
+
 template <int K, bool GLOBAL, class Sink, int BH = kBandHalf>
-__device__ int fast_traceback(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
-    using G = FastGeom<K, BH>;
+__device__ __forceinline__ int fast_traceback(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
+    return fast_traceback_g<TraceGeo<K, BH, FastGeom<K, BH>::kLp, 1>, GLOBAL, Sink>(band, Q, R, max_tb, out, sink);
+}
+
+template <class GEO, bool GLOBAL, class Sink>
+__device__ int fast_traceback_g(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
+    using G = GEO;
+    constexpr int K = GEO::K, BH = GEO::BH;
     const BandMap<K, BH> bm(Q, R);
     const int lane = lane_id();
-    // bit position of row r inside a band word (rows 0-2 in bits 0-14, rows 3-5 in bits 16-30): one 5-bit entry per row
-    constexpr uint32_t kShTab = 0u | (5u << 5) | (10u << 10) | (16u << 15) | (21u << 20) | (26u << 25);
+    // 5-bit pointer of cell (row r of virtual lane v, window position t)
+    auto code_at = [&](int v, int r, int t) -> uint32_t {
+        constexpr uint32_t kSh = 0u | (5u << 5) | (10u << 10) | (16u << 15) | (21u << 20) | (26u << 25);
+        const int hi = (GEO::W > 1 && r >= 6) ? 1 : 0;
+        uint32_t w;
+        if (GLOBAL) w = __ldcg(band + ((size_t)v * G::kLp + (size_t)t) * GEO::W + hi);
+        else        w = band[(v * G::kLp + t) * GEO::W + hi];                // shared memory: 32-bit index arithmetic
+        return (w >> ((kSh >> (5 * (r - 6 * hi))) & 31u)) & 31u;
+    };
+    // (bit position of row r inside a band word: rows 0-2 in bits 0-14, rows 3-5 in bits 16-30 -- see code_at)
     // i = i0 - is, j = j0 - js: the loop of Processor.cpp:613-618 runs while is < min(Q, max_tb) and js < min(R, max_tb)
     const int lim_i = min(Q, max_tb), lim_j = min(R, max_tb);
     int i = Q - 1, j = R - 1;
@@ -389,9 +412,7 @@ __device__ int fast_traceback(const uint32_t* band, int Q, int R, int max_tb, Ti
             const int v = (ok ? ii : 0) / K, r = (ok ? ii : 0) - v * K;
             const int t = bm.t_of(jj, v);
             ok = ok && (unsigned)t < (unsigned)G::kL;
-            uint32_t w = 0;
-            if (ok) w = GLOBAL ? __ldcg(band + (size_t)v * G::kLp + t) : band[v * G::kLp + t];
-            const uint32_t code = (w >> ((kShTab >> (5 * r)) & 31u)) & 31u;
+            const uint32_t code = ok ? code_at(v, r, t) : 0u;
             const uint32_t is_m = __ballot_sync(0xffffffffu, ok && (code >> 2) == FT_DIAG);
             const int run = (is_m == 0xffffffffu) ? 32 : __ffs(~is_m) - 1;
             if (run > 0) {                                                       // a DIAG pointer in DIAG state: M, stay in DIAG
@@ -404,8 +425,7 @@ __device__ int fast_traceback(const uint32_t* band, int Q, int R, int max_tb, Ti
         const int v = i / K, r = i - v * K;
         const int t = bm.t_of(j, v);
         if ((unsigned)t >= (unsigned)G::kL) { off_band = true; break; }
-        const uint32_t w = GLOBAL ? __ldcg(band + (size_t)v * G::kLp + t) : band[v * G::kLp + t];
-        const uint32_t code = (w >> ((kShTab >> (5 * r)) & 31u)) & 31u;
+        const uint32_t code = code_at(v, r, t);
         // a DIAG-state cell whose pointer is DEL/INS switches state and is re-read by the reference (:628-633):
         // nothing moves in between, so the gap step is taken right away
         st = (where == FT_DIAG) ? (code >> 2) : where;
