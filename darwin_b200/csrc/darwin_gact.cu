@@ -171,7 +171,8 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
     if (t.Q <= 0 || t.R <= 0) return;                                       // Processor.cpp:177-182
     const bool se = t.flags & DARWIN_START_END;
     if (K > 0) {
-        constexpr int KK = (K == 0 ? 4 : K);
+        constexpr int KK = (K == 0 ? 4 : K);                              // rows per virtual lane of single-strip tiles
+        constexpr int KM = (KK > 6 ? 4 : KK);                            // ... of the multi-strip variant (one band word per lane-step)
         const FastConst& fc = ks.fc;
         const int smax = fc.match * min(t.Q, t.R);
         const bool narrow = fc.eligible && do_traceback && se && smax <= fc.max_score;        // 11 score bits suffice
@@ -202,17 +203,17 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
                 if (single || !xok || !large || has_n) {
                     int score;
                     if (!has_n) score = single ? fast_forward<KK>(fc, v, t.Q, t.R)
-                                      : !wide ? fast_forward_multi<KK, 5, kBandHalf>(fc, mv, gband, t.Q, t.R)
-                                              : fast_forward_multi<KK, 4, kBandHalfWide>(ks.fcw, mv, gband, t.Q, t.R);
+                                      : !wide ? fast_forward_multi<KM, 5, kBandHalf>(fc, mv, gband, t.Q, t.R)
+                                              : fast_forward_multi<KM, 4, kBandHalfWide>(ks.fcw, mv, gband, t.Q, t.R);
                     else        score = single ? fast_forward<KK, true>(fc, v, t.Q, t.R)
-                                      : !wide ? fast_forward_multi<KK, 5, kBandHalf, true>(fc, mv, gband, t.Q, t.R)
-                                              : fast_forward_multi<KK, 4, kBandHalfWide, true>(ks.fcw, mv, gband, t.Q, t.R);
+                                      : !wide ? fast_forward_multi<KM, 5, kBandHalf, true>(fc, mv, gband, t.Q, t.R)
+                                              : fast_forward_multi<KM, 4, kBandHalfWide, true>(ks.fcw, mv, gband, t.Q, t.R);
                     // warp-uniform traceback on a copy of the sink: committed only when the clean rule holds
                     Sink trial = sink;
                     TileOut o2{};
                     const int rc = single ? fast_traceback<KK, false>(v.band, t.Q, t.R, t.max_tb, o2, trial)
-                                 : !wide ? fast_traceback<KK, true>(gband, t.Q, t.R, t.max_tb, o2, trial)
-                                         : fast_traceback<KK, true, Sink, kBandHalfWide>(gband, t.Q, t.R, t.max_tb, o2, trial);
+                                 : !wide ? fast_traceback<KM, true>(gband, t.Q, t.R, t.max_tb, o2, trial)
+                                         : fast_traceback<KM, true, Sink, kBandHalfWide>(gband, t.Q, t.R, t.max_tb, o2, trial);
                     if (rc == FAST_OK) {
                         sink = trial; out = o2;
                         out.score = score; out.ref_max_pos = t.R - 1; out.query_max_pos = t.Q - 1;
@@ -285,7 +286,7 @@ __device__ __forceinline__ void flush_counters(const WarpCtx& cx, unsigned int* 
 // BatchAlignmentSIMD (Processor.cpp:718-762) for n independent tiles: persistent warps pull tiles from a
 // global counter.
 template <int K>
-__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 4 : 11)
+__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 4 : (K == 8) ? 5 : 11)
 tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
              const DarwinTileReq* __restrict__ req, int n, int do_traceback,
              DarwinTileRes* __restrict__ res, uint64_t* __restrict__ tb_words, int tb_words_per_req,
@@ -528,7 +529,7 @@ __global__ void filter_finish_kernel(const DarwinFilterCand* __restrict__ cands,
 
 // extender_body::operator() (extender.cpp:9-1065): persistent warps pull ANCHORS and walk their tiles.
 template <int K>
-__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 3 : 11)
+__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 3 : (K == 8) ? 5 : 11)
 extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ ExtendArgs ea,
               uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base) {
     __shared__ int ssub[32];
@@ -731,13 +732,16 @@ struct DarwinGpu {
     KernelScoring ks{}; FilterConst filt{}; bool have_scoring = false;
     int ctas_filter = 0;
     int sm_count = 0, max_warps = 0;
-    int ctas_tiles[4] = {0, 0, 0, 0}, ctas_extend[4] = {0, 0, 0, 0};   // persistent grid per kernel variant (K = 0,4,5,6)
+    int ctas_tiles[5] = {0, 0, 0, 0, 0}, ctas_extend[5] = {0, 0, 0, 0, 0};   // persistent grid per kernel variant (K = 0,4,5,6,8)
     int ctas_pair[4] = {0, 0, 0, 0};            // pair kernel (two tiles per warp), K = 4,5,6
-    bool use_pairs = true;                      // DARWIN_GPU_PAIRS=0 keeps the one-tile-per-warp kernel (A/B measurements)
+    // Measured on B200 (profiles/r2_pair_kernel_ab.log): the pair kernel executes 13 % fewer ALU-pipe cycles per tile, but its
+    // two bands per warp leave room for 5 warps per SM instead of 11 and the issue slots go idle during tracebacks and
+    // staging: 1 321 vs 1 391 GCUPS at T = 320, 1 345 vs 1 504 at T = 384.  It stays opt-in (DARWIN_GPU_PAIRS=1).
+    bool use_pairs = false;
     uint8_t* d_trace = nullptr; size_t trace_stride = 0; ChainRec* d_bound = nullptr;
     unsigned int* d_counter = nullptr;
     // growable device buffers
-    void* d_buf[12] = {nullptr}; size_t d_cap[12] = {0};
+    void* d_buf[13] = {nullptr}; size_t d_cap[13] = {0};
     DarwinGpuStats stats{};
     std::string err;
     SeedIndex seed_ix;                          // D-SOFT seed position table (dsoft_host.cuh); lanes share the parent's
@@ -787,7 +791,7 @@ static int ensure_scratch(DarwinGpu* h, size_t need) {
 }
 
 
-static int variant_index(int K) { return K == 0 ? 0 : K - 3; }                 // K in {0,4,5,6} -> 0..3
+static int variant_index(int K) { return K == 0 ? 0 : K == 8 ? 4 : K - 3; }    // K in {0,4,5,6,8} -> 0..4
 
 // Smallest fast-path geometry that holds a maxdim x maxdim tile (0 = exact path only).
 static int pick_k(const DarwinGpu* h, int maxdim, int do_traceback) {
@@ -795,7 +799,7 @@ static int pick_k(const DarwinGpu* h, int maxdim, int do_traceback) {
     if (maxdim <= 256) return 4;
     if (maxdim <= 320) return 5;
     if (maxdim <= 384) return 6;
-    if (maxdim <= 512) return 4;            // two strips of 256 rows (multi-strip fast path)
+    if (maxdim <= 512) return 8;            // one strip of 512 rows, two band words per lane-step (5 warps per SM)
     return 6;                               // strips of 384 rows (large tiles, T up to 1024 where the score range allows)
 }
 
@@ -832,7 +836,7 @@ static int configure_pair_variant(DarwinGpu* h) {
 static int configure_kernels(DarwinGpu* h) {
     int rc;
     if ((rc = configure_variant<0>(h)) || (rc = configure_variant<4>(h)) || (rc = configure_variant<5>(h)) ||
-        (rc = configure_variant<6>(h))) return rc;
+        (rc = configure_variant<6>(h)) || (rc = configure_variant<8>(h))) return rc;
     if ((rc = configure_pair_variant<4>(h)) || (rc = configure_pair_variant<5>(h)) || (rc = configure_pair_variant<6>(h))) return rc;
     int f = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, filter_kernel, kFilterWarps * 32, 0));
@@ -886,7 +890,7 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     DarwinGpu* h = new DarwinGpu();
     h->device = device;
     h->timing_dbg = getenv("DARWIN_GPU_TIMING") != nullptr;
-    { const char* e = getenv("DARWIN_GPU_PAIRS"); if (e && e[0] == '0') h->use_pairs = false; }
+    { const char* e = getenv("DARWIN_GPU_PAIRS"); h->use_pairs = e && e[0] == '1'; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
@@ -938,7 +942,7 @@ int darwin_gpu_destroy(DarwinGpu* h) {
     }
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (int i = 0; i < 12; i++) if (h->d_buf[i]) cudaFree(h->d_buf[i]);
+    for (int i = 0; i < 13; i++) if (h->d_buf[i]) cudaFree(h->d_buf[i]);
     if (h->d_trace) cudaFree(h->d_trace);
     if (h->d_bound) cudaFree(h->d_bound);
     if (h->d_counter) cudaFree(h->d_counter);
@@ -1086,7 +1090,7 @@ int darwin_gpu_upload_spans(DarwinGpu* h, const DarwinSpan* spans, int n_spans) 
 
 static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_req, int n,
                         DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR,
-                        const unsigned int* idx_list = nullptr, const unsigned int* idx_count = nullptr);
+                        const unsigned int* idx_list = nullptr, const unsigned int* idx_count = nullptr, int list_len = 0);
 
 // Score-only tiles (do_traceback = 0): packed filter path first, then the exact path on whatever it handed over.
 static int launch_filter_tiles(DarwinGpu* h, const DarwinTileReq* d_req, int n, DarwinTileRes* d_res, int maxQ, int maxR) {
@@ -1105,7 +1109,7 @@ static int launch_filter_tiles(DarwinGpu* h, const DarwinTileReq* d_req, int n, 
 
 static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_req, int n,
                         DarwinTileRes* d_res, uint64_t* d_tb, int tb_words_per_req, int maxQ, int maxR,
-                        const unsigned int* idx_list, const unsigned int* idx_count) {
+                        const unsigned int* idx_list, const unsigned int* idx_count, int list_len) {
     if (!do_traceback && !idx_list && h->filt.eligible) return launch_filter_tiles(h, d_req, n, d_res, maxQ, maxR);
     // per-warp scratch: exact-path trace (1 B/cell) or the multi-strip fast path's band, whichever is larger
     int rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)), multi_band_bytes<4, kBandHalfWide>(std::max(maxQ, 1))),
@@ -1113,7 +1117,7 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
     if (rc) return rc;
     const int K = pick_k(h, std::max(maxQ, maxR), do_traceback);
     // corner-traceback batches whose tiles fit one strip: two tiles per warp
-    if (h->use_pairs && do_traceback && !idx_list && K >= 4 && std::max(maxQ, maxR) <= 64 * K && n >= 2) {
+    if (h->use_pairs && do_traceback && !idx_list && K >= 4 && K <= 6 && std::max(maxQ, maxR) <= 64 * K && n >= 2) {
         const int ctas = std::max(1, std::min(h->ctas_pair[variant_index(K)], (n + 1) / 2));
         CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));
 #define LAUNCH_PAIR(KK) tiles_pair_kernel<KK><<<ctas, 32, PairKernelGeom<KK>::kSmem, h->stream>>>( \
@@ -1129,7 +1133,7 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
         return DARWIN_OK;
     }
     int ctas = h->ctas_tiles[variant_index(K)];
-    if (idx_list) ctas = std::min(ctas, h->sm_count);                           // hand-over lists are short
+    if (idx_list) ctas = list_len > 0 ? std::max(1, std::min(ctas, list_len)) : std::min(ctas, h->sm_count);   // hand-over lists are short
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));      // queue head; [1..3] accumulate
 #define LAUNCH_TILES(KK) tiles_kernel<KK><<<ctas, KernelGeom<KK>::kWarps * 32, KernelGeom<KK>::kSmem, h->stream>>>( \
         h->d_arena, h->ks, d_req, n, do_traceback, d_res, d_tb, tb_words_per_req, h->d_trace, h->trace_stride, h->d_bound, h->d_counter, \
@@ -1138,6 +1142,7 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
         case 4: LAUNCH_TILES(4); break;
         case 5: LAUNCH_TILES(5); break;
         case 6: LAUNCH_TILES(6); break;
+        case 8: LAUNCH_TILES(8); break;
         default: LAUNCH_TILES(0); break;
     }
 #undef LAUNCH_TILES
@@ -1167,6 +1172,49 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
     if ((rc = grow_dev(h, 0, req_b)) || (rc = grow_dev(h, 1, res_b)) || (rc = grow_dev(h, 2, tb_row * n + 8))) return rc;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int) * kCounters, h->stream));
     CK(cudaMemcpyAsync(h->d_buf[0], req, req_b, cudaMemcpyHostToDevice, h->stream));
+    // Geometry is a property of the TILE, not of the call: when the requests of one call fall into different shape classes
+    // (one 400-wide tile among 320 x 320 ones used to push the whole batch onto the two-strip variant), every class gets its
+    // own launch over an index list, each with the geometry pick_k chooses for that class.
+    if (do_traceback && h->ks.fc.eligible) {
+        static const int kClassK[4] = {4, 5, 6, 8};
+        std::vector<uint32_t> lists[4];
+        int cmaxQ[4] = {0, 0, 0, 0}, cmaxR[4] = {0, 0, 0, 0};
+        for (int i = 0; i < n; i++) {
+            const int k = pick_k(h, std::max<int>(req[i].query_size, req[i].ref_size), 1);
+            const int c = k == 8 ? 3 : k - 4;
+            lists[c].push_back((uint32_t)i);
+            cmaxQ[c] = std::max<int>(cmaxQ[c], req[i].query_size); cmaxR[c] = std::max<int>(cmaxR[c], req[i].ref_size);
+        }
+        int used_classes = 0;
+        for (int c = 0; c < 4; c++) used_classes += !lists[c].empty();
+        if (used_classes > 1) {
+            if ((rc = grow_dev(h, 11, (size_t)(n + 4) * sizeof(uint32_t)))) return rc;
+            uint32_t* d_lists = (uint32_t*)h->d_buf[11];
+            uint32_t counts[4], offs[4], at = 4;
+            for (int c = 0; c < 4; c++) { counts[c] = (uint32_t)lists[c].size(); offs[c] = at; at += counts[c]; }
+            CK(cudaMemcpyAsync(d_lists, counts, sizeof(counts), cudaMemcpyHostToDevice, h->stream));
+            for (int c = 0; c < 4; c++)
+                if (counts[c]) CK(cudaMemcpyAsync(d_lists + offs[c], lists[c].data(), counts[c] * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+            // scratch for the largest tile of the call once: a re-allocation between the launches would pull it from under a running kernel
+            if ((rc = ensure_scratch(h, std::max(std::max(exact_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)), multi_band_bytes<4, kBandHalfWide>(std::max(maxQ, 1))),
+                                                 xfast_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1)))))) return rc;
+            CK(cudaEventRecord(h->ev0, h->stream));
+            for (int c = 0; c < 4; c++) {
+                if (!counts[c]) continue;
+                (void)kClassK;
+                if ((rc = launch_tiles(h, 1, (const DarwinTileReq*)h->d_buf[0], n, (DarwinTileRes*)h->d_buf[1], (uint64_t*)h->d_buf[2], tb_words_per_req,
+                                       cmaxQ[c], cmaxR[c], d_lists + offs[c], d_lists + c, (int)counts[c]))) return rc;
+            }
+            CK(cudaEventRecord(h->ev1, h->stream));
+            CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaMemcpyAsync(tb_words, h->d_buf[2], tb_row * n, cudaMemcpyDeviceToHost, h->stream));
+            if ((rc = read_counters(h))) return rc;
+            CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
+            h->stats.cells += cells;
+            for (int i = 0; i < n; i++) if ((res[i].status & 0x0F) == 2) { h->err = "tb_words_per_req too small"; return DARWIN_ERR_CAPACITY; }
+            return DARWIN_OK;
+        }
+    }
     // Chunked pipeline: kernel(c+1) on the compute stream overlaps the D2H of chunk c on the copy stream.  Page-locked
     // caller buffers receive the DMA directly; pageable ones go through the two pinned staging buffers.
     const bool pin_res = is_pinned(res), pin_tb = !do_traceback || is_pinned(tb_words);
@@ -1324,6 +1372,7 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
         case 4: LAUNCH_EXTEND(4); break;
         case 5: LAUNCH_EXTEND(5); break;
         case 6: LAUNCH_EXTEND(6); break;
+        case 8: LAUNCH_EXTEND(8); break;
         default: LAUNCH_EXTEND(0); break;
     }
 #undef LAUNCH_EXTEND

@@ -38,8 +38,9 @@ template <int K, int BH = kBandHalf> struct FastGeom {
     static constexpr int kSteps = kRows + 63;
     static constexpr int kL     = 2 * BH + 1;
     static constexpr int kLp    = kL + (((kL - K - 1) & 1) ? 0 : 1);   // lane stride kLp-(K+1) odd -> conflict-free stores
+    static constexpr int kW     = (K + 5) / 6;      // band words per (virtual lane, step): six 5-bit pointers per word (K = 8: two)
     static constexpr int kPWords = kRows + 128;     // packed reference pairs P[j + 32] = r[j] | r[j-32] << 16
-    static constexpr size_t kBandWords = (size_t)64 * kLp;
+    static constexpr size_t kBandWords = (size_t)64 * kLp * kW;
     static constexpr size_t kSmemBytes = (kBandWords + kPWords) * 4 + 2 * kRows;    // + staged byte sequences
 };
 
@@ -213,8 +214,8 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
     uint32_t rq_next = v.P[32 - lane];                                   // step 0: j = -lane (dummy unless lane 0)
     // band window of my two virtual lanes: t = s - (K+1)*v + c1 (t(i,j) with j = s - v)
     int t_lo = -(K + 1) * lane + bm.c1;                                  // at s = 0
-    uint32_t* bp = v.band + lane * G::kLp + t_lo;                        // &band[v_lo * kLp + t_lo]; hi: + 32*(kLp - (K+1))
-    constexpr int kHiOff = 32 * (G::kLp - (K + 1));
+    uint32_t* bp = v.band + (lane * G::kLp + t_lo) * G::kW;              // &band[(v_lo * kLp + t_lo) * kW]; hi: + 32*(kLp - (K+1)) steps
+    constexpr int kHiOff = 32 * (G::kLp - (K + 1)) * G::kW;
 
     for (int s = 0; s < steps; s++) {
         // values from the virtual lane above: rotate by one lane; lane 0 shifts lane 31's low half up and
@@ -230,18 +231,25 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
         const uint32_t rq = rq_next;
         rq_next = v.P[32 + s + 1 - lane];                                // prefetch next step's reference pair
         uint32_t d = diag_in;
-        uint32_t acc0 = 0, acc1 = 0;
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int r = 0; r < K; r++) {
             const uint32_t code = fast_cell<5, HASN>(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
-            if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
+            acc[r / 3] += code << (5 * (r % 3));
         }
         diag_in = inH;
         sendH = Hm[K - 1]; sendF = F; sendFL = FL;
-        // band store: one word per (virtual lane, step): rows 0-2 in bits 0-14, rows 3-5 in bits 16-30
-        if ((unsigned)t_lo < (unsigned)G::kL) bp[0] = __byte_perm(acc0, acc1, 0x5410);
-        if ((unsigned)(t_lo - 32 * (K + 1)) < (unsigned)G::kL) bp[kHiOff] = __byte_perm(acc0, acc1, 0x7632);
-        t_lo++; bp++;
+        // band store: kW words per (virtual lane, step): rows 0-2 in bits 0-14, rows 3-5 in bits 16-30 (word 1: rows 6-11)
+        if (G::kW == 1) {
+            if ((unsigned)t_lo < (unsigned)G::kL) bp[0] = __byte_perm(acc[0], acc[1], 0x5410);
+            if ((unsigned)(t_lo - 32 * (K + 1)) < (unsigned)G::kL) bp[kHiOff] = __byte_perm(acc[0], acc[1], 0x7632);
+        } else {
+            if ((unsigned)t_lo < (unsigned)G::kL)
+                *reinterpret_cast<uint2*>(bp) = make_uint2(__byte_perm(acc[0], acc[1], 0x5410), __byte_perm(acc[2], acc[3], 0x5410));
+            if ((unsigned)(t_lo - 32 * (K + 1)) < (unsigned)G::kL)
+                *reinterpret_cast<uint2*>(bp + kHiOff) = make_uint2(__byte_perm(acc[0], acc[1], 0x7632), __byte_perm(acc[2], acc[3], 0x7632));
+        }
+        t_lo++; bp += G::kW;
     }
     __syncwarp();
     uint32_t corner = 0;
@@ -377,7 +385,7 @@ __device__ int fast_traceback_g(const uint32_t* band, int Q, int R, int max_tb, 
 
 template <int K, bool GLOBAL, class Sink, int BH = kBandHalf>
 __device__ __forceinline__ int fast_traceback(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
-    return fast_traceback_g<TraceGeo<K, BH, FastGeom<K, BH>::kLp, 1>, GLOBAL, Sink>(band, Q, R, max_tb, out, sink);
+    return fast_traceback_g<TraceGeo<K, BH, FastGeom<K, BH>::kLp, GLOBAL ? 1 : FastGeom<K, BH>::kW>, GLOBAL, Sink>(band, Q, R, max_tb, out, sink);
 }
 
 template <class GEO, bool GLOBAL, class Sink>
