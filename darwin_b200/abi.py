@@ -78,7 +78,7 @@ class GpuStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("tiles_fast", C.c_uint64), ("tiles_exact", C.c_uint64),
                 ("tiles_rerun", C.c_uint64), ("cells", C.c_uint64), ("cells_exact", C.c_uint64), ("tiles_xfast", C.c_uint64), ("last_kernel_ms", C.c_float), ("reserved", C.c_float),
                 ("tiles_filter", C.c_uint64), ("last_seed_ms", C.c_float), ("last_filter_ms", C.c_float), ("last_extend_ms", C.c_float),
-                ("reserved2", C.c_float), ("tiles_scoreonly", C.c_uint64), ("tiles_paired", C.c_uint64)]
+                ("reserved2", C.c_float), ("tiles_scoreonly", C.c_uint64)]
 
 
 TILE_REQ = np.dtype([

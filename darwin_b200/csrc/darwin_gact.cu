@@ -18,7 +18,6 @@
 #include "gact_fast.cuh"
 #include "gact_xfast.cuh"
 #include "gact_score.cuh"
-#include "gact_pair.cuh"
 #include "gact_extend.cuh"
 #include "gact_filter.cuh"
 #include "dsoft.cuh"
@@ -326,111 +325,6 @@ tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelSc
     flush_counters(cx, counter);
 }
 
-// ---- two tiles per warp (gact_pair.cuh) ----------------------------------------------------------------------------
-// Shared-memory layout of a warp of the pair kernel: the pair view (two bands, packed reference pairs, four staged
-// sequences), four raw TMA windows, and -- at the very end, where neither layout ever writes data -- the mbarrier.  The
-// single-tile layout (KernelGeom<K>) aliases the front of the same region for tiles that cannot be paired.
-template <int K> struct PairKernelGeom {
-    static constexpr int K2 = 2 * K;
-    using PG = PairGeom<K2>;
-    static constexpr int kRawStride = ((PG::kRows / 2 + 32) + 15) & ~15;            // packed window of <= kRows bases, 16-byte rounded
-    static constexpr size_t kRawOff = (PG::kSmemBytes + 15) & ~(size_t)15;
-    static constexpr size_t kPairEnd = kRawOff + 4 * (size_t)kRawStride;
-    static constexpr size_t kSingleEnd = KernelGeom<K>::kMbarOff;                   // the single layout's data ends where its mbarrier was
-    static constexpr size_t kMbarOff = ((kPairEnd > kSingleEnd ? kPairEnd : kSingleEnd) + 15) & ~(size_t)15;
-    static constexpr size_t kPerWarp = kMbarOff + 16;
-    static constexpr size_t kSmem = kPerWarp;                                       // one warp per CTA
-};
-
-__device__ __forceinline__ void write_tile_result(DarwinTileRes* res, unsigned int idx, const DarwinTileReq& rq, const TileOut& out,
-                                                  int overflow, bool too_big) {
-    DarwinTileRes r;
-    r.score = out.score; r.ref_offset = (uint16_t)out.ref_offset; r.query_offset = (uint16_t)out.query_offset;
-    r.ref_max_pos = (uint16_t)out.ref_max_pos; r.query_max_pos = (uint16_t)out.query_max_pos;
-    r.total_TB_pointers = (uint16_t)out.total; r.index = (uint8_t)rq.index;
-    r.status = (uint8_t)((too_big ? 1 : (overflow ? 2 : 0)) | ((out.tflags & 1u) ? DARWIN_TILE_LONG_INS_PATH : 0));
-    res[idx] = r;
-}
-
-// BatchAlignmentSIMD for n independent tiles, corner traceback: persistent warps pull PAIRS of consecutive requests; two
-// requests of the same shape that qualify for the single-strip fast path run together (pair_forward), everything else --
-// and any tile whose clean traceback is refused -- goes through process_tile like in tiles_kernel.
-template <int K>
-__global__ void __launch_bounds__(32, 6)
-tiles_pair_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
-                  const DarwinTileReq* __restrict__ req, int n,
-                  DarwinTileRes* __restrict__ res, uint64_t* __restrict__ tb_words, int tb_words_per_req,
-                  uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base, unsigned int* counter) {
-    using PKG = PairKernelGeom<K>;
-    using PG = typename PKG::PG;
-    constexpr int K2 = PKG::K2;
-    __shared__ int ssub[32];
-    extern __shared__ __align__(16) unsigned char dyn_smem[];
-    load_scoring(ks.sc, ssub);
-    const int lane = lane_id();
-    WarpCtx cx = make_ctx<K>(arena, ssub, dyn_smem, PKG::kPerWarp, trace_base, trace_stride, bound_base, PKG::kMbarOff);
-    const FastConst& fc = ks.fc;
-    uint32_t n_pair = 0;
-
-    for (;;) {
-        unsigned int idx = 0;
-        if (lane == 0) idx = atomicAdd(counter, 2u);
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= (unsigned)n) break;
-        const bool two = idx + 1 < (unsigned)n;
-        const DarwinTileReq rq[2] = {req[idx], req[two ? idx + 1 : idx]};
-        TileJob t[2];
-        bool big[2], ok[2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            t[k] = TileJob{rq[k].ref_bases_start_addr, rq[k].query_bases_start_addr, (int)rq[k].ref_size, (int)rq[k].query_size,
-                           rq[k].align_fields, (int)rq[k].max_tb_steps};
-            big[k] = t[k].Q > kMaxTile || t[k].R > kMaxTile;
-            ok[k] = fc.eligible && (t[k].flags & DARWIN_START_END) && t[k].Q > 0 && t[k].R > 0 && t[k].Q <= PG::kRows && t[k].R <= PG::kRows &&
-                    fc.match * min(t[k].Q, t[k].R) <= fc.max_score;
-        }
-        bool done[2] = {false, !two};
-        if (two && ok[0] && ok[1] && t[0].Q == t[1].Q && t[0].R == t[1].R) {
-            PairSmemView<K2> pv(cx.wsmem);
-            bool has_n = false;
-#pragma unroll
-            for (int k = 0; k < 2; k++) {
-                TmaStage ts{cx.wsmem + PKG::kRawOff + 2 * k * PKG::kRawStride, PKG::kRawStride, cx.ts_small.mbar, cx.ts_small.phase};
-                has_n |= stage_sequences(cx.arena, t[k], pv.sref[k], pv.sqry[k], ts);
-                cx.ts_small.phase = ts.phase;
-            }
-            if (!has_n) {
-                int score[2];
-                pair_forward<K2>(fc, pv, t[0].Q, t[0].R, score[0], score[1]);
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    TbWordSink sink(tb_words + (size_t)(idx + k) * tb_words_per_req, tb_words_per_req, lane == 0);
-                    TileOut out{};
-                    const int rc = fast_traceback_g<typename PG::Trace, false>(pv.band[k], t[k].Q, t[k].R, t[k].max_tb, out, sink);
-                    if (rc == FAST_OK) {
-                        out.score = score[k]; out.ref_max_pos = t[k].R - 1; out.query_max_pos = t[k].Q - 1;
-                        if (lane == 0) { sink.finish(); write_tile_result(res, idx + k, rq[k], out, sink.overflow, false); }
-                        done[k] = true; cx.n_fast++;
-                    }
-                }
-                n_pair++;
-                __syncwarp();
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            if (done[k]) continue;
-            TileOut out{};
-            TbWordSink sink(tb_words + (size_t)(idx + k) * tb_words_per_req, tb_words_per_req, lane == 0);
-            if (!big[k]) process_tile<K>(cx, ks, t[k], true, out, sink);
-            if (lane == 0) { sink.finish(); write_tile_result(res, idx + k, rq[k], out, sink.overflow, big[k]); }
-            __syncwarp();
-        }
-    }
-    flush_counters(cx, counter);
-    if (lane == 0 && n_pair) atomicAdd(counter + 10, n_pair);
-}
-
 // First-tile filter tiles (filter.cpp:28-122 / :131-223 -> BatchAlignmentSIMD with do_traceback = 0, max-cell mode):
 // persistent warps pull PAIRS of tiles and run them in the two 16-bit halves of the packed score-only path
 // (gact_filter.cuh).  Tiles the packed path cannot take (N bases, odd shapes, start_end, score range) are appended to
@@ -718,7 +612,7 @@ __global__ void int_peak_kernel(uint32_t* out, const uint32_t* in, int iters) {
 // =====================================================================================================
 // Host side: handle + C-ABI
 // =====================================================================================================
-constexpr int kCounters = 16;    // [0] queue head, [1] fast, [2] exact, [3] rerun, [4,5] cells_exact, [6] xfast, [7] score-only large tiles, [8] filter hand-over count, [9] filter tiles, [10] pairs run by the pair kernel
+constexpr int kCounters = 16;    // [0] queue head, [1] fast, [2] exact, [3] rerun, [4,5] cells_exact, [6] xfast, [7] score-only large tiles, [8] filter hand-over count, [9] filter tiles
 
 struct DarwinGpu {
     int device = 0;
@@ -733,11 +627,6 @@ struct DarwinGpu {
     int ctas_filter = 0;
     int sm_count = 0, max_warps = 0;
     int ctas_tiles[5] = {0, 0, 0, 0, 0}, ctas_extend[5] = {0, 0, 0, 0, 0};   // persistent grid per kernel variant (K = 0,4,5,6,8)
-    int ctas_pair[4] = {0, 0, 0, 0};            // pair kernel (two tiles per warp), K = 4,5,6
-    // Measured on B200 (profiles/r2_pair_kernel_ab.log): the pair kernel executes 13 % fewer ALU-pipe cycles per tile, but its
-    // two bands per warp leave room for 5 warps per SM instead of 11 and the issue slots go idle during tracebacks and
-    // staging: 1 321 vs 1 391 GCUPS at T = 320, 1 345 vs 1 504 at T = 384.  It stays opt-in (DARWIN_GPU_PAIRS=1).
-    bool use_pairs = false;
     uint8_t* d_trace = nullptr; size_t trace_stride = 0; ChainRec* d_bound = nullptr;
     unsigned int* d_counter = nullptr;
     // growable device buffers
@@ -821,23 +710,10 @@ static int configure_variant(DarwinGpu* h) {
     return DARWIN_OK;
 }
 
-template <int K>
-static int configure_pair_variant(DarwinGpu* h) {
-    const size_t smem = PairKernelGeom<K>::kSmem;
-    CK(cudaFuncSetAttribute(tiles_pair_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(tiles_pair_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int a = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, tiles_pair_kernel<K>, 32, smem));
-    a = std::max(1, std::min(a, h->max_warps / h->sm_count));
-    h->ctas_pair[variant_index(K)] = h->sm_count * a;
-    return DARWIN_OK;
-}
-
 static int configure_kernels(DarwinGpu* h) {
     int rc;
     if ((rc = configure_variant<0>(h)) || (rc = configure_variant<4>(h)) || (rc = configure_variant<5>(h)) ||
         (rc = configure_variant<6>(h)) || (rc = configure_variant<8>(h))) return rc;
-    if ((rc = configure_pair_variant<4>(h)) || (rc = configure_pair_variant<5>(h)) || (rc = configure_pair_variant<6>(h))) return rc;
     int f = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, filter_kernel, kFilterWarps * 32, 0));
     h->ctas_filter = h->sm_count * std::max(1, f);
@@ -853,7 +729,6 @@ static int read_counters(DarwinGpu* h) {
     h->stats.tiles_xfast += c[6];
     h->stats.tiles_scoreonly += c[7];
     h->stats.tiles_filter += c[9];
-    h->stats.tiles_paired += 2ull * c[10];
     return DARWIN_OK;
 }
 
@@ -890,7 +765,6 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     DarwinGpu* h = new DarwinGpu();
     h->device = device;
     h->timing_dbg = getenv("DARWIN_GPU_TIMING") != nullptr;
-    { const char* e = getenv("DARWIN_GPU_PAIRS"); h->use_pairs = e && e[0] == '1'; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
@@ -1116,22 +990,6 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
                                         xfast_trace_bytes(std::max(maxQ, 1), std::max(maxR, 1))));
     if (rc) return rc;
     const int K = pick_k(h, std::max(maxQ, maxR), do_traceback);
-    // corner-traceback batches whose tiles fit one strip: two tiles per warp
-    if (h->use_pairs && do_traceback && !idx_list && K >= 4 && K <= 6 && std::max(maxQ, maxR) <= 64 * K && n >= 2) {
-        const int ctas = std::max(1, std::min(h->ctas_pair[variant_index(K)], (n + 1) / 2));
-        CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));
-#define LAUNCH_PAIR(KK) tiles_pair_kernel<KK><<<ctas, 32, PairKernelGeom<KK>::kSmem, h->stream>>>( \
-        h->d_arena, h->ks, d_req, n, d_res, d_tb, tb_words_per_req, h->d_trace, h->trace_stride, h->d_bound, h->d_counter)
-        switch (K) {
-            case 4: LAUNCH_PAIR(4); break;
-            case 5: LAUNCH_PAIR(5); break;
-            default: LAUNCH_PAIR(6); break;
-        }
-#undef LAUNCH_PAIR
-        CK(cudaGetLastError());
-        h->stats.kernel_launches++;
-        return DARWIN_OK;
-    }
     int ctas = h->ctas_tiles[variant_index(K)];
     if (idx_list) ctas = list_len > 0 ? std::max(1, std::min(ctas, list_len)) : std::min(ctas, h->sm_count);   // hand-over lists are short
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));      // queue head; [1..3] accumulate

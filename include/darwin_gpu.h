@@ -235,7 +235,6 @@ typedef struct DarwinGpuStats {
     float    last_extend_ms;    /*   ... of the extension kernels (anchor walking + score / compaction) */
     float    reserved2;
     uint64_t tiles_scoreonly;   /* large tiles settled by the score-only pre-pass (corner ZERO: no traceback needed) */
-    uint64_t tiles_paired;      /* tiles whose forward pass ran two-per-warp (pair geometry; subset of tiles_fast + reruns) */
 } DarwinGpuStats;
 
 typedef struct DarwinGpu DarwinGpu;   /* opaque */

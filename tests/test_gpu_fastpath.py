@@ -283,30 +283,6 @@ def test_large_tiles_score_only_prepass(gpu, vals):
     p.close()
 
 
-def test_pair_kernel_matches_single_tile_kernel(gpu, monkeypatch):
-    """The opt-in pair geometry (two tiles per warp, gact_pair.cuh; DARWIN_GPU_PAIRS=1) gives the single-tile kernel's answers:
-    uniform batches (paired), a ragged batch (mostly unpaired), reruns (band exits / long-gap ties) and an odd tile count."""
-    sc = abi.Scoring.from_values()
-    cases = [synth.tile_batch_fast(77, 3001, 320), synth.tile_batch_fast(78, 2000, 384), synth.tile_batch_fast(79, 2000, 200),
-             _ragged_batch(80, 500, 320, long_indel=70)]
-    for arena, req in cases:
-        monkeypatch.delenv("DARWIN_GPU_PAIRS", raising=False)
-        p1 = gpu(len(arena), sc)
-        p1.InitializeReferenceMemory(0, arena)
-        r1, t1 = p1.BatchAlignmentSIMD(req, 1)
-        monkeypatch.setenv("DARWIN_GPU_PAIRS", "1")
-        p2 = gpu(len(arena), sc)
-        p2.InitializeReferenceMemory(0, arena)
-        st0 = p2.stats()
-        r2, t2 = p2.BatchAlignmentSIMD(req, 1)
-        paired = p2.stats().tiles_paired - st0.tiles_paired
-        assert tiles_equal(r1, t1, r2, t2) == []
-        assert p1.stats().tiles_paired == 0
-        assert paired > 0 and (paired >= len(req) - 1 or req["ref_size"].min() != req["ref_size"].max())
-        p1.close()
-        p2.close()
-
-
 def test_mixed_shapes_keep_their_own_geometry(gpu):
     """Geometry is chosen per tile: a batch of 320 x 320 tiles with a handful of 400-, 512- and 700-wide ones in between gives
     the oracle's answers, and the 320 x 320 tiles do not fall off a cliff (before: one wide tile put the whole call on the
