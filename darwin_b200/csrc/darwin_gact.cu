@@ -127,11 +127,13 @@ template <int K> struct KernelGeom {
     static constexpr size_t kNeed2 = kNeed > sizeof(ExactSmem) ? kNeed : sizeof(ExactSmem);
     static constexpr size_t kBigEnd = (K == 0) ? 0 : 16000 + 2 * (size_t)kRawBig;      // big raw windows live at offset 16000
     static constexpr size_t kTileBytes = ((kNeed2 > kBigEnd ? kNeed2 : kBigEnd) + 15) & ~(size_t)15;
-    // raw packed windows for the TMA staging: single-strip fast tiles use a small pair behind the tile region; bigger
-    // tiles (multi-strip / packed exact / unpacked exact) use the spare space of the tile region (K > 0) or a big pair (K = 0)
-    static constexpr int kRawSmallStride = (K == 0) ? kRawBig : ((32 * K + 32 + 15) & ~15);
-    static constexpr size_t kRawOff = kTileBytes;                        // offset of the small raw pair
-    static constexpr size_t kMbarOff = kRawOff + 2 * kRawSmallStride;
+    // raw packed windows for the TMA staging: single-strip fast tiles use a small pair at the START of the tile region (the
+    // fast view's band, dead while a tile is being staged; the unpacked sequences live behind it); bigger tiles (multi-strip /
+    // packed exact / unpacked exact) use the spare space of the tile region (K > 0) or a big pair behind it (K = 0)
+    static constexpr int kRawSmallStride = (K == 0) ? kRawBig : FastGeom<(K == 0 ? 4 : K)>::kRawStride;
+    static constexpr size_t kRawOff = (K == 0) ? kTileBytes : 0;         // offset of the small raw pair
+    static constexpr size_t kMbarOff = (K == 0) ? kRawOff + 2 * kRawSmallStride : kTileBytes;
+    static_assert(K == 0 || 2 * (size_t)kRawSmallStride <= FastGeom<(K == 0 ? 4 : K)>::kBandWords * 4, "small raw windows alias the band");
     static constexpr size_t kBigRawOff = (K == 0) ? kRawOff : 16000;     // MultiSmemView / XSmemView / ExactSmem end below 16000
     static_assert(K == 0 || 16000 + 2 * (size_t)kRawBig <= kTileBytes, "spare space for the big raw windows");
     static constexpr size_t kPerWarp = kMbarOff + 16;                    // tiles kernel
@@ -285,7 +287,7 @@ __device__ __forceinline__ void flush_counters(const WarpCtx& cx, unsigned int* 
 // BatchAlignmentSIMD (Processor.cpp:718-762) for n independent tiles: persistent warps pull tiles from a
 // global counter.
 template <int K>
-__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 4 : (K == 8) ? 5 : 11)
+__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 4 : (K == 8) ? 5 : 12)
 tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
              const DarwinTileReq* __restrict__ req, int n, int do_traceback,
              DarwinTileRes* __restrict__ res, uint64_t* __restrict__ tb_words, int tb_words_per_req,
@@ -625,7 +627,7 @@ struct DarwinGpu {
     cudaEvent_t ev_chunk[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     KernelScoring ks{}; FilterConst filt{}; bool have_scoring = false;
     int ctas_filter = 0;
-    int sm_count = 0, max_warps = 0;
+    int sm_count = 0, max_warps = 0, tune_max_ctas = 0;
     int ctas_tiles[5] = {0, 0, 0, 0, 0}, ctas_extend[5] = {0, 0, 0, 0, 0};   // persistent grid per kernel variant (K = 0,4,5,6,8)
     uint8_t* d_trace = nullptr; size_t trace_stride = 0; ChainRec* d_bound = nullptr;
     unsigned int* d_counter = nullptr;
@@ -703,7 +705,8 @@ static int configure_variant(DarwinGpu* h) {
     int a = 0, b = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, tiles_kernel<K>, threads, smem_t));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, extend_kernel<K>, threads, smem_e));
-    const int cap = h->max_warps / h->sm_count / KernelGeom<K>::kWarps;       // scratch bound
+    int cap = h->max_warps / h->sm_count / KernelGeom<K>::kWarps;             // scratch bound
+    if (K > 0 && h->tune_max_ctas > 0) cap = std::min(cap, h->tune_max_ctas);  // DARWIN_GPU_MAX_CTAS_PER_SM (A/B measurements)
     a = std::max(1, std::min(a, cap)); b = std::max(1, std::min(b, cap));
     h->ctas_tiles[variant_index(K)] = h->sm_count * a;                        // persistent grids: multiples of the SM count
     h->ctas_extend[variant_index(K)] = h->sm_count * b;
@@ -765,6 +768,7 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     DarwinGpu* h = new DarwinGpu();
     h->device = device;
     h->timing_dbg = getenv("DARWIN_GPU_TIMING") != nullptr;
+    { const char* e = getenv("DARWIN_GPU_MAX_CTAS_PER_SM"); h->tune_max_ctas = e ? atoi(e) : 0; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }

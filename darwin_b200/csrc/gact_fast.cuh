@@ -39,9 +39,13 @@ template <int K, int BH = kBandHalf> struct FastGeom {
     static constexpr int kL     = 2 * BH + 1;
     static constexpr int kLp    = kL + (((kL - K - 1) & 1) ? 0 : 1);   // lane stride kLp-(K+1) odd -> conflict-free stores
     static constexpr int kW     = (K + 5) / 6;      // band words per (virtual lane, step): six 5-bit pointers per word (K = 8: two)
-    static constexpr int kPWords = kRows + 128;     // packed reference pairs P[j + 32] = r[j] | r[j-32] << 16
+    static constexpr int kPWords = kRows + 128;     // one 16-bit word per reference column pair (j, j - 32): P[j + 32], see fast_forward
     static constexpr size_t kBandWords = (size_t)64 * kLp * kW;
-    static constexpr size_t kSmemBytes = (kBandWords + kPWords) * 4 + 2 * kRows;    // + staged byte sequences
+    // the staged byte sequences alias the band: they are dead once P[] and the query tables are built, before the first band store
+    static constexpr int kRawStride = (32 * K + 32 + 15) & ~15;     // one raw packed TMA window (<= kRows bases, 16-byte rounded)
+    static constexpr int kSeqOff = 2 * kRawStride;  // behind the two raw TMA windows at the start of the region (KernelGeom)
+    static constexpr size_t kSmemBytes = kBandWords * 4 + kPWords * 2;
+    static_assert(kSeqOff + 2 * kRows <= kBandWords * 4, "staged sequences fit inside the band");
 };
 
 struct FastConst {                                  // packed constants derived from the scoring (both halves equal)
@@ -58,6 +62,8 @@ struct FastConst {                                  // packed constants derived 
     int32_t  gea;         // ge*32 * 65537
     int32_t  lgoa, lgea;  // (lgo*32 + L tag) * 65537, lge*32 * 65537
     uint32_t geh, lgeh;   // ge*32 and lge*32 as two's-complement halves (operand b of VIADDMNMX.U16x2)
+    uint32_t goh, gofh, lgoh;   // go*32, go*32 + INS tag, lgo*32 + L tag as halves: the OPEN candidates as VIADDMNMX addends
+    uint32_t fmark;       // F's "extended" marker, both halves
     int32_t  bias;        // B
     int32_t  max_score;   // largest corner score representable: 2047 - B
     int32_t  eligible;    // scoring admits the fast path
@@ -65,6 +71,7 @@ struct FastConst {                                  // packed constants derived 
     uint32_t nmul;        // (sub_N - mismatch) * U / 4: multiplier of the packed "N involved" flags (value 4 per half)
     int32_t  n_ok;        // tiles containing N may stay on the packed path (mismatch <= sub_N <= 0)
     uint32_t one[4];      // all 1, opaque to the compiler: `x * one[k] + c` stays an IMAD (fma pipe) instead of an ALU add
+    uint32_t shl16;       // 65536, opaque likewise: lane 0's `x * shl16 + boundary` stays an IMAD instead of a shift + add
 };
 
 constexpr uint32_t FT_DEL = 0, FT_INS = 1, FT_DIAG = 2, FT_ZERO = 3, FT_L = 4;
@@ -82,7 +89,7 @@ __host__ inline FastConst make_fast_const(const DevScoring& sc, int S = 5) {
     f.eligible = sc.uniform && m > 0 && mm < 0 && go <= ge && ge < 0 && lgo <= lge && lge <= 0 && B < 512;
     auto pk = [](int v) { return (uint32_t)(v & 0xFFFF) * 0x00010001u; };
     const int U = 1 << S, ts = S - 3;                          // score unit, position of the 3-bit source field
-    f.bias = B; f.match = m; f.max_score = (65536 / U - 1) - B - m; f.one[0] = f.one[1] = f.one[2] = f.one[3] = 1;
+    f.bias = B; f.match = m; f.max_score = (65536 / U - 1) - B - m; f.one[0] = f.one[1] = f.one[2] = f.one[3] = 1; f.shl16 = 65536u;
     f.zeroc = pk((B << S) | (FT_ZERO << ts));
     f.hm_init = pk(((B + mm) << S) | (FT_DIAG << ts));
     f.e_init = pk((B + go) << S);
@@ -96,6 +103,8 @@ __host__ inline FastConst make_fast_const(const DevScoring& sc, int S = 5) {
     f.gea = (ge * U) * 65537;
     f.lgoa = (lgo * U + (int)(FT_L << ts)) * 65537; f.lgea = (lge * U) * 65537;
     f.geh = pk(ge * U); f.lgeh = pk(lge * U);
+    f.goh = pk(go * U); f.gofh = pk(go * U + (int)(FT_INS << ts)); f.lgoh = pk(lgo * U + (int)(FT_L << ts));
+    f.fmark = S == 5 ? 0x00020002u : 0x00010001u;
     // N bases (Nt2Int code 4, Processor.cpp:21-46; sub_N for N against anything, :50-74): see fast_cell<S, true>
     f.n_ok = f.eligible && sc.subn <= 0 && sc.subn >= mm;
     f.nmul = (uint32_t)((sc.subn - mm) * U / 4);
@@ -105,13 +114,13 @@ __host__ inline FastConst make_fast_const(const DevScoring& sc, int S = 5) {
 // Per-warp shared memory of the fast path, carved from the dynamic shared memory of the CTA.
 template <int K> struct FastSmemView {
     uint32_t* band;       // [kSteps][kNB]
-    uint32_t* P;          // [kPWords]
-    uint8_t*  sref;       // [kRows]
+    uint16_t* P;          // [kPWords]
+    uint8_t*  sref;       // [kRows]   (inside the band, see FastGeom)
     uint8_t*  sqry;       // [kRows]
     __device__ explicit FastSmemView(unsigned char* base) {
         band = reinterpret_cast<uint32_t*>(base);
-        P = band + FastGeom<K>::kBandWords;
-        sref = reinterpret_cast<uint8_t*>(P + FastGeom<K>::kPWords);
+        P = reinterpret_cast<uint16_t*>(band + FastGeom<K>::kBandWords);
+        sref = base + FastGeom<K>::kSeqOff;
         sqry = sref + FastGeom<K>::kRows;
     }
 };
@@ -129,10 +138,10 @@ template <int K, int BH = kBandHalf> struct BandMap {
 
 // Scoring constants of one tile in registers.
 struct FastRegs {
-    uint32_t zeroc, pkc32, negc32, diaga, goa, gofa, lgoa, geh, lgeh, one0, one1, one2, one3, nmul;
+    uint32_t zeroc, pkc32, negc32, diaga, gea, lgea, goh, gofh, lgoh, fmark, one0, one1, one2, one3, nmul;
     __device__ explicit FastRegs(const FastConst& fc)
-        : zeroc(fc.zeroc), pkc32(fc.pkc32), negc32((uint32_t)fc.negc32), diaga((uint32_t)fc.diaga), goa((uint32_t)fc.goa),
-          gofa((uint32_t)fc.gofa), lgoa((uint32_t)fc.lgoa), geh(fc.geh), lgeh(fc.lgeh),
+        : zeroc(fc.zeroc), pkc32(fc.pkc32), negc32((uint32_t)fc.negc32), diaga((uint32_t)fc.diaga), gea((uint32_t)fc.gea),
+          lgea((uint32_t)fc.lgea), goh(fc.goh), gofh(fc.gofh), lgoh(fc.lgoh), fmark(fc.fmark),
           one0(fc.one[0]), one1(fc.one[1]), one2(fc.one[2]), one3(fc.one[3]), nmul(fc.nmul) {}
 };
 
@@ -144,16 +153,18 @@ struct FastRegs {
 // HASN: the tile contains N.  Reference N is code 4, query N is remapped to 12 when the rows are loaded, so an N on either
 // side always counts as a "mismatch" (x != 0, also N against N) and bit 2 of (rq | qq) says "N involved"; the substitution
 // score then becomes sub_N: sb + 4 * nmul = (sub_N - mismatch) * U on top of the mismatch already folded into d.
-template <int S = 5, bool HASN = false>
-__device__ __forceinline__ uint32_t fast_cell(const FastRegs& k, uint32_t rq, uint32_t qq, uint32_t& d, uint32_t& Hm,
-                                              uint32_t& E, uint32_t& EL, uint32_t& F, uint32_t& FL) {
-    const uint32_t x  = rq ^ qq;
-    const uint32_t t  = __vminu2(x, 0x00010001u);                // 1 = mismatch, per half
-    uint32_t sb = t * k.negc32 + k.pkc32;                        // IMAD: (match-mismatch)*32 or 0
-    if (HASN) sb = ((rq | qq) & 0x00040004u) * k.nmul + sb;      // LOP3 + IMAD: N involved -> sub_N
+// core: sb = substitution addend of the cell pair ((match - mismatch) * U where the bases match, 0 otherwise; the mismatch
+// score itself is folded into d)
+// (Measured and dropped: carrying F's extend candidate Fx = (F | marker) + extend down the rows as its own max chain, which
+// takes the OR and the IMAD off the F chain at the price of one more VIADDMNMX per cell pair: no gain on the tile kernel,
+// -2 % on the extension kernel.)
+template <int S = 5>
+__device__ __forceinline__ uint32_t fast_cell_core(const FastRegs& k, uint32_t sb, uint32_t& d, uint32_t& Hm,
+                                                   uint32_t& E, uint32_t& EL, uint32_t& F, uint32_t& FL) {
     const uint32_t hd = __viaddmax_u16x2(d, sb, k.zeroc);        // max(Hdiag + s, 0)          :298-299
-    const uint32_t h1 = __vimax3_u16x2(hd, E, F);
-    const uint32_t Hk = __vimax3_u16x2(h1, EL, FL);              // H with the winner's tag      :300-303
+    // (the row's own E and E_L first: F and F_L arrive through the dependent chain of the rows above)
+    const uint32_t h1 = __vimax3_u16x2(hd, E, EL);
+    const uint32_t Hk = __vimax3_u16x2(h1, F, FL);               // H with the winner's tag      :300-303
     uint32_t code, Hc;
     if (S == 5) {
         const uint32_t em = E | F;
@@ -168,12 +179,47 @@ __device__ __forceinline__ uint32_t fast_cell(const FastRegs& k, uint32_t rq, ui
     }
     d = Hm;
     Hm = Hc * k.one0 + k.diaga;                                  // IMADs: keeps the adds off the ALU pipe
-    const uint32_t Ho = Hc * k.one1 + k.goa, HoF = Hc * k.one2 + k.gofa, HoL = Hc * k.one3 + k.lgoa;
-    E  = __viaddmax_u16x2(E | 0x00010001u, k.geh, Ho);           // ties extend                  :336-337,:353
-    F  = __viaddmax_u16x2(F | (S == 5 ? 0x00020002u : 0x00010001u), k.geh, HoF);   //            :363-364,:369
-    EL = __viaddmax_u16x2(EL, k.lgeh, HoL);                      //                              :339-340
-    FL = __viaddmax_u16x2(FL, k.lgeh, HoL);                      //                              :365-366
+    // gap updates max(gap + extend, H + open): the OPEN candidate takes the add of VIADDMNMX (H -> clean -> VIADDMNMX stays on
+    // the ALU pipe: this is the dependent chain that runs down the rows of a step through F and F_L), the EXTEND candidate
+    // is formed by an IMAD off that chain
+    const uint32_t Ee = (E | 0x00010001u) * k.one1 + k.gea;      // ties extend                  :336-337,:353
+    const uint32_t Fe = (F | k.fmark) * k.one2 + k.gea;          //                              :363-364,:369
+    const uint32_t ELe = EL * k.one3 + k.lgea, FLe = FL * k.one3 + k.lgea;             //        :339-340, :365-366
+    E  = __viaddmax_u16x2(Hc, k.goh, Ee);
+    F  = __viaddmax_u16x2(Hc, k.gofh, Fe);
+    EL = __viaddmax_u16x2(Hc, k.lgoh, ELe);
+    FL = __viaddmax_u16x2(Hc, k.lgoh, FLe);
     return code;
+}
+
+template <int S = 5, bool HASN = false>
+__device__ __forceinline__ uint32_t fast_cell(const FastRegs& k, uint32_t rq, uint32_t qq, uint32_t& d, uint32_t& Hm,
+                                              uint32_t& E, uint32_t& EL, uint32_t& F, uint32_t& FL) {
+    const uint32_t x  = rq ^ qq;
+    const uint32_t t  = __vminu2(x, 0x00010001u);                // 1 = mismatch, per half
+    uint32_t sb = t * k.negc32 + k.pkc32;                        // IMAD: (match-mismatch)*32 or 0
+    if (HASN) sb = ((rq | qq) & 0x00040004u) * k.nmul + sb;      // LOP3 + IMAD: N involved -> sub_N
+    return fast_cell_core<S>(k, sb, d, Hm, E, EL, F, FL);
+}
+
+// ---- table look-up of the mismatch flags (tiles without N) -----------------------------------------------------------------
+// The query rows of a virtual lane are fixed for the whole tile, the reference base changes every step: each row keeps a
+// 4-byte table "does reference base b differ from my query base" (one register per half), and ONE PRMT per cell pair picks
+// the flag of the low half's row from table a and of the high half's row from table b -- instead of XOR + VMIN.  The
+// selector is stored per reference column, ready made, in P[] (see fast_forward): nibble 0 = base of column j, nibble 2 =
+// 4 + base of column j - 32, nibbles 1 and 3 = 8 (replicate the sign of a 0/1 byte: zero).  Columns outside the tile (the
+// dummy base that mismatches everything) matter only while the wavefront fills: there the flag is derived from the step.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+    return d;
+}
+// ptxas likes to re-derive loop-invariant per-lane values (lane tests, masks) inside the loop instead of keeping them in a
+// register, on the very ALU pipe the loop is bound by; an empty asm makes the value opaque
+template <class T> __device__ __forceinline__ void keep_in_register(T& x) { asm volatile("" : "+r"(x)); }
+__device__ __forceinline__ uint32_t qry_table(uint32_t q) { return q < 4u ? (0x01010101u ^ (1u << (8u * q))) : 0x01010101u; }
+__device__ __forceinline__ uint32_t ref_selector(uint32_t lo, bool in_lo, uint32_t hi, bool in_hi) {
+    return 0x8480u + (in_lo ? lo : 0u) + ((in_hi ? hi : 0u) << 8);
 }
 
 // Forward pass of one tile.  Sequences must already be staged (codes 0..3) in v.sref / v.sqry.
@@ -183,78 +229,121 @@ constexpr uint32_t kDummyRef = 16u, kDummyQry = 32u;
 // query base as the cell update wants it: N (4) becomes 12 in tiles that contain N (see fast_cell)
 template <bool HASN> __device__ __forceinline__ uint32_t qry_code(uint32_t c) { return HASN ? (c | ((c & 4u) << 1)) : c; }
 
+// State of one warp's wavefront between steps.
+template <int K> struct FwdState {
+    uint32_t qa[K], qb[K];            // !HASN: mismatch tables of my low / high virtual lane's rows; HASN: qa = packed query codes
+    uint32_t Hm[K], E[K], EL[K];
+    uint32_t sendH, sendF, sendFL;    // state below my last row (previous step)
+    uint32_t diag_in;                 // Hm(row above, previous column)
+    uint32_t rq_next;                 // P word of the next step
+    int t_lo;                         // band window position of my low virtual lane
+    uint32_t* bp;
+};
+
+// Steps [s0, s1) of the wavefront.  FILL: some virtual lanes are still left of column 0 (dummy base: mismatch forced).
+template <int K, bool HASN, bool FILL>
+__device__ __forceinline__ void fast_steps(const FastRegs& kr, FwdState<K>& st, const uint16_t* Pl, int s0, int s1,
+                                           int src, uint32_t mulL, uint32_t addH, uint32_t addF, uint32_t addFL) {
+    using G = FastGeom<K>;
+    constexpr int kHiOff = 32 * (G::kLp - (K + 1)) * G::kW;
+    const int lane = lane_id();
+    for (int s = s0; s < s1; s++) {
+        // values from the virtual lane above: rotate by one lane; lane 0 shifts lane 31's low half up and takes the top
+        // boundary in its low half -- as one IMAD per value (x * 65536 + boundary in lane 0, x * 1 + 0 elsewhere)
+        const uint32_t inH = __shfl_sync(0xffffffffu, st.sendH, src) * mulL + addH;
+        uint32_t F  = __shfl_sync(0xffffffffu, st.sendF, src) * mulL + addF;
+        uint32_t FL = __shfl_sync(0xffffffffu, st.sendFL, src) * mulL + addFL;
+        const uint32_t rq = HASN ? __byte_perm(st.rq_next, 0u, 0x4140) : st.rq_next;   // HASN: codes of (j, j - 32) into the two halves
+        st.rq_next = Pl[s + 1];                                          // prefetch next step's reference word
+        uint32_t dm = 0;
+        if (!HASN && FILL) dm = (s < lane ? 1u : 0u) | (s < lane + 32 ? 0x10000u : 0u);   // my column is left of the tile
+        uint32_t d = st.diag_in;
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int r = 0; r < K; r++) {
+            uint32_t code;
+            if (HASN) {
+                code = fast_cell<5, true>(kr, rq, st.qa[r], d, st.Hm[r], st.E[r], st.EL[r], F, FL);
+            } else {
+                uint32_t t = prmt(st.qa[r], st.qb[r], rq);               // 1 = mismatch, per half
+                if (FILL) t |= dm;
+                const uint32_t sb = t * kr.negc32 + kr.pkc32;            // IMAD: (match-mismatch)*32 or 0
+                code = fast_cell_core<5>(kr, sb, d, st.Hm[r], st.E[r], st.EL[r], F, FL);
+            }
+            acc[r / 3] += code << (5 * (r % 3));
+        }
+        st.diag_in = inH;
+        st.sendH = st.Hm[K - 1]; st.sendF = F; st.sendFL = FL;
+        // band store: kW words per (virtual lane, step): rows 0-2 in bits 0-14, rows 3-5 in bits 16-30 (word 1: rows 6-11)
+        if (G::kW == 1) {
+            if ((unsigned)st.t_lo < (unsigned)G::kL) st.bp[0] = __byte_perm(acc[0], acc[1], 0x5410);
+            if ((unsigned)(st.t_lo - 32 * (K + 1)) < (unsigned)G::kL) st.bp[kHiOff] = __byte_perm(acc[0], acc[1], 0x7632);
+        } else {
+            if ((unsigned)st.t_lo < (unsigned)G::kL)
+                *reinterpret_cast<uint2*>(st.bp) = make_uint2(__byte_perm(acc[0], acc[1], 0x5410), __byte_perm(acc[2], acc[3], 0x5410));
+            if ((unsigned)(st.t_lo - 32 * (K + 1)) < (unsigned)G::kL)
+                *reinterpret_cast<uint2*>(st.bp + kHiOff) = make_uint2(__byte_perm(acc[0], acc[1], 0x7632), __byte_perm(acc[2], acc[3], 0x7632));
+        }
+        st.t_lo++; st.bp += G::kW;
+    }
+}
+
 template <int K, bool HASN = false>
 __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q, int R) {
     using G = FastGeom<K>;
     const int lane = lane_id();
-    // packed reference pairs: P[32 + j] = r[j] | r[j-32] << 16, dummy base outside [0,R)
+    // per reference column: HASN: code pair P[32 + j] = r[j] | r[j-32] << 8, dummy base outside [0,R); otherwise the PRMT
+    // selector of the pair (ref_selector)
     for (int k = lane; k < G::kPWords; k += 32) {
         const int j = k - 32;
-        const uint32_t lo = (j >= 0 && j < R) ? v.sref[j] : kDummyRef;
-        const uint32_t hi = (j - 32 >= 0 && j - 32 < R) ? v.sref[j - 32] : kDummyRef;
-        v.P[k] = lo | (hi << 16);
+        const bool in_lo = (unsigned)j < (unsigned)R, in_hi = (unsigned)(j - 32) < (unsigned)R;
+        const uint32_t lo = in_lo ? v.sref[j] : kDummyRef, hi = in_hi ? v.sref[j - 32] : kDummyRef;
+        v.P[k] = (uint16_t)(HASN ? (lo | (hi << 8)) : ref_selector(lo, in_lo, hi, in_hi));
     }
-    uint32_t qq[K], Hm[K], E[K], EL[K];
+    FwdState<K> st;
 #pragma unroll
     for (int r = 0; r < K; r++) {
         const int ilo = K * lane + r, ihi = K * (lane + 32) + r;
-        qq[r] = (ilo < Q ? qry_code<HASN>(v.sqry[ilo]) : kDummyQry) | ((ihi < Q ? qry_code<HASN>(v.sqry[ihi]) : kDummyQry) << 16);
-        Hm[r] = fc.hm_init; E[r] = fc.e_init; EL[r] = fc.el_init;
+        const uint32_t qlo = ilo < Q ? v.sqry[ilo] : kDummyQry, qhi = ihi < Q ? v.sqry[ihi] : kDummyQry;
+        if (HASN) { st.qa[r] = qry_code<true>(qlo) | (qry_code<true>(qhi) << 16); st.qb[r] = 0; }
+        else      { st.qa[r] = qry_table(qlo); st.qb[r] = qry_table(qhi); }
+        st.Hm[r] = fc.hm_init; st.E[r] = fc.e_init; st.EL[r] = fc.el_init;
     }
     __syncwarp();
     const BandMap<K> bm(Q, R);
     const int vc = (Q - 1) / K, rc = (Q - 1) - vc * K, sc_step = R - 1 + vc;
     const FastRegs kr(fc);                                               // scoring constants in registers
-    uint32_t sendH = fc.hm_init, sendF = fc.f_top, sendFL = fc.fl_top;   // state below my last row (previous step)
-    uint32_t diag_in = fc.hm_init;                                       // Hm(row above, previous column)
-    const int src = (lane + 31) & 31;
+    st.sendH = fc.hm_init; st.sendF = fc.f_top; st.sendFL = fc.fl_top;
+    st.diag_in = fc.hm_init;
+    int src = (lane + 31) & 31;
+    uint32_t mulL = lane == 0 ? fc.shl16 : fc.one[0];             // both opaque to the compiler
+    uint32_t addH = lane == 0 ? (fc.hm_init & 0xFFFFu) : 0u, addF = lane == 0 ? (fc.f_top & 0xFFFFu) : 0u,
+             addFL = lane == 0 ? (fc.fl_top & 0xFFFFu) : 0u;
+    keep_in_register(src); keep_in_register(mulL); keep_in_register(addH); keep_in_register(addF); keep_in_register(addFL);
     // the corner cell (Q-1, R-1) is the last valid cell of the wavefront (step R-1+vc): nothing after it is ever read,
     // so the loop ends there and the corner score is simply what its owner holds afterwards
     const int steps = sc_step + 1;
-    uint32_t rq_next = v.P[32 - lane];                                   // step 0: j = -lane (dummy unless lane 0)
+    const uint16_t* Pl = v.P + 32 - lane;                                // step s: column j = s - lane (low), j - 32 (high)
+    st.rq_next = Pl[0];
     // band window of my two virtual lanes: t = s - (K+1)*v + c1 (t(i,j) with j = s - v)
-    int t_lo = -(K + 1) * lane + bm.c1;                                  // at s = 0
-    uint32_t* bp = v.band + (lane * G::kLp + t_lo) * G::kW;              // &band[(v_lo * kLp + t_lo) * kW]; hi: + 32*(kLp - (K+1)) steps
-    constexpr int kHiOff = 32 * (G::kLp - (K + 1)) * G::kW;
-
-    for (int s = 0; s < steps; s++) {
-        // values from the virtual lane above: rotate by one lane; lane 0 shifts lane 31's low half up and
-        // takes the top boundary in its low half
-        uint32_t inH = __shfl_sync(0xffffffffu, sendH, src);
-        uint32_t F   = __shfl_sync(0xffffffffu, sendF, src);
-        uint32_t FL  = __shfl_sync(0xffffffffu, sendFL, src);
-        if (lane == 0) {
-            inH = __byte_perm(fc.hm_init, inH, 0x5410);
-            F   = __byte_perm(fc.f_top, F, 0x5410);
-            FL  = __byte_perm(fc.fl_top, FL, 0x5410);
-        }
-        const uint32_t rq = rq_next;
-        rq_next = v.P[32 + s + 1 - lane];                                // prefetch next step's reference pair
-        uint32_t d = diag_in;
-        uint32_t acc[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int r = 0; r < K; r++) {
-            const uint32_t code = fast_cell<5, HASN>(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
-            acc[r / 3] += code << (5 * (r % 3));
-        }
-        diag_in = inH;
-        sendH = Hm[K - 1]; sendF = F; sendFL = FL;
-        // band store: kW words per (virtual lane, step): rows 0-2 in bits 0-14, rows 3-5 in bits 16-30 (word 1: rows 6-11)
-        if (G::kW == 1) {
-            if ((unsigned)t_lo < (unsigned)G::kL) bp[0] = __byte_perm(acc[0], acc[1], 0x5410);
-            if ((unsigned)(t_lo - 32 * (K + 1)) < (unsigned)G::kL) bp[kHiOff] = __byte_perm(acc[0], acc[1], 0x7632);
-        } else {
-            if ((unsigned)t_lo < (unsigned)G::kL)
-                *reinterpret_cast<uint2*>(bp) = make_uint2(__byte_perm(acc[0], acc[1], 0x5410), __byte_perm(acc[2], acc[3], 0x5410));
-            if ((unsigned)(t_lo - 32 * (K + 1)) < (unsigned)G::kL)
-                *reinterpret_cast<uint2*>(bp + kHiOff) = make_uint2(__byte_perm(acc[0], acc[1], 0x7632), __byte_perm(acc[2], acc[3], 0x7632));
-        }
-        t_lo++; bp += G::kW;
+    st.t_lo = -(K + 1) * lane + bm.c1;                                   // at s = 0
+    st.bp = v.band + (lane * G::kLp + st.t_lo) * G::kW;                  // &band[(v_lo * kLp + t_lo) * kW]; hi: + 32*(kLp - (K+1)) steps
+    if (HASN) {
+        fast_steps<K, true, false>(kr, st, Pl, 0, steps, src, mulL, addH, addF, addFL);
+    } else {
+        // fill: until virtual lane 63 reaches column 0 some lanes chew the dummy base (flag OR-ed into the PRMT result);
+        // afterwards every virtual lane is inside the tile or past its last column, where nothing it computes is ever read.
+        // (Measured and dropped: unrolling the step loop by two and step loops specialised by band-window phase save 3 of 73
+        // ALU-pipe instructions per step but gain nothing -- the loop is bound by its dependent chain and the issue rate --
+        // and the larger code costs the extension kernel 12 %.)
+        const int fill = min(steps, 63);
+        fast_steps<K, false, true>(kr, st, Pl, 0, fill, src, mulL, addH, addF, addFL);
+        fast_steps<K, false, false>(kr, st, Pl, fill, steps, src, mulL, addH, addF, addFL);
     }
     __syncwarp();
     uint32_t corner = 0;
 #pragma unroll
-    for (int r = 0; r < K; r++) if (r == rc) corner = Hm[r] - kr.diaga;
+    for (int r = 0; r < K; r++) if (r == rc) corner = st.Hm[r] - kr.diaga;
     // corner owner: virtual lane vc -> physical lane vc & 31, half vc >> 5
     uint32_t cw = __shfl_sync(0xffffffffu, corner, vc & 31);
     cw = (vc >= 32) ? (cw >> 16) : (cw & 0xFFFFu);
@@ -410,30 +499,36 @@ __device__ int fast_traceback_g(const uint32_t* band, int Q, int R, int max_tb, 
     int left_i = lim_i, left_j = lim_j;           // steps still allowed in each direction
     uint32_t where = FT_DIAG, st = FT_DIAG;
     bool off_band = false;
+    constexpr uint32_t kOffBand = 0x80000000u;                                       // "this cell is outside the stored band"
     for (;;) {
         const int lim = min(left_i, left_j);
         if (lim <= 0) break;
+        uint32_t code;                                                               // pointer of the cell the generic step handles
         if (where == FT_DIAG) {
             // probe the diagonal: lane k looks at cell (i - k, j - k)
             const int ii = i - lane, jj = j - lane;
-            bool ok = lane < lim;                                                // implies ii >= 0 and jj >= 0
-            const int v = (ok ? ii : 0) / K, r = (ok ? ii : 0) - v * K;
+            const bool ok = lane < lim;                                              // implies ii >= 0 and jj >= 0
+            const unsigned uii = ok ? (unsigned)ii : 0u;
+            const int v = (int)(uii / (unsigned)K), r = (int)uii - v * K;
             const int t = bm.t_of(jj, v);
-            ok = ok && (unsigned)t < (unsigned)G::kL;
-            const uint32_t code = ok ? code_at(v, r, t) : 0u;
-            const uint32_t is_m = __ballot_sync(0xffffffffu, ok && (code >> 2) == FT_DIAG);
+            const uint32_t c = !ok ? 0u : ((unsigned)t < (unsigned)G::kL) ? code_at(v, r, t) : kOffBand;
+            const uint32_t is_m = __ballot_sync(0xffffffffu, ok && (c >> 2) == FT_DIAG);
             const int run = (is_m == 0xffffffffu) ? 32 : __ffs(~is_m) - 1;
-            if (run > 0) {                                                       // a DIAG pointer in DIAG state: M, stay in DIAG
+            if (run > 0) {                                                           // DIAG pointers in DIAG state: M, stay in DIAG
                 sink.run_m(run);
                 i -= run; j -= run; left_i -= run; left_j -= run;
-                continue;
             }
+            if (run >= lim || run == 32) continue;                                   // step limit reached / the diagonal goes on
+            // lane `run` has already loaded the cell that ends the run: it is handled right here instead of being probed again
+            code = __shfl_sync(0xffffffffu, c, run);
+            if (code == kOffBand) { off_band = true; break; }
+        } else {
+            // gap states: one cell at a time, same in every lane
+            const int v = i / K, r = i - v * K;
+            const int t = bm.t_of(j, v);
+            if ((unsigned)t >= (unsigned)G::kL) { off_band = true; break; }
+            code = code_at(v, r, t);
         }
-        // generic step on cell (i, j) -- same in every lane
-        const int v = i / K, r = i - v * K;
-        const int t = bm.t_of(j, v);
-        if ((unsigned)t >= (unsigned)G::kL) { off_band = true; break; }
-        const uint32_t code = code_at(v, r, t);
         // a DIAG-state cell whose pointer is DEL/INS switches state and is re-read by the reference (:628-633):
         // nothing moves in between, so the gap step is taken right away
         st = (where == FT_DIAG) ? (code >> 2) : where;

@@ -29,7 +29,7 @@ def load_library():
         if not os.path.exists(_LIB_PATH):
             raise FileNotFoundError(_LIB_PATH + " is missing: run `python __graft_entry__.py` (nvcc, sm_100a). "
                                     "There is no CPU fallback for the GACT path.")
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(os.environ.get("DARWIN_GPU_LIB", _LIB_PATH))      # override: A/B of differently built libraries (scripts/)
         L.darwin_gpu_version.restype = C.c_char_p
         L.darwin_gpu_last_error.restype = C.c_char_p
         L.darwin_gpu_last_error.argtypes = [C.c_void_p]
