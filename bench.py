@@ -38,7 +38,7 @@ OPS_PER_CELL = 32          # algorithmic integer ops per DP cell
 # ALU-pipe utilisation of the dominant kernel in the committed `ncu --set full` capture (profiles/, sm__inst_executed_pipe_alu
 # .avg.pct_of_peak_sustained_active); the honest ceiling figure next to roofline.frac, which the tagged-score formulation
 # pushes above 1 (it needs fewer than the 32 nominal ops per cell)
-NCU_ALU_PIPE_BUSY = {"value": 80.2, "source": "profiles/r1_s4_tiles_kernel5_ncu_summary.txt"}
+NCU_ALU_PIPE_BUSY = {"value": 78.3, "source": "profiles/r2_tiles_kernel5_ncu_summary.txt"}
 
 
 class ClockSampler(threading.Thread):
@@ -245,7 +245,7 @@ class ReadLeg:
         self.procs[0].build_seed_index(self.abi.SeedParams.stock(do_overlap), self.chroms, ref_size)
         self.index_s = time.perf_counter() - t0
 
-    def one_pass(self, params, n_reads=None):
+    def one_pass(self, params, n_reads=None, lanes=None):
         """All reads of the shard (or the first n_reads) through upload + darwin_gpu_align_reads, chunk by chunk.
         Returns dict(wall_s, kernel_ms, seed_ms, filter_ms, extend_ms, alignments, locations, cells, ops, h2d, d2h)."""
         n = self.n if n_reads is None else min(self.n, n_reads)
@@ -284,7 +284,7 @@ class ReadLeg:
                 errs.append(e)
 
         t0 = time.perf_counter()
-        th = [threading.Thread(target=lane, args=(k,)) for k in range(len(self.procs))]
+        th = [threading.Thread(target=lane, args=(k,)) for k in range(min(lanes or len(self.procs), len(self.procs)))]
         for x in th:
             x.start()
         for x in th:
@@ -340,12 +340,17 @@ def run_read_leg(name, note, local, rank, world, dist, barrier, sc, int_peak, ge
             acc = t if acc is None else {k: (acc[k] + t[k]) for k in acc}
         barrier()
         acc["wall_s"] = time.perf_counter() - t0
-        a = _agg(dist, dev, world, acc, ["wall_s", "kernel_ms", "extend_ms", "seed_ms", "filter_ms"],
-                 ["reads", "alignments", "locations", "cells", "ops", "h2d", "d2h", "score_sum"])
+        # one more pass from ONE lane over a few chunks: kernels of different lanes share the device, so the per-stage CUDA-event
+        # times above overlap; the single-lane pass gives the extension kernel's own rate (the roofline fraction of this leg)
+        solo = leg.one_pass(prm, n_reads=min(leg.n, 2 * leg.chunk), lanes=1)
+        acc["solo_extend_ms"], acc["solo_cells"] = solo["extend_ms"], solo["cells"]
+        a = _agg(dist, dev, world, acc, ["wall_s", "kernel_ms", "extend_ms", "seed_ms", "filter_ms", "solo_extend_ms"],
+                 ["reads", "alignments", "locations", "cells", "ops", "h2d", "d2h", "score_sum", "solo_cells"])
         lanes_n = len(leg.procs)
         # kernel times are summed over the lanes' calls, which overlap on the device: the device-time rate uses the per-lane
         # share as a lower bound of the busy time, the end-to-end rate uses the wall clock
         gcups_ext = a["cells"] / world / (a["extend_ms"] * 1e-3) / 1e9 if a["extend_ms"] else None
+        gcups_solo = a["solo_cells"] / world / (a["solo_extend_ms"] * 1e-3) / 1e9 if a["solo_extend_ms"] else None
         info = {"workload": name, "reference_bp": genome_len, "reads": int(a["reads"] / passes), "read_len": read_len,
                 "error_profile_sub_ins_del": list(err), "tile_size": T, "tile_overlap": O, "do_overlap": do_overlap,
                 "scaling": "strong" if strong else "weak", "passes": passes, "lanes": lanes_n, "chunk_reads": leg.chunk,
@@ -354,8 +359,11 @@ def run_read_leg(name, note, local, rank, world, dist, barrier, sc, int_peak, ge
                 "wall_ms": a["wall_s"] * 1e3 / passes,
                 "extend_kernel_ms_slowest_rank": a["extend_ms"] / passes, "seed_kernel_ms": a["seed_ms"] / passes,
                 "filter_kernel_ms": a["filter_ms"] / passes,
-                "gcups_extend_kernel_per_gpu": gcups_ext,
-                "roofline_frac_extend_kernel": (gcups_ext * OPS_PER_CELL / int_peak) if (gcups_ext and int_peak) else None,
+                "gcups_extend_kernel_lanes_overlapped": gcups_ext,
+                "gcups_extend_kernel_per_gpu": gcups_solo,
+                "roofline_frac_extend_kernel": (gcups_solo * OPS_PER_CELL / int_peak) if (gcups_solo and int_peak) else None,
+                "extend_kernel_note": "gcups_extend_kernel_per_gpu: single-lane pass over %d reads per rank (kernel alone on the device, slowest rank); "
+                                      "..._lanes_overlapped: cells / summed CUDA-event times of the timed passes, whose lanes share the device (lower bound)" % min(leg.n, 2 * leg.chunk),
                 "h2d_bytes": int(a["h2d"] / passes), "d2h_bytes": int(a["d2h"] / passes),
                 "index_build_s": leg.index_s, "reference_upload_s": leg.ref_upload_s, "score_checksum": int(a["score_sum"] / passes),
                 "note": note}
@@ -420,7 +428,7 @@ def main():
     ap.add_argument("--config4-reads", type=int, default=200000,
                     help="configs[3]: 250 Mbp replicated reference, a FIXED set of this many 10 kbp reads strong-sharded over the ranks (0 = skip)")
     ap.add_argument("--config4-genome", type=int, default=250000000)
-    ap.add_argument("--config5-reads", type=int, default=2000,
+    ap.add_argument("--config5-reads", type=int, default=4000,
                     help="configs[4]: ONT-like 50 kbp reads per GPU, tile_size 256/512/1024 + de novo overlap mode (0 = skip)")
     ap.add_argument("--read-lanes", type=int, default=2, help="host threads (lanes) feeding the read-level legs")
     args = ap.parse_args()
@@ -684,11 +692,11 @@ def main():
         read_legs.update(run_read_leg(
             "config5", "BASELINE.json configs[4]: ONT-like 50 kbp reads at 12 % (sub 4 / ins 3 / del 5) against a 20 Mbp reference, tile_overlap 64",
             local, rank, world, dist, barrier, sc, int_peak, 20000000, args.config5_reads, False, 50000, ONT, 51,
-            1000, [(256, 64), (512, 64), (1024, 64)], passes=1, lanes=args.read_lanes))
+            max(1000, args.config5_reads // 2), [(256, 64), (512, 64), (1024, 64)], passes=1, lanes=args.read_lanes))
         read_legs.update(run_read_leg(
             "config5_denovo", "BASELINE.json configs[4], de novo mode (argv[3] = 1): the read set is its own reference, all-vs-all, "
             "50 kbp ONT-like reads at ~5x coverage of a 10 Mbp genome, tile_size 256",
-            local, rank, world, dist, barrier, sc, int_peak, 10000000, max(200, args.config5_reads // 2), False, 50000, ONT, 52,
+            local, rank, world, dist, barrier, sc, int_peak, 10000000, max(200, args.config5_reads // 4), False, 50000, ONT, 52,
             500, [(256, 64)], passes=1, lanes=args.read_lanes, self_reference=True, do_overlap=1))
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # the reference's CPU chain on bounded samples of the same read sets (reported baseline, N = 1 only)
@@ -715,10 +723,10 @@ def main():
         per_gpu_gcups = value / world
         roof = {"bound": "int_alu", "achieved": per_gpu_gcups * OPS_PER_CELL, "peak": int_peak,
                 "unit": "Gint-op/s", "frac": (per_gpu_gcups * OPS_PER_CELL / int_peak) if int_peak else None,
-                # dram__bytes_read+write of tiles_kernel<5> from the committed ncu capture (profiles/r1_s4_tiles_kernel5_*:
-                # 76.6 MB read + 12.6 MB written per 200k-tile launch = 446 B per tile), scaled to this launch's tile count;
+                # dram__bytes_read+write of tiles_kernel<5> from the committed ncu capture (profiles/r2_tiles_kernel5_*:
+                # 76.6 MB read + 11.6 MB written per 200k-tile launch = 441 B per tile), scaled to this launch's tile count;
                 # algorithmic bytes: ~460 B per tile (320 B packed bases + 32 B request + 16 B result + the used TB words)
-                "traffic": 446.0 * n, "traffic_source": "constant_from_ncu (profiles/: dram__bytes_read+write per tile of the committed capture x tiles; not a live counter)",
+                "traffic": 441.0 * n, "traffic_source": "constant_from_ncu (profiles/: dram__bytes_read+write per tile of the committed capture x tiles; not a live counter)",
                 "alu_pipe_busy_ncu_pct": NCU_ALU_PIPE_BUSY,
                 "peak_detail_glaneops": dict(zip(["vimnmx_u16x2", "viaddmnmx_u16x2", "vimnmx3_u16x2", "iadd3", "lop3_3reg", "imad", "lop3_2reg", "lop3_imm", "prmt", "shfl_idx"], int_detail)) if int_detail else None,
                 "note": "SURVEY 8(d) integer-pipe roofline: 32 algorithmic int-ops per cell; peak = measured packed "
