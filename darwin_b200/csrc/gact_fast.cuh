@@ -23,6 +23,7 @@
 //   (match * min(Q,R) + bias) < 2048, Q <= 64*K, R <= 64*K, corner traceback.  Tiles containing N run the HASN
 //   instantiation (one extra ALU-pipe and one FMA-pipe instruction per cell pair) when mismatch <= sub_N <= 0.
 #pragma once
+#include <type_traits>
 #include "gact_common.cuh"
 
 namespace gact {
@@ -380,66 +381,99 @@ __device__ int fast_forward_multi(const FastConst& fc, const MultiSmemView& v, u
     const int nstrips = (Q + 64 * K - 1) / (64 * K);
     const int vc = (Q - 1) / K, rc = (Q - 1) - vc * K;                   // global virtual lane / row of the corner
     const int sc_step = R - 1 + (vc & 63);                               // step of the corner inside the last strip
-    const int src = (lane + 31) & 31;
+    int src = (lane + 31) & 31;
+    uint32_t mulL = lane == 0 ? fc.shl16 : fc.one[0];                    // lane 0: x * 65536 + boundary (see fast_steps)
+    keep_in_register(src); keep_in_register(mulL);
     const int steps = R + 63;
     constexpr int kHiOff = 32 * (G::kLp - (K + 1));
+    const uint16_t* bHF16 = reinterpret_cast<const uint16_t*>(v.bHF);    // [2j] = Hm, [2j + 1] = F below the previous strip
     uint32_t corner = 0;
+    if (!HASN) {
+        // virtual lanes past the last column read up to 63 bytes behind the reference (nothing they compute is ever read):
+        // keep those bytes valid PRMT indices
+        for (int k = R + lane; k < R + 64; k += 32) v.sref[k] = 0;
+        __syncwarp();
+    }
 
     for (int strip = 0; strip < nstrips; strip++) {
         const int row0 = strip * 64 * K;
-        uint32_t qq[K], Hm[K], E[K], EL[K];
+        uint32_t qa[K], qb[K], Hm[K], E[K], EL[K];
 #pragma unroll
         for (int r = 0; r < K; r++) {
             const int ilo = row0 + K * lane + r, ihi = row0 + K * (lane + 32) + r;
-            qq[r] = (ilo < Q ? qry_code<HASN>(v.sqry[ilo]) : kDummyQry) | ((ihi < Q ? qry_code<HASN>(v.sqry[ihi]) : kDummyQry) << 16);
+            const uint32_t qlo = ilo < Q ? v.sqry[ilo] : kDummyQry, qhi = ihi < Q ? v.sqry[ihi] : kDummyQry;
+            if (HASN) { qa[r] = qry_code<true>(qlo) | (qry_code<true>(qhi) << 16); qb[r] = 0; }
+            else      { qa[r] = qry_table(qlo); qb[r] = qry_table(qhi); }
             Hm[r] = fc.hm_init; E[r] = fc.e_init; EL[r] = fc.el_init;
         }
         uint32_t sendH = fc.hm_init, sendF = fc.f_top, sendFL = fc.fl_top;
         uint32_t diag_in = fc.hm_init;
-        // top boundary of this strip for lane 0's low half, prefetched one step ahead
-        uint32_t topHF = fc.hm_init & 0xFFFFu | (fc.f_top << 16), topFL = fc.fl_top & 0xFFFFu;
-        uint32_t nextHF = topHF, nextFL = topFL;
-        if (strip > 0 && lane == 0) { nextHF = v.bHF[0]; nextFL = v.bFL[0]; }
+        // top boundary of this strip: addends of lane 0's low half (zero in the other lanes); strips below the first read
+        // them per column from shared memory, one step ahead
+        const bool top_smem = strip > 0 && lane == 0;
+        uint32_t addH = lane == 0 ? (fc.hm_init & 0xFFFFu) : 0u, addF = lane == 0 ? (fc.f_top & 0xFFFFu) : 0u,
+                 addFL = lane == 0 ? (fc.fl_top & 0xFFFFu) : 0u;
+        uint32_t nH = addH, nF = addF, nFL = addFL;
+        if (top_smem) { nH = bHF16[0]; nF = bHF16[1]; nFL = v.bFL[0]; }
         const int vg = strip * 64 + lane;                                // my low-half global virtual lane
         int t_lo = -lane - K * vg + bm.c1;                               // t(i,j) at s = 0 (j = -lane)
         uint32_t* bp = gband + (size_t)vg * G::kLp + t_lo;
-        uint32_t rlo = (lane == 0 && R > 0) ? v.sref[0] : kDummyRef, rhi = kDummyRef;  // reference bases of step 0
+        uint32_t rlo = (lane == 0 && R > 0) ? v.sref[0] : (HASN ? kDummyRef : 0u), rhi = HASN ? kDummyRef : 0u;   // bases of step 0
 
         // the corner is the last valid cell of the last strip: its loop ends there (nothing later is ever read)
         const int strip_steps = (strip == nstrips - 1) ? sc_step + 1 : steps;
-        for (int s = 0; s < strip_steps; s++) {
-            uint32_t inH = __shfl_sync(0xffffffffu, sendH, src);
-            uint32_t F   = __shfl_sync(0xffffffffu, sendF, src);
-            uint32_t FL  = __shfl_sync(0xffffffffu, sendFL, src);
-            if (lane == 0) {
-                if (strip > 0) { topHF = nextHF; topFL = nextFL; if (s + 1 < R) { nextHF = v.bHF[s + 1]; nextFL = v.bFL[s + 1]; } }
-                inH = __byte_perm(topHF, inH, 0x5410);                   // low half: boundary Hm; high half: lane 31's low
-                F   = __byte_perm(topHF, F, 0x5432);                     // low half: boundary F (upper half of topHF)
-                FL  = __byte_perm(topFL, FL, 0x5410);
-            }
-            const uint32_t rq = rlo | (rhi << 16);
-            {   // prefetch the reference bases of step s+1: columns s+1-lane and s+1-lane-32
-                const int jl = s + 1 - lane, jh = jl - 32;
-                rlo = ((unsigned)jl < (unsigned)R) ? v.sref[jl] : kDummyRef;
-                rhi = ((unsigned)jh < (unsigned)R) ? v.sref[jh] : kDummyRef;
-            }
-            uint32_t d = diag_in;
-            uint32_t acc0 = 0, acc1 = 0;
+        // FILL: the first 63 steps of a strip, while some virtual lanes are still left of column 0 (dummy base)
+        auto run = [&](auto fill_c, int s0, int s1) {
+            constexpr bool FILL = decltype(fill_c)::value;
+            for (int s = s0; s < s1; s++) {
+                if (top_smem) {
+                    addH = nH; addF = nF; addFL = nFL;
+                    if (s + 1 < R) { nH = bHF16[2 * (s + 1)]; nF = bHF16[2 * (s + 1) + 1]; nFL = v.bFL[s + 1]; }
+                }
+                const uint32_t inH = __shfl_sync(0xffffffffu, sendH, src) * mulL + addH;
+                uint32_t F  = __shfl_sync(0xffffffffu, sendF, src) * mulL + addF;
+                uint32_t FL = __shfl_sync(0xffffffffu, sendFL, src) * mulL + addFL;
+                const uint32_t rq = HASN ? (rlo | (rhi << 16)) : (rhi * 256u + rlo + 0x8480u);   // !HASN: PRMT selector (ref_selector)
+                uint32_t dm = 0;
+                if (!HASN && FILL) dm = (s < lane ? 1u : 0u) | (s < lane + 32 ? 0x10000u : 0u);
+                {   // prefetch the reference bases of step s+1: columns s+1-lane and s+1-lane-32
+                    const int jl = s + 1 - lane, jh = jl - 32;
+                    if (HASN || FILL) {
+                        rlo = ((unsigned)jl < (unsigned)R) ? v.sref[jl] : (HASN ? kDummyRef : 0u);
+                        rhi = ((unsigned)jh < (unsigned)R) ? v.sref[jh] : (HASN ? kDummyRef : 0u);
+                    } else {
+                        rlo = v.sref[jl]; rhi = v.sref[jh];               // both >= 0 after the fill; tail bytes zeroed above
+                    }
+                }
+                uint32_t d = diag_in;
+                uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
-            for (int r = 0; r < K; r++) {
-                const uint32_t code = fast_cell<S, HASN>(kr, rq, qq[r], d, Hm[r], E[r], EL[r], F, FL);
-                if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
+                for (int r = 0; r < K; r++) {
+                    uint32_t code;
+                    if (HASN) {
+                        code = fast_cell<S, true>(kr, rq, qa[r], d, Hm[r], E[r], EL[r], F, FL);
+                    } else {
+                        uint32_t t = prmt(qa[r], qb[r], rq);             // 1 = mismatch, per half
+                        if (FILL) t |= dm;
+                        const uint32_t sb = t * kr.negc32 + kr.pkc32;
+                        code = fast_cell_core<S>(kr, sb, d, Hm[r], E[r], EL[r], F, FL);
+                    }
+                    if (r < 3) acc0 += code << (5 * r); else acc1 += code << (5 * (r - 3));
+                }
+                diag_in = inH;
+                sendH = Hm[K - 1]; sendF = F; sendFL = FL;
+                if (lane == 31 && strip + 1 < nstrips && (unsigned)(s - 63) < (unsigned)R) {   // bottom row of the strip
+                    v.bHF[s - 63] = __byte_perm(sendH, sendF, 0x7632);
+                    v.bFL[s - 63] = (uint16_t)(sendFL >> 16);
+                }
+                if ((unsigned)t_lo < (unsigned)G::kL) __stcg(bp, __byte_perm(acc0, acc1, 0x5410));
+                if ((unsigned)(t_lo - 32 * (K + 1)) < (unsigned)G::kL) __stcg(bp + kHiOff, __byte_perm(acc0, acc1, 0x7632));
+                t_lo++; bp++;
             }
-            diag_in = inH;
-            sendH = Hm[K - 1]; sendF = F; sendFL = FL;
-            if (lane == 31 && strip + 1 < nstrips && (unsigned)(s - 63) < (unsigned)R) {   // bottom row of the strip
-                v.bHF[s - 63] = __byte_perm(sendH, sendF, 0x7632);
-                v.bFL[s - 63] = (uint16_t)(sendFL >> 16);
-            }
-            if ((unsigned)t_lo < (unsigned)G::kL) __stcg(bp, __byte_perm(acc0, acc1, 0x5410));
-            if ((unsigned)(t_lo - 32 * (K + 1)) < (unsigned)G::kL) __stcg(bp + kHiOff, __byte_perm(acc0, acc1, 0x7632));
-            t_lo++; bp++;
-        }
+        };
+        const int fill = min(strip_steps, 63);
+        run(std::true_type{}, 0, fill);
+        run(std::false_type{}, fill, strip_steps);
         __syncwarp();
         if (strip == nstrips - 1) {
 #pragma unroll
