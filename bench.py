@@ -130,14 +130,14 @@ def cpu_reference_leg(arena, req, seconds_target, threads=None):
         # ~0.2 GCUPS/core: size the sample for `seconds_target`
         n = int(min(len(req), max(cores * 8, seconds_target * cores * 0.2e9 / cells_per_tile)))
         sample = np.ascontiguousarray(req[:n])
-        _, _, secs = ref.tiles(arena, sample, 1, tb_words_per_req=44, threads=cores)
+        _, _, secs = ref.tiles(arena, sample, 1, tb_words_per_req=22, threads=cores)
     else:
         port = oracle.port(abi.Scoring.from_values())
         cores = 1
         n = int(min(len(req), max(8, seconds_target * 0.02e9 / cells_per_tile)))
         sample = np.ascontiguousarray(req[:n])
         t0 = time.time()
-        port.tiles(arena, sample, 1, oracle.Port.STREAM, tb_words_per_req=44)
+        port.tiles(arena, sample, 1, oracle.Port.STREAM, tb_words_per_req=22)
         secs = time.time() - t0
     gcups = n * cells_per_tile / secs / 1e9
     return {"value": gcups, "unit": "GCUPS", "cores": cores, "kind": kind,
@@ -453,7 +453,9 @@ def main():
     arena, req = make_workload(args.tiles, 1 + rank)          # each rank owns an independent shard (weak scaling)
     n = len(req)
     cells = float(n) * TILE * TILE
-    tbw = 2 * TILE // 16 + 2
+    # TB words per tile: a corner traceback takes at most Q + R = 2 * TILE steps, 32 two-bit ops per 64-bit word
+    # (Processor.cpp:568-582) -> 20 words at T = 320, + 2 spare; the reference returns only the used words per tile
+    tbw = 2 * TILE // 32 + 2
     sc = abi.Scoring.from_values()
     proc = darwin_b200.Processor(len(arena), local)
     proc.InitializeScoringParameters(sc)
