@@ -717,6 +717,9 @@ static int configure_kernels(DarwinGpu* h) {
     int rc;
     if ((rc = configure_variant<0>(h)) || (rc = configure_variant<4>(h)) || (rc = configure_variant<5>(h)) ||
         (rc = configure_variant<6>(h)) || (rc = configure_variant<8>(h))) return rc;
+    // the packing kernel runs beside the resident tile / extension kernels of other lanes: same shared-memory carve-out as
+    // theirs, so that an SM does not have to drain to switch its L1 / shared-memory split
+    CK(cudaFuncSetAttribute(pack_arena_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int f = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f, filter_kernel, kFilterWarps * 32, 0));
     h->ctas_filter = h->sm_count * std::max(1, f);

@@ -16,13 +16,20 @@
 
 namespace {
 
-// appends "<count><op>" at out[pos...]; returns false when it does not fit (pos keeps counting so the caller learns the size)
+// appends "<count><op>" at out[pos...]; returns false when it does not fit (pos keeps counting so the caller learns the size).
+// Hand-rolled decimal conversion: a 10 kbp alignment at 15 % error has ~3 000 runs, and snprintf per run was the largest
+// host cost of the SAM stage.
 inline bool put_run(char* out, uint64_t cap, uint64_t& pos, uint64_t count, char op) {
     char buf[24];
-    const int n = snprintf(buf, sizeof(buf), "%llu%c", (unsigned long long)count, op);
-    const bool fits = pos + (uint64_t)n <= cap;
-    if (fits && out) memcpy(out + pos, buf, (size_t)n);
-    pos += (uint64_t)n;
+    int n = 0;
+    do { buf[n++] = (char)('0' + count % 10); count /= 10; } while (count);
+    const bool fits = pos + (uint64_t)n + 1 <= cap;
+    if (fits && out) {
+        char* w = out + pos;
+        for (int k = n - 1; k >= 0; k--) *w++ = buf[k];
+        *w = op;
+    }
+    pos += (uint64_t)n + 1;
     return fits;
 }
 
