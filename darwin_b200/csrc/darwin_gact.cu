@@ -203,16 +203,16 @@ __device__ void process_tile(WarpCtx& cx, const KernelScoring& ks, const TileJob
                 // shapes the packed exact path accepts go there directly
                 if (single || !xok || !large || has_n) {
                     int score;
-                    if (!has_n) score = single ? fast_forward<KK>(fc, v, t.Q, t.R)
+                    if (!has_n) score = single ? fast_forward<KK>(fc, v, t.Q, t.R, t.band_shift)
                                       : !wide ? fast_forward_multi<KM, 5, kBandHalf>(fc, mv, gband, t.Q, t.R)
                                               : fast_forward_multi<KM, 4, kBandHalfWide>(ks.fcw, mv, gband, t.Q, t.R);
-                    else        score = single ? fast_forward<KK, true>(fc, v, t.Q, t.R)
+                    else        score = single ? fast_forward<KK, true>(fc, v, t.Q, t.R, t.band_shift)
                                       : !wide ? fast_forward_multi<KM, 5, kBandHalf, true>(fc, mv, gband, t.Q, t.R)
                                               : fast_forward_multi<KM, 4, kBandHalfWide, true>(ks.fcw, mv, gband, t.Q, t.R);
                     // warp-uniform traceback on a copy of the sink: committed only when the clean rule holds
                     Sink trial = sink;
                     TileOut o2{};
-                    const int rc = single ? fast_traceback<KK, false>(v.band, t.Q, t.R, t.max_tb, o2, trial)
+                    const int rc = single ? fast_traceback<KK, false>(v.band, t.Q, t.R, t.max_tb, o2, trial, t.band_shift)
                                  : !wide ? fast_traceback<KM, true>(gband, t.Q, t.R, t.max_tb, o2, trial)
                                          : fast_traceback<KM, true, Sink, kBandHalfWide>(gband, t.Q, t.R, t.max_tb, o2, trial);
                     if (rc == FAST_OK) {
@@ -423,6 +423,8 @@ __global__ void filter_finish_kernel(const DarwinFilterCand* __restrict__ cands,
     out[k] = r;
 }
 
+constexpr int kMaxBandShift = 20;       // the corner itself must stay well inside the +-32 band
+
 // extender_body::operator() (extender.cpp:9-1065): persistent warps pull ANCHORS and walk their tiles.
 template <int K>
 __global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 3 : (K == 8) ? 5 : 11)
@@ -454,6 +456,9 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
         const uint32_t lcap = ea.slot_left[idx], rcap = ea.slot_size[idx] - lcap;
         uint32_t overflow = 0;
         const uint32_t rerun0 = cx.n_rerun;
+        // running estimate of (query - reference) bases consumed per tile: reads with more insertions than deletions drift off
+        // the corner diagonal by that much per tile, and a band centred on the corner diagonal loses their paths (exact rerun)
+        int drift = 0;
 
         while (!(a.ldone && a.rdone)) {
             const int left = !a.ldone;
@@ -461,6 +466,7 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
             TileJob t; int rt, qt;
             next_tile(a, T, t, rt, qt);
             t.max_tb = 2 * T;                                                    // extender.cpp:127
+            t.band_shift = a.large ? 0 : max(-kMaxBandShift, min(kMaxBandShift, (drift * 5) / 8));   // ~ half the drift over a full tile
             if (a.large) a.n_large++;
             a.n_tiles++; a.cells += (uint64_t)t.R * (uint64_t)t.Q;
             int crt = T, cqt = T;
@@ -484,6 +490,7 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
                 a.cq = min(a.cq + cr_.qry_steps, a.QL);
                 a.nright += cr_.consumed;
             }
+            if (!a.large && cr_.consumed) drift = (drift + (int)cr_.qry_steps - (int)cr_.ref_steps) / 2;
             if (tfl & 1) a.flags |= DARWIN_ALN_LONG_INS_PATH;
             if (tfl & 0x100) overflow = 1;
             after_tile(a, len);

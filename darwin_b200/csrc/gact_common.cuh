@@ -34,6 +34,8 @@ struct TileJob {
     int R, Q;             // ref_size, query_size
     uint32_t flags;       // align_fields
     int max_tb;           // max_tb_steps
+    int band_shift;       // single-strip fast path: the stored band is centred this many cells off the corner diagonal (0 = centred);
+                          // a scheduling hint of the anchor walker -- it decides fast path vs exact rerun, never the result
 };
 
 struct TileOut {

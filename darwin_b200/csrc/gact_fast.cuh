@@ -129,10 +129,12 @@ template <int K> struct FastSmemView {
 // Band addressing shared by the forward pass and the traceback.
 template <int K, int BH = kBandHalf> struct BandMap {
     int c1;               // t(i,j) = j - K*v + c1
-    __device__ BandMap(int Q, int R) {
+    __device__ BandMap(int Q, int R, int shift = 0) {
         // virtual lane v crosses the corner diagonal (i - j = Q - R) at its middle row K*v + K/2:
-        // step s_c(v) = (K+1)*v + K/2 - (Q - R); window t = s - s_c(v) + BH
-        c1 = (Q - R) - K / 2 + BH;
+        // step s_c(v) = (K+1)*v + K/2 - (Q - R); window t = s - s_c(v) + BH.
+        // The band covers the diagonals (i - j) - (Q - R) in [-BH - K/2 - shift, BH + K/2 - 1 - shift]: shift > 0 moves it towards
+        // paths that consume more query than reference on their way from the corner to the origin (insertion-rich reads).
+        c1 = (Q - R) - K / 2 + BH - shift;
     }
     __device__ __forceinline__ int t_of(int j, int v) const { return j - K * v + c1; }
 };
@@ -290,7 +292,7 @@ __device__ __forceinline__ void fast_steps(const FastRegs& kr, FwdState<K>& st, 
 }
 
 template <int K, bool HASN = false>
-__device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q, int R) {
+__device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q, int R, int band_shift = 0) {
     using G = FastGeom<K>;
     const int lane = lane_id();
     // per reference column: HASN: code pair P[32 + j] = r[j] | r[j-32] << 8, dummy base outside [0,R); otherwise the PRMT
@@ -311,7 +313,7 @@ __device__ int fast_forward(const FastConst& fc, const FastSmemView<K>& v, int Q
         st.Hm[r] = fc.hm_init; st.E[r] = fc.e_init; st.EL[r] = fc.el_init;
     }
     __syncwarp();
-    const BandMap<K> bm(Q, R);
+    const BandMap<K> bm(Q, R, band_shift);
     const int vc = (Q - 1) / K, rc = (Q - 1) - vc * K, sc_step = R - 1 + vc;
     const FastRegs kr(fc);                                               // scoring constants in registers
     st.sendH = fc.hm_init; st.sendF = fc.f_top; st.sendFL = fc.fl_top;
@@ -504,18 +506,18 @@ template <int K_, int BH_, int LP_, int W_ = 1> struct TraceGeo {
 };
 
 template <class GEO, bool GLOBAL, class Sink>
-__device__ int fast_traceback_g(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink);
+__device__ int fast_traceback_g(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink, int band_shift);
 
 template <int K, bool GLOBAL, class Sink, int BH = kBandHalf>
-__device__ __forceinline__ int fast_traceback(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
-    return fast_traceback_g<TraceGeo<K, BH, FastGeom<K, BH>::kLp, GLOBAL ? 1 : FastGeom<K, BH>::kW>, GLOBAL, Sink>(band, Q, R, max_tb, out, sink);
+__device__ __forceinline__ int fast_traceback(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink, int band_shift = 0) {
+    return fast_traceback_g<TraceGeo<K, BH, FastGeom<K, BH>::kLp, GLOBAL ? 1 : FastGeom<K, BH>::kW>, GLOBAL, Sink>(band, Q, R, max_tb, out, sink, band_shift);
 }
 
 template <class GEO, bool GLOBAL, class Sink>
-__device__ int fast_traceback_g(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink) {
+__device__ int fast_traceback_g(const uint32_t* band, int Q, int R, int max_tb, TileOut& out, Sink& sink, int band_shift) {
     using G = GEO;
     constexpr int K = GEO::K, BH = GEO::BH;
-    const BandMap<K, BH> bm(Q, R);
+    const BandMap<K, BH> bm(Q, R, band_shift);
     const int lane = lane_id();
     // 5-bit pointer of cell (row r of virtual lane v, window position t)
     auto code_at = [&](int v, int r, int t) -> uint32_t {
