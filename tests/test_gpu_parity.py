@@ -117,6 +117,28 @@ def test_extend_random_vs_oracle(gpu):
     p.close()
 
 
+@pytest.mark.parametrize("err", [(0.015, 0.09, 0.045), (0.015, 0.045, 0.09)], ids=["insertion_rich", "deletion_rich"])
+def test_extend_drifting_reads_vs_oracle(gpu, err):
+    """Reads whose paths drift off the tile diagonal (PacBio-like 9 % insertions, and the mirror image): the anchor walker centres
+    the band of the next tile on the drift of the previous ones (TileJob::band_shift) -- a scheduling hint that must never show
+    in the result, and that keeps these tiles on the packed path."""
+    from test_host_logic import synthetic_anchor_set
+    sc = abi.Scoring.from_values()
+    arena, anchors, hits = synthetic_anchor_set(seed=33, n_reads=32, read_len=6000, ref_len=120000, err=err)
+    p = gpu(len(arena), sc)
+    p.InitializeReferenceMemory(0, arena)
+    for (T, O) in ((384, 64), (320, 128), (256, 64)):
+        st0 = p.stats()
+        res, ops = p.extender_body(anchors, hits, T, O, 0)
+        st = p.stats()
+        pres, pops = oracle.port(sc).extend(arena, abi.ExtendParams(T, O, 0, 0), anchors, hits, oracle.Port.STREAM)
+        assert alignments_equal(pres, pops, res, ops, ALN_FIELDS_OURS) == []
+        assert (res["flags"] & 1).sum() > 0
+        tiles = int(res["n_tiles"].sum())
+        assert (st.tiles_rerun - st0.tiles_rerun) < 0.25 * tiles                 # (half of the reads carry indel runs of up to 50 bases)
+    p.close()
+
+
 def test_upload_spans_equals_single_upload(gpu):
     """darwin_gpu_upload_spans (many spans, shared staging buffers, odd boundaries, one span larger than a staging buffer)
     leaves the arena exactly as one darwin_gpu_upload of the whole range does."""

@@ -7,7 +7,7 @@ import oracle
 from darwin_b200 import abi, synth, gact
 
 
-def synthetic_anchor_set(seed, n_reads, read_len, ref_len=60000):
+def synthetic_anchor_set(seed, n_reads, read_len, ref_len=60000, err=(0.05, 0.05, 0.05)):
     """Arena laid out like the reference's (Index.cpp:10-17, main.cpp:430-456, :645-686): 128 'N', one padded
     chromosome, then 128-aligned 'N'-padded reads.  One anchor per read at its true position, with chained
     hits every ~60 bases along the true diagonal (ascending left list, descending right list)."""
@@ -28,7 +28,7 @@ def synthetic_anchor_set(seed, n_reads, read_len, ref_len=60000):
         else:
             g0 = int(rng.integers(0, ref_len - L))
         src = genome[g0:min(ref_len, g0 + L)]
-        read = synth.mutate(rng, src, 0.05, 0.05, 0.05, indel_run=(2, 50) if k % 2 else None)
+        read = synth.mutate(rng, src, err[0], err[1], err[2], indel_run=(2, 50) if k % 2 else None)
         strand = k % 2
         fwd = synth.revcomp(read) if strand else read     # what is stored in the arena is the forward read
         rl = len(fwd)
