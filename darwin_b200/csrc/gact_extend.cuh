@@ -62,7 +62,11 @@ struct SmemOpSink {
     __device__ __forceinline__ int count() const { return n; }
     __device__ __forceinline__ void finish() { if (shift) { if (n <= cap) *wptr = cur; else overflow = 1; } }
 };
-constexpr int kOpsSmemBytes = 1024;                 // 4096 ops >= i_steps + j_steps of the largest tile (1984 + 960)
+constexpr int kOpsSmemBytes = 1024;                 // K = 0 kernels: 4096 ops >= i_steps + j_steps of the largest tile (1984 + 960)
+// K > 0 kernels keep a small dedicated buffer (tiles with Q + R <= kOpsSmallOps: every single-strip tile) so that 12 warps fit
+// an SM; larger tiles (tile_size 1024, the 1984x960 stall tiles) record their ops in the big raw TMA windows of the warp, which
+// are dead once the tile has been staged and which none of their paths (multi-strip, packed / unpacked exact) touches again
+constexpr int kOpsSmallBytes = 336, kOpsSmallOps = kOpsSmallBytes * 4;
 
 // ... and the whole warp consumes them (extender.cpp:280-331 / :427-466 and the rc twins): one 32-op TB word per
 // iteration, one lane per op.  The reference's `break` leaves only the 32-op loop, so inside word w the ops up to and
