@@ -326,6 +326,10 @@ def run_read_leg(name, note, local, rank, world, dist, barrier, sc, int_peak, ge
     else:
         lo, hi = 0, n_total
         seed = seed + 1000 * rank                                       # weak scaling: every rank owns its own read set
+    if strong:
+        # strong scaling: keep at least four chunks per rank (two per lane) so that a rank's uploads, host work and op D2H still
+        # overlap the other lane's kernels when its shard gets small; never below what fills the device a few times over
+        chunk_reads = max(4000, min(chunk_reads, -(-(hi - lo) // 4)))
     leg = ReadLeg(local, sc, genome_len, n_total, lo, hi, read_len, err, seed, chunk_reads, lanes, self_reference)
     leg.build_index(do_overlap)
     out = {}
