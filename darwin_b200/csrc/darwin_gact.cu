@@ -138,7 +138,7 @@ template <int K> struct KernelGeom {
     static_assert(K == 0 || 16000 + 2 * (size_t)kRawBig <= kTileBytes, "spare space for the big raw windows");
     static constexpr size_t kPerWarp = kMbarOff + 16;                    // tiles kernel
     static constexpr size_t kOpsOff = kPerWarp;
-    static constexpr size_t kPerWarpExtend = kPerWarp + (K == 0 ? kOpsSmemBytes : kOpsSmallBytes);   // + op buffer of the anchor walker
+    static constexpr size_t kPerWarpExtend = kPerWarp + (K == 0 ? kOpsSmemBytes : OpsSmall<K>::kBytes);   // + op buffer of the anchor walker
     static constexpr size_t kSmemExtend = kPerWarpExtend * kWarps;
     static constexpr size_t kSmem = kPerWarp * kWarps;
 };
@@ -472,9 +472,9 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
             int crt = T, cqt = T;
             if (a.large && ea.do_overlap == 0) { crt = rt; cqt = qt; }           // extender.cpp:261 / :408
             // lane 0 walks the traceback and records the ops in shared memory; the warp then consumes them together
-            const bool small_ops = K == 0 || t.Q + t.R <= kOpsSmallOps;          // (K = 0: one buffer for every tile)
+            const bool small_ops = K == 0 || t.Q + t.R <= OpsSmall<K>::kOps;     // (K = 0: one buffer for every tile)
             uint32_t* opbuf = reinterpret_cast<uint32_t*>(cx.wsmem + (small_ops ? KernelGeom<K>::kOpsOff : KernelGeom<K>::kBigRawOff));
-            SmemOpSink sink{opbuf, 0, K == 0 ? kOpsSmemBytes * 4 : small_ops ? kOpsSmallOps : 2 * kRawBig * 4, 0, 0u, 0, lane == 0};
+            SmemOpSink sink{opbuf, 0, K == 0 ? kOpsSmemBytes * 4 : small_ops ? OpsSmall<K>::kOps : 2 * kRawBig * 4, 0, 0u, 0, lane == 0};
             TileOut out{};
             process_tile<K>(cx, ks, t, true, out, sink);
             if (lane == 0) sink.finish();

@@ -63,10 +63,12 @@ struct SmemOpSink {
     __device__ __forceinline__ void finish() { if (shift) { if (n <= cap) *wptr = cur; else overflow = 1; } }
 };
 constexpr int kOpsSmemBytes = 1024;                 // K = 0 kernels: 4096 ops >= i_steps + j_steps of the largest tile (1984 + 960)
-// K > 0 kernels keep a small dedicated buffer (tiles with Q + R <= kOpsSmallOps: every single-strip tile) so that 12 warps fit
-// an SM; larger tiles (tile_size 1024, the 1984x960 stall tiles) record their ops in the big raw TMA windows of the warp, which
-// are dead once the tile has been staged and which none of their paths (multi-strip, packed / unpacked exact) touches again
-constexpr int kOpsSmallBytes = 336, kOpsSmallOps = kOpsSmallBytes * 4;
+// K > 0 kernels keep a small dedicated buffer -- as many ops as the largest single-strip tile of the geometry can produce
+// (Q + R <= 128 K) -- so that 12 warps fit an SM (K <= 6: 18 096 + 192 B of dynamic + 128 B of static + 1 KB of reserved shared
+// memory per warp); larger tiles (tile_size 1024, the 1984x960 stall tiles) record their ops in the big raw TMA windows of the
+// warp, which are dead once the tile has been staged and which none of their paths (multi-strip, packed / unpacked exact)
+// touches again
+template <int K> struct OpsSmall { static constexpr int kOps = 128 * (K == 0 ? 1 : K), kBytes = kOps / 4; };
 
 // ... and the whole warp consumes them (extender.cpp:280-331 / :427-466 and the rc twins): one 32-op TB word per
 // iteration, one lane per op.  The reference's `break` leaves only the 32-op loop, so inside word w the ops up to and
