@@ -314,7 +314,7 @@ def _agg(dist, dev, world, tot, keys_max, keys_sum):
 
 
 def run_read_leg(name, note, local, rank, world, dist, barrier, sc, int_peak, genome_len, n_total, strong, read_len, err, seed,
-                 chunk_reads, tiles, passes=1, lanes=2, self_reference=False, do_overlap=0):
+                 chunk_reads, tiles, passes=1, lanes=2, self_reference=False, do_overlap=0, wave_sized=False):
     """tiles: list of (tile_size, tile_overlap) run on the same resident case; returns {name or name_T<T>: info}."""
     import torch
     from darwin_b200 import abi, workloads
@@ -333,20 +333,30 @@ def run_read_leg(name, note, local, rank, world, dist, barrier, sc, int_peak, ge
     leg = ReadLeg(local, sc, genome_len, n_total, lo, hi, read_len, err, seed, chunk_reads, lanes, self_reference)
     leg.build_index(do_overlap)
     out = {}
+    chunk_cap, n_target = leg.chunk, leg.n
     for (T, O) in tiles:
         prm = abi.AlignParams.stock(T, O, do_overlap)
-        leg.one_pass(prm, n_reads=min(leg.n, 2 * leg.chunk * len(leg.procs)))       # warm-up: buffers grown, pools filled
+        slots, n_run = None, leg.n
+        if wave_sized:
+            # few long reads: one warp per anchor, ~270 tiles each -- a launch runs in whole waves of `slots` anchors, so a chunk is
+            # a little under a whole number of waves (darwin_gpu_extend_slots; 2 003 anchors on 1 776 warps took two wave times)
+            slots = leg.procs[0].extend_slots(T)
+            waves = max(1, -(-1500 // slots))
+            leg.chunk = max(1, min(chunk_cap, int(0.96 * slots * waves)))
+            per_round = leg.chunk * len(leg.procs)
+            n_run = min(n_target, per_round * max(1, int(round(n_target / per_round))))
+        leg.one_pass(prm, n_reads=min(n_run, 2 * leg.chunk * len(leg.procs)))       # warm-up: buffers grown, pools filled
         acc = None
         barrier()
         t0 = time.perf_counter()
         for _ in range(passes):
-            t = leg.one_pass(prm)
+            t = leg.one_pass(prm, n_reads=n_run)
             acc = t if acc is None else {k: (acc[k] + t[k]) for k in acc}
         barrier()
         acc["wall_s"] = time.perf_counter() - t0
         # one more pass from ONE lane over a few chunks: kernels of different lanes share the device, so the per-stage CUDA-event
         # times above overlap; the single-lane pass gives the extension kernel's own rate (the roofline fraction of this leg)
-        solo = leg.one_pass(prm, n_reads=min(leg.n, 2 * leg.chunk), lanes=1)
+        solo = leg.one_pass(prm, n_reads=min(n_run, 2 * leg.chunk), lanes=1)
         acc["solo_extend_ms"], acc["solo_cells"] = solo["extend_ms"], solo["cells"]
         a = _agg(dist, dev, world, acc, ["wall_s", "kernel_ms", "extend_ms", "seed_ms", "filter_ms", "solo_extend_ms"],
                  ["reads", "alignments", "locations", "cells", "ops", "h2d", "d2h", "score_sum", "solo_cells"])
@@ -367,7 +377,8 @@ def run_read_leg(name, note, local, rank, world, dist, barrier, sc, int_peak, ge
                 "gcups_extend_kernel_per_gpu": gcups_solo,
                 "roofline_frac_extend_kernel": (gcups_solo * OPS_PER_CELL / int_peak) if (gcups_solo and int_peak) else None,
                 "extend_kernel_note": "gcups_extend_kernel_per_gpu: single-lane pass over %d reads per rank (kernel alone on the device, slowest rank); "
-                                      "..._lanes_overlapped: cells / summed CUDA-event times of the timed passes, whose lanes share the device (lower bound)" % min(leg.n, 2 * leg.chunk),
+                                      "..._lanes_overlapped: cells / summed CUDA-event times of the timed passes, whose lanes share the device (lower bound)" % min(n_run, 2 * leg.chunk),
+                "extend_slots": slots,
                 "h2d_bytes": int(a["h2d"] / passes), "d2h_bytes": int(a["d2h"] / passes),
                 "index_build_s": leg.index_s, "reference_upload_s": leg.ref_upload_s, "score_checksum": int(a["score_sum"] / passes),
                 "note": note}
@@ -698,7 +709,7 @@ def main():
         read_legs.update(run_read_leg(
             "config5", "BASELINE.json configs[4]: ONT-like 50 kbp reads at 12 % (sub 4 / ins 3 / del 5) against a 20 Mbp reference, tile_overlap 64",
             local, rank, world, dist, barrier, sc, int_peak, 20000000, args.config5_reads, False, 50000, ONT, 51,
-            max(1000, args.config5_reads // 2), [(256, 64), (512, 64), (1024, 64)], passes=1, lanes=args.read_lanes))
+            max(1000, int(args.config5_reads * 0.6)), [(256, 64), (512, 64), (1024, 64)], passes=1, lanes=args.read_lanes, wave_sized=True))
         read_legs.update(run_read_leg(
             "config5_denovo", "BASELINE.json configs[4], de novo mode (argv[3] = 1): the read set is its own reference, all-vs-all, "
             "50 kbp ONT-like reads at ~5x coverage of a 10 Mbp genome, tile_size 256",

@@ -1024,6 +1024,19 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
     return DARWIN_OK;
 }
 
+int darwin_gpu_extend_slots(DarwinGpu* h, int tile_size, int* slots) {
+    if (!h || !slots || tile_size <= 0 || tile_size > kMaxTile) return DARWIN_ERR_INVALID;
+    if (!h->have_scoring) return DARWIN_ERR_NOT_READY;
+    switch (pick_k(h, tile_size, 1)) {
+        case 4: *slots = h->ctas_extend[variant_index(4)] * KernelGeom<4>::kWarps; break;
+        case 5: *slots = h->ctas_extend[variant_index(5)] * KernelGeom<5>::kWarps; break;
+        case 6: *slots = h->ctas_extend[variant_index(6)] * KernelGeom<6>::kWarps; break;
+        case 8: *slots = h->ctas_extend[variant_index(8)] * KernelGeom<8>::kWarps; break;
+        default: *slots = h->ctas_extend[variant_index(0)] * KernelGeom<0>::kWarps; break;
+    }
+    return DARWIN_OK;
+}
+
 int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, int n,
                      DarwinTileRes* res, uint64_t* tb_words, int tb_words_per_req) try {
     if (!h || n < 0 || (n && (!req || !res))) return DARWIN_ERR_INVALID;

@@ -56,13 +56,14 @@ def load_library():
         L.darwin_gpu_cigar.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.darwin_gpu_sam_select.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
         L.darwin_gpu_int_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.darwin_gpu_extend_slots.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
 
 EXPORTS = ("darwin_gpu_create", "darwin_gpu_create_shared", "darwin_gpu_destroy", "darwin_gpu_set_scoring", "darwin_gpu_upload",
            "darwin_gpu_tiles", "darwin_gpu_tiles_device", "darwin_gpu_extend", "darwin_gpu_filter", "darwin_gpu_seed_index",
-           "darwin_gpu_seed_index_share", "darwin_gpu_seed_index_read", "darwin_gpu_seed", "darwin_gpu_align_reads", "darwin_gpu_host_alloc", "darwin_gpu_host_free", "darwin_gpu_upload_spans", "darwin_gpu_stats", "darwin_gpu_int_peak",
+           "darwin_gpu_seed_index_share", "darwin_gpu_seed_index_read", "darwin_gpu_seed", "darwin_gpu_align_reads", "darwin_gpu_host_alloc", "darwin_gpu_host_free", "darwin_gpu_upload_spans", "darwin_gpu_stats", "darwin_gpu_int_peak", "darwin_gpu_extend_slots",
            "darwin_gpu_last_error", "darwin_gpu_version", "darwin_gpu_cigar", "darwin_gpu_sam_select")
 
 
@@ -244,6 +245,12 @@ class Processor:
                                                abi.ptr(hp) if len(hp) else None, C.c_uint64(len(hp)),
                                                abi.ptr(res), abi.ptr(ops), C.c_uint64(ops_cap)))
         return res, ops
+
+    def extend_slots(self, tile_size):
+        """Anchors one extension launch keeps in flight at this tile_size (darwin_gpu_extend_slots): the wave size of long reads."""
+        n = C.c_int(0)
+        self._check(self.lib.darwin_gpu_extend_slots(self.h, int(tile_size), C.byref(n)))
+        return n.value
 
     def int_peak(self):
         """Measured issue rates (G lane-ops/s): VIMNMX.U16x2, VIADDMNMX.U16x2, VIMNMX3.U16x2, IADD3, LOP3 (3 regs),

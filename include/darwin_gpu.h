@@ -343,6 +343,12 @@ void  darwin_gpu_host_free(void* p);
 
 int darwin_gpu_stats(DarwinGpu* h, DarwinGpuStats* out);
 
+/* Batch sizing hint for darwin_gpu_extend / darwin_gpu_align_reads (no counterpart in the reference, whose batch is one read,
+ * main.cpp:299,:688): *slots = number of anchors one launch keeps in flight at this tile_size (one persistent warp per
+ * anchor).  With many short anchors it does not matter; a batch of FEW LONG reads (50 kbp: ~270 tiles per anchor) runs in
+ * whole waves of that size, so a host that has the choice hands over a little under a multiple of it.  Needs the scoring. */
+int darwin_gpu_extend_slots(DarwinGpu* h, int tile_size, int* slots);
+
 /* Roofline denominator: measured issue rate, in 1e9 32-bit lane-ops per second, of packed-int16 /
  * integer instructions on this GPU (8 independent chains per thread, operands all loop-variant):
  * out[0] VIMNMX.U16x2 (2-input min/max), out[1] VIADDMNMX.U16x2, out[2] VIMNMX3.U16x2, out[3] IADD3, out[4] LOP3,
