@@ -283,6 +283,27 @@ def test_large_tiles_score_only_prepass(gpu, vals):
     p.close()
 
 
+def test_extend_slots_reports_whole_waves(gpu):
+    """darwin_gpu_extend_slots: anchors one launch keeps in flight -- a multiple of the SM count for every tile size, refused
+    before the scoring is set (the geometry depends on it) and for tile sizes beyond the largest tile."""
+    import torch
+    import darwin_b200
+    from darwin_b200.gact import DarwinGpuError
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    raw = darwin_b200.Processor(1 << 20)
+    with pytest.raises(DarwinGpuError):
+        raw.extend_slots(384)
+    raw.close()
+    p = gpu(1 << 20, abi.Scoring.from_values())
+    for T in (128, 256, 320, 384, 512, 1024):
+        s = p.extend_slots(T)
+        assert s >= sms and s % sms == 0
+    assert p.extend_slots(384) >= p.extend_slots(512)          # K = 8 keeps two band words per lane-step: fewer resident warps
+    with pytest.raises(DarwinGpuError):
+        p.extend_slots(4096)
+    p.close()
+
+
 def test_mixed_shapes_keep_their_own_geometry(gpu):
     """Geometry is chosen per tile: a batch of 320 x 320 tiles with a handful of 400-, 512- and 700-wide ones in between gives
     the oracle's answers, and the 320 x 320 tiles do not fall off a cliff (before: one wide tile put the whole call on the
