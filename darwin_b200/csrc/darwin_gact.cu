@@ -644,6 +644,7 @@ struct DarwinGpu {
     DarwinGpuStats stats{};
     std::string err;
     SeedIndex seed_ix;                          // D-SOFT seed position table (dsoft_host.cuh); lanes share the parent's
+    bool tune_cub_sort = false;                 // DARWIN_GPU_SEED_SORT=cub: D-SOFT sorts through cub::DeviceSegmentedSort (A/B, fallback test)
     bool timing_dbg = false;                    // DARWIN_GPU_TIMING=1: per-phase host timings of darwin_gpu_extend on stderr
     DarwinGpu* parent = nullptr;                // lanes: the handle that owns the arena replica and the seed position table
     std::vector<DarwinGpu*> lanes;              // parent: live lanes (guarded by g_lane_mutex)
@@ -779,6 +780,7 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     DarwinGpu* h = new DarwinGpu();
     h->device = device;
     h->timing_dbg = getenv("DARWIN_GPU_TIMING") != nullptr;
+    { const char* e = getenv("DARWIN_GPU_SEED_SORT"); h->tune_cub_sort = e && std::string(e) == "cub"; }
     { const char* e = getenv("DARWIN_GPU_MAX_CTAS_PER_SM"); h->tune_max_ctas = e ? atoi(e) : 0; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
     cudaDeviceProp prop;

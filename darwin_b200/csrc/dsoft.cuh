@@ -211,20 +211,24 @@ __global__ void carry_kernel(int* __restrict__ carry, int n_chroms, int chunks_p
 __global__ void hit_count_kernel(const SeedConst sc, const uint32_t* __restrict__ buckets, const uint32_t* __restrict__ positions,
                                  const uint64_t* __restrict__ seeds, const uint32_t* __restrict__ seed_base,
                                  const uint32_t* __restrict__ n_seeds, int n_strands, uint32_t slots_per_strand_max,
-                                 uint32_t* __restrict__ cnt) {
+                                 uint32_t* __restrict__ cnt, uint32_t* __restrict__ first) {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t strand = (uint32_t)(g / slots_per_strand_max), slot = (uint32_t)(g % slots_per_strand_max);
     if (strand >= (uint32_t)n_strands) return;
     const uint32_t cap = seed_base[strand + 1] - seed_base[strand];
     if (slot >= cap) return;
-    uint32_t c = 0;
+    uint32_t c = 0, f = 0;
     if (slot < n_seeds[strand]) {
         const uint64_t sd = seeds[seed_base[strand] + slot];
         const uint32_t offset = (uint32_t)(sd >> 32), m = (uint32_t)sd;
         const uint32_t s = buckets[m], e = buckets[m + 1];
-        if (e - s <= sc.max_occ) for (uint32_t j = s; j < e; j++) c += positions[j] >= offset;
+        if (e - s <= sc.max_occ) {
+            for (uint32_t j = s; j < e; j++) c += positions[j] >= offset;
+            f = e - c;                                           // buckets are ascending: the hits are the suffix [f, e)
+        }
     }
     cnt[seed_base[strand] + slot] = c;
+    first[seed_base[strand] + slot] = f;
 }
 
 __global__ void hit_fill_kernel(const SeedConst sc, const uint32_t* __restrict__ buckets, const uint32_t* __restrict__ positions,
@@ -248,6 +252,125 @@ __global__ void hit_fill_kernel(const SeedConst sc, const uint32_t* __restrict__
             at++;
         }
     }
+}
+
+// ---- segment sorts in shared memory ---------------------------------------------------------------------------------
+// The two sorts of D-SOFT work on short independent segments (the hits of one read strand: a few thousand; the SV window
+// of one candidate: a few hundred), so each segment is sorted by ONE CTA in shared memory and touches HBM once on the way
+// in and once on the way out.  Bitonic network on 64-bit keys; the stages whose partner distance is <= 32 stay inside
+// the 64-element block a warp holds and need only a warp barrier (57 of the 78 stages at 4096 keys).
+__device__ __forceinline__ uint32_t pow2_ceil(uint32_t n) { return n <= 64u ? 64u : 1u << (32 - __clz(n - 1)); }
+
+__device__ __forceinline__ void cmpx(uint64_t* a, uint32_t t, uint32_t j, uint32_t k) {
+    const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+    const uint64_t x = a[i], y = a[p];
+    if ((x > y) == ((i & k) == 0)) { a[i] = y; a[p] = x; }
+}
+// a[0, npad) ascending; npad a power of two >= 64; called by every thread of the CTA (blockDim a multiple of 32)
+__device__ __forceinline__ void bitonic_sort_smem(uint64_t* a, uint32_t npad) {
+    const uint32_t half = npad >> 1;
+    for (uint32_t k = 2; k <= npad; k <<= 1) {
+        uint32_t j = k >> 1;
+        for (; j > 32; j >>= 1) {
+            for (uint32_t t = threadIdx.x; t < half; t += blockDim.x) cmpx(a, t, j, k);
+            __syncthreads();
+        }
+        for (uint32_t t = threadIdx.x; t < half; t += blockDim.x) {      // a warp's 32 pairs = one 64-element block
+            for (uint32_t jj = j; jj > 0; jj >>= 1) { cmpx(a, t, jj, k); __syncwarp(); }
+        }
+        __syncthreads();
+    }
+}
+
+// inclusive block scan over blockDim (<= 1024) threads; warp_tot: 32 ints of shared memory
+__device__ __forceinline__ int block_scan_sum_any(int v, int* warp_tot) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) warp_tot[wid] = v;
+    __syncthreads();
+    int pre = 0;
+    for (int k = 0; k < wid && k < nw; k++) pre += warp_tot[k];
+    __syncthreads();
+    return v + pre;
+}
+
+// Hits of one strand: fill (positions[first .. first + cnt) of every visited seed, in seed order = ascending read offset),
+// STABLE sort by bin -- the input is already in (offset, hit) order, so this is the reference's std::stable_sort by
+// (bin, offset) with ties in ascending hit order (seed_pos_table.cpp:338) -- and the sequential bin-coverage rule
+// (:352-392), which restarts at every new bin and pushes at most once per bin: one thread per run of equal bins.
+// Shared memory: key_s[npad_max] u64 (bin << 32 | index in fill order), off_s[cap], hit_s[cap].
+// Output: keys (bin << 32 | offset), vals (hit) in sorted order; cand_tmp[lo ..): indices of the strand's candidates, ascending.
+__global__ void hit_sort_kernel(const SeedConst sc, const uint32_t* __restrict__ positions, const uint64_t* __restrict__ seeds,
+                                const uint32_t* __restrict__ seed_base, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ first,
+                                const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ strand_hit_off, uint32_t cap, uint32_t npad_max,
+                                uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t* __restrict__ n_cand, uint32_t* __restrict__ cand_tmp) {
+    extern __shared__ __align__(16) unsigned char dsoft_smem[];
+    __shared__ int warp_tot[32];
+    uint64_t* key_s = reinterpret_cast<uint64_t*>(dsoft_smem);
+    uint32_t* off_s = reinterpret_cast<uint32_t*>(key_s + npad_max);
+    uint32_t* hit_s = off_s + cap;
+    const uint32_t s = blockIdx.x, lo = strand_hit_off[s], n = strand_hit_off[s + 1] - lo;
+    if (n == 0) { if (threadIdx.x == 0) n_cand[s] = 0; return; }
+    const uint32_t npad = pow2_ceil(n);
+    for (uint32_t i = n + threadIdx.x; i < npad; i += blockDim.x) key_s[i] = ~0ull;
+    const uint32_t base = seed_base[s], slots = seed_base[s + 1] - base;
+    for (uint32_t slot = threadIdx.x; slot < slots; slot += blockDim.x) {
+        const uint32_t c = cnt[base + slot];
+        if (!c) continue;
+        const uint32_t at = hit_off[base + slot] - lo, offset = (uint32_t)(seeds[base + slot] >> 32), p0 = first[base + slot];
+        for (uint32_t j = 0; j < c; j++) {
+            const uint32_t hit = positions[p0 + j];
+            off_s[at + j] = offset; hit_s[at + j] = hit;
+            key_s[at + j] = ((uint64_t)((hit - offset) / sc.bin_size) << 32) | (at + j);
+        }
+    }
+    __syncthreads();
+    bitonic_sort_smem(key_s, npad);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t k = key_s[i];
+        const uint32_t idx = (uint32_t)k;
+        const uint64_t out = (k & 0xFFFFFFFF00000000ull) | off_s[idx];
+        keys[lo + i] = out; vals[lo + i] = hit_s[idx];
+        key_s[i] = out;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) hit_s[i] = 0;       // now the push flags
+    __syncthreads();
+    const uint32_t ks = (uint32_t)sc.k, thr = (uint32_t)sc.threshold;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t k = key_s[i];
+        const uint32_t bin = (uint32_t)(k >> 32);
+        if (i && (uint32_t)(key_s[i - 1] >> 32) == bin) continue;             // not the head of its run
+        uint32_t curr = ks, last_offset = (uint32_t)k;
+        if (curr >= thr) { hit_s[i] = 1; continue; }
+        for (uint32_t j = i + 1; j < n; j++) {
+            const uint64_t kj = key_s[j];
+            if ((uint32_t)(kj >> 32) != bin) break;
+            const uint32_t offset = (uint32_t)kj;
+            curr = ((offset - last_offset > ks) || curr == 0) ? curr + ks : curr + (offset - last_offset);
+            if (curr >= thr) { hit_s[j] = 1; break; }
+            last_offset = offset;
+        }
+    }
+    __syncthreads();
+    // ordered compaction: every thread owns a contiguous range
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x, a = min(n, threadIdx.x * per), b = min(n, a + per);
+    int mine = 0;
+    for (uint32_t i = a; i < b; i++) mine += (int)hit_s[i];
+    const int incl = block_scan_sum_any(mine, warp_tot);
+    uint32_t out = lo + (uint32_t)(incl - mine);
+    for (uint32_t i = a; i < b; i++) if (hit_s[i]) cand_tmp[out++] = lo + i;
+    if (threadIdx.x == blockDim.x - 1) n_cand[s] = (uint32_t)incl;
+}
+
+// largest segment of a prefix-sum array (sizes the shared memory of the segment sorts)
+__global__ void seg_max_kernel(const uint32_t* __restrict__ off, int n_seg, uint32_t* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = s < n_seg ? off[s + 1] - off[s] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
 }
 
 // candidate bins of one strand (seed_pos_table.cpp:352-392).  FILL = false: count only.
@@ -284,7 +407,8 @@ __global__ void candidate_kernel(const SeedConst sc, const uint64_t* __restrict_
 __global__ void window_size_kernel(const SeedConst sc, const uint64_t* __restrict__ keys, const uint32_t* __restrict__ strand_hit_off,
                                    const uint32_t* __restrict__ cand_off, int n_strands, const uint32_t* __restrict__ cand_hit_idx,
                                    uint32_t n_cands, uint32_t* __restrict__ cand_strand, uint32_t* __restrict__ win_lo,
-                                   uint32_t* __restrict__ win_n) {
+                                   uint32_t* __restrict__ win_n, const uint32_t* __restrict__ cand_tmp, uint32_t* __restrict__ cand_hit_out,
+                                   uint32_t* __restrict__ win_max) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cands) return;
     // strand of this candidate: binary search in cand_off
@@ -293,7 +417,10 @@ __global__ void window_size_kernel(const SeedConst sc, const uint64_t* __restric
     const uint32_t s = (uint32_t)a;
     cand_strand[c] = s;
     const uint32_t lo = strand_hit_off[s], hi = strand_hit_off[s + 1];
-    const uint32_t cb = (uint32_t)(keys[cand_hit_idx[c]] >> 32);
+    uint32_t ci;
+    if (cand_tmp) { ci = cand_tmp[lo + (c - cand_off[s])]; cand_hit_out[c] = ci; }      // hit_sort_kernel left the list per strand
+    else ci = cand_hit_idx[c];
+    const uint32_t cb = (uint32_t)(keys[ci] >> 32);
     const uint32_t bmin = cb >= sc.sv_bins ? cb - sc.sv_bins : 0u, bmax = cb + sc.sv_bins;   // bmin <= bin < bmax
     uint32_t x = lo, y = hi;
     while (x < y) { const uint32_t mid = (x + y) >> 1; if ((uint32_t)(keys[mid] >> 32) < bmin) x = mid + 1; else y = mid; }
@@ -301,6 +428,25 @@ __global__ void window_size_kernel(const SeedConst sc, const uint64_t* __restric
     y = hi;
     while (x < y) { const uint32_t mid = (x + y) >> 1; if ((uint32_t)(keys[mid] >> 32) < bmax) x = mid + 1; else y = mid; }
     win_lo[c] = ws; win_n[c] = x - ws;
+    if (win_max) atomicMax(win_max, x - ws);
+}
+
+// SV window of one candidate, sorted by (hit, offset) (seed_pos_table.cpp:403-428): one CTA per candidate, straight from
+// the strand's sorted hits into shared memory, out as (hit << 32 | offset) keys ((hit, offset) pairs are unique)
+__global__ void window_sort_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                   const uint32_t* __restrict__ win_lo, const uint32_t* __restrict__ win_n,
+                                   const uint64_t* __restrict__ win_off, uint64_t* __restrict__ wkeys) {
+    extern __shared__ __align__(16) unsigned char dsoft_smem[];
+    uint64_t* a = reinterpret_cast<uint64_t*>(dsoft_smem);
+    const uint32_t c = blockIdx.x, n = win_n[c], lo = win_lo[c];
+    if (n == 0) return;
+    const uint32_t npad = pow2_ceil(n);
+    for (uint32_t j = threadIdx.x; j < npad; j += blockDim.x)
+        a[j] = j < n ? ((uint64_t)vals[lo + j] << 32) | (uint32_t)keys[lo + j] : ~0ull;
+    __syncthreads();
+    bitonic_sort_smem(a, npad);
+    uint64_t* out = wkeys + win_off[c];
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) out[j] = a[j];
 }
 
 // copy every candidate's window as (hit << 32 | offset) keys; one warp per candidate

@@ -130,6 +130,7 @@ __global__ void gather_u32_kernel(const uint32_t* __restrict__ src, const uint32
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[idx[i]];
 }
+constexpr size_t kSortSmemMax = 220 * 1024;     // shared memory one CTA of the segment sorts may use (227 KB per CTA on sm_100)
 __global__ void widen_kernel(const uint32_t* __restrict__ src, uint32_t n, uint64_t* __restrict__ dst) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
@@ -165,19 +166,22 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     uint64_t bases = 0, slots64 = 0;
     for (int r = 0; r < n; r++) { bases += reads[r].read_len; slots64 += 2ull * (seed_base[2 * r + 1] - seed_base[2 * r]); }
     if (bases > 1500000000ull || slots64 != slots) { h->err = "seeding batch too large (more than 1.5 G read bases in one call)"; return DARWIN_ERR_INVALID; }
-    DevBuf d_jobs, d_base, d_seeds, d_nseeds, d_cnt, d_hoff, d_soff;
+    DevBuf d_jobs, d_base, d_seeds, d_nseeds, d_cnt, d_first, d_hoff, d_soff, d_max;
     CKS(d_jobs.alloc(sizeof(MinJob) * ns, h->stream)); CKS(d_base.alloc(sizeof(uint32_t) * (ns + 1), h->stream)); CKS(d_seeds.alloc(sizeof(uint64_t) * slots, h->stream));
     CKS(d_nseeds.alloc(sizeof(uint32_t) * ns, h->stream)); CKS(d_cnt.alloc(sizeof(uint32_t) * ((size_t)slots + 1), h->stream)); CKS(d_hoff.alloc(sizeof(uint32_t) * ((size_t)slots + 1), h->stream));
-    CKS(d_soff.alloc(sizeof(uint32_t) * (ns + 1), h->stream));
+    CKS(d_first.alloc(sizeof(uint32_t) * ((size_t)slots + 1), h->stream));
+    CKS(d_soff.alloc(sizeof(uint32_t) * (ns + 1), h->stream)); CKS(d_max.alloc(sizeof(uint32_t) * 2, h->stream));
     CKS(cudaMemcpyAsync(d_jobs.p, jobs.data(), sizeof(MinJob) * ns, cudaMemcpyHostToDevice, h->stream));
     CKS(cudaMemcpyAsync(d_base.p, seed_base.data(), sizeof(uint32_t) * (ns + 1), cudaMemcpyHostToDevice, h->stream));
     CKS(cudaMemsetAsync(d_cnt.p, 0, sizeof(uint32_t) * ((size_t)slots + 1), h->stream));
+    CKS(cudaMemsetAsync(d_max.p, 0, sizeof(uint32_t) * 2, h->stream));
     CKS(cudaEventRecord(h->ev0, h->stream));
     minimizer_kernel<0><<<ns, kMinThreads, 0, h->stream>>>(h->d_arena, sc, d_jobs.as<MinJob>(), d_seeds.as<uint64_t>(), d_nseeds.as<uint32_t>(), nullptr, nullptr, nullptr, 0u);
     CKS(cudaGetLastError());
     const uint64_t grid_threads = (uint64_t)ns * max_cap;
     const unsigned gb = (unsigned)((grid_threads + 255) / 256);
-    hit_count_kernel<<<gb, 256, 0, h->stream>>>(sc, ix.d_buckets, ix.d_positions, d_seeds.as<uint64_t>(), d_base.as<uint32_t>(), d_nseeds.as<uint32_t>(), ns, max_cap, d_cnt.as<uint32_t>());
+    hit_count_kernel<<<gb, 256, 0, h->stream>>>(sc, ix.d_buckets, ix.d_positions, d_seeds.as<uint64_t>(), d_base.as<uint32_t>(), d_nseeds.as<uint32_t>(), ns, max_cap,
+                                               d_cnt.as<uint32_t>(), d_first.as<uint32_t>());
     CKS(cudaGetLastError());
     int rc;
     // The hit offsets are 32-bit: the total (slots x up to max_occ hits each -- NOT bounded by the base count above) is
@@ -191,29 +195,45 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     if ((rc = exclusive_sum(h, d_cnt.as<uint32_t>(), d_hoff.as<uint32_t>(), (int64_t)slots + 1))) return rc;
     gather_u32_kernel<<<(ns + 1 + 255) / 256, 256, 0, h->stream>>>(d_hoff.as<uint32_t>(), d_base.as<uint32_t>(), ns + 1, d_soff.as<uint32_t>());
     CKS(cudaGetLastError());
-    uint32_t n_hits = 0;
-    CKS(cudaMemcpyAsync(&n_hits, d_hoff.as<uint32_t>() + slots, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-    CKS(cudaStreamSynchronize(h->stream));
-    DevBuf d_k0, d_k1, d_v0, d_v1, d_tmp;
-    CKS(d_k0.alloc(sizeof(uint64_t) * n_hits, h->stream)); CKS(d_k1.alloc(sizeof(uint64_t) * n_hits, h->stream));
-    CKS(d_v0.alloc(sizeof(uint32_t) * n_hits, h->stream)); CKS(d_v1.alloc(sizeof(uint32_t) * n_hits, h->stream));
-    hit_fill_kernel<<<gb, 256, 0, h->stream>>>(sc, ix.d_buckets, ix.d_positions, d_seeds.as<uint64_t>(), d_base.as<uint32_t>(), d_nseeds.as<uint32_t>(), ns, max_cap,
-                                              d_hoff.as<uint32_t>(), d_k0.as<uint64_t>(), d_v0.as<uint32_t>());
+    seg_max_kernel<<<(ns + 255) / 256, 256, 0, h->stream>>>(d_soff.as<uint32_t>(), ns, d_max.as<uint32_t>());
     CKS(cudaGetLastError());
-    // std::stable_sort by bin_offset (seed_pos_table.cpp:338): ties (same seed) keep ascending hit order
-    size_t tmp_bytes = 0;
-    CKS(cub::DeviceSegmentedSort::StableSortPairs(nullptr, tmp_bytes, d_k0.as<uint64_t>(), d_k1.as<uint64_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(),
-                                                  (int64_t)n_hits, (int64_t)ns, d_soff.as<uint32_t>(), d_soff.as<uint32_t>() + 1, h->stream));
-    CKS(d_tmp.alloc(tmp_bytes, h->stream));
-    CKS(cub::DeviceSegmentedSort::StableSortPairs(d_tmp.p, tmp_bytes, d_k0.as<uint64_t>(), d_k1.as<uint64_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(),
-                                                  (int64_t)n_hits, (int64_t)ns, d_soff.as<uint32_t>(), d_soff.as<uint32_t>() + 1, h->stream));
-    const uint64_t* keys = d_k1.as<uint64_t>(); const uint32_t* vals = d_v1.as<uint32_t>();
-    // candidate bins: count, scan, fill
-    DevBuf d_ncand, d_coff;
+    const uint32_t n_hits = (uint32_t)hits64;
+    uint32_t seg_max = 0;
+    CKS(cudaMemcpyAsync(&seg_max, d_max.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    CKS(cudaStreamSynchronize(h->stream));
+    // One CTA sorts one strand's hits in shared memory (hit_sort_kernel) when the largest strand fits; a batch with a
+    // larger strand (reads beyond ~100 kbp, or a very repetitive table) takes CUB's segmented sort instead.
+    uint32_t seg_pad = 64; while (seg_pad < seg_max) seg_pad <<= 1;
+    const size_t sort_smem = (size_t)seg_pad * 8 + (size_t)seg_max * 8;
+    const bool smem_sort = !h->tune_cub_sort && sort_smem <= kSortSmemMax;
+    DevBuf d_k0, d_k1, d_v0, d_v1, d_tmp, d_ncand, d_coff, d_ctmp;
+    CKS(d_k1.alloc(sizeof(uint64_t) * n_hits, h->stream)); CKS(d_v1.alloc(sizeof(uint32_t) * n_hits, h->stream));
     CKS(d_ncand.alloc(sizeof(uint32_t) * (ns + 1), h->stream)); CKS(d_coff.alloc(sizeof(uint32_t) * (ns + 1), h->stream));
     CKS(cudaMemsetAsync(d_ncand.p, 0, sizeof(uint32_t) * (ns + 1), h->stream));
-    candidate_kernel<false><<<(ns + 127) / 128, 128, 0, h->stream>>>(sc, keys, d_soff.as<uint32_t>(), ns, d_ncand.as<uint32_t>(), nullptr, nullptr);
-    CKS(cudaGetLastError());
+    if (smem_sort) {
+        CKS(d_ctmp.alloc(sizeof(uint32_t) * n_hits, h->stream));
+        const int threads = seg_pad <= 4096 ? 256 : seg_pad <= 8192 ? 512 : 1024;
+        CKS(cudaFuncSetAttribute(hit_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemMax));
+        hit_sort_kernel<<<ns, threads, sort_smem, h->stream>>>(sc, ix.d_positions, d_seeds.as<uint64_t>(), d_base.as<uint32_t>(), d_cnt.as<uint32_t>(), d_first.as<uint32_t>(),
+                                                              d_hoff.as<uint32_t>(), d_soff.as<uint32_t>(), seg_max, seg_pad,
+                                                              d_k1.as<uint64_t>(), d_v1.as<uint32_t>(), d_ncand.as<uint32_t>(), d_ctmp.as<uint32_t>());
+        CKS(cudaGetLastError());
+    } else {
+        CKS(d_k0.alloc(sizeof(uint64_t) * n_hits, h->stream)); CKS(d_v0.alloc(sizeof(uint32_t) * n_hits, h->stream));
+        hit_fill_kernel<<<gb, 256, 0, h->stream>>>(sc, ix.d_buckets, ix.d_positions, d_seeds.as<uint64_t>(), d_base.as<uint32_t>(), d_nseeds.as<uint32_t>(), ns, max_cap,
+                                                  d_hoff.as<uint32_t>(), d_k0.as<uint64_t>(), d_v0.as<uint32_t>());
+        CKS(cudaGetLastError());
+        // std::stable_sort by bin_offset (seed_pos_table.cpp:338): ties (same seed) keep ascending hit order
+        size_t tmp_bytes = 0;
+        CKS(cub::DeviceSegmentedSort::StableSortPairs(nullptr, tmp_bytes, d_k0.as<uint64_t>(), d_k1.as<uint64_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(),
+                                                      (int64_t)n_hits, (int64_t)ns, d_soff.as<uint32_t>(), d_soff.as<uint32_t>() + 1, h->stream));
+        CKS(d_tmp.alloc(tmp_bytes, h->stream));
+        CKS(cub::DeviceSegmentedSort::StableSortPairs(d_tmp.p, tmp_bytes, d_k0.as<uint64_t>(), d_k1.as<uint64_t>(), d_v0.as<uint32_t>(), d_v1.as<uint32_t>(),
+                                                      (int64_t)n_hits, (int64_t)ns, d_soff.as<uint32_t>(), d_soff.as<uint32_t>() + 1, h->stream));
+        candidate_kernel<false><<<(ns + 127) / 128, 128, 0, h->stream>>>(sc, d_k1.as<uint64_t>(), d_soff.as<uint32_t>(), ns, d_ncand.as<uint32_t>(), nullptr, nullptr);
+        CKS(cudaGetLastError());
+    }
+    const uint64_t* keys = d_k1.as<uint64_t>(); const uint32_t* vals = d_v1.as<uint32_t>();
     if ((rc = exclusive_sum(h, d_ncand.as<uint32_t>(), d_coff.as<uint32_t>(), (int64_t)ns + 1))) return rc;
     CKS(cudaMemcpyAsync(anchor_begin, d_coff.p, sizeof(uint32_t) * (ns + 1), cudaMemcpyDeviceToHost, h->stream));
     CKS(cudaStreamSynchronize(h->stream));
@@ -224,33 +244,47 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     DevBuf d_cidx, d_cstr, d_wlo, d_wn, d_wn64, d_woff;
     CKS(d_cidx.alloc(sizeof(uint32_t) * n_cands, h->stream)); CKS(d_cstr.alloc(sizeof(uint32_t) * n_cands, h->stream)); CKS(d_wlo.alloc(sizeof(uint32_t) * n_cands, h->stream));
     CKS(d_wn.alloc(sizeof(uint32_t) * ((size_t)n_cands + 1), h->stream)); CKS(d_wn64.alloc(sizeof(uint64_t) * ((size_t)n_cands + 1), h->stream)); CKS(d_woff.alloc(sizeof(uint64_t) * ((size_t)n_cands + 1), h->stream));
-    candidate_kernel<true><<<(ns + 127) / 128, 128, 0, h->stream>>>(sc, keys, d_soff.as<uint32_t>(), ns, nullptr, d_coff.as<uint32_t>(), d_cidx.as<uint32_t>());
-    CKS(cudaGetLastError());
+    if (!smem_sort) {
+        candidate_kernel<true><<<(ns + 127) / 128, 128, 0, h->stream>>>(sc, keys, d_soff.as<uint32_t>(), ns, nullptr, d_coff.as<uint32_t>(), d_cidx.as<uint32_t>());
+        CKS(cudaGetLastError());
+    }
     CKS(cudaMemsetAsync(d_wn.p, 0, sizeof(uint32_t) * ((size_t)n_cands + 1), h->stream));
-    window_size_kernel<<<(n_cands + 127) / 128, 128, 0, h->stream>>>(sc, keys, d_soff.as<uint32_t>(), d_coff.as<uint32_t>(), ns, d_cidx.as<uint32_t>(), n_cands,
-                                                                    d_cstr.as<uint32_t>(), d_wlo.as<uint32_t>(), d_wn.as<uint32_t>());
+    window_size_kernel<<<(n_cands + 127) / 128, 128, 0, h->stream>>>(sc, keys, d_soff.as<uint32_t>(), d_coff.as<uint32_t>(), ns, smem_sort ? nullptr : d_cidx.as<uint32_t>(), n_cands,
+                                                                    d_cstr.as<uint32_t>(), d_wlo.as<uint32_t>(), d_wn.as<uint32_t>(),
+                                                                    smem_sort ? d_ctmp.as<uint32_t>() : nullptr, d_cidx.as<uint32_t>(), d_max.as<uint32_t>() + 1);
     CKS(cudaGetLastError());
     widen_kernel<<<(n_cands + 1 + 255) / 256, 256, 0, h->stream>>>(d_wn.as<uint32_t>(), n_cands + 1, d_wn64.as<uint64_t>());
     CKS(cudaGetLastError());
     if ((rc = exclusive_sum(h, d_wn64.as<uint64_t>(), d_woff.as<uint64_t>(), (int64_t)n_cands + 1))) return rc;
-    uint64_t n_win = 0;
+    uint64_t n_win = 0; uint32_t win_max = 0;
     CKS(cudaMemcpyAsync(&n_win, d_woff.as<uint64_t>() + n_cands, sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+    CKS(cudaMemcpyAsync(&win_max, d_max.as<uint32_t>() + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
     CKS(cudaStreamSynchronize(h->stream));
     const uint64_t need_pool = n_win + n_cands;
     *n_pool = need_pool;
     if (keep_pool) { anchor_vec->resize(n_cands); anchors = anchor_vec->data(); }
     else if (n_cands > anchors_cap || need_pool > pool_cap) { h->err = "seed output capacity: need " + std::to_string(n_cands) + " anchors, " + std::to_string(need_pool) + " pool entries"; return DARWIN_ERR_CAPACITY; }
     DevBuf d_w0, d_w1, d_pool, d_tanc, d_anc, d_tmp2;
-    CKS(d_w0.alloc(sizeof(uint64_t) * n_win, h->stream)); CKS(d_w1.alloc(sizeof(uint64_t) * n_win, h->stream)); CKS(d_pool.alloc(sizeof(uint64_t) * need_pool, h->stream));
+    CKS(d_w1.alloc(sizeof(uint64_t) * n_win, h->stream)); CKS(d_pool.alloc(sizeof(uint64_t) * need_pool, h->stream));
     CKS(d_tanc.alloc(sizeof(DarwinSeedAnchor) * n_cands, h->stream)); CKS(d_anc.alloc(sizeof(DarwinSeedAnchor) * n_cands, h->stream));
-    window_copy_kernel<<<(unsigned)(((uint64_t)n_cands * 32 + 255) / 256), 256, 0, h->stream>>>(keys, vals, n_cands, d_wlo.as<uint32_t>(), d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w0.as<uint64_t>());
-    CKS(cudaGetLastError());
-    tmp_bytes = 0;
-    CKS(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, d_w0.as<uint64_t>(), d_w1.as<uint64_t>(), (int64_t)n_win, (int64_t)n_cands,
-                                           d_woff.as<uint64_t>(), d_woff.as<uint64_t>() + 1, h->stream));
-    CKS(d_tmp2.alloc(tmp_bytes, h->stream));
-    CKS(cub::DeviceSegmentedSort::SortKeys(d_tmp2.p, tmp_bytes, d_w0.as<uint64_t>(), d_w1.as<uint64_t>(), (int64_t)n_win, (int64_t)n_cands,
-                                           d_woff.as<uint64_t>(), d_woff.as<uint64_t>() + 1, h->stream));
+    uint32_t win_pad = 64; while (win_pad < win_max) win_pad <<= 1;
+    if (!h->tune_cub_sort && (size_t)win_pad * 8 <= kSortSmemMax) {
+        // one CTA per candidate sorts its window in shared memory
+        const int threads = win_pad <= 512 ? 128 : win_pad <= 4096 ? 256 : 1024;
+        CKS(cudaFuncSetAttribute(window_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemMax));
+        window_sort_kernel<<<n_cands, threads, (size_t)win_pad * 8, h->stream>>>(keys, vals, d_wlo.as<uint32_t>(), d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w1.as<uint64_t>());
+        CKS(cudaGetLastError());
+    } else {
+        CKS(d_w0.alloc(sizeof(uint64_t) * n_win, h->stream));
+        window_copy_kernel<<<(unsigned)(((uint64_t)n_cands * 32 + 255) / 256), 256, 0, h->stream>>>(keys, vals, n_cands, d_wlo.as<uint32_t>(), d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w0.as<uint64_t>());
+        CKS(cudaGetLastError());
+        size_t tmp_bytes = 0;
+        CKS(cub::DeviceSegmentedSort::SortKeys(nullptr, tmp_bytes, d_w0.as<uint64_t>(), d_w1.as<uint64_t>(), (int64_t)n_win, (int64_t)n_cands,
+                                               d_woff.as<uint64_t>(), d_woff.as<uint64_t>() + 1, h->stream));
+        CKS(d_tmp2.alloc(tmp_bytes, h->stream));
+        CKS(cub::DeviceSegmentedSort::SortKeys(d_tmp2.p, tmp_bytes, d_w0.as<uint64_t>(), d_w1.as<uint64_t>(), (int64_t)n_win, (int64_t)n_cands,
+                                               d_woff.as<uint64_t>(), d_woff.as<uint64_t>() + 1, h->stream));
+    }
     chain_kernel<<<(n_cands + 127) / 128, 128, 0, h->stream>>>(keys, vals, d_cidx.as<uint32_t>(), n_cands, d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w1.as<uint64_t>(),
                                                               d_pool.as<uint64_t>(), d_tanc.as<DarwinSeedAnchor>());
     CKS(cudaGetLastError());

@@ -22,8 +22,12 @@ def _case(seed, n_reads, overlap):
     return ref, n_reads
 
 
+@pytest.mark.parametrize("sort", ["smem", "cub"])
 @pytest.mark.parametrize("seed,overlap", [(11, 0), (12, 1)])
-def test_gpu_seeding_matches_reference(gpu, seed, overlap):
+def test_gpu_seeding_matches_reference(gpu, seed, overlap, sort, monkeypatch):
+    """Both sort paths of the seeding call: one CTA per segment in shared memory (default) and CUB's segmented sort (the
+    fallback for strands / windows that do not fit shared memory; DARWIN_GPU_SEED_SORT is read when the handle is made)."""
+    monkeypatch.setenv("DARWIN_GPU_SEED_SORT", sort)
     ref, n_reads = _case(seed, 40, overlap)
     try:
         ref.seed(0, n_reads)
@@ -217,3 +221,49 @@ def test_seed_index_over_many_short_chromosomes(gpu):
     with pytest.raises(darwin_b200.DarwinGpuError) as e:
         p.build_seed_index(prm, chroms[:0], ref_size)
     assert e.value.code == abi.ERR_INVALID
+
+
+@pytest.mark.parametrize("overlap", [0, 1])
+def test_seed_sort_paths_agree_at_scale(gpu, overlap, monkeypatch):
+    """3 000 reads of 0.2 - 12 kbp against 3 Mbp with repeats (strands of very different hit counts, windows from a few to a
+    few thousand hits): the shared-memory sorts and the CUB path give the same anchors and the same chained hits."""
+    rng = np.random.default_rng(77 + overlap)
+    G = 3_000_000
+    genome = synth.random_seq(rng, G)
+    for k in range(12):                                                # repeats: multi-hit buckets, crowded bins
+        a, b = int(rng.integers(0, G - 5000)), int(rng.integers(0, G - 5000))
+        genome[b:b + 4000] = genome[a:a + 4000]
+    lens = rng.integers(200, 12000, 3000)
+    stride = [int(L + ((-L) % 128)) for L in lens]
+    ref_end = 128 + G + ((-G) % 128)
+    arena = np.full(ref_end + sum(stride) + 128, ord("N"), np.uint8)
+    arena[128:128 + G] = genome
+    reads = np.zeros(len(lens), abi.SEED_READ)
+    at = ref_end
+    for k, L in enumerate(lens):
+        p0 = int(rng.integers(0, G - L))
+        r = synth.mutate_fast(rng, genome[p0:p0 + L], 0.03, 0.04, 0.04)[:L]
+        if k & 1:
+            r = synth.revcomp(r)
+        arena[at:at + len(r)] = r
+        reads[k]["read_addr"], reads[k]["read_len"] = at, len(r)
+        at += stride[k]
+    chroms = np.zeros(1, abi.CHROM); chroms["start"] = 128; chroms["len_unpadded"] = G
+    out = {}
+    for sort in ("smem", "cub"):
+        monkeypatch.setenv("DARWIN_GPU_SEED_SORT", sort)
+        p = gpu(len(arena), abi.Scoring.from_values())
+        p.InitializeReferenceMemory(0, arena)
+        p.build_seed_index(abi.SeedParams.stock(overlap), chroms, ref_end)
+        out[sort] = p.seeder_body(reads)
+        p.close()
+    (b0, a0, p0), (b1, a1, p1) = out["smem"], out["cub"]
+    assert len(a0) > 2000
+    assert np.array_equal(b0, b1) and np.array_equal(a0, a1) and len(p0) == len(p1)
+    # the pool region of a candidate is window + 1 entries long; only the two chains are defined
+    used = np.zeros(len(p0) + 1, np.int64)
+    for side in ("left", "right"):
+        lo, n = a0[side + "_off"].astype(np.int64), a0[side + "_n"].astype(np.int64)
+        np.add.at(used, lo, 1); np.add.at(used, lo + n, -1)
+    used = np.cumsum(used)[:-1] > 0
+    assert used.sum() > len(a0) and np.array_equal(p0[used], p1[used])
