@@ -644,6 +644,8 @@ struct DarwinGpu {
     DarwinGpuStats stats{};
     std::string err;
     SeedIndex seed_ix;                          // D-SOFT seed position table (dsoft_host.cuh); lanes share the parent's
+    bool spin_sync = false;                     // DARWIN_GPU_SYNC=spin: host waits spin (CUDA's default) instead of blocking on an event
+    cudaEvent_t ev_wait = nullptr;              // blocking-sync event behind stream_wait()
     bool tune_cub_sort = false;                 // DARWIN_GPU_SEED_SORT=cub: D-SOFT sorts through cub::DeviceSegmentedSort (A/B, fallback test)
     bool timing_dbg = false;                    // DARWIN_GPU_TIMING=1: per-phase host timings of darwin_gpu_extend on stderr
     DarwinGpu* parent = nullptr;                // lanes: the handle that owns the arena replica and the seed position table
@@ -652,6 +654,15 @@ struct DarwinGpu {
 static std::mutex g_lane_mutex;
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DARWIN_ERR_CUDA; } } while (0)
+
+// Host waits.  cudaStreamSynchronize spins on a core by default; with one host thread per lane and several lanes per GPU
+// an 8-GPU node has as many spinning threads as cores, and they compete with the threads that feed the other lanes.  The
+// library therefore waits on a cudaEventBlockingSync event (the thread sleeps until the interrupt) unless DARWIN_GPU_SYNC=spin.
+static cudaError_t stream_wait(DarwinGpu* h, cudaStream_t st) {
+    if (h->spin_sync || !h->ev_wait) return cudaStreamSynchronize(st);
+    cudaError_t e = cudaEventRecord(h->ev_wait, st);
+    return e != cudaSuccess ? e : cudaEventSynchronize(h->ev_wait);
+}
 
 // No C++ exception crosses the C boundary: host allocations that fail become a status.
 static int on_exception(DarwinGpu* h, const std::exception& e) {
@@ -738,7 +749,7 @@ static int configure_kernels(DarwinGpu* h) {
 static int read_counters(DarwinGpu* h) {
     unsigned int c[kCounters] = {0};
     CK(cudaMemcpyAsync(c, h->d_counter, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h, h->stream));
     h->stats.tiles_fast += c[1]; h->stats.tiles_exact += c[2]; h->stats.tiles_rerun += c[3];
     h->stats.cells_exact += ((uint64_t)c[5] << 32) | c[4];
     h->stats.tiles_xfast += c[6];
@@ -780,6 +791,7 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     DarwinGpu* h = new DarwinGpu();
     h->device = device;
     h->timing_dbg = getenv("DARWIN_GPU_TIMING") != nullptr;
+    { const char* e = getenv("DARWIN_GPU_SYNC"); h->spin_sync = e && std::string(e) == "spin"; }
     { const char* e = getenv("DARWIN_GPU_SEED_SORT"); h->tune_cub_sort = e && std::string(e) == "cub"; }
     { const char* e = getenv("DARWIN_GPU_MAX_CTAS_PER_SM"); h->tune_max_ctas = e ? atoi(e) : 0; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
@@ -789,6 +801,7 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     *out = h;
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+    CK(cudaEventCreateWithFlags(&h->ev_wait, cudaEventDisableTiming | cudaEventBlockingSync));
     {   // stream-ordered allocations (seeding scratch) stay in the device's pool instead of going back to the driver
         cudaMemPool_t pool; uint64_t keep = ~0ull;
         CK(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -810,9 +823,9 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     for (int b = 0; b < 2; b++) {
         CK(cudaMallocHost(&h->h_stage[b], h->stage_bytes));
         CK(cudaMalloc(&h->d_stage[b], h->stage_bytes));
-        CK(cudaEventCreateWithFlags(&h->ev_stage[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_stage[b], cudaEventDisableTiming | (h->spin_sync ? 0 : cudaEventBlockingSync)));
         CK(cudaEventCreateWithFlags(&h->ev_chunk[b], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&h->ev_copied[b], cudaEventDisableTiming | (h->spin_sync ? 0 : cudaEventBlockingSync)));
     }
     pair_lut_kernel<<<256, 256, 0, h->stream>>>();                             // per device; idempotent
     CK(cudaGetLastError());
@@ -820,7 +833,7 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     h->max_warps = h->sm_count * 16;                                           // scratch is sized for this many resident warps
     int rc = configure_kernels(h);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h, h->stream));
     return DARWIN_OK;
 }
 
@@ -832,7 +845,7 @@ int darwin_gpu_destroy(DarwinGpu* h) {
         if (h->parent) { auto& v = h->parent->lanes; v.erase(std::remove(v.begin(), v.end(), h), v.end()); h->parent = nullptr; }
     }
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->stream);
+    stream_wait(h, h->stream);
     for (int i = 0; i < 13; i++) if (h->d_buf[i]) cudaFree(h->d_buf[i]);
     if (h->d_trace) cudaFree(h->d_trace);
     if (h->d_bound) cudaFree(h->d_bound);
@@ -847,6 +860,7 @@ int darwin_gpu_destroy(DarwinGpu* h) {
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     free_index(h->seed_ix);
     if (h->d_arena && h->owns_arena) cudaFree(h->d_arena);
+    if (h->ev_wait) cudaEventDestroy(h->ev_wait);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -926,7 +940,7 @@ int darwin_gpu_upload(DarwinGpu* h, uint64_t arena_addr, const char* ascii, uint
         CK(cudaEventRecord(h->ev_stage[b], h->stream));
         done += chunk;
     }
-    CK(cudaStreamSynchronize(h->stream));                            // synchronous like the reference's memcpy into g_DRAM
+    CK(stream_wait(h, h->stream));                            // synchronous like the reference's memcpy into g_DRAM
     return DARWIN_OK;
 }
 
@@ -975,7 +989,7 @@ int darwin_gpu_upload_spans(DarwinGpu* h, const DarwinSpan* spans, int n_spans) 
         fill = off + n;
     }
     if ((rc = flush(n_spans))) return rc;
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h, h->stream));
     return DARWIN_OK;
 } GUARDED_END
 
@@ -1138,7 +1152,7 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
         }
     }
     CK(cudaEventRecord(h->ev1, h->stream));
-    CK(cudaStreamSynchronize(h->copy_stream));
+    CK(stream_wait(h, h->copy_stream));
     if ((rc = read_counters(h))) return rc;
     CK(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
     h->stats.cells += cells;
@@ -1292,7 +1306,7 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     h->stats.kernel_launches++;
     CK(cudaMemcpyAsync(res, h->d_buf[1], res_b, cudaMemcpyDeviceToHost, h->stream));
     if (used && ops_pool) CK(cudaMemcpyAsync(ops_pool, d_dense, used, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    CK(stream_wait(h, h->stream));
     TMARK("compact+D2H");
     *used_out = used;
     return DARWIN_OK;
@@ -1514,7 +1528,7 @@ int darwin_gpu_int_peak(DarwinGpu* h, double out[10]) {
             }
             CK(cudaGetLastError());
             CK(cudaEventRecord(h->ev1, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
+            CK(stream_wait(h, h->stream));
             float ms = 0; CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
             if (rep > 0 && ms < best) best = ms;
             h->stats.kernel_launches++;

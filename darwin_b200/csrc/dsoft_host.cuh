@@ -75,7 +75,7 @@ static int seed_index_build(DarwinGpu* h, SeedIndex& ix, const DarwinSeedParams*
     h->stats.kernel_launches += 3;
     unsigned long long n_min = 0;
     CKS(cudaMemcpyAsync(&n_min, d_cursor.p, sizeof(n_min), cudaMemcpyDeviceToHost, h->stream));
-    CKS(cudaStreamSynchronize(h->stream));
+    CKS(stream_wait(h, h->stream));
     if (n_min > 0xFFFFFFFFull) { h->err = "more than 2^32 minimizers"; return DARWIN_ERR_INVALID; }
     ix.n_positions = n_min;
     // buckets = prefix sums of the histogram (seed_pos_table.cpp:66-101); hist was counted at [m + 1]
@@ -91,7 +91,7 @@ static int seed_index_build(DarwinGpu* h, SeedIndex& ix, const DarwinSeedParams*
     bucket_sort_kernel<<<(unsigned)((ix.n_buckets + 255) / 256), 256, 0, h->stream>>>(ix.d_buckets, ix.n_buckets, sc.max_occ, ix.d_positions);
     CKS(cudaGetLastError());
     h->stats.kernel_launches += 2;
-    CKS(cudaStreamSynchronize(h->stream));
+    CKS(stream_wait(h, h->stream));
     // chromosome table for the resident pipeline: padded lengths = distance to the next chromosome (Index::chr_len)
     ix.chr_start.resize(n_chroms); ix.chr_len.resize(n_chroms);
     for (int c = 0; c < n_chroms; c++) {
@@ -122,7 +122,7 @@ static int sum_u64(DarwinGpu* h, const uint32_t* in, int64_t n, uint64_t* out) {
     CKS(tmp.alloc(bytes, h->stream));
     CKS(cub::DeviceReduce::Sum(tmp.p, bytes, it, d_out.as<uint64_t>(), n, h->stream));
     CKS(cudaMemcpyAsync(out, d_out.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
-    CKS(cudaStreamSynchronize(h->stream));
+    CKS(stream_wait(h, h->stream));
     return DARWIN_OK;
 }
 
@@ -200,7 +200,7 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     const uint32_t n_hits = (uint32_t)hits64;
     uint32_t seg_max = 0;
     CKS(cudaMemcpyAsync(&seg_max, d_max.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-    CKS(cudaStreamSynchronize(h->stream));
+    CKS(stream_wait(h, h->stream));
     // One CTA sorts one strand's hits in shared memory (hit_sort_kernel) when the largest strand fits; a batch with a
     // larger strand (reads beyond ~100 kbp, or a very repetitive table) takes CUB's segmented sort instead.
     uint32_t seg_pad = 64; while (seg_pad < seg_max) seg_pad <<= 1;
@@ -236,11 +236,11 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     const uint64_t* keys = d_k1.as<uint64_t>(); const uint32_t* vals = d_v1.as<uint32_t>();
     if ((rc = exclusive_sum(h, d_ncand.as<uint32_t>(), d_coff.as<uint32_t>(), (int64_t)ns + 1))) return rc;
     CKS(cudaMemcpyAsync(anchor_begin, d_coff.p, sizeof(uint32_t) * (ns + 1), cudaMemcpyDeviceToHost, h->stream));
-    CKS(cudaStreamSynchronize(h->stream));
+    CKS(stream_wait(h, h->stream));
     const uint32_t n_cands = anchor_begin[ns];
     *n_anchors = n_cands;
     h->stats.kernel_launches += 6;
-    if (n_cands == 0) { *n_pool = 0; CKS(cudaEventRecord(h->ev1, h->stream)); CKS(cudaStreamSynchronize(h->stream)); CKS(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1)); return DARWIN_OK; }
+    if (n_cands == 0) { *n_pool = 0; CKS(cudaEventRecord(h->ev1, h->stream)); CKS(stream_wait(h, h->stream)); CKS(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1)); return DARWIN_OK; }
     DevBuf d_cidx, d_cstr, d_wlo, d_wn, d_wn64, d_woff;
     CKS(d_cidx.alloc(sizeof(uint32_t) * n_cands, h->stream)); CKS(d_cstr.alloc(sizeof(uint32_t) * n_cands, h->stream)); CKS(d_wlo.alloc(sizeof(uint32_t) * n_cands, h->stream));
     CKS(d_wn.alloc(sizeof(uint32_t) * ((size_t)n_cands + 1), h->stream)); CKS(d_wn64.alloc(sizeof(uint64_t) * ((size_t)n_cands + 1), h->stream)); CKS(d_woff.alloc(sizeof(uint64_t) * ((size_t)n_cands + 1), h->stream));
@@ -259,7 +259,7 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     uint64_t n_win = 0; uint32_t win_max = 0;
     CKS(cudaMemcpyAsync(&n_win, d_woff.as<uint64_t>() + n_cands, sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
     CKS(cudaMemcpyAsync(&win_max, d_max.as<uint32_t>() + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-    CKS(cudaStreamSynchronize(h->stream));
+    CKS(stream_wait(h, h->stream));
     const uint64_t need_pool = n_win + n_cands;
     *n_pool = need_pool;
     if (keep_pool) { anchor_vec->resize(n_cands); anchors = anchor_vec->data(); }
@@ -295,7 +295,7 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     CKS(cudaMemcpyAsync(anchors, d_anc.p, sizeof(DarwinSeedAnchor) * n_cands, cudaMemcpyDeviceToHost, h->stream));
     if (keep_pool) { keep_pool->p = d_pool.p; keep_pool->st = h->stream; d_pool.p = nullptr; }
     else CKS(cudaMemcpyAsync(pool, d_pool.p, sizeof(uint64_t) * need_pool, cudaMemcpyDeviceToHost, h->stream));
-    CKS(cudaStreamSynchronize(h->stream));
+    CKS(stream_wait(h, h->stream));
     CKS(cudaEventElapsedTime(&h->stats.last_kernel_ms, h->ev0, h->ev1));
     return DARWIN_OK;
 }
