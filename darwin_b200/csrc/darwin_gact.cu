@@ -644,7 +644,7 @@ struct DarwinGpu {
     DarwinGpuStats stats{};
     std::string err;
     SeedIndex seed_ix;                          // D-SOFT seed position table (dsoft_host.cuh); lanes share the parent's
-    bool spin_sync = false;                     // DARWIN_GPU_SYNC=spin: host waits spin (CUDA's default) instead of blocking on an event
+    bool spin_sync = true;                      // DARWIN_GPU_SYNC=block: host waits sleep on a blocking-sync event instead of spinning (CUDA's default)
     cudaEvent_t ev_wait = nullptr;              // blocking-sync event behind stream_wait()
     bool tune_cub_sort = false;                 // DARWIN_GPU_SEED_SORT=cub: D-SOFT sorts through cub::DeviceSegmentedSort (A/B, fallback test)
     bool timing_dbg = false;                    // DARWIN_GPU_TIMING=1: per-phase host timings of darwin_gpu_extend on stderr
@@ -656,8 +656,9 @@ static std::mutex g_lane_mutex;
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DARWIN_ERR_CUDA; } } while (0)
 
 // Host waits.  cudaStreamSynchronize spins on a core by default; with one host thread per lane and several lanes per GPU
-// an 8-GPU node has as many spinning threads as cores, and they compete with the threads that feed the other lanes.  The
-// library therefore waits on a cudaEventBlockingSync event (the thread sleeps until the interrupt) unless DARWIN_GPU_SYNC=spin.
+// an 8-GPU node has as many spinning threads as cores.  DARWIN_GPU_SYNC=block makes every wait sleep on a
+// cudaEventBlockingSync event instead.  Measured (profiles/r2_sync_mode_ab.log): no difference on 1 GPU / 16 cores, spinning
+// 3 % ahead end to end on 8 GPUs / 32 cores -- so spinning stays the default and blocking is for hosts short of cores.
 static cudaError_t stream_wait(DarwinGpu* h, cudaStream_t st) {
     if (h->spin_sync || !h->ev_wait) return cudaStreamSynchronize(st);
     cudaError_t e = cudaEventRecord(h->ev_wait, st);
@@ -791,7 +792,7 @@ static int create_handle(DarwinGpu** out, int device, uint64_t arena_bytes, Darw
     DarwinGpu* h = new DarwinGpu();
     h->device = device;
     h->timing_dbg = getenv("DARWIN_GPU_TIMING") != nullptr;
-    { const char* e = getenv("DARWIN_GPU_SYNC"); h->spin_sync = e && std::string(e) == "spin"; }
+    { const char* e = getenv("DARWIN_GPU_SYNC"); h->spin_sync = !(e && std::string(e) == "block"); }
     { const char* e = getenv("DARWIN_GPU_SEED_SORT"); h->tune_cub_sort = e && std::string(e) == "cub"; }
     { const char* e = getenv("DARWIN_GPU_MAX_CTAS_PER_SM"); h->tune_max_ctas = e ? atoi(e) : 0; }
     if (cudaSetDevice(device) != cudaSuccess) { delete h; return DARWIN_ERR_NO_DEVICE; }
