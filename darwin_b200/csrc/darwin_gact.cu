@@ -1061,14 +1061,24 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
     if (do_traceback && (!tb_words || tb_words_per_req <= 0)) return DARWIN_ERR_INVALID;
     if (n == 0) return DARWIN_OK;
     CK(cudaSetDevice(h->device));
+    // one pass over the requests (1 M per bench step: this loop is serial host time in front of every launch): bounds, cell
+    // count and the shape class of every tile; index lists are only built when a call really mixes classes
     int maxQ = 0, maxR = 0; uint64_t cells = 0;
+    const bool by_class = do_traceback && h->ks.fc.eligible;
+    uint32_t counts[4] = {0, 0, 0, 0};
+    int cmaxQ[4] = {0, 0, 0, 0}, cmaxR[4] = {0, 0, 0, 0};
+    auto class_of = [](int q, int r) { const int m = q > r ? q : r; return m <= 256 ? 0 : m <= 320 ? 1 : m <= 384 ? 2 : m <= 512 ? 3 : 2; };   // pick_k: K = 4, 5, 6, 8, 6
     for (int i = 0; i < n; i++) {
-        maxQ = std::max<int>(maxQ, req[i].query_size); maxR = std::max<int>(maxR, req[i].ref_size);
-        cells += (uint64_t)req[i].query_size * req[i].ref_size;
-        if (req[i].query_size > kMaxTile || req[i].ref_size > kMaxTile) { h->err = "tile larger than 1984"; return DARWIN_ERR_INVALID; }
-        const uint64_t re = req[i].ref_bases_start_addr + req[i].ref_size, qe = req[i].query_bases_start_addr + req[i].query_size;
+        const int q = req[i].query_size, r = req[i].ref_size;
+        cells += (uint64_t)q * r;
+        if (q > kMaxTile || r > kMaxTile) { h->err = "tile larger than 1984"; return DARWIN_ERR_INVALID; }
+        const uint64_t re = req[i].ref_bases_start_addr + r, qe = req[i].query_bases_start_addr + q;
         if (re > h->arena_bytes || qe > h->arena_bytes) { h->err = "tile outside arena"; return DARWIN_ERR_INVALID; }
+        const int c = class_of(q, r);
+        counts[c]++;
+        cmaxQ[c] = std::max(cmaxQ[c], q); cmaxR[c] = std::max(cmaxR[c], r);
     }
+    for (int c = 0; c < 4; c++) { maxQ = std::max(maxQ, cmaxQ[c]); maxR = std::max(maxR, cmaxR[c]); }
     const size_t req_b = (size_t)n * sizeof(DarwinTileReq), res_b = (size_t)n * sizeof(DarwinTileRes);
     const size_t tb_row = do_traceback ? (size_t)tb_words_per_req * sizeof(uint64_t) : 0;
     int rc;
@@ -1078,23 +1088,17 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
     // Geometry is a property of the TILE, not of the call: when the requests of one call fall into different shape classes
     // (one 400-wide tile among 320 x 320 ones used to push the whole batch onto the two-strip variant), every class gets its
     // own launch over an index list, each with the geometry pick_k chooses for that class.
-    if (do_traceback && h->ks.fc.eligible) {
-        static const int kClassK[4] = {4, 5, 6, 8};
-        std::vector<uint32_t> lists[4];
-        int cmaxQ[4] = {0, 0, 0, 0}, cmaxR[4] = {0, 0, 0, 0};
-        for (int i = 0; i < n; i++) {
-            const int k = pick_k(h, std::max<int>(req[i].query_size, req[i].ref_size), 1);
-            const int c = k == 8 ? 3 : k - 4;
-            lists[c].push_back((uint32_t)i);
-            cmaxQ[c] = std::max<int>(cmaxQ[c], req[i].query_size); cmaxR[c] = std::max<int>(cmaxR[c], req[i].ref_size);
-        }
+    if (by_class) {
         int used_classes = 0;
-        for (int c = 0; c < 4; c++) used_classes += !lists[c].empty();
+        for (int c = 0; c < 4; c++) used_classes += counts[c] != 0;
         if (used_classes > 1) {
+            std::vector<uint32_t> lists[4];
+            for (int c = 0; c < 4; c++) lists[c].reserve(counts[c]);
+            for (int i = 0; i < n; i++) lists[class_of(req[i].query_size, req[i].ref_size)].push_back((uint32_t)i);
             if ((rc = grow_dev(h, 11, (size_t)(n + 4) * sizeof(uint32_t)))) return rc;
             uint32_t* d_lists = (uint32_t*)h->d_buf[11];
-            uint32_t counts[4], offs[4], at = 4;
-            for (int c = 0; c < 4; c++) { counts[c] = (uint32_t)lists[c].size(); offs[c] = at; at += counts[c]; }
+            uint32_t offs[4], at = 4;
+            for (int c = 0; c < 4; c++) { offs[c] = at; at += counts[c]; }
             CK(cudaMemcpyAsync(d_lists, counts, sizeof(counts), cudaMemcpyHostToDevice, h->stream));
             for (int c = 0; c < 4; c++)
                 if (counts[c]) CK(cudaMemcpyAsync(d_lists + offs[c], lists[c].data(), counts[c] * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
@@ -1104,7 +1108,6 @@ int darwin_gpu_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* req, i
             CK(cudaEventRecord(h->ev0, h->stream));
             for (int c = 0; c < 4; c++) {
                 if (!counts[c]) continue;
-                (void)kClassK;
                 if ((rc = launch_tiles(h, 1, (const DarwinTileReq*)h->d_buf[0], n, (DarwinTileRes*)h->d_buf[1], (uint64_t*)h->d_buf[2], tb_words_per_req,
                                        cmaxQ[c], cmaxR[c], d_lists + offs[c], d_lists + c, (int)counts[c]))) return rc;
             }
