@@ -286,9 +286,20 @@ __device__ __forceinline__ void flush_counters(const WarpCtx& cx, unsigned int* 
 
 // BatchAlignmentSIMD (Processor.cpp:718-762) for n independent tiles: persistent warps pull tiles from a
 // global counter.
+// Register budget of the tile kernels.  12 warps of 168 registers fill the register file either way; what a cap changes is
+// ptxas' allocation and scheduling of the forward loop, and that is worth +-4 % (same-box A/B of __maxnreg__ caps and of
+// __launch_bounds__(32, 12), identical result digests: profiles/r2_regcap_ab.log).  __maxnreg__(160) is best for K = 4, 5 and 8
+// (T = 256: 1 408 -> 1 465, T = 320: 1 544 -> 1 610, T = 512: 1 500 -> 1 524 GCUPS), __launch_bounds__ for K = 6 (1 704; the cap
+// gives 1 634) -- __maxnreg__ takes a literal only, hence two entry points over one body.  The extension kernels keep
+// __launch_bounds__ (every cap measured slower).
+#define TILES_KERNEL_PARAMS const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,                          \
+             const DarwinTileReq* __restrict__ req, int n, int do_traceback,                                                    \
+             DarwinTileRes* __restrict__ res, uint64_t* __restrict__ tb_words, int tb_words_per_req,                            \
+             uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base, unsigned int* counter,                             \
+             const unsigned int* __restrict__ idx_list, const unsigned int* __restrict__ idx_count
+#define TILES_KERNEL_ARGS arena, ks, req, n, do_traceback, res, tb_words, tb_words_per_req, trace_base, trace_stride, bound_base, counter, idx_list, idx_count
 template <int K>
-__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 4 : (K == 8) ? 5 : 12)
-tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelScoring ks,
+__device__ __forceinline__ void tiles_body(const uint8_t* __restrict__ arena, const KernelScoring& ks,
              const DarwinTileReq* __restrict__ req, int n, int do_traceback,
              DarwinTileRes* __restrict__ res, uint64_t* __restrict__ tb_words, int tb_words_per_req,
              uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base, unsigned int* counter,
@@ -325,6 +336,18 @@ tiles_kernel(const uint8_t* __restrict__ arena, const __grid_constant__ KernelSc
         __syncwarp();
     }
     flush_counters(cx, counter);
+}
+
+template <int K>
+__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 4 : (K == 8) ? 5 : 12)
+tiles_kernel(TILES_KERNEL_PARAMS) { tiles_body<K>(TILES_KERNEL_ARGS); }
+template <int K>
+__global__ void __maxnreg__(160)
+tiles_kernel_r160(TILES_KERNEL_PARAMS) { tiles_body<K>(TILES_KERNEL_ARGS); }
+template <int K>
+static auto tiles_entry() {
+    if constexpr (K == 4 || K == 5 || K == 8) return &tiles_kernel_r160<K>;
+    else return &tiles_kernel<K>;
 }
 
 // First-tile filter tiles (filter.cpp:28-122 / :131-223 -> BatchAlignmentSIMD with do_traceback = 0, max-cell mode):
@@ -426,8 +449,11 @@ __global__ void filter_finish_kernel(const DarwinFilterCand* __restrict__ cands,
 constexpr int kMaxBandShift = 20;       // the corner itself must stay well inside the +-32 band
 
 // extender_body::operator() (extender.cpp:9-1065): persistent warps pull ANCHORS and walk their tiles.
+#ifndef DARWIN_EXTEND_REGCAP
+#define DARWIN_EXTEND_REGCAP __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 3 : (K == 8) ? 5 : 12)
+#endif
 template <int K>
-__global__ void __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 3 : (K == 8) ? 5 : 12)
+__global__ void DARWIN_EXTEND_REGCAP
 extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ ExtendArgs ea,
               uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base) {
     __shared__ int ssub[32];
@@ -719,12 +745,12 @@ template <int K>
 static int configure_variant(DarwinGpu* h) {
     const size_t smem_t = KernelGeom<K>::kSmem, smem_e = KernelGeom<K>::kSmemExtend;
     const int threads = KernelGeom<K>::kWarps * 32;
-    CK(cudaFuncSetAttribute(tiles_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaFuncSetAttribute(tiles_entry<K>(), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(extend_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(tiles_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(tiles_entry<K>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
     if (smem_e > 48 * 1024) CK(cudaFuncSetAttribute(extend_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
     int a = 0, b = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, tiles_kernel<K>, threads, smem_t));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, tiles_entry<K>(), threads, smem_t));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, extend_kernel<K>, threads, smem_e));
     int cap = h->max_warps / h->sm_count / KernelGeom<K>::kWarps;             // scratch bound
     if (K > 0 && h->tune_max_ctas > 0) cap = std::min(cap, h->tune_max_ctas);  // DARWIN_GPU_MAX_CTAS_PER_SM (A/B measurements)
@@ -1025,7 +1051,7 @@ static int launch_tiles(DarwinGpu* h, int do_traceback, const DarwinTileReq* d_r
     int ctas = h->ctas_tiles[variant_index(K)];
     if (idx_list) ctas = list_len > 0 ? std::max(1, std::min(ctas, list_len)) : std::min(ctas, h->sm_count);   // hand-over lists are short
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), h->stream));      // queue head; [1..3] accumulate
-#define LAUNCH_TILES(KK) tiles_kernel<KK><<<ctas, KernelGeom<KK>::kWarps * 32, KernelGeom<KK>::kSmem, h->stream>>>( \
+#define LAUNCH_TILES(KK) tiles_entry<KK>()<<<ctas, KernelGeom<KK>::kWarps * 32, KernelGeom<KK>::kSmem, h->stream>>>( \
         h->d_arena, h->ks, d_req, n, do_traceback, d_res, d_tb, tb_words_per_req, h->d_trace, h->trace_stride, h->d_bound, h->d_counter, \
         idx_list, idx_count)
     switch (K) {
