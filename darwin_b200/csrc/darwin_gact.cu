@@ -1269,10 +1269,18 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
         size[i] = lcap[i] + 2u * (a.read_len - a.query_pos) + slack;
         base[i] = total; total += size[i];
     }
-    // queue order: longest reads first (their walks are the longest), so the tail of the launch is made of short ones
-    std::vector<uint32_t> order(n);
-    for (int i = 0; i < n; i++) order[i] = (uint32_t)i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return anchors[x].read_len > anchors[y].read_len; });
+    // queue order: longest walks first, so the tail of the launch is made of short ones.  A walk ends where either sequence
+    // ends: min(query, reference) bases to the left of the anchor plus min(query, reference) bases to its right -- the read
+    // length against a chromosome, the length of the overlap when the reference is another read (de novo mode, where every
+    // read has the same length and the overlaps do not).  A scheduling hint only: any permutation gives the same results.
+    std::vector<uint32_t> order(n), walk(n);
+    for (int i = 0; i < n; i++) {
+        const DarwinAnchor& a = anchors[i];
+        const uint32_t rpos = a.reference_pos - a.chr_start;
+        walk[i] = std::min(a.query_pos, rpos) + std::min(a.read_len - a.query_pos, a.ref_len - rpos);
+        order[i] = (uint32_t)i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return walk[x] > walk[y]; });
     TMARK("slots");
     int rc;
     const size_t an_b = (size_t)n * sizeof(DarwinAnchor), res_b = (size_t)n * sizeof(DarwinAlnRes);

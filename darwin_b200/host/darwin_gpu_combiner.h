@@ -268,21 +268,35 @@ private:
             }
             if (rc) { fail_all(batch, rc, "darwin_gpu_align_reads"); return; }
             // every caller's locations are contiguous inside the forward part and inside the reverse part (sorted by read)
-            size_t at = 0;
-            for (auto* b : batch) {
+            // (one pass over the locations finds each caller's share, so that its vectors are sized once: the op strings are
+            // ~11 kB per location and this copy runs while the lane's device is not being fed)
+            std::vector<size_t> first(batch.size() + 1, 0);
+            for (size_t k2 = 0; k2 < batch.size(); k2++) first[k2 + 1] = first[k2] + (size_t)batch[k2]->n;
+            std::vector<uint64_t> n_loc(batch.size(), 0), n_ops(batch.size(), 0);
+            std::vector<uint32_t> owner(n_out);
+            for (uint64_t i = 0; i < n_out; i++) {
+                const size_t rn = (size_t)anchors[i].read_num;
+                const size_t k2 = (size_t)(std::upper_bound(first.begin(), first.end(), rn) - first.begin()) - 1;
+                owner[i] = (uint32_t)k2;
+                n_loc[k2]++;
+                const DarwinAlnRes& r = res[i];
+                if ((r.flags & DARWIN_ALN_EMITTED) && !(r.flags & DARWIN_ALN_OPS_OVERFLOW)) n_ops[k2] += r.n_ops;
+            }
+            for (size_t k2 = 0; k2 < batch.size(); k2++) {
+                Request* b = batch[k2];
                 b->aanchors->clear(); b->ares_v->clear(); b->ops->clear();
-                for (uint64_t i = 0; i < n_out; i++) {
-                    const int rn = anchors[i].read_num;
-                    if (rn < (int)at || rn >= (int)(at + (size_t)b->n)) continue;
-                    DarwinAnchor a = anchors[i]; a.read_num = rn - (int)at;
-                    DarwinAlnRes r = res[i];
-                    const bool has = (r.flags & DARWIN_ALN_EMITTED) && !(r.flags & DARWIN_ALN_OPS_OVERFLOW) && r.n_ops;
-                    const uint64_t off = b->ops->size();
-                    if (has) b->ops->insert(b->ops->end(), ops + r.ops_offset, ops + r.ops_offset + r.n_ops);
-                    r.ops_offset = off;
-                    b->aanchors->push_back(a); b->ares_v->push_back(r);
-                }
-                at += (size_t)b->n;
+                b->aanchors->reserve(n_loc[k2]); b->ares_v->reserve(n_loc[k2]); b->ops->reserve(n_ops[k2]);
+            }
+            for (uint64_t i = 0; i < n_out; i++) {                 // location order is kept per caller
+                const size_t k2 = owner[i];
+                Request* b = batch[k2];
+                DarwinAnchor a = anchors[i]; a.read_num -= (int)first[k2];
+                DarwinAlnRes r = res[i];
+                const bool has = (r.flags & DARWIN_ALN_EMITTED) && !(r.flags & DARWIN_ALN_OPS_OVERFLOW) && r.n_ops;
+                const uint64_t off = b->ops->size();
+                if (has) b->ops->insert(b->ops->end(), ops + r.ops_offset, ops + r.ops_offset + r.n_ops);
+                r.ops_offset = off;
+                b->aanchors->push_back(a); b->ares_v->push_back(r);
             }
         } else if (k == SEED) {
             std::vector<DarwinSeedRead> reads; reads.reserve(total);

@@ -193,3 +193,82 @@ extern "C" int combiner_selftest(const DarwinScoring* s, const char* dram, uint6
         if (n_cands && memcmp(r.data(), f_res.data(), sizeof(DarwinFilterRes) * n_cands)) return 53; }
     return 0;
 }
+
+// ---- ALIGN requests (darwin_gpu_align_reads behind gpu_align_body / gpu_sam_body): merge + scatter with a synthetic
+// stand-in whose output depends only on a read's arena address, laid out like the library's (forward-strand locations
+// sorted by read, then the reverse-strand ones; dense op strings in that order).
+static int n_fwd(uint64_t addr) { return (int)((addr / 128) % 3); }
+static int n_rev(uint64_t addr) { return (int)((addr / 128 + 1) % 2); }
+static uint32_t loc_ops(uint64_t addr, int strand, int j) { return (j == 1 && strand == 0) ? 0u : (uint32_t)(addr % 97) + 5u * (uint32_t)j + 1u; }
+static uint8_t op_byte(uint64_t addr, int strand, int j, uint32_t p) { return (uint8_t)((addr / 128 + 7u * (uint32_t)strand + 3u * (uint32_t)j + p) % 3 + 1); }
+static int f_align(DarwinGpu* h, const DarwinAlignParams*, const DarwinSeedRead* reads, int n, DarwinAnchor* an, DarwinAlnRes* res, uint64_t cap,
+                   uint64_t* n_out, uint8_t* ops, uint64_t ops_cap) {
+    fake(h)->device_calls++; device_latency();
+    uint64_t total = 0, bytes = 0;
+    for (int r = 0; r < n; r++) total += (uint64_t)(n_fwd(reads[r].read_addr) + n_rev(reads[r].read_addr));
+    *n_out = total;
+    if (total > cap) return DARWIN_ERR_CAPACITY;
+    uint64_t at = 0;
+    for (int strand = 0; strand < 2; strand++)
+        for (int r = 0; r < n; r++) {
+            const uint64_t addr = reads[r].read_addr;
+            const int cnt = strand ? n_rev(addr) : n_fwd(addr);
+            for (int j = 0; j < cnt; j++, at++) {
+                an[at] = DarwinAnchor{}; res[at] = DarwinAlnRes{};
+                an[at].read_addr = addr; an[at].read_len = reads[r].read_len; an[at].read_num = r; an[at].strand = (uint8_t)strand;
+                an[at].reference_pos = (uint32_t)addr + (uint32_t)j;
+                const uint32_t no = loc_ops(addr, strand, j);
+                res[at].flags = no ? DARWIN_ALN_EMITTED : 0; res[at].n_ops = no; res[at].ops_offset = bytes; res[at].score = (int32_t)(addr % 1000) + j;
+                if (bytes + no > ops_cap) return DARWIN_ERR_CAPACITY;
+                for (uint32_t p = 0; p < no; p++) ops[bytes + p] = op_byte(addr, strand, j, p);
+                bytes += no;
+            }
+        }
+    return 0;
+}
+
+extern "C" int combiner_align_selftest(int threads, int reads_per_request, int rounds, uint64_t* stats_out) {
+    Fake fk; fk.dram = nullptr; fk.dram_bytes = 0; fk.device_calls = 0; fk.fail_filter = 0; fk.ix = nullptr;
+    DarwinGpu* h = reinterpret_cast<DarwinGpu*>(&fk);
+    GpuCalls calls{f_upload, f_tiles, f_filter, f_extend, f_err, f_seed, f_align};
+    GpuCombiner gc(h, calls);
+    DarwinAlignParams prm{};
+    prm.extend.tile_size = 384; prm.extend.tile_overlap = 64;
+    std::atomic<int> bad(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) {
+        th.emplace_back([&, t] {
+            const std::vector<UploadSpan> none;
+            for (int round = 0; round < rounds; round++) {
+                const int n = (t == 1 && round == 1) ? 0 : reads_per_request + (t % 3);       // one caller comes with no reads at all
+                std::vector<DarwinSeedRead> reads(n);
+                for (int i = 0; i < n; i++) reads[i] = DarwinSeedRead{128ull * (uint64_t)(1 + i + 1000 * t + 100000 * round), 500u + (uint32_t)i, 0};
+                std::vector<DarwinAnchor> an; std::vector<DarwinAlnRes> res; std::vector<uint8_t> ops;
+                std::string err;
+                if (gc.align(prm, none, reads.data(), n, &an, &res, &ops, &err)) { bad |= 1; continue; }
+                size_t at = 0; uint64_t bytes = 0;
+                for (int strand = 0; strand < 2; strand++)
+                    for (int i = 0; i < n; i++) {
+                        const uint64_t addr = reads[i].read_addr;
+                        const int cnt = strand ? n_rev(addr) : n_fwd(addr);
+                        for (int j = 0; j < cnt; j++, at++) {
+                            if (at >= an.size() || at >= res.size()) { bad |= 2; continue; }
+                            const uint32_t no = loc_ops(addr, strand, j);
+                            if (an[at].read_num != i || an[at].read_addr != addr || an[at].strand != strand || an[at].reference_pos != (uint32_t)addr + (uint32_t)j) bad |= 4;
+                            if (res[at].n_ops != no || res[at].score != (int32_t)(addr % 1000) + j || (no != 0) != ((res[at].flags & DARWIN_ALN_EMITTED) != 0)) bad |= 8;
+                            if (no) {
+                                if (res[at].ops_offset != bytes || bytes + no > ops.size()) { bad |= 16; continue; }
+                                for (uint32_t p = 0; p < no; p++) if (ops[bytes + p] != op_byte(addr, strand, j, p)) bad |= 32;
+                                bytes += no;
+                            }
+                        }
+                    }
+                if (at != an.size() || at != res.size() || bytes != ops.size()) bad |= 64;
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    const CombinerStats st = gc.stats();
+    stats_out[0] = st.device_calls[4]; stats_out[1] = st.requests[4]; stats_out[2] = st.max_merged[4]; stats_out[3] = st.items[4];
+    return bad.load() ? 100 + bad.load() : 0;
+}

@@ -51,3 +51,20 @@ def test_combiner_merges_and_scatters(selftest_lib, threads):
         assert list(calls) == list(requests)
     else:
         assert (calls < requests).all() and (merged >= 2).all()             # requests really rode together
+
+
+@pytest.mark.parametrize("threads", [1, 7])
+def test_combiner_align_requests_merge_and_scatter(selftest_lib, threads):
+    """ALIGN requests (gpu_align_body / gpu_sam_body -> darwin_gpu_align_reads): every caller gets exactly its own reads'
+    locations -- forward part then reverse part, read numbers rebased to its own batch, op strings dense in that order --
+    whatever it was merged with, including a caller that brings no reads."""
+    stats = np.zeros(4, np.uint64)
+    rounds = 4
+    rc = selftest_lib.combiner_align_selftest(threads, 9, rounds, abi.ptr(stats))
+    assert rc == 0, rc
+    calls, requests, merged = int(stats[0]), int(stats[1]), int(stats[2])
+    assert requests == threads * rounds
+    if threads == 1:
+        assert calls == requests and merged == 1
+    else:
+        assert calls < requests and merged >= 2
