@@ -14,6 +14,8 @@
 // CPU with stand-in entry points (tests/cpp/test_combiner.cpp).
 #pragma once
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +56,7 @@ struct CombinerStats {
     uint64_t requests[5];       // requests submitted by host threads
     uint64_t items[5];          // tiles / candidates / anchors / reads / reads
     uint64_t max_merged[5];     // largest number of requests served by one device call
+    uint64_t phase_ns[3];       // where the combining threads' time went: [0] uploads, [1] inside the device call, [2] merging + scattering
 };
 
 class GpuCombiner {
@@ -101,7 +104,12 @@ public:
         Request r; r.kind = TILES; r.do_tb = 0; r.up = &up; r.n = 0;
         return run(r, err);
     }
-    CombinerStats stats() { std::lock_guard<std::mutex> g(m_); return st_; }
+    CombinerStats stats() {
+        std::lock_guard<std::mutex> g(m_);
+        CombinerStats s = st_;
+        for (int k = 0; k < 3; k++) s.phase_ns[k] = phase_ns_[k].load();
+        return s;
+    }
     DarwinGpu* handle() const { return h_; }
 
 private:
@@ -185,7 +193,17 @@ private:
         for (auto* b : batch) { b->rc = rc; b->err = msg; }
     }
 
+    static uint64_t now_ns() { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    // accounts the time between two marks of the combining thread to one of CombinerStats::phase_ns
+    struct PhaseClock {
+        std::atomic<uint64_t>* acc; uint64_t last;
+        explicit PhaseClock(std::atomic<uint64_t>* a) : acc(a), last(now_ns()) {}
+        void mark(int phase) { const uint64_t t = now_ns(); acc[phase] += t - last; last = t; }
+    };
+
     void execute(std::vector<Request*>& batch) {
+        PhaseClock clock(phase_ns_);
+        struct Rest { PhaseClock& c; ~Rest() { c.mark(2); } } rest{clock};     // whatever follows the last mark is merge / scatter work
         if (c_.upload_spans) {
             std::vector<DarwinSpan> all;
             for (auto* b : batch)
@@ -202,6 +220,7 @@ private:
                         if (rc) { fail_all(batch, rc, "darwin_gpu_upload"); return; }
                     }
         }
+        clock.mark(0);
         size_t total = 0;
         for (auto* b : batch) total += (size_t)b->n;
         const Kind k = batch[0]->kind;
@@ -263,7 +282,9 @@ private:
                 anchors.resize(cap); res.resize(cap);
                 ops = ops_buffer(ops_cap);
                 if (!ops) { fail_all(batch, DARWIN_ERR_CAPACITY, "host buffer for the op strings"); return; }
+                clock.mark(2);
                 rc = c_.align(h_, &batch[0]->ap, reads.data(), (int)total, anchors.data(), res.data(), cap, &n_out, ops, ops_cap);
+                clock.mark(1);
                 if (rc == DARWIN_ERR_CAPACITY) { if (n_out > cap) cap = n_out; else ops_cap *= 2; }
             }
             if (rc) { fail_all(batch, rc, "darwin_gpu_align_reads"); return; }
@@ -348,8 +369,10 @@ private:
             for (int attempt = 0; attempt < 4 && rc == DARWIN_ERR_CAPACITY; attempt++) {     // like ALIGN: grow the op pool and retry
                 ops = ops_buffer(cap);
                 if (!ops) { fail_all(batch, DARWIN_ERR_CAPACITY, "host buffer for the op strings"); return; }
+                clock.mark(2);
                 rc = c_.extend(h_, &batch[0]->ep, anchors.data(), (int)total, pool.empty() ? nullptr : pool.data(), pool.size(),
                                res.data(), ops, cap);
+                clock.mark(1);
                 if (rc == DARWIN_ERR_CAPACITY) cap *= 2;
             }
             if (rc) { fail_all(batch, rc, "darwin_gpu_extend"); return; }
@@ -381,6 +404,7 @@ private:
     std::deque<Request*> q_;
     bool busy_ = false;
     CombinerStats st_;
+    std::atomic<uint64_t> phase_ns_[3] = {};
     uint8_t* ops_buf_ = nullptr; uint64_t ops_cap_ = 0;
 };
 

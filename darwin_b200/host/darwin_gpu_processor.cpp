@@ -120,6 +120,7 @@ CombinerStats combiner_stats_total() {
             t.device_calls[k] += s.device_calls[k]; t.requests[k] += s.requests[k]; t.items[k] += s.items[k];
             if (s.max_merged[k] > t.max_merged[k]) t.max_merged[k] = s.max_merged[k];
         }
+        for (int k = 0; k < 3; k++) t.phase_ns[k] += s.phase_ns[k];
     }
     return t;
 }

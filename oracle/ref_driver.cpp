@@ -868,6 +868,14 @@ void dref_combiner_stats(uint64_t* out) {
 
 void dref_host_profile(double* out3) { darwin_gpu_host::host_profile(out3); }
 
+// where the combining threads' time went, summed over all combiners since they were created (seconds): uploads, inside
+// the device calls, merging + scattering; then device calls / requests / reads of the ALIGN kind
+void dref_combiner_phases(double* out6) {
+    darwin_gpu_host::CombinerStats s = darwin_gpu_host::combiner_stats_total();
+    for (int k = 0; k < 3; k++) out6[k] = (double)s.phase_ns[k] * 1e-9;
+    out6[3] = (double)s.device_calls[4]; out6[4] = (double)s.requests[4]; out6[5] = (double)s.items[4];
+}
+
 // seed position table on the GPUs (after dref_gpu_init)
 int dref_gpu_seed_index(void) {
     try { darwin_gpu_host::BuildSeedIndex(); } catch (const std::exception& e) { fprintf(stderr, "dref_gpu_seed_index: %s\n", e.what()); return -1; }
