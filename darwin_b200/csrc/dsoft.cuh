@@ -10,9 +10,9 @@
 //   hit_count / hit_fill   one thread per seed: bucket look-up, hits at or beyond the seed's read offset
 //   (segmented stable sort by (bin, read offset); ties keep ascending hit order like std::stable_sort)
 //   candidate_kernel   one thread per strand: the sequential bin-coverage scan (curr_count rule), count pass + fill pass
-//   window_kernel      one warp per candidate: copies the hits of its SV window as (hit << 32 | offset) keys
-//   (segmented sort of every candidate's window by that key)
-//   chain_kernel       one thread per candidate: greedy collinear chains to the left and right of the anchor
+//   window_chain_kernel   one CTA per candidate: its SV window as (hit << 32 | offset) keys sorted in shared memory, the
+//                      greedy collinear chains to the left and right of the anchor as min / max scans over the sorted window
+//   (windows beyond shared memory: window_copy_kernel -> CUB segmented sort -> chain_kernel, one thread per candidate)
 //   order_kernel       one thread per strand: final order (chained hits descending, hit_offset ascending)
 #pragma once
 #include <vector>
@@ -431,22 +431,99 @@ __global__ void window_size_kernel(const SeedConst sc, const uint64_t* __restric
     if (win_max) atomicMax(win_max, x - ws);
 }
 
-// SV window of one candidate, sorted by (hit, offset) (seed_pos_table.cpp:403-428): one CTA per candidate, straight from
-// the strand's sorted hits into shared memory, out as (hit << 32 | offset) keys ((hit, offset) pairs are unique)
-__global__ void window_sort_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                   const uint32_t* __restrict__ win_lo, const uint32_t* __restrict__ win_n,
-                                   const uint64_t* __restrict__ win_off, uint64_t* __restrict__ wkeys) {
+// Exclusive scan over the CTA's threads (blockDim a multiple of 32, <= 1024) for any associative op; *total = the fold over
+// all threads (every thread gets it).  warp_tot: 32 words of shared memory.
+template <class Op>
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t ident, uint32_t* warp_tot, uint32_t* total, Op op) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (int)(blockDim.x >> 5);
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = op(t, inc); }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    uint32_t pre = ident, all = ident;
+    for (int k = 0; k < nw; k++) { const uint32_t w = warp_tot[k]; if (k < wid) pre = op(pre, w); all = op(all, w); }
+    __syncthreads();
+    uint32_t ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) ex = ident;
+    if (total) *total = all;
+    return op(pre, ex);
+}
+struct OpMinU { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a < b ? a : b; } };
+struct OpMaxU { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } };
+struct OpAddU { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a + b; } };
+
+// One side of the greedy collinear chain (seed_pos_table.cpp:430-497) on a window sorted by (hit, offset), as a scan.
+// The reference walks away from the anchor and takes a hit v when hit(cur) >= hit(v) && offset(cur) >= offset(v) (left; <=
+// on the right), then cur = v.  Walking a sorted window the hit condition always holds, so a hit is taken iff its offset is
+// <= (>=) the offset of the last hit taken -- and since a hit that is NOT taken has an offset beyond that bound, the bound
+// is simply the running minimum (maximum) of ALL offsets seen so far, anchor included: an exclusive min / max scan.
+// Elements are a[first + DIR * p], p = 0 (next to the anchor) .. count - 1; the K hits taken go to out[K - 1 - r], r = their
+// rank walking away from the anchor (left chain ascending, right chain descending, as the reference stores them).
+template <int DIR>
+__device__ __forceinline__ uint32_t chain_side(const uint64_t* a, uint32_t first, uint32_t count, uint32_t anchor_off,
+                                               uint64_t* __restrict__ out, uint32_t* warp_tot) {
+    const uint32_t seg = (count + blockDim.x - 1) / blockDim.x;
+    const uint32_t p0 = min(count, threadIdx.x * seg), p1 = min(count, p0 + seg);
+    uint32_t ext = DIR < 0 ? 0xFFFFFFFFu : 0u;
+    for (uint32_t p = p0; p < p1; p++) {
+        const uint32_t o = (uint32_t)a[DIR < 0 ? first - p : first + p];
+        ext = DIR < 0 ? min(ext, o) : max(ext, o);
+    }
+    uint32_t bound = DIR < 0 ? block_scan_excl(ext, 0xFFFFFFFFu, warp_tot, nullptr, OpMinU())
+                             : block_scan_excl(ext, 0u, warp_tot, nullptr, OpMaxU());
+    bound = DIR < 0 ? min(bound, anchor_off) : max(bound, anchor_off);
+    uint32_t cnt = 0, b = bound;
+    for (uint32_t p = p0; p < p1; p++) {
+        const uint32_t o = (uint32_t)a[DIR < 0 ? first - p : first + p];
+        if (DIR < 0 ? o <= b : o >= b) { cnt++; b = o; }
+    }
+    uint32_t K = 0;
+    uint32_t rank = block_scan_excl(cnt, 0u, warp_tot, &K, OpAddU());
+    b = bound;
+    for (uint32_t p = p0; p < p1; p++) {
+        const uint64_t v = a[DIR < 0 ? first - p : first + p];
+        const uint32_t o = (uint32_t)v;
+        if (DIR < 0 ? o <= b : o >= b) { out[K - 1 - rank] = v; rank++; b = o; }
+    }
+    return K;
+}
+
+// SV window of one candidate, sorted by (hit, offset) in shared memory (seed_pos_table.cpp:403-428) AND chained there
+// (:430-497): one CTA per candidate, straight from the strand's sorted hits, without a round trip of the sorted windows
+// through HBM and with the chains as parallel scans (chain_side) instead of one thread per candidate walking its window
+// twice per side.  A launch serves the candidates whose window
+// size is in (n_lo, n_hi]: windows differ by two orders of magnitude, and a CTA sized for the largest one wastes the SM on
+// the many small ones.  Output as chain_kernel: pool[win_off[c] + c ..): left chain ascending, then right chain descending.
+__global__ void window_chain_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                    const uint32_t* __restrict__ cand_hit_idx, const uint32_t* __restrict__ win_lo,
+                                    const uint32_t* __restrict__ win_n, const uint64_t* __restrict__ win_off, uint32_t n_lo, uint32_t n_hi,
+                                    uint64_t* __restrict__ pool, DarwinSeedAnchor* __restrict__ tmp_anchor) {
     extern __shared__ __align__(16) unsigned char dsoft_smem[];
+    __shared__ uint32_t warp_tot[32];
     uint64_t* a = reinterpret_cast<uint64_t*>(dsoft_smem);
     const uint32_t c = blockIdx.x, n = win_n[c], lo = win_lo[c];
-    if (n == 0) return;
+    if (n > n_hi || (n <= n_lo && n_lo != 0)) return;             // another launch's size class (block-uniform)
     const uint32_t npad = pow2_ceil(n);
     for (uint32_t j = threadIdx.x; j < npad; j += blockDim.x)
         a[j] = j < n ? ((uint64_t)vals[lo + j] << 32) | (uint32_t)keys[lo + j] : ~0ull;
     __syncthreads();
     bitonic_sort_smem(a, npad);
-    uint64_t* out = wkeys + win_off[c];
-    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) out[j] = a[j];
+    const uint32_t hi_idx = cand_hit_idx[c];
+    const uint64_t anchor = ((uint64_t)vals[hi_idx] << 32) | (uint32_t)keys[hi_idx];
+    uint32_t x = 0, y = n;                                          // position of the anchor ((hit, offset) pairs are unique)
+    while (x < y) { const uint32_t mid = (x + y) >> 1; if (a[mid] < anchor) x = mid + 1; else y = mid; }
+    const uint32_t ai = x;
+    const uint64_t base = win_off[c] + c;                          // regions are win_n + 1 long
+    uint64_t* out = pool + base;
+    const uint32_t kl = chain_side<-1>(a, ai - 1, ai, (uint32_t)anchor, out, warp_tot);
+    const uint32_t kr = chain_side<+1>(a, ai + 1, n > ai ? n - ai - 1 : 0u, (uint32_t)anchor, out + kl + 1, warp_tot);
+    if (threadIdx.x == 0) {
+        out[kl] = anchor; out[kl + 1 + kr] = anchor;
+        DarwinSeedAnchor an;
+        an.hit_offset = anchor; an.left_off = base; an.left_n = kl + 1; an.right_off = base + kl + 1; an.right_n = kr + 1;
+        tmp_anchor[c] = an;
+    }
 }
 
 // copy every candidate's window as (hit << 32 | offset) keys; one warp per candidate

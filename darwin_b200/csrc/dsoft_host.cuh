@@ -265,17 +265,28 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
     if (keep_pool) { anchor_vec->resize(n_cands); anchors = anchor_vec->data(); }
     else if (n_cands > anchors_cap || need_pool > pool_cap) { h->err = "seed output capacity: need " + std::to_string(n_cands) + " anchors, " + std::to_string(need_pool) + " pool entries"; return DARWIN_ERR_CAPACITY; }
     DevBuf d_w0, d_w1, d_pool, d_tanc, d_anc, d_tmp2;
-    CKS(d_w1.alloc(sizeof(uint64_t) * n_win, h->stream)); CKS(d_pool.alloc(sizeof(uint64_t) * need_pool, h->stream));
+    CKS(d_pool.alloc(sizeof(uint64_t) * need_pool, h->stream));
     CKS(d_tanc.alloc(sizeof(DarwinSeedAnchor) * n_cands, h->stream)); CKS(d_anc.alloc(sizeof(DarwinSeedAnchor) * n_cands, h->stream));
     uint32_t win_pad = 64; while (win_pad < win_max) win_pad <<= 1;
     if (!h->tune_cub_sort && (size_t)win_pad * 8 <= kSortSmemMax) {
-        // one CTA per candidate sorts its window in shared memory
-        const int threads = win_pad <= 512 ? 128 : win_pad <= 4096 ? 256 : 1024;
-        CKS(cudaFuncSetAttribute(window_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemMax));
-        window_sort_kernel<<<n_cands, threads, (size_t)win_pad * 8, h->stream>>>(keys, vals, d_wlo.as<uint32_t>(), d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w1.as<uint64_t>());
-        CKS(cudaGetLastError());
+        // one CTA per candidate sorts its window in shared memory and chains it there (window_chain_kernel); one launch per
+        // size class, so that the many small windows are not held to the CTA shape of the largest one
+        CKS(cudaFuncSetAttribute(window_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSortSmemMax));
+        const uint32_t cls_hi[3] = {1024u, 4096u, win_pad};
+        const int cls_threads[3] = {128, 256, 1024};
+        uint32_t n_lo = 0;
+        for (int k = 0; k < 3; k++) {
+            const uint32_t n_hi = std::min(cls_hi[k], win_pad);
+            window_chain_kernel<<<n_cands, cls_threads[k], (size_t)n_hi * 8, h->stream>>>(
+                keys, vals, d_cidx.as<uint32_t>(), d_wlo.as<uint32_t>(), d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), n_lo, n_hi,
+                d_pool.as<uint64_t>(), d_tanc.as<DarwinSeedAnchor>());
+            CKS(cudaGetLastError());
+            h->stats.kernel_launches++;
+            if (n_hi >= win_pad) break;
+            n_lo = n_hi;
+        }
     } else {
-        CKS(d_w0.alloc(sizeof(uint64_t) * n_win, h->stream));
+        CKS(d_w0.alloc(sizeof(uint64_t) * n_win, h->stream)); CKS(d_w1.alloc(sizeof(uint64_t) * n_win, h->stream));
         window_copy_kernel<<<(unsigned)(((uint64_t)n_cands * 32 + 255) / 256), 256, 0, h->stream>>>(keys, vals, n_cands, d_wlo.as<uint32_t>(), d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w0.as<uint64_t>());
         CKS(cudaGetLastError());
         size_t tmp_bytes = 0;
@@ -284,14 +295,15 @@ static int seed_query(DarwinGpu* h, const SeedIndex& ix, const DarwinSeedRead* r
         CKS(d_tmp2.alloc(tmp_bytes, h->stream));
         CKS(cub::DeviceSegmentedSort::SortKeys(d_tmp2.p, tmp_bytes, d_w0.as<uint64_t>(), d_w1.as<uint64_t>(), (int64_t)n_win, (int64_t)n_cands,
                                                d_woff.as<uint64_t>(), d_woff.as<uint64_t>() + 1, h->stream));
+        chain_kernel<<<(n_cands + 127) / 128, 128, 0, h->stream>>>(keys, vals, d_cidx.as<uint32_t>(), n_cands, d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w1.as<uint64_t>(),
+                                                                  d_pool.as<uint64_t>(), d_tanc.as<DarwinSeedAnchor>());
+        CKS(cudaGetLastError());
+        h->stats.kernel_launches += 2;
     }
-    chain_kernel<<<(n_cands + 127) / 128, 128, 0, h->stream>>>(keys, vals, d_cidx.as<uint32_t>(), n_cands, d_wn.as<uint32_t>(), d_woff.as<uint64_t>(), d_w1.as<uint64_t>(),
-                                                              d_pool.as<uint64_t>(), d_tanc.as<DarwinSeedAnchor>());
-    CKS(cudaGetLastError());
     order_kernel<<<(ns + 127) / 128, 128, 0, h->stream>>>(d_coff.as<uint32_t>(), ns, d_tanc.as<DarwinSeedAnchor>(), d_anc.as<DarwinSeedAnchor>());
     CKS(cudaGetLastError());
     CKS(cudaEventRecord(h->ev1, h->stream));
-    h->stats.kernel_launches += 7;
+    h->stats.kernel_launches += 5;
     CKS(cudaMemcpyAsync(anchors, d_anc.p, sizeof(DarwinSeedAnchor) * n_cands, cudaMemcpyDeviceToHost, h->stream));
     if (keep_pool) { keep_pool->p = d_pool.p; keep_pool->st = h->stream; d_pool.p = nullptr; }
     else CKS(cudaMemcpyAsync(pool, d_pool.p, sizeof(uint64_t) * need_pool, cudaMemcpyDeviceToHost, h->stream));
