@@ -98,3 +98,45 @@ def test_synthetic_anchor_set_runs_through_oracle():
     res2, ops2 = port.extend(arena, abi.ExtendParams(384, 64, 0, 0), anchors, hits, oracle.Port.CLEAN)
     from conftest import alignments_equal, ALN_FIELDS_OURS
     assert alignments_equal(res, ops, res2, ops2, ALN_FIELDS_OURS) == []
+
+
+def test_collinear_chain_is_a_running_minimum_scan():
+    """dsoft.cuh chain_side: on a window sorted by (hit, offset) the reference's greedy chain (seed_pos_table.cpp:430-497:
+    walk away from the anchor, take v when hit(cur) >= hit(v) and offset(cur) >= offset(v), then cur = v) takes exactly the
+    hits whose offset is <= the minimum (>= the maximum on the right) of ALL offsets seen before them, anchor included --
+    the identity that lets window_chain_kernel build the chains as block scans."""
+    import random
+
+    def greedy(w, ai):
+        cur, left = w[ai], []
+        for h in range(ai - 1, -1, -1):
+            if cur[0] >= w[h][0] and cur[1] >= w[h][1]:
+                left.append(w[h]); cur = w[h]
+        cur, right = w[ai], []
+        for h in range(ai + 1, len(w)):
+            if cur[0] <= w[h][0] and cur[1] <= w[h][1]:
+                right.append(w[h]); cur = w[h]
+        return left, right
+
+    def scans(w, ai):
+        m, left = w[ai][1], []
+        for h in range(ai - 1, -1, -1):
+            if w[h][1] <= m:
+                left.append(w[h])
+            m = min(m, w[h][1])
+        m, right = w[ai][1], []
+        for h in range(ai + 1, len(w)):
+            if w[h][1] >= m:
+                right.append(w[h])
+            m = max(m, w[h][1])
+        return left, right
+
+    rng = random.Random(7)
+    for _ in range(5000):
+        n = rng.randint(1, 48)
+        s = set()
+        while len(s) < n:
+            s.add((rng.randint(0, 14), rng.randint(0, 14)))         # many equal hits and equal offsets
+        w = sorted(s)
+        ai = rng.randrange(n)
+        assert greedy(w, ai) == scans(w, ai)
