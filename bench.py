@@ -38,7 +38,7 @@ OPS_PER_CELL = 32          # algorithmic integer ops per DP cell
 # ALU-pipe utilisation of the dominant kernel in the committed `ncu --set full` capture (profiles/, sm__inst_executed_pipe_alu
 # .avg.pct_of_peak_sustained_active); the honest ceiling figure next to roofline.frac, which the tagged-score formulation
 # pushes above 1 (it needs fewer than the 32 nominal ops per cell)
-NCU_ALU_PIPE_BUSY = {"value": 78.9, "source": "profiles/r2_final_tiles_kernel_r160_5_ncu_summary.txt"}
+NCU_ALU_PIPE_BUSY = {"value": 81.6, "source": "profiles/r2_final_tiles_kernel_r160_5_ncu_summary.txt"}
 
 
 class ClockSampler(threading.Thread):
@@ -740,12 +740,12 @@ def main():
         per_gpu_gcups = value / world
         roof = {"bound": "int_alu", "achieved": per_gpu_gcups * OPS_PER_CELL, "peak": int_peak,
                 "unit": "Gint-op/s", "frac": (per_gpu_gcups * OPS_PER_CELL / int_peak) if int_peak else None,
-                # dram__bytes_read+write of tiles_kernel_r160<5> from the committed ncu capture
-                # (profiles/r2_final_tiles_kernel_r160_5_*: 76.7 MB read + 16.1 MB written per 200k-tile launch = 464 B per tile;
-                # the writes vary between captures with what L2 still holds at the end: 11.6 MB in profiles/r2_tiles_kernel5_*),
+                # dram__bytes_read+write of tiles_kernel_r160<5> from the committed ncu capture of the shipped build
+                # (profiles/r2_final_tiles_kernel_r160_5_*: 76.7 MB read + 11.8 MB written per 200k-tile launch = 442 B per tile;
+                # the writes vary between captures with what L2 still holds at the end: 16.1 MB in r2_final_narrow_*),
                 # scaled to this launch's tile count; algorithmic bytes: ~460 B per tile (320 B packed bases + 32 B request +
                 # 16 B result + the used TB words)
-                "traffic": 464.0 * n, "traffic_source": "constant_from_ncu (profiles/: dram__bytes_read+write per tile of the committed capture x tiles; not a live counter)",
+                "traffic": 442.0 * n, "traffic_source": "constant_from_ncu (profiles/: dram__bytes_read+write per tile of the committed capture x tiles; not a live counter)",
                 "alu_pipe_busy_ncu_pct": NCU_ALU_PIPE_BUSY,
                 "peak_detail_glaneops": dict(zip(["vimnmx_u16x2", "viaddmnmx_u16x2", "vimnmx3_u16x2", "iadd3", "lop3_3reg", "imad", "lop3_2reg", "lop3_imm", "prmt", "shfl_idx"], int_detail)) if int_detail else None,
                 "note": "SURVEY 8(d) integer-pipe roofline: 32 algorithmic int-ops per cell; peak = measured packed "
