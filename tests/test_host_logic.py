@@ -140,3 +140,14 @@ def test_collinear_chain_is_a_running_minimum_scan():
         w = sorted(s)
         ai = rng.randrange(n)
         assert greedy(w, ai) == scans(w, ai)
+
+
+def test_build_reports_the_code_shape_of_the_library():
+    """__graft_entry__.build() selects the build shape by the register count of the headline tile kernel (DESIGN 4.1 'code
+    shape'): the probe must find that kernel in the library build() left in the tree."""
+    import shutil
+    import __graft_entry__ as g
+    if not os.path.exists(g.LIB) or shutil.which("cuobjdump") is None and not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
+        pytest.skip("no built library / no cuobjdump")
+    regs = g._probe_regs(g.LIB)
+    assert regs is not None and 32 <= regs <= 255
