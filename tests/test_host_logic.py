@@ -146,6 +146,7 @@ def test_build_reports_the_code_shape_of_the_library():
     """__graft_entry__.build() selects the build shape by the register count of the headline tile kernel (DESIGN 4.1 'code
     shape'): the probe must find that kernel in the library build() left in the tree."""
     import shutil
+    import pytest
     import __graft_entry__ as g
     if not os.path.exists(g.LIB) or shutil.which("cuobjdump") is None and not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
         pytest.skip("no built library / no cuobjdump")
