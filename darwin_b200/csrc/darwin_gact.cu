@@ -20,13 +20,21 @@
 #include "gact_score.cuh"
 #include "gact_extend.cuh"
 #include "gact_filter.cuh"
+#ifndef DARWIN_TU_EXTEND
 #include "dsoft.cuh"
+#endif
 
 using namespace gact;
 
 // =====================================================================================================
 // Kernels
 // =====================================================================================================
+// Translation units.  This file is compiled twice (__graft_entry__.py): once as the library proper (DARWIN_SPLIT_TUS) and
+// once with DARWIN_TU_EXTEND, which keeps only the device code the extension kernels need, extend_kernel<K> itself and
+// darwin_extend_kernel_ptr().  nvcc emits a translation unit in one of two code shapes, the tile kernels are
+// faster in one and the extension kernels in the other: two units let build() pick a shape for each.  Without either
+// macro the file is one unit as before.
+#ifndef DARWIN_TU_EXTEND
 
 // ASCII -> 4-bit arena codes (Nt2Int, Processor.cpp:21-46: ACGT either case -> 0..3, everything else -> N).
 __device__ __forceinline__ uint32_t nt_code(char c) {
@@ -78,6 +86,8 @@ __global__ void __launch_bounds__(128) pack_arena_kernel(uint8_t* __restrict__ a
         arena[b] = (uint8_t)out;
     }
 }
+
+#endif  // !DARWIN_TU_EXTEND
 
 struct TbWordSink {                 // AddToTracebackPointers, Processor.cpp:568-582 (32 ops per u64; written as 2 x u32)
     uint32_t* wptr; uint32_t* wend; uint32_t* wbeg; int n; uint32_t cur; int shift; int overflow; bool wr;
@@ -284,6 +294,7 @@ __device__ __forceinline__ void flush_counters(const WarpCtx& cx, unsigned int* 
     }
 }
 
+#ifndef DARWIN_TU_EXTEND
 // BatchAlignmentSIMD (Processor.cpp:718-762) for n independent tiles: persistent warps pull tiles from a
 // global counter.
 // Register budget of the tile kernels.  12 warps of 168 registers fill the register file either way; what a cap changes is
@@ -446,9 +457,11 @@ __global__ void filter_finish_kernel(const DarwinFilterCand* __restrict__ cands,
     out[k] = r;
 }
 
-constexpr int kMaxBandShift = 20;       // the corner itself must stay well inside the +-32 band
+#endif  // !DARWIN_TU_EXTEND
 
 // extender_body::operator() (extender.cpp:9-1065): persistent warps pull ANCHORS and walk their tiles.
+#if !defined(DARWIN_SPLIT_TUS) || defined(DARWIN_TU_EXTEND)
+constexpr int kMaxBandShift = 20;       // the corner itself must stay well inside the +-32 band
 #ifndef DARWIN_EXTEND_REGCAP
 #define DARWIN_EXTEND_REGCAP __launch_bounds__(KernelGeom<K>::kWarps * 32, (K == 0) ? 3 : (K == 8) ? 5 : 12)
 #endif
@@ -539,7 +552,25 @@ extend_kernel(const __grid_constant__ KernelScoring ks, const __grid_constant__ 
     }
     flush_counters(cx, ea.counter);
 }
+#endif  // extend_kernel<K> lives in this unit
 
+// The host side reaches extend_kernel<K> through its function pointer (cudaFuncSetAttribute, the occupancy query and
+// cudaLaunchKernel all take one), so that the kernel can live in a translation unit of its own.
+#if defined(DARWIN_SPLIT_TUS) && !defined(DARWIN_TU_EXTEND)
+extern "C" __attribute__((visibility("hidden"))) const void* darwin_extend_kernel_ptr(int K);
+#else
+extern "C" __attribute__((visibility("hidden"))) const void* darwin_extend_kernel_ptr(int K) {
+    switch (K) {
+        case 4: return (const void*)extend_kernel<4>;
+        case 5: return (const void*)extend_kernel<5>;
+        case 6: return (const void*)extend_kernel<6>;
+        case 8: return (const void*)extend_kernel<8>;
+        default: return (const void*)extend_kernel<0>;
+    }
+}
+#endif
+
+#ifndef DARWIN_TU_EXTEND
 // AlignmentScore (extender.cpp:1161-1200) + compaction of the op slots into a dense pool.
 // One WARP per alignment, 32 ops per iteration.  The reference walks the two gapped strings left to right; per aligned
 // column it adds sub(r, q) and, if a run of gap columns (I and D mixed) precedes it, max(go + (L-1) ge, lgo + (L-1) lge)
@@ -746,12 +777,13 @@ static int configure_variant(DarwinGpu* h) {
     const size_t smem_t = KernelGeom<K>::kSmem, smem_e = KernelGeom<K>::kSmemExtend;
     const int threads = KernelGeom<K>::kWarps * 32;
     CK(cudaFuncSetAttribute(tiles_entry<K>(), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CK(cudaFuncSetAttribute(extend_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    const void* ext = darwin_extend_kernel_ptr(K);
+    CK(cudaFuncSetAttribute(ext, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (smem_t > 48 * 1024) CK(cudaFuncSetAttribute(tiles_entry<K>(), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-    if (smem_e > 48 * 1024) CK(cudaFuncSetAttribute(extend_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
+    if (smem_e > 48 * 1024) CK(cudaFuncSetAttribute(ext, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_e));
     int a = 0, b = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, tiles_entry<K>(), threads, smem_t));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, extend_kernel<K>, threads, smem_e));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ext, threads, smem_e));
     int cap = h->max_warps / h->sm_count / KernelGeom<K>::kWarps;             // scratch bound
     if (K > 0 && h->tune_max_ctas > 0) cap = std::min(cap, h->tune_max_ctas);  // DARWIN_GPU_MAX_CTAS_PER_SM (A/B measurements)
     a = std::max(1, std::min(a, cap)); b = std::max(1, std::min(b, cap));
@@ -1306,8 +1338,11 @@ static int extend_chunk(DarwinGpu* h, const DarwinExtendParams* p, const DarwinA
     CK(cudaEventRecord(h->ev0, h->stream));
     const int K = pick_k(h, p->tile_size, 1);
     const int ctas = h->ctas_extend[variant_index(K)];
-#define LAUNCH_EXTEND(KK) extend_kernel<KK><<<ctas, KernelGeom<KK>::kWarps * 32, KernelGeom<KK>::kSmemExtend, h->stream>>>( \
-        h->ks, ea, h->d_trace, h->trace_stride, h->d_bound)
+    // extend_kernel<K>(KernelScoring, ExtendArgs, uint8_t* trace_base, size_t trace_stride, ChainRec* bound_base)
+    KernelScoring a_ks = h->ks; ExtendArgs a_ea = ea; uint8_t* a_trace = h->d_trace; size_t a_stride = h->trace_stride; ChainRec* a_bound = h->d_bound;
+    void* ext_args[5] = {&a_ks, &a_ea, &a_trace, &a_stride, &a_bound};
+#define LAUNCH_EXTEND(KK) CK(cudaLaunchKernel(darwin_extend_kernel_ptr(KK), dim3((unsigned)ctas), dim3(KernelGeom<KK>::kWarps * 32), ext_args, \
+                                              KernelGeom<KK>::kSmemExtend, h->stream))
     switch (K) {
         case 4: LAUNCH_EXTEND(4); break;
         case 5: LAUNCH_EXTEND(5); break;
@@ -1590,3 +1625,4 @@ int darwin_gpu_stats(DarwinGpu* h, DarwinGpuStats* out) {
 }
 
 } // extern "C"
+#endif  // !DARWIN_TU_EXTEND

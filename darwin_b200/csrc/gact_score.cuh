@@ -49,7 +49,7 @@ __host__ inline ScoreConst make_score_const(const DevScoring& sc, const FastCons
 }
 
 // true (warp-uniform) when the tile provably returns zero traceback pointers.  Sequences staged in v.sref / v.sqry.
-__device__ bool score_only_corner_is_zero(const ScoreConst& sc, const MultiSmemView& v, int Q, int R) {
+static __device__ bool score_only_corner_is_zero(const ScoreConst& sc, const MultiSmemView& v, int Q, int R) {
     constexpr int K = SK;
     const int lane = lane_id();
     const uint32_t zeroc = sc.zeroc, pkc = sc.pkc, negc = sc.negc, mma = sc.mma, goa = sc.goa, lgoa = sc.lgoa;

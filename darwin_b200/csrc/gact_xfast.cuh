@@ -75,7 +75,7 @@ __host__ __device__ inline size_t xfast_trace_bytes(int Q, int R) {
 __host__ __device__ inline bool xfast_shape_ok(int Q) { return Q >= 16 && (((Q + 15) >> 4) % XK) == 0; }
 
 // Forward pass; returns the corner score.  trace: warp's global scratch, bound: >= R records of 16 bytes.
-__device__ int xfast_forward(const XConst& xc, const XSmemView& v, uint32_t* trace, uint4* bound, int Q, int R) {
+static __device__ int xfast_forward(const XConst& xc, const XSmemView& v, uint32_t* trace, uint4* bound, int Q, int R) {
     constexpr int K = XK;
     constexpr uint32_t CLEAN = 0xFFE0FFE0u;
     const int lane = lane_id();
