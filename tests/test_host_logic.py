@@ -143,12 +143,13 @@ def test_collinear_chain_is_a_running_minimum_scan():
 
 
 def test_build_reports_the_code_shape_of_the_library():
-    """__graft_entry__.build() selects the build shape by the register count of the headline tile kernel (DESIGN 4.1 'code
-    shape'): the probe must find that kernel in the library build() left in the tree."""
+    """__graft_entry__.build() selects the build shape of each translation unit by the register count of one of its kernels
+    (DESIGN 4.1 'code shape'): the probes must find those kernels in the library build() left in the tree."""
     import shutil
     import pytest
     import __graft_entry__ as g
     if not os.path.exists(g.LIB) or shutil.which("cuobjdump") is None and not os.path.exists("/usr/local/cuda/bin/cuobjdump"):
         pytest.skip("no built library / no cuobjdump")
-    regs = g._probe_regs(g.LIB)
-    assert regs is not None and 32 <= regs <= 255
+    for _, _, probe, _, _ in g.UNITS:                        # the probe kernel of every translation unit
+        regs = g._probe_regs(g.LIB, probe)
+        assert regs is not None and 32 <= regs <= 255, probe
