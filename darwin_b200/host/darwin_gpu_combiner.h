@@ -297,6 +297,8 @@ private:
             std::vector<uint32_t> owner(n_out);
             for (uint64_t i = 0; i < n_out; i++) {
                 const size_t rn = (size_t)anchors[i].read_num;
+                owner[i] = UINT32_MAX;
+                if (anchors[i].read_num < 0 || rn >= total) continue;            // not a read of this call: nobody's
                 const size_t k2 = (size_t)(std::upper_bound(first.begin(), first.end(), rn) - first.begin()) - 1;
                 owner[i] = (uint32_t)k2;
                 n_loc[k2]++;
@@ -310,6 +312,7 @@ private:
             }
             for (uint64_t i = 0; i < n_out; i++) {                 // location order is kept per caller
                 const size_t k2 = owner[i];
+                if (k2 == UINT32_MAX) continue;
                 Request* b = batch[k2];
                 DarwinAnchor a = anchors[i]; a.read_num -= (int)first[k2];
                 DarwinAlnRes r = res[i];
